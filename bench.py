@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline measurement (contract: see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, libodevit.so)
+    python bench.py --impl reference --gpus N ...            # reference arm: CPU PyTorch path (oracle port)
+
+A "step" is one optimizer step of ODE-ViT CE training on one synthetic batch: patch embed ->
+fixed-grid solve of the vector field (the hot path, libodevit.so) -> head -> cross-entropy ->
+backward (reverse sweep through the solver) -> [gradient all-reduce] -> clip 1.0 -> AdamW.
+Workload at N=1 = BASELINE.json configs[1] (the C100 shape of SURVEY section 8: 224 px, patch 16,
+D=768, H=12, mlp_ratio 1, 10 registers, N=207 tokens, Euler over 24 grid points, 64 images per
+GPU), weak scaling over N.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1]; YAML experiment_vit_edo.yaml solver/batch, SURVEY 8 "C100" shape
+    "c100": dict(cfg=dict(img_size=224, patch_size=16, num_classes=100, embed_dim=768, num_heads=12,
+                          mlp_ratio=1.0, emulate_depth=12, time_interval=1.0, num_eval_steps=24,
+                          solver="euler", register_tokens=10),
+                 batch=64, cpu_sample_batch=8,
+                 name="ODE-ViT C100-shape CE training (224px p16 D768 H12 r1 R10 N207, euler T=24)"),
+    # BASELINE.json configs[0]: the CIFAR-10 model, RK4 (3/8), T=5
+    "c10": dict(cfg=dict(img_size=32, patch_size=4, num_classes=10, embed_dim=192, num_heads=3,
+                         mlp_ratio=4.0, emulate_depth=12, time_interval=1.0, num_eval_steps=5,
+                         solver="rk4", register_tokens=4),
+                batch=512, cpu_sample_batch=8,
+                name="ODE-ViT CIFAR-10 CE training (32px p4 D192 H3 r4 R4 N69, rk4 T=5)"),
+}
+STAGES = {"euler": 1, "midpoint": 2, "rk4": 4}
+
+
+def field_flops_fwd(cfg) -> float:
+    """forward FLOPs of one field evaluation for one image = 8ND^2 + 4rND^2 + 4N^2D."""
+    D = cfg["embed_dim"]
+    N = (cfg["img_size"] // cfg["patch_size"]) ** 2 + 1 + cfg["register_tokens"]
+    hid = int(D * cfg["mlp_ratio"])
+    return 8.0 * N * D * D + 4.0 * N * D * hid + 4.0 * N * N * D
+
+
+def class_flops(cfg, B) -> dict:
+    """Algorithmic FLOPs of ONE launch of each GEMM-shaped kernel class (B images per launch)."""
+    D = cfg["embed_dim"]
+    N = (cfg["img_size"] // cfg["patch_size"]) ** 2 + 1 + cfg["register_tokens"]
+    hid = int(D * cfg["mlp_ratio"])
+    M = B * N
+    g_in, g_out, att = 2.0 * M * D * (3 * D + hid), 2.0 * M * D * (D + hid), 2.0 * B * N * N * D
+    return {"gemm_in_qkv_fc1": g_in, "gemm_out_rk": g_out, "attn_qk": att, "attn_pv": att,
+            "fused_attn": 2 * att, "bwd_gemm_doh": g_out, "bwd_gemm_g2": g_out, "bwd_attn": att,
+            "bwd_gemm_dx": g_in, "bwd_gemm_g1": g_in, "fused_attn_bwd": 4 * att}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU every 100 ms while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons = index, threading.Event(), [], set()
+        self.max_mhz, self.ok = None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:  # noqa: BLE001 -- NVML missing: report clocks as unavailable
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.1)
+
+    def result(self):
+        self.stop_flag.set()
+        if self.is_alive():
+            self.join(2.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def synthetic_batch(cfg, B, seed_off=0):
+    """pixel_values ~ N(0,1) (seed 1234), labels uniform (seed 1235), on the host."""
+    S, C = cfg["img_size"], cfg["num_classes"]
+    px = torch.randn(B, 3, S, S, generator=torch.Generator().manual_seed(1234 + seed_off))
+    lb = torch.randint(0, C, (B,), generator=torch.Generator().manual_seed(1235 + seed_off))
+    return px, lb
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the CPU PyTorch path (oracle port of the reference's modules)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step_factory(cfg, B):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import odevit_oracle as orc  # test infrastructure, used here as the timed CPU baseline only
+    sd = orc.reference_like_init(cfg, cfg["num_classes"], seed=0)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.AdamW(list(params.values()), lr=1e-4, weight_decay=5e-2)
+    px, lb = synthetic_batch(cfg, B)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        out = orc.vit_ode_forward(params, cfg, px, labels=lb)
+        out["loss"].backward()
+        torch.nn.utils.clip_grad_norm_(list(params.values()), 1.0)
+        opt.step()
+        return float(out["loss"].detach())
+
+    return step
+
+
+def time_cpu_reference(cfg, B, steps, warmup):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_reference_step_factory(cfg, B)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return B / dt, dt, cores
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, B = wl["cfg"], wl["cpu_sample_batch"]
+    ips, dt, cores = time_cpu_reference(cfg, B, args.steps, max(1, args.warmup))
+    nfe = (cfg["num_eval_steps"] - 1) * STAGES[cfg["solver"]]
+    sample = f"{B} images per step of the same model/grid (full workload: {wl['batch']} per GPU)"
+    line = {
+        "impl": "reference", "metric": "train_images_per_sec", "value": ips, "unit": "img/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "sample_batch": B, "device": "cpu"},
+        "field_evals_per_sec": ips * nfe,
+        "cpu_baseline": {"value": ips, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": ips, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import odevit_b200 as ob
+    from odevit_b200 import _lib
+    from odevit_b200.dp import FlatGradAllReduce
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (odevit_b200 has no CPU path; use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg, B = wl["cfg"], args.batch or wl["batch"]
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    torch.manual_seed(0)
+    model = ob.ViTNeuralODE(**cfg).to(dev).train()      # the reference's own init (:494-513), dropout 0
+    model.precision = args.precision
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=5e-2, fused=True)
+    reducer = FlatGradAllReduce(params)
+
+    px_h, lb_h = synthetic_batch(cfg, B, seed_off=rank)
+    px_h, lb_h = px_h.pin_memory(), lb_h.pin_memory()
+    px_d, lb_d = px_h.to(dev), lb_h.to(dev)
+
+    def step(px, lb):
+        opt.zero_grad(set_to_none=True)
+        out = model(px, labels=lb)
+        out["loss"].backward()
+        reducer()
+        torch.nn.utils.clip_grad_norm_(params, 1.0, foreach=True)
+        opt.step()
+        return out["loss"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / k
+
+    for _ in range(args.warmup):
+        step(px_d, lb_d)
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- device-resident number ("value"); per-class kernel timing rides along in the same region
+    _lib.profile_enable(True)
+    ob.reset_launch_count()
+    ms_step = timed(lambda: step(px_d, lb_d), args.steps)
+    launches = ob.launch_count()
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+
+    # ---- end to end: host buffers in, loss out, every step
+    def e2e_step():
+        px = px_h.to(dev, non_blocking=True)
+        lb = lb_h.to(dev, non_blocking=True)
+        return float(step(px, lb).item())
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.result()
+
+    # ---- kernel-only forward (inference) of the same batch: field evaluations per second
+    model.eval()
+    with torch.no_grad():
+        for _ in range(2):
+            model(px_d)
+        ms_inf = timed(lambda: model(px_d), max(2, args.steps))
+    model.train()
+
+    nfe = (cfg["num_eval_steps"] - 1) * STAGES[cfg["solver"]]
+    ips = world * B / (ms_step * 1e-3)
+    ips_e2e = world * B / (ms_e2e * 1e-3)
+    step_flops = 3.0 * B * nfe * field_flops_fwd(cfg)
+
+    # ---- roofline of the dominant kernel class (largest share of device time in the timed region)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PF sustained"
+    cf = class_flops(cfg, B)
+    total_ms = sum(v[0] for v in prof.values()) or 1.0
+    shares = {k: round(v[0] / total_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+    roofline = None
+    gemm_classes = [(k, v) for k, v in prof.items() if k in cf]
+    if gemm_classes:
+        k, (ms, n) = max(gemm_classes, key=lambda kv: kv[1][0])
+        achieved = cf[k] / (ms / n * 1e-3) / 1e12
+        roofline = {"kernel": k, "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                    "frac": achieved / tensor_peak, "traffic": None, "peak_source": peak_src,
+                    "avg_launch_us": ms / n * 1e3, "launches": n, "share_of_kernel_time": shares.get(k)}
+
+    if rank == 0:
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            cb = wl["cpu_sample_batch"]
+            c_ips, c_dt, cores = time_cpu_reference(cfg, cb, 3, 1)
+            cpu_baseline = {"value": c_ips, "unit": "img/s", "cores": cores, "kind": "port",
+                            "sample": f"{cb} images per step of the same model/grid, 3 steps after 1 warm-up"}
+        line = {
+            "metric": "train_images_per_sec", "value": ips, "unit": "img/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "per_gpu_batch": B, "global_batch": B * world,
+                       "parallelism": f"dp{world}", "precision_mode": args.precision,
+                       "l2_note": "working set per step (trajectory + stage buffers) is far larger than the 126 MB L2"},
+            "field_evals_per_sec": ips * nfe,
+            "train_tflops_algorithmic": step_flops * world / (ms_step * 1e-3) / 1e12,
+            "inference_images_per_sec": world * B / (ms_inf * 1e-3),
+            "inference_field_evals_per_sec": world * B * nfe / (ms_inf * 1e-3),
+            "e2e": {"value": ips_e2e, "unit": "img/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": px_h.numel() * 4 + lb_h.numel() * 8, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "kernel_time_shares": shares,
+            "cpu_baseline": cpu_baseline,
+            "grad_allreduce_bytes": reducer.bucket_bytes if world > 1 else 0,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c100", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,206 @@
+/*
+ * odevit.h -- C ABI of libodevit.so: the B200-native (sm_100a) implementation of ODE-ViT's hot
+ * path, the vector field f(t, x) evaluated by a fixed-step solver over the integration grid.
+ *
+ * The reference (Bycarkos/ODE-ViT) is pure Python: it has no FFI layer, its "plugin" surface is
+ * the nn.Module API.  This header declares what a binding for the hot path binds; each entry
+ * point names the reference interface it replaces (paths relative to the reference root):
+ *
+ *   odevit_field_fwd   <-  ViT_ODEFunc.forward(t, x)            models/ode_transformer_gpt.py:317-330
+ *                          (= ParallelAttentionMLP.forward :274-277, CenterNorm :79-83,
+ *                             MultiheadSelfAttention :226-232, MLP :193-200, L2SelfAttention :34-63)
+ *                          and macaron ViT_ODEFunc.forward       models/macaron.py:106-123, :146-150
+ *   odevit_solve_fwd   <-  odeint(odefunc, tokens, t_grid, method=solver)
+ *                                                                models/ode_transformer_gpt.py:571-578
+ *                                                                models/macaron.py:323, :326
+ *                          (third-party torchdiffeq fixed-grid euler / midpoint / rk4 = 3/8 rule)
+ *   odevit_solve_bwd   <-  loss.backward() through that call     train.py:57-67, loss_trainer.py:365
+ *                          (reference gradient mode: autograd through the unrolled solver; here a
+ *                           reverse sweep that recomputes each step from the stored trajectory row)
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; no torch types; every device buffer, including the workspace,
+ *     is owned by the caller; the library never allocates device memory and never synchronises;
+ *   - all work is enqueued on `stream` and is asynchronous with respect to the host;
+ *   - `t_grid` is a HOST pointer (the per-step dt = t[i+1]-t[i] is formed on the host in fp32,
+ *     exactly as torchdiffeq forms it);
+ *   - weights are read at call time (modules may be re-assigned between calls);
+ *   - returns 0 on success, a negative odevit_status otherwise; never throws across the ABI;
+ *     odevit_last_error_string() describes the last failure on the calling thread;
+ *   - there is NO CPU fallback: a host pointer where a device pointer is expected is an error.
+ *
+ * Tensor layouts: tokens are row-major [B, N, D] fp32 (rows = B*N); attention maps [B, H, N, N]
+ * fp32; trajectories [T, B, N, D] fp32.  Weights use the reference's state_dict layouts
+ * (nn.Linear: [out, in]; packed in_proj_weight [3D, D] with rows [Wq; Wk; Wv]).
+ */
+#ifndef ODEVIT_H_
+#define ODEVIT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ODEVIT_ABI_VERSION 1
+
+typedef struct CUstream_st* odevit_stream_t; /* == cudaStream_t */
+
+typedef enum {
+  ODEVIT_OK = 0,
+  ODEVIT_ERR_INVALID_ARG = -1,   /* bad shape / null pointer / unsupported combination        */
+  ODEVIT_ERR_WORKSPACE = -2,     /* workspace too small or misaligned                          */
+  ODEVIT_ERR_CUDA = -3,          /* a CUDA runtime / driver call failed (sticky errors too)    */
+  ODEVIT_ERR_UNSUPPORTED = -4,   /* shape outside what the kernels cover                       */
+  ODEVIT_ERR_NOT_DEVICE_PTR = -5 /* a host pointer was passed where device memory is required  */
+} odevit_status;
+
+typedef enum {
+  ODEVIT_FIELD_PARALLEL = 0, /* MLP(CN x) + MHA(CN x)          ode_transformer_gpt.py:274-277 */
+  ODEVIT_FIELD_PARALLEL_L2 = 1, /* same with L2SelfAttention   ode_transformer_gpt.py:34-63   */
+  ODEVIT_FIELD_MACARON = 2   /* half-FFN, MHA, half-FFN        macaron.py:106-123             */
+} odevit_variant;
+
+typedef enum {
+  ODEVIT_FP32 = 0, /* fp32 storage and FFMA arithmetic: <= 1e-4 of the reference              */
+  ODEVIT_BF16 = 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate/state: <= 2e-2   */
+} odevit_precision;
+
+typedef enum {
+  ODEVIT_EULER = 0,
+  ODEVIT_MIDPOINT = 1,
+  ODEVIT_RK4_38 = 2 /* torchdiffeq method="rk4" (rk4_alt_step_func, Kutta 3/8 rule)           */
+} odevit_method;
+
+/* Problem descriptor. */
+typedef struct {
+  int32_t abi_version; /* ODEVIT_ABI_VERSION */
+  int32_t batch;       /* B: images in this call                                              */
+  int32_t tokens;      /* N: tokens per image (cls + patches + registers [+ dist])            */
+  int32_t dim;         /* D: embed_dim                                                        */
+  int32_t heads;       /* H: num_heads (head dim d = D/H, d <= 128, d % 8 == 0)               */
+  int32_t hidden;      /* int(D * mlp_ratio)                                                  */
+  int32_t variant;     /* odevit_variant                                                      */
+  int32_t precision;   /* odevit_precision                                                    */
+  float scaler;        /* ViT_ODEFunc.scaler (emulate_depth if time_interval == 1 else 1)     */
+  int32_t reserved[7];
+} odevit_desc;
+
+/* Weights of the vector field, fp32 device pointers in state_dict layout; unused = NULL.
+ *   PARALLEL:    norm_a = block.norm_attn, norm_b = block.norm_mlp (CenterNorm, no eps);
+ *                in_proj_w [3D,D], out_proj_w [D,D], fc1_w [hid,D], fc2_w [D,hid]; no biases.
+ *   PARALLEL_L2: in_proj_w/in_proj_b hold [q_proj;k_proj;v_proj] stacked ([3D,D] / [3D]);
+ *                out_proj_w/out_proj_b = out_proj.
+ *   MACARON:     norm_a = norm1, norm_b = norm2, norm_c = norm3 (LayerNorm, eps 1e-5);
+ *                fc1 = ffn.0, fc2 = ffn.3 (shared by both half steps), all biases present;
+ *                res_scale [1].
+ * mod_*: optional per-call modulation vectors [D] from models/time_emb.py::ScaleShift applied to
+ * the normalised activations as n*(1+scale)+shift (NULL = off, the reference's behaviour). */
+typedef struct {
+  const float* norm_a_w; const float* norm_a_b;
+  const float* norm_b_w; const float* norm_b_b;
+  const float* norm_c_w; const float* norm_c_b;
+  const float* in_proj_w; const float* in_proj_b;
+  const float* out_proj_w; const float* out_proj_b;
+  const float* fc1_w; const float* fc1_b;
+  const float* fc2_w; const float* fc2_b;
+  const float* res_scale;
+  const float* mod_attn_scale; const float* mod_attn_shift;
+  const float* mod_mlp_scale; const float* mod_mlp_shift;
+  const void* reserved[5];
+} odevit_weights;
+
+/* Gradient accumulators, same layouts; the library ADDS into them (caller zero-fills). */
+typedef struct {
+  float* norm_a_w; float* norm_a_b;
+  float* norm_b_w; float* norm_b_b;
+  float* norm_c_w; float* norm_c_b;
+  float* in_proj_w; float* in_proj_b;
+  float* out_proj_w; float* out_proj_b;
+  float* fc1_w; float* fc1_b;
+  float* fc2_w; float* fc2_b;
+  float* res_scale;
+  void* reserved[9];
+} odevit_weight_grads;
+
+/* What a workspace is sized for. */
+typedef enum {
+  ODEVIT_WS_FIELD = 0,     /* odevit_field_fwd                                                 */
+  ODEVIT_WS_SOLVE_FWD = 1, /* odevit_solve_fwd                                                 */
+  ODEVIT_WS_SOLVE_BWD = 2  /* odevit_solve_bwd                                                 */
+} odevit_ws_kind;
+
+/* ABI / build identification. */
+int odevit_abi_version(void);
+const char* odevit_build_info(void);             /* "sm_100a, nvcc x.y, <date>"                */
+const char* odevit_last_error_string(void);      /* thread-local, never NULL                    */
+
+/* Bytes of device workspace needed (0 on invalid desc; then see odevit_last_error_string). The
+ * workspace must be 1024-byte aligned. `method` matters for the solve kinds (stage buffers). */
+size_t odevit_workspace_bytes(const odevit_desc* desc, int32_t ws_kind, int32_t method);
+
+/* One evaluation of the vector field: dx = f(t, x).  Replaces ViT_ODEFunc.forward(t, x).
+ *   x   [B,N,D] in, dx [B,N,D] out (may not alias);
+ *   p_out [B,H,N,N] or NULL: the attention map P of this evaluation (block.attentions). */
+int odevit_field_fwd(const odevit_desc* desc, const odevit_weights* w,
+                     const float* x, float* dx, float* p_out,
+                     void* workspace, size_t workspace_bytes, odevit_stream_t stream);
+
+/* The fixed-grid solve.  Replaces odeint(odefunc, x0, t_grid, method=...).
+ *   t_grid_host [T] fp32, strictly monotonic, HOST memory;
+ *   states [T,B,N,D] or NULL.  If given, row 0 := x0 and row j := state after step j (what odeint
+ *          returns).  If NULL only final_state is produced (inference without trajectory);
+ *   final_state [B,N,D] or NULL (required when states == NULL);
+ *   p_last [B,H,N,N] or NULL: P of the LAST field evaluation (block.attentions after the solve);
+ *   p_traj [(n_evals - p_traj_first_eval), B,H,N,N] or NULL: P of every evaluation e >=
+ *          p_traj_first_eval, e = step*stages + stage (odefunc.attention_trajectory). */
+int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t method,
+                     const float* x0, const float* t_grid_host, int32_t n_grid,
+                     float* states, float* final_state,
+                     float* p_last, float* p_traj, int32_t p_traj_first_eval,
+                     void* workspace, size_t workspace_bytes, odevit_stream_t stream);
+
+/* Reverse sweep through the solve (backprop-through-solver semantics, per-step recomputation).
+ *   states [T,B,N,D]: the trajectory odevit_solve_fwd produced (row j = input of step j);
+ *   g_states [T,B,N,D] or NULL: cotangent of every trajectory row;
+ *   g_rows [n_g_rows,B,N,D] + g_row_index_host [n_g_rows] (HOST ints, may repeat): cotangents of
+ *          selected rows (final state, control points) -- added on top of g_states;
+ *   g_p_last [B,H,N,N] or NULL: cotangent of p_last (the `attentions` output);
+ *   g_x0 [B,N,D] out: cotangent of x0 (flows on into the patch embedding);
+ *   gw: weight-gradient accumulators (+=). */
+int odevit_solve_bwd(const odevit_desc* desc, const odevit_weights* w, int32_t method,
+                     const float* t_grid_host, int32_t n_grid, const float* states,
+                     const float* g_states,
+                     const float* g_rows, const int32_t* g_row_index_host, int32_t n_g_rows,
+                     const float* g_p_last,
+                     float* g_x0, const odevit_weight_grads* gw,
+                     void* workspace, size_t workspace_bytes, odevit_stream_t stream);
+
+/* Vector-Jacobian product of ONE field evaluation (autograd of odevit_field_fwd):
+ *   g_dx [B,N,D] cotangent of dx, g_p [B,H,N,N] or NULL cotangent of p_out;
+ *   g_x [B,N,D] out; gw accumulators (+=). Workspace kind ODEVIT_WS_SOLVE_BWD with EULER. */
+int odevit_field_bwd(const odevit_desc* desc, const odevit_weights* w,
+                     const float* x, const float* g_dx, const float* g_p,
+                     float* g_x, const odevit_weight_grads* gw,
+                     void* workspace, size_t workspace_bytes, odevit_stream_t stream);
+
+/* Number of kernels the library launched on this thread since the last reset (bench.py's
+ * gpu_launches claim is counted, not estimated). */
+int64_t odevit_launch_count(void);
+void odevit_reset_launch_count(void);
+
+/* Per-kernel-class device timing for bench.py's roofline line (no reference counterpart).
+ * While enabled, each launch is bracketed by a CUDA event pair on its stream (a few microseconds
+ * of host time per launch).  odevit_profile_read synchronises on the recorded events, so call it
+ * after the work has been enqueued; it returns the summed milliseconds and the launch count of
+ * class `kclass` since the last enable, or a negative status.  Thread-local like the counter. */
+int odevit_profile_enable(int32_t on);
+int odevit_profile_num_classes(void);
+const char* odevit_profile_class_name(int32_t kclass);
+int odevit_profile_read(int32_t kclass, double* total_ms, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODEVIT_H_ */

@@ -1,0 +1,11 @@
+"""odevit_b200 -- B200-native (sm_100a) implementation of ODE-ViT's hot path: the vector field
+f(t, x) evaluated by a fixed-step solver over the integration grid, behind the reference's
+nn.Module surface.  See DESIGN.md; the C ABI is include/odevit.h (csrc/libodevit.so)."""
+from ._lib import OdevitError, LIB_PATH, launch_count, reset_launch_count  # noqa: F401
+from .ops import FieldSpec, field_eval, ode_solve  # noqa: F401
+from .vit_ode import (CenterNorm, MLP, MultiheadSelfAttention, ParallelAttentionMLP, PatchEmbed,  # noqa: F401
+                      ViT_ODEFunc, ViTNeuralODE, odeint)
+
+__all__ = ["OdevitError", "LIB_PATH", "FieldSpec", "field_eval", "ode_solve", "CenterNorm", "MLP",
+           "MultiheadSelfAttention", "ParallelAttentionMLP", "PatchEmbed", "ViT_ODEFunc", "ViTNeuralODE",
+           "odeint", "launch_count", "reset_launch_count"]

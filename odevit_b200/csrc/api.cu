@@ -1,0 +1,773 @@
+// libodevit.so -- orchestration of the hot path and the C ABI (include/odevit.h).
+//
+// One vector-field evaluation f(u) of the PARALLEL variant (ode_transformer_gpt.py:274-277,
+// :317-330) is four launches groups here:
+//   1. center_rows        xc = u - mean_D(u)                        (CenterNorm core, :80-81)
+//   2. GEMM1 + EPI_FWD1   [q|k|v|h] = xc @ W1cat^T + b1cat, GELU on the fc1 columns
+//                         (both CenterNorm affines, the 1/sqrt(d) of MHA and both projections folded
+//                          into one weight: see rows.cu::fold_w1_kernel)
+//   3. attention          P = softmax(q k^T), O = P v  per (image, head)
+//   4. GEMM2 + EPI_RK     scaler * ([O|h] @ [Wo|W2]^T)  fused with the Runge-Kutta stage combine
+//                         (writes the next stage input / the next trajectory row directly)
+// The solver loop (torchdiffeq fixed grid: euler, midpoint, rk4 = 3/8 rule) runs on the host and
+// only enqueues launches; dt_j = t[j+1]-t[j] is formed in fp32 on the host like torchdiffeq does.
+//
+// The reverse sweep recomputes each step's stage intermediates from the stored trajectory row
+// (no stage tensor survives the forward) and applies the exact VJP of the unrolled RK step.
+#include <cmath>
+#include <cstring>
+
+#include "internal.h"
+
+#define ODEVIT_STR2(x) #x
+#define ODEVIT_STR(x) ODEVIT_STR2(x)
+
+namespace odevit {
+
+// ------------------------------------------------------------------------------------------------
+// thread-local error text + launch counter
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "ok";
+static thread_local int64_t g_launches = 0;
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void count_launch(int n) { g_launches += n; }
+
+// ---- per-class event timing ------------------------------------------------------------------
+namespace {
+constexpr int kMaxProfPairs = 1 << 16;
+struct ProfState {
+  bool on = false;
+  int used = 0;
+  int cap = 0;
+  cudaEvent_t* ev = nullptr;  // 2 per pair
+  int* cls = nullptr;
+};
+thread_local ProfState g_prof;
+const char* const kClassNames[KC_COUNT] = {
+    "center_rows", "gemm_in_qkv_fc1", "attn_qk", "softmax", "attn_pv", "gemm_out_rk",
+    "bwd_gemm_doh", "bwd_gemm_g2", "bwd_attn", "bwd_softmax", "bwd_gemm_dx", "bwd_gemm_g1",
+    "bwd_colsum", "combine", "weights", "fused_attn", "other"};
+}  // namespace
+
+ProfScope::ProfScope(int c, cudaStream_t st) : cls(c), s(st), slot(-1) {
+  ProfState& p = g_prof;
+  if (!p.on) return;
+  if (p.used >= p.cap) {
+    if (p.cap >= kMaxProfPairs) return;
+    if (cudaEventCreate(&p.ev[2 * p.cap]) != cudaSuccess || cudaEventCreate(&p.ev[2 * p.cap + 1]) != cudaSuccess) return;
+    ++p.cap;
+  }
+  slot = p.used++;
+  p.cls[slot] = c;
+  cudaEventRecord(p.ev[2 * slot], s);
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_prof.ev[2 * slot + 1], s);
+}
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Butcher tableaux of the fixed-grid methods (torchdiffeq _impl/fixed_grid.py, rk_common.py)
+// ------------------------------------------------------------------------------------------------
+struct Tableau {
+  int S;
+  float a[4][4];  // u_m = y + dt * sum_l a[m][l] * k_l   (m >= 1)
+  float b[4];     // y_next = y + dt * sum_l b[l] * k_l
+};
+const Tableau kEuler = {1, {{0}}, {1.f}};
+const Tableau kMidpoint = {2, {{0}, {0.5f}}, {0.f, 1.f}};
+const Tableau kRk38 = {4,
+                       {{0}, {1.f / 3.f}, {-1.f / 3.f, 1.f}, {1.f, -1.f, 1.f}},
+                       {0.125f, 0.375f, 0.375f, 0.125f}};
+
+const Tableau* tableau_for(int method) {
+  switch (method) {
+    case ODEVIT_EULER: return &kEuler;
+    case ODEVIT_MIDPOINT: return &kMidpoint;
+    case ODEVIT_RK4_38: return &kRk38;
+    default: return nullptr;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan + workspace arena
+// ------------------------------------------------------------------------------------------------
+struct Plan {
+  int B, N, D, H, hid, d, M;
+  int variant, precision, act;  // act = DType of activation buffers
+  float scaler;
+  long long BHNN;
+};
+
+int make_plan(const odevit_desc* desc, Plan* p) {
+  if (!desc) return set_error(ODEVIT_ERR_INVALID_ARG, "desc is NULL");
+  if (desc->abi_version != ODEVIT_ABI_VERSION)
+    return set_error(ODEVIT_ERR_INVALID_ARG, "abi_version %d != %d", desc->abi_version, ODEVIT_ABI_VERSION);
+  p->B = desc->batch; p->N = desc->tokens; p->D = desc->dim; p->H = desc->heads; p->hid = desc->hidden;
+  p->variant = desc->variant; p->precision = desc->precision; p->scaler = desc->scaler;
+  if (p->B <= 0 || p->N <= 0 || p->D <= 1 || p->H <= 0 || p->hid <= 0)
+    return set_error(ODEVIT_ERR_INVALID_ARG, "non-positive dimension (B=%d N=%d D=%d H=%d hid=%d)", p->B, p->N,
+                     p->D, p->H, p->hid);
+  if (p->D % p->H) return set_error(ODEVIT_ERR_INVALID_ARG, "dim %d not divisible by heads %d", p->D, p->H);
+  if (p->D > 1024 || p->N > 1024)
+    return set_error(ODEVIT_ERR_UNSUPPORTED, "dim %d / tokens %d above 1024", p->D, p->N);
+  if (p->precision != ODEVIT_FP32 && p->precision != ODEVIT_BF16)
+    return set_error(ODEVIT_ERR_INVALID_ARG, "unknown precision %d", p->precision);
+  if (p->variant != ODEVIT_FIELD_PARALLEL)
+    return set_error(ODEVIT_ERR_UNSUPPORTED, "variant %d not built yet", p->variant);
+  p->d = p->D / p->H;
+  p->M = p->B * p->N;
+  p->act = (p->precision == ODEVIT_BF16) ? DT_BF16 : DT_F32;
+  p->BHNN = (long long)p->B * p->H * p->N * p->N;
+  return 0;
+}
+
+struct Arena {
+  char* base;
+  size_t off = 0;
+  explicit Arena(void* b) : base(reinterpret_cast<char*>(b)) {}
+  void* take(size_t bytes) {
+    off = (off + 1023) & ~size_t(1023);
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+  float* f32(size_t n) { return reinterpret_cast<float*>(take(n * 4)); }
+};
+
+struct WeightBufs {
+  void *w1cat, *w1catT, *w2cat, *w2catT;
+  float *b1cat, *b2;
+};
+struct StageCtx {
+  void *xc, *qkv, *oh, *hpre;
+};
+
+WeightBufs take_weights(const Plan& p, Arena& a) {
+  const size_t e = dtype_size(p.act);
+  const size_t R = 3 * (size_t)p.D + p.hid, K2 = (size_t)p.D + p.hid;
+  WeightBufs w;
+  w.w1cat = a.take(R * p.D * e);
+  w.w1catT = a.take(R * p.D * e);
+  w.w2cat = a.take(K2 * p.D * e);
+  w.w2catT = a.take(K2 * p.D * e);
+  w.b1cat = a.f32(R);
+  w.b2 = a.f32(p.D);
+  return w;
+}
+StageCtx take_ctx(const Plan& p, Arena& a, bool with_hpre) {
+  const size_t e = dtype_size(p.act);
+  StageCtx c;
+  c.xc = a.take((size_t)p.M * p.D * e);
+  c.qkv = a.take((size_t)p.M * 3 * p.D * e);
+  c.oh = a.take((size_t)p.M * (p.D + p.hid) * e);
+  c.hpre = with_hpre ? a.take((size_t)p.M * p.hid * e) : nullptr;
+  return c;
+}
+
+struct FwdBufs {
+  WeightBufs w;
+  StageCtx ctx;
+  float* P;
+  float* u;
+  float* k[3];
+  float* ytmp[2];
+};
+FwdBufs layout_fwd(const Plan& p, Arena& a, int S) {
+  FwdBufs f;
+  f.w = take_weights(p, a);
+  f.ctx = take_ctx(p, a, false);
+  f.P = a.f32(p.BHNN);
+  f.u = a.f32((size_t)p.M * p.D);
+  for (int i = 0; i < 3; ++i) f.k[i] = (i < S - 1) ? a.f32((size_t)p.M * p.D) : nullptr;
+  f.ytmp[0] = a.f32((size_t)p.M * p.D);
+  f.ytmp[1] = a.f32((size_t)p.M * p.D);
+  return f;
+}
+
+struct BwdBufs {
+  WeightBufs w;
+  StageCtx ctx[4];
+  float *P, *dP;
+  float* u;
+  float* k[3];
+  void *dd, *dO, *dz;
+  float* zsum;
+  float* mu[4];
+  float* gy;
+  float *G1, *c1, *G2, *c2;
+  size_t acc_bytes;  // G1..c2 are contiguous: one memset
+};
+BwdBufs layout_bwd(const Plan& p, Arena& a, int S) {
+  const size_t e = dtype_size(p.act);
+  const size_t MD = (size_t)p.M * p.D;
+  const size_t R = 3 * (size_t)p.D + p.hid, K2 = (size_t)p.D + p.hid;
+  BwdBufs b;
+  b.w = take_weights(p, a);
+  for (int i = 0; i < 4; ++i) b.ctx[i] = (i < S) ? take_ctx(p, a, true) : StageCtx{nullptr, nullptr, nullptr, nullptr};
+  b.P = a.f32(p.BHNN);
+  b.dP = a.f32(p.BHNN);
+  b.u = a.f32(MD);
+  for (int i = 0; i < 3; ++i) b.k[i] = (i < S - 1) ? a.f32(MD) : nullptr;
+  b.dd = a.take(MD * e);
+  b.dO = a.take(MD * e);
+  b.dz = a.take((size_t)p.M * R * e);
+  b.zsum = a.f32(MD);
+  for (int i = 0; i < 4; ++i) b.mu[i] = (i >= 1 && i < S) ? a.f32(MD) : nullptr;
+  b.gy = a.f32(MD);
+  // accumulators, contiguous (sizes are multiples of 4 bytes; keep them packed for one memset)
+  const size_t acc_floats = R * p.D + R + K2 * p.D + p.D;
+  float* acc = a.f32(acc_floats);
+  b.G1 = acc;
+  b.c1 = acc ? acc + R * p.D : nullptr;
+  b.G2 = acc ? acc + R * p.D + R : nullptr;
+  b.c2 = acc ? acc + R * p.D + R + K2 * p.D : nullptr;
+  b.acc_bytes = acc_floats * 4;
+  return b;
+}
+
+int check_ws(const void* ws, size_t have, size_t need) {
+  if (!ws) return set_error(ODEVIT_ERR_WORKSPACE, "workspace is NULL");
+  if (reinterpret_cast<uintptr_t>(ws) & 1023) return set_error(ODEVIT_ERR_WORKSPACE, "workspace not 1024-byte aligned");
+  if (have < need) return set_error(ODEVIT_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", have, need);
+  return 0;
+}
+
+int check_device_ptr(const void* p, const char* what) {
+  if (!p) return set_error(ODEVIT_ERR_INVALID_ARG, "%s is NULL", what);
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(ODEVIT_ERR_NOT_DEVICE_PTR, "%s: cudaPointerGetAttributes failed: %s", what, cudaGetErrorString(e));
+  }
+  if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)
+    return set_error(ODEVIT_ERR_NOT_DEVICE_PTR, "%s is not device memory (no CPU fallback)", what);
+  // this library carries its own (static) CUDA runtime: follow the caller's device
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != attr.device) {
+    cudaError_t e2 = cudaSetDevice(attr.device);
+    if (e2 != cudaSuccess)
+      return set_error(ODEVIT_ERR_CUDA, "cudaSetDevice(%d) failed: %s", attr.device, cudaGetErrorString(e2));
+  }
+  return 0;
+}
+
+int check_weights(const Plan& p, const odevit_weights* w) {
+  if (!w) return set_error(ODEVIT_ERR_INVALID_ARG, "weights is NULL");
+  if (!w->norm_a_w || !w->norm_a_b || !w->norm_b_w || !w->norm_b_b || !w->in_proj_w || !w->out_proj_w ||
+      !w->fc1_w || !w->fc2_w)
+    return set_error(ODEVIT_ERR_INVALID_ARG, "PARALLEL variant needs norm_a/norm_b/in_proj/out_proj/fc1/fc2 weights");
+  (void)p;
+  return check_device_ptr(w->in_proj_w, "weights.in_proj_w");
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM dispatch: tcgen05 in bf16 mode where the kernel covers the shape, FFMA otherwise
+// ------------------------------------------------------------------------------------------------
+int gemm(const Plan& p, const GemmArgs& g, cudaStream_t s) {
+  if (p.precision == ODEVIT_BF16 && gemm_tc_supports(g)) return gemm_tc(g, s);
+  return gemm_simt(g, s);
+}
+
+int prepare_weights(const Plan& p, const odevit_weights* w, const WeightBufs& wb, cudaStream_t s) {
+  FoldArgs f;
+  f.D = p.D; f.hid = p.hid; f.heads = p.H; f.w = w;
+  f.w1cat = wb.w1cat; f.w1catT = wb.w1catT; f.w_type = p.act;
+  f.b1cat = wb.b1cat; f.w2cat = wb.w2cat; f.w2catT = wb.w2catT; f.b2 = wb.b2;
+  return fold_weights_parallel(f, s);
+}
+
+// q / k / v views of the packed qkv buffer for batch z = (image b, head h)
+struct HeadView {
+  long long bo, bi, rs;
+};
+HeadView qkv_view(const Plan& p) { return {(long long)p.N * 3 * p.D, (long long)p.d, (long long)3 * p.D}; }
+
+// Forward evaluation at stage input `u`.  `rk` (nullable) is the epilogue of GEMM2.
+int eval_forward(const Plan& p, const WeightBufs& wb, const StageCtx& c, const float* u, float* P,
+                 float* p_copy, const Epi* rk, cudaStream_t s) {
+  const int D = p.D, hid = p.hid, R = 3 * D + hid, K2 = D + hid;
+  ODV_TRY(center_rows(u, c.xc, p.act, nullptr, 0.f, p.M, D, s));
+  {
+    GemmArgs g;
+    g.M = p.M; g.N = R; g.K = D;
+    g.A = c.xc; g.a_type = p.act; g.a_rs = D; g.a_cs = 1;
+    g.B = wb.w1cat; g.b_type = p.act; g.b_rs = D; g.b_cs = 1;
+    g.epi_mode = EPI_FWD1;
+    g.kclass = KC_GEMM_IN;
+    g.epi.bias = wb.b1cat;
+    g.epi.out = c.qkv; g.epi.out_type = p.act; g.epi.ld_out = 3 * D;
+    g.epi.split = 3 * D;
+    g.epi.out2 = reinterpret_cast<char*>(c.oh) + (size_t)D * dtype_size(p.act); g.epi.ld_out2 = K2;
+    g.epi.out3 = c.hpre; g.epi.ld_out3 = hid;
+    g.epi.aux_type = p.act;
+    ODV_TRY(gemm(p, g, s));
+  }
+  const HeadView hv = qkv_view(p);
+  const char* qkv = reinterpret_cast<const char*>(c.qkv);
+  const size_t e = dtype_size(p.act);
+  {  // S = q k^T  (the 1/sqrt(d) is folded into the Wq rows)
+    GemmArgs g;
+    g.M = p.N; g.N = p.N; g.K = p.d;
+    g.A = qkv; g.a_type = p.act; g.a_rs = hv.rs; g.a_cs = 1; g.a_bo = hv.bo; g.a_bi = hv.bi;
+    g.B = qkv + (size_t)D * e; g.b_type = p.act; g.b_rs = hv.rs; g.b_cs = 1; g.b_bo = hv.bo; g.b_bi = hv.bi;
+    g.batch_outer = p.B; g.batch_inner = p.H;
+    g.epi_mode = EPI_STORE;
+    g.epi.out = P; g.epi.out_type = DT_F32; g.epi.ld_out = p.N;
+    g.epi.out_bo = (long long)p.H * p.N * p.N; g.epi.out_bi = (long long)p.N * p.N;
+    g.kclass = KC_ATTN_S;
+    ODV_TRY(gemm_simt(g, s));
+  }
+  ODV_TRY(softmax_rows(P, p_copy, (long long)p.B * p.H * p.N, p.N, s));
+  {  // O = P v  -> columns [h*d, (h+1)*d) of the [O|h] buffer
+    GemmArgs g;
+    g.M = p.N; g.N = p.d; g.K = p.N;
+    g.A = P; g.a_type = DT_F32; g.a_rs = p.N; g.a_cs = 1;
+    g.a_bo = (long long)p.H * p.N * p.N; g.a_bi = (long long)p.N * p.N;
+    g.B = qkv + (size_t)2 * D * e; g.b_type = p.act; g.b_rs = 1; g.b_cs = hv.rs; g.b_bo = hv.bo; g.b_bi = hv.bi;
+    g.batch_outer = p.B; g.batch_inner = p.H;
+    g.epi_mode = EPI_STORE;
+    g.epi.out = c.oh; g.epi.out_type = p.act; g.epi.ld_out = K2;
+    g.epi.out_bo = (long long)p.N * K2; g.epi.out_bi = p.d;
+    g.kclass = KC_ATTN_PV;
+    ODV_TRY(gemm_simt(g, s));
+  }
+  if (rk) {
+    GemmArgs g;
+    g.M = p.M; g.N = D; g.K = K2;
+    g.A = c.oh; g.a_type = p.act; g.a_rs = K2; g.a_cs = 1;
+    g.B = wb.w2cat; g.b_type = p.act; g.b_rs = K2; g.b_cs = 1;
+    g.epi_mode = EPI_RK;
+    g.kclass = KC_GEMM_OUT;
+    g.epi = *rk;
+    g.epi.bias = wb.b2;
+    g.epi.alpha = p.scaler;
+    g.epi.ld_out = D;
+    ODV_TRY(gemm(p, g, s));
+  }
+  return 0;
+}
+
+// Epilogue of stage `st` of a step starting at y with step dt: produces the next stage input
+// (or the step result when st == S-1) into `out`; stores k_st when a later stage needs it.
+Epi rk_epilogue(const Tableau& tb, int st, float dt, const float* y, float* const* k, float* out) {
+  Epi e;
+  e.out = out;
+  e.y = y;
+  e.y_coef = 1.f;
+  const bool last = (st == tb.S - 1);
+  const float* row = last ? tb.b : tb.a[st + 1];
+  e.c_new = dt * row[st];
+  for (int l = 0; l < st && l < 3; ++l) {
+    if (row[l] != 0.f) { e.kin[l] = k[l]; e.c_k[l] = dt * row[l]; }
+  }
+  e.k_store = (!last && st < 3) ? k[st] : nullptr;
+  return e;
+}
+
+// VJP of one field evaluation: given dd = scaler * lambda (cotangent of the pre-scaler output, in
+// the activation type), the stage intermediates `c`, produce zsum = dL/d(xc) (fp32, un-centred)
+// and accumulate G1, c1, G2, c2.
+int eval_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b, const float* g_p,
+             bool need_c2, cudaStream_t s) {
+  const int D = p.D, hid = p.hid, R = 3 * D + hid, K2 = D + hid;
+  const size_t e = dtype_size(p.act);
+  char* dz = reinterpret_cast<char*>(b.dz);
+  {  // d[O|h] = dd @ [Wo|W2];  GELU' on the h half
+    GemmArgs g;
+    g.M = p.M; g.N = K2; g.K = D;
+    g.A = b.dd; g.a_type = p.act; g.a_rs = D; g.a_cs = 1;
+    g.B = wb.w2catT; g.b_type = p.act; g.b_rs = D; g.b_cs = 1;
+    g.epi_mode = EPI_BWD3;
+    g.kclass = KC_BWD_GEMM_DOH;
+    g.epi.out = b.dO; g.epi.out_type = p.act; g.epi.ld_out = D;
+    g.epi.split = D;
+    g.epi.out2 = dz + (size_t)3 * D * e; g.epi.ld_out2 = R;
+    g.epi.aux = c.hpre; g.epi.ld_aux = hid; g.epi.aux_type = p.act;
+    ODV_TRY(gemm(p, g, s));
+  }
+  {  // G2 += dd^T @ [O|h]
+    GemmArgs g;
+    g.M = D; g.N = K2; g.K = p.M;
+    g.A = b.dd; g.a_type = p.act; g.a_rs = 1; g.a_cs = D;
+    g.B = c.oh; g.b_type = p.act; g.b_rs = 1; g.b_cs = K2;
+    g.epi_mode = EPI_ACCUM;
+    g.epi.out = b.G2; g.epi.ld_out = K2;
+    g.kclass = KC_BWD_GEMM_G2;
+    ODV_TRY(gemm(p, g, s));
+  }
+  if (need_c2) ODV_TRY(colsum_accum(b.dd, p.act, D, p.M, D, b.c2, s));
+
+  // ---- attention VJP per (image, head); P is recomputed from q, k -----------------------------
+  const HeadView hv = qkv_view(p);
+  const char* qkv = reinterpret_cast<const char*>(c.qkv);
+  const long long pbo = (long long)p.H * p.N * p.N, pbi = (long long)p.N * p.N;
+  auto head_gemm = [&](GemmArgs& g) {
+    g.batch_outer = p.B; g.batch_inner = p.H;
+    g.kclass = KC_BWD_ATTN;
+    return gemm_simt(g, s);
+  };
+  {  // S
+    GemmArgs g;
+    g.M = p.N; g.N = p.N; g.K = p.d;
+    g.A = qkv; g.a_type = p.act; g.a_rs = hv.rs; g.a_cs = 1; g.a_bo = hv.bo; g.a_bi = hv.bi;
+    g.B = qkv + (size_t)D * e; g.b_type = p.act; g.b_rs = hv.rs; g.b_cs = 1; g.b_bo = hv.bo; g.b_bi = hv.bi;
+    g.epi.out = b.P; g.epi.ld_out = p.N; g.epi.out_bo = pbo; g.epi.out_bi = pbi;
+    ODV_TRY(head_gemm(g));
+  }
+  ODV_TRY(softmax_rows(b.P, nullptr, (long long)p.B * p.H * p.N, p.N, s));
+  {  // dP = dO v^T
+    GemmArgs g;
+    g.M = p.N; g.N = p.N; g.K = p.d;
+    g.A = b.dO; g.a_type = p.act; g.a_rs = D; g.a_cs = 1; g.a_bo = (long long)p.N * D; g.a_bi = p.d;
+    g.B = qkv + (size_t)2 * D * e; g.b_type = p.act; g.b_rs = hv.rs; g.b_cs = 1; g.b_bo = hv.bo; g.b_bi = hv.bi;
+    g.epi.out = b.dP; g.epi.ld_out = p.N; g.epi.out_bo = pbo; g.epi.out_bi = pbi;
+    ODV_TRY(head_gemm(g));
+  }
+  ODV_TRY(softmax_bwd_rows(b.P, b.dP, g_p, (long long)p.B * p.H * p.N, p.N, s));
+  {  // dq = dS k      (dq is the cotangent of the already-scaled q: the scale lives in W1cat)
+    GemmArgs g;
+    g.M = p.N; g.N = p.d; g.K = p.N;
+    g.A = b.dP; g.a_type = DT_F32; g.a_rs = p.N; g.a_cs = 1; g.a_bo = pbo; g.a_bi = pbi;
+    g.B = qkv + (size_t)D * e; g.b_type = p.act; g.b_rs = 1; g.b_cs = hv.rs; g.b_bo = hv.bo; g.b_bi = hv.bi;
+    g.epi.out = dz; g.epi.out_type = p.act; g.epi.ld_out = R; g.epi.out_bo = (long long)p.N * R; g.epi.out_bi = p.d;
+    ODV_TRY(head_gemm(g));
+  }
+  {  // dk = dS^T q
+    GemmArgs g;
+    g.M = p.N; g.N = p.d; g.K = p.N;
+    g.A = b.dP; g.a_type = DT_F32; g.a_rs = 1; g.a_cs = p.N; g.a_bo = pbo; g.a_bi = pbi;
+    g.B = qkv; g.b_type = p.act; g.b_rs = 1; g.b_cs = hv.rs; g.b_bo = hv.bo; g.b_bi = hv.bi;
+    g.epi.out = dz + (size_t)D * e; g.epi.out_type = p.act; g.epi.ld_out = R;
+    g.epi.out_bo = (long long)p.N * R; g.epi.out_bi = p.d;
+    ODV_TRY(head_gemm(g));
+  }
+  {  // dv = P^T dO
+    GemmArgs g;
+    g.M = p.N; g.N = p.d; g.K = p.N;
+    g.A = b.P; g.a_type = DT_F32; g.a_rs = 1; g.a_cs = p.N; g.a_bo = pbo; g.a_bi = pbi;
+    g.B = b.dO; g.b_type = p.act; g.b_rs = 1; g.b_cs = D; g.b_bo = (long long)p.N * D; g.b_bi = p.d;
+    g.epi.out = dz + (size_t)2 * D * e; g.epi.out_type = p.act; g.epi.ld_out = R;
+    g.epi.out_bo = (long long)p.N * R; g.epi.out_bi = p.d;
+    ODV_TRY(head_gemm(g));
+  }
+  {  // zsum = dz @ W1cat          (dL/d xc, before the centring VJP)
+    GemmArgs g;
+    g.M = p.M; g.N = D; g.K = R;
+    g.A = b.dz; g.a_type = p.act; g.a_rs = R; g.a_cs = 1;
+    g.B = wb.w1catT; g.b_type = p.act; g.b_rs = R; g.b_cs = 1;
+    g.epi_mode = EPI_STORE;
+    g.epi.out = b.zsum; g.epi.out_type = DT_F32; g.epi.ld_out = D;
+    g.kclass = KC_BWD_GEMM_DX;
+    ODV_TRY(gemm(p, g, s));
+  }
+  {  // G1 += dz^T @ xc
+    GemmArgs g;
+    g.M = R; g.N = D; g.K = p.M;
+    g.A = b.dz; g.a_type = p.act; g.a_rs = 1; g.a_cs = R;
+    g.B = c.xc; g.b_type = p.act; g.b_rs = 1; g.b_cs = D;
+    g.epi_mode = EPI_ACCUM;
+    g.epi.out = b.G1; g.epi.ld_out = D;
+    g.kclass = KC_BWD_GEMM_G1;
+    ODV_TRY(gemm(p, g, s));
+  }
+  ODV_TRY(colsum_accum(b.dz, p.act, R, p.M, R, b.c1, s));
+  return 0;
+}
+
+int finish_grads(const Plan& p, const odevit_weights* w, const odevit_weight_grads* gw, const BwdBufs& b,
+                 cudaStream_t s) {
+  UnfoldArgs u;
+  u.D = p.D; u.hid = p.hid; u.heads = p.H; u.w = w; u.gw = gw;
+  u.G1 = b.G1; u.c1 = b.c1; u.G2 = b.G2; u.c2 = b.c2;
+  return unfold_grads_parallel(u, s);
+}
+
+bool wants_c2(const odevit_weight_grads* gw) { return gw && (gw->out_proj_b || gw->fc2_b); }
+
+}  // namespace
+}  // namespace odevit
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using namespace odevit;
+
+extern "C" {
+
+int odevit_abi_version(void) { return ODEVIT_ABI_VERSION; }
+
+const char* odevit_build_info(void) {
+  return "libodevit sm_100a (nvcc " ODEVIT_STR(__CUDACC_VER_MAJOR__) "." ODEVIT_STR(__CUDACC_VER_MINOR__) ", " __DATE__ ")";
+}
+
+const char* odevit_last_error_string(void) { return g_err; }
+
+int64_t odevit_launch_count(void) { return g_launches; }
+void odevit_reset_launch_count(void) { g_launches = 0; }
+
+int odevit_profile_enable(int32_t on) {
+  ProfState& p = g_prof;
+  if (on) {
+    if (!p.ev) {
+      p.ev = new cudaEvent_t[2 * kMaxProfPairs];
+      p.cls = new int[kMaxProfPairs];
+      p.cap = 0;
+    }
+    p.used = 0;
+    p.on = true;
+  } else {
+    p.on = false;
+  }
+  return 0;
+}
+int odevit_profile_num_classes(void) { return KC_COUNT; }
+const char* odevit_profile_class_name(int32_t k) { return (k >= 0 && k < KC_COUNT) ? kClassNames[k] : "?"; }
+int odevit_profile_read(int32_t kclass, double* total_ms, int64_t* launches) {
+  ProfState& p = g_prof;
+  if (kclass < 0 || kclass >= KC_COUNT || !total_ms || !launches)
+    return set_error(ODEVIT_ERR_INVALID_ARG, "odevit_profile_read: bad arguments");
+  double t = 0;
+  int64_t n = 0;
+  for (int i = 0; i < p.used; ++i) {
+    if (p.cls[i] != kclass) continue;
+    float ms = 0.f;
+    ODV_CUDA(cudaEventSynchronize(p.ev[2 * i + 1]));
+    ODV_CUDA(cudaEventElapsedTime(&ms, p.ev[2 * i], p.ev[2 * i + 1]));
+    t += ms;
+    ++n;
+  }
+  *total_ms = t;
+  *launches = n;
+  return 0;
+}
+
+size_t odevit_workspace_bytes(const odevit_desc* desc, int32_t ws_kind, int32_t method) {
+  Plan p;
+  if (make_plan(desc, &p)) return 0;
+  Arena a(nullptr);
+  if (ws_kind == ODEVIT_WS_FIELD) {
+    layout_fwd(p, a, 1);
+  } else {
+    const Tableau* tb = tableau_for(method);
+    if (!tb) { set_error(ODEVIT_ERR_INVALID_ARG, "unknown method %d", method); return 0; }
+    if (ws_kind == ODEVIT_WS_SOLVE_FWD) layout_fwd(p, a, tb->S);
+    else if (ws_kind == ODEVIT_WS_SOLVE_BWD) layout_bwd(p, a, tb->S);
+    else { set_error(ODEVIT_ERR_INVALID_ARG, "unknown workspace kind %d", ws_kind); return 0; }
+  }
+  return a.off + 1024;
+}
+
+int odevit_field_fwd(const odevit_desc* desc, const odevit_weights* w, const float* x, float* dx,
+                     float* p_out, void* workspace, size_t workspace_bytes, odevit_stream_t stream) {
+  Plan p;
+  ODV_TRY(make_plan(desc, &p));
+  ODV_TRY(check_weights(p, w));
+  ODV_TRY(check_device_ptr(x, "x"));
+  ODV_TRY(check_device_ptr(dx, "dx"));
+  if (x == dx) return set_error(ODEVIT_ERR_INVALID_ARG, "x and dx may not alias");
+  Arena a(workspace);
+  FwdBufs f = layout_fwd(p, a, 1);
+  ODV_TRY(check_ws(workspace, workspace_bytes, a.off));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  ODV_TRY(prepare_weights(p, w, f.w, s));
+  Epi rk;
+  rk.out = dx;
+  rk.y = nullptr;
+  rk.c_new = 1.f;
+  return eval_forward(p, f.w, f.ctx, x, f.P, p_out, &rk, s);
+}
+
+int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t method, const float* x0,
+                     const float* t_grid_host, int32_t n_grid, float* states, float* final_state,
+                     float* p_last, float* p_traj, int32_t p_traj_first_eval, void* workspace,
+                     size_t workspace_bytes, odevit_stream_t stream) {
+  Plan p;
+  ODV_TRY(make_plan(desc, &p));
+  ODV_TRY(check_weights(p, w));
+  const Tableau* tb = tableau_for(method);
+  if (!tb) return set_error(ODEVIT_ERR_INVALID_ARG, "unknown method %d", method);
+  if (!t_grid_host || n_grid < 1) return set_error(ODEVIT_ERR_INVALID_ARG, "t_grid must hold >= 1 point");
+  if (!states && !final_state) return set_error(ODEVIT_ERR_INVALID_ARG, "states and final_state both NULL");
+  ODV_TRY(check_device_ptr(x0, "x0"));
+  if (states) ODV_TRY(check_device_ptr(states, "states"));
+  for (int j = 0; j + 2 < n_grid; ++j) {
+    const float d0 = t_grid_host[j + 1] - t_grid_host[j], d1 = t_grid_host[j + 2] - t_grid_host[j + 1];
+    if (!(d0 * d1 > 0.f)) return set_error(ODEVIT_ERR_INVALID_ARG, "t must be strictly increasing or decreasing");
+  }
+  if (n_grid == 2 && t_grid_host[1] == t_grid_host[0])
+    return set_error(ODEVIT_ERR_INVALID_ARG, "t must be strictly increasing or decreasing");
+  Arena a(workspace);
+  FwdBufs f = layout_fwd(p, a, tb->S);
+  ODV_TRY(check_ws(workspace, workspace_bytes, a.off));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const size_t MD = (size_t)p.M * p.D;
+  ODV_TRY(prepare_weights(p, w, f.w, s));
+
+  const float* y = x0;
+  if (states) {
+    ODV_CUDA(cudaMemcpyAsync(states, x0, MD * 4, cudaMemcpyDeviceToDevice, s));
+    y = states;
+  }
+  const int S = tb->S;
+  const long long n_evals = (long long)(n_grid - 1) * S;
+  for (int j = 0; j + 1 < n_grid; ++j) {
+    const float dt = t_grid_host[j + 1] - t_grid_host[j];
+    float* y_next = states ? states + (size_t)(j + 1) * MD
+                           : ((j + 2 == n_grid) ? final_state : f.ytmp[j & 1]);
+    for (int st = 0; st < S; ++st) {
+      const long long e = (long long)j * S + st;
+      const float* u = (st == 0) ? y : f.u;
+      float* out = (st == S - 1) ? y_next : f.u;
+      Epi rk = rk_epilogue(*tb, st, dt, y, f.k, out);
+      float* p_copy = nullptr;
+      if (p_traj && e >= p_traj_first_eval) p_copy = p_traj + (size_t)(e - p_traj_first_eval) * p.BHNN;
+      else if (p_last && e == n_evals - 1) p_copy = p_last;
+      ODV_TRY(eval_forward(p, f.w, f.ctx, u, f.P, p_copy, &rk, s));
+      if (p_last && e == n_evals - 1 && p_copy != p_last)
+        ODV_CUDA(cudaMemcpyAsync(p_last, p_copy, (size_t)p.BHNN * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    y = y_next;
+  }
+  if (final_state && (states || n_grid == 1)) {
+    ODV_CUDA(cudaMemcpyAsync(final_state, y, MD * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  return 0;
+}
+
+int odevit_solve_bwd(const odevit_desc* desc, const odevit_weights* w, int32_t method,
+                     const float* t_grid_host, int32_t n_grid, const float* states, const float* g_states,
+                     const float* g_rows, const int32_t* g_row_index_host, int32_t n_g_rows,
+                     const float* g_p_last, float* g_x0, const odevit_weight_grads* gw, void* workspace,
+                     size_t workspace_bytes, odevit_stream_t stream) {
+  Plan p;
+  ODV_TRY(make_plan(desc, &p));
+  ODV_TRY(check_weights(p, w));
+  const Tableau* tb = tableau_for(method);
+  if (!tb) return set_error(ODEVIT_ERR_INVALID_ARG, "unknown method %d", method);
+  if (!t_grid_host || n_grid < 1) return set_error(ODEVIT_ERR_INVALID_ARG, "t_grid must hold >= 1 point");
+  if (!gw) return set_error(ODEVIT_ERR_INVALID_ARG, "weight-gradient struct is NULL");
+  ODV_TRY(check_device_ptr(states, "states"));
+  ODV_TRY(check_device_ptr(g_x0, "g_x0"));
+  if (n_g_rows > 0 && (!g_rows || !g_row_index_host))
+    return set_error(ODEVIT_ERR_INVALID_ARG, "g_rows / g_row_index_host missing");
+  for (int i = 0; i < n_g_rows; ++i)
+    if (g_row_index_host[i] < 0 || g_row_index_host[i] >= n_grid)
+      return set_error(ODEVIT_ERR_INVALID_ARG, "g_row_index[%d]=%d outside [0,%d)", i, g_row_index_host[i], n_grid);
+  Arena a(workspace);
+  BwdBufs b = layout_bwd(p, a, tb->S);
+  ODV_TRY(check_ws(workspace, workspace_bytes, a.off));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const size_t MD = (size_t)p.M * p.D;
+  const int S = tb->S;
+  const bool need_c2 = wants_c2(gw);
+  ODV_TRY(prepare_weights(p, w, b.w, s));
+  ODV_CUDA(cudaMemsetAsync(b.G1, 0, b.acc_bytes, s));
+
+  // cotangent of trajectory row j = g_states[j] + sum of g_rows whose index is j
+  auto inject = [&](int row) -> int {
+    if (g_states) ODV_TRY(axpy_f32(b.gy, g_states + (size_t)row * MD, 1.f, (long long)MD, s));
+    for (int i = 0; i < n_g_rows; ++i)
+      if (g_row_index_host[i] == row) ODV_TRY(axpy_f32(b.gy, g_rows + (size_t)i * MD, 1.f, (long long)MD, s));
+    return 0;
+  };
+  ODV_CUDA(cudaMemsetAsync(b.gy, 0, MD * 4, s));
+  ODV_TRY(inject(n_grid - 1));
+
+  for (int j = n_grid - 2; j >= 0; --j) {
+    const float dt = t_grid_host[j + 1] - t_grid_host[j];
+    const float* y = states + (size_t)j * MD;
+    // (1) recompute the stage intermediates of this step (the last stage skips GEMM2)
+    for (int st = 0; st < S; ++st) {
+      const float* u = (st == 0) ? y : b.u;
+      if (st < S - 1) {
+        Epi rk = rk_epilogue(*tb, st, dt, y, b.k, b.u);
+        ODV_TRY(eval_forward(p, b.w, b.ctx[st], u, b.P, nullptr, &rk, s));
+      } else {
+        ODV_TRY(eval_forward(p, b.w, b.ctx[st], u, b.P, nullptr, nullptr, s));
+      }
+    }
+    // (2) reverse through the stages
+    //     lambda_st = dt*(b[st]*G + sum_{m>st} a[m][st]*mu_m),  mu_st = J(u_st)^T lambda_st,
+    //     dL/dy = G + sum_st mu_st
+    {
+      CombineArgs c0;
+      c0.n_terms = 1; c0.term[0] = b.gy; c0.coef[0] = dt * tb->b[S - 1];
+      c0.out_dd = b.dd; c0.dd_type = p.act; c0.dd_scale = p.scaler;
+      ODV_TRY(vjp_combine(c0, p.M, p.D, s));
+    }
+    for (int st = S - 1; st >= 0; --st) {
+      const bool last_eval = (j == n_grid - 2 && st == S - 1);
+      ODV_TRY(eval_vjp(p, b.w, b.ctx[st], b, last_eval ? g_p_last : nullptr, need_c2, s));
+      CombineArgs c;
+      c.zsum = b.zsum;
+      if (st > 0) {
+        // store mu_st, form lambda_{st-1} -> dd
+        c.mu_out = b.mu[st];
+        const int t = st - 1;
+        c.coef_mu = dt * tb->a[st][t];
+        int n = 0;
+        c.term[n] = b.gy; c.coef[n] = dt * tb->b[t]; ++n;
+        for (int m = st + 1; m < S; ++m)
+          if (tb->a[m][t] != 0.f) { c.term[n] = b.mu[m]; c.coef[n] = dt * tb->a[m][t]; ++n; }
+        c.n_terms = n;
+        c.out_dd = b.dd; c.dd_type = p.act; c.dd_scale = p.scaler;
+      } else {
+        // dL/dy_j = G + mu_0 + sum_{m>=1} mu_m   (in place over G)
+        c.coef_mu = 1.f;
+        int n = 0;
+        c.term[n] = b.gy; c.coef[n] = 1.f; ++n;
+        for (int m = 1; m < S; ++m) { c.term[n] = b.mu[m]; c.coef[n] = 1.f; ++n; }
+        c.n_terms = n;
+        c.out_f32 = b.gy;
+      }
+      ODV_TRY(vjp_combine(c, p.M, p.D, s));
+    }
+    ODV_TRY(inject(j));
+  }
+  ODV_CUDA(cudaMemcpyAsync(g_x0, b.gy, MD * 4, cudaMemcpyDeviceToDevice, s));
+  return finish_grads(p, w, gw, b, s);
+}
+
+int odevit_field_bwd(const odevit_desc* desc, const odevit_weights* w, const float* x, const float* g_dx,
+                     const float* g_p, float* g_x, const odevit_weight_grads* gw, void* workspace,
+                     size_t workspace_bytes, odevit_stream_t stream) {
+  Plan p;
+  ODV_TRY(make_plan(desc, &p));
+  ODV_TRY(check_weights(p, w));
+  if (!gw) return set_error(ODEVIT_ERR_INVALID_ARG, "weight-gradient struct is NULL");
+  ODV_TRY(check_device_ptr(x, "x"));
+  ODV_TRY(check_device_ptr(g_dx, "g_dx"));
+  ODV_TRY(check_device_ptr(g_x, "g_x"));
+  Arena a(workspace);
+  BwdBufs b = layout_bwd(p, a, 1);
+  ODV_TRY(check_ws(workspace, workspace_bytes, a.off));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  ODV_TRY(prepare_weights(p, w, b.w, s));
+  ODV_CUDA(cudaMemsetAsync(b.G1, 0, b.acc_bytes, s));
+  ODV_TRY(eval_forward(p, b.w, b.ctx[0], x, b.P, nullptr, nullptr, s));
+  {
+    CombineArgs c0;
+    c0.n_terms = 1; c0.term[0] = g_dx; c0.coef[0] = 1.f;
+    c0.out_dd = b.dd; c0.dd_type = p.act; c0.dd_scale = p.scaler;
+    ODV_TRY(vjp_combine(c0, p.M, p.D, s));
+  }
+  ODV_TRY(eval_vjp(p, b.w, b.ctx[0], b, g_p, wants_c2(gw), s));
+  {
+    CombineArgs c;
+    c.zsum = b.zsum; c.coef_mu = 1.f; c.out_f32 = g_x;
+    ODV_TRY(vjp_combine(c, p.M, p.D, s));
+  }
+  return finish_grads(p, w, gw, b, s);
+}
+
+}  // extern "C"

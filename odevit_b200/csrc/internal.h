@@ -1,0 +1,199 @@
+// Internal declarations shared by the translation units of libodevit.so.
+// Not part of the ABI (that is include/odevit.h).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/odevit.h"
+
+namespace odevit {
+
+// ---------------------------------------------------------------------------------------------
+// error handling + launch accounting (thread-local: the ABI is thread-safe for distinct streams)
+// ---------------------------------------------------------------------------------------------
+int set_error(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define ODV_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (call);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return ::odevit::set_error(ODEVIT_ERR_CUDA, "%s failed: %s (%s:%d)", #call,        \
+                                 cudaGetErrorString(_e), __FILE__, __LINE__);            \
+  } while (0)
+
+#define ODV_TRY(call)          \
+  do {                         \
+    int _s = (call);           \
+    if (_s != 0) return _s;    \
+  } while (0)
+
+#define ODV_LAUNCH_CHECK()                                                               \
+  do {                                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess)                                                               \
+      return ::odevit::set_error(ODEVIT_ERR_CUDA, "kernel launch failed: %s (%s:%d)",    \
+                                 cudaGetErrorString(_e), __FILE__, __LINE__);            \
+    ::odevit::count_launch();                                                            \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// per-kernel-class device timing (bench.py's roofline numbers): when enabled through
+// odevit_profile_enable(), every launch site brackets its launch with a CUDA event pair on the
+// launching stream; odevit_profile_read() sums the pairs per class.  Off by default (no events).
+// ---------------------------------------------------------------------------------------------
+enum KClass : int {
+  KC_CENTER = 0,   // center_rows
+  KC_GEMM_IN,      // xc @ W1cat^T (packed in-proj + fc1, GELU epilogue)
+  KC_ATTN_S,       // q k^T per (image, head)
+  KC_SOFTMAX,      // softmax rows (+ P export)
+  KC_ATTN_PV,      // P v per (image, head)
+  KC_GEMM_OUT,     // [O|h] @ [Wo|W2]^T + RK stage-combine epilogue
+  KC_BWD_GEMM_DOH, // dd @ [Wo|W2]   (+ GELU' epilogue)
+  KC_BWD_GEMM_G2,  // G2 += dd^T [O|h]
+  KC_BWD_ATTN,     // attention VJP products (dP, dq, dk, dv)
+  KC_BWD_SOFTMAX,  // softmax VJP rows
+  KC_BWD_GEMM_DX,  // zsum = dz @ W1cat
+  KC_BWD_GEMM_G1,  // G1 += dz^T xc
+  KC_BWD_COLSUM,   // bias-gradient column sums
+  KC_COMBINE,      // reverse-mode stage combine / axpy
+  KC_WEIGHTS,      // weight fold / gradient unfold
+  KC_FUSED_ATTN,   // fused attention (S, softmax, PV in one kernel)
+  KC_OTHER,
+  KC_COUNT
+};
+struct ProfScope {
+  int cls;
+  cudaStream_t s;
+  int slot;
+  ProfScope(int cls, cudaStream_t s);
+  ~ProfScope();
+};
+
+// ---------------------------------------------------------------------------------------------
+// element types of activation buffers
+// ---------------------------------------------------------------------------------------------
+enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
+static inline size_t dtype_size(int t) { return t == DT_F32 ? 4 : 2; }
+
+// ---------------------------------------------------------------------------------------------
+// GEMM:  C[m,n] = sum_k A(m,k) * B(n,k)   (both operands addressed by element strides)
+// ---------------------------------------------------------------------------------------------
+enum EpiMode : int {
+  EPI_STORE = 0,  // out[m,n] = alpha*acc + bias[n]
+  EPI_FWD1 = 1,   // n <  split: out[m,n] = acc + bias[n]          (q|k|v)
+                  // n >= split: out3[m,n-split] = v (opt), out2[m,n-split] = gelu(v)   (fc1)
+  EPI_RK = 2,     // v = alpha*(acc + bias[n]); kstore (opt) = v;
+                  // out[m,n] = y_coef*y[m,n] + c_new*v + sum_i c_k[i]*kin[i][m,n]
+  EPI_BWD3 = 3,   // n <  split: out[m,n] = acc                    (dO)
+                  // n >= split: out2[m,n-split] = acc * gelu'(aux[m,n-split])   (d h_pre)
+  EPI_ACCUM = 4   // out[m,n] += alpha*acc   (fp32; atomic when split-K)
+};
+
+struct Epi {
+  float alpha = 1.f;
+  const float* bias = nullptr;
+  void* out = nullptr;
+  int out_type = DT_F32;
+  long long ld_out = 0, out_bo = 0, out_bi = 0;
+  int split = 0;
+  void* out2 = nullptr;
+  long long ld_out2 = 0;
+  void* out3 = nullptr;
+  long long ld_out3 = 0;
+  int aux_type = DT_F32;  // type of out2/out3/aux buffers
+  const float* y = nullptr;
+  const float* kin[3] = {nullptr, nullptr, nullptr};
+  float y_coef = 1.f, c_new = 0.f, c_k[3] = {0.f, 0.f, 0.f};
+  float* k_store = nullptr;
+  const void* aux = nullptr;
+  long long ld_aux = 0;
+};
+
+struct GemmArgs {
+  int M = 0, N = 0, K = 0;
+  const void* A = nullptr;
+  int a_type = DT_F32;
+  long long a_rs = 0, a_cs = 1, a_bo = 0, a_bi = 0;
+  const void* B = nullptr;
+  int b_type = DT_F32;
+  long long b_rs = 0, b_cs = 1, b_bo = 0, b_bi = 0;
+  int batch_outer = 1, batch_inner = 1;
+  int epi_mode = EPI_STORE;
+  Epi epi;
+  int kclass = KC_OTHER;
+};
+
+// CUDA-core (FFMA) GEMM: any strides, any M/N/K, fp32 or bf16 operands, fp32 accumulate.
+int gemm_simt(const GemmArgs& g, cudaStream_t s);
+
+// tcgen05 / TMA GEMM (bf16 operands, fp32 accumulate in TMEM).  Returns ODEVIT_ERR_UNSUPPORTED
+// for shapes/layouts it does not cover (caller then reports the error; there is no silent
+// fallback in the bf16 product path except for the batched per-head attention products).
+int gemm_tc(const GemmArgs& g, cudaStream_t s);
+bool gemm_tc_supports(const GemmArgs& g);
+
+// ---------------------------------------------------------------------------------------------
+// row-wise / elementwise kernels (odevit_rows.cu)
+// ---------------------------------------------------------------------------------------------
+// xc[r,:] = x[r,:] - mean(x[r,:]);  if rstd_out: also divide by sqrt(var+eps) (LayerNorm core)
+int center_rows(const float* x, void* xc, int xc_type, float* rstd_out, float eps, int rows,
+                int D, cudaStream_t s);
+// in-place softmax over rows of length n (fp32); optional second copy
+int softmax_rows(float* p, float* copy_to, long long rows, int n, cudaStream_t s);
+// ds = p * (dp + dpx - sum_j p*(dp+dpx)), written over dp.  dpx nullable.
+int softmax_bwd_rows(const float* p, float* dp, const float* dpx, long long rows, int n,
+                     cudaStream_t s);
+// acc[j] += sum_r X[r, j]
+int colsum_accum(const void* X, int x_type, long long ld, int rows, int cols, float* acc,
+                 cudaStream_t s);
+
+// Reverse-mode stage combine (see odevit_api.cu):  optional mu = center(zsum) stored to mu_out,
+// then  v = sum_i coef[i]*term[i]  (+ coef_mu*mu) ; writes out_f32 = v and/or out_dd = cast(dd_scale*v)
+struct CombineArgs {
+  const float* zsum = nullptr;  // raw d/d(xc) from GEMM5 (nullable)
+  float* mu_out = nullptr;      // centered zsum (nullable)
+  float coef_mu = 0.f;
+  int n_terms = 0;
+  const float* term[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float coef[6] = {0, 0, 0, 0, 0, 0};
+  float* out_f32 = nullptr;
+  void* out_dd = nullptr;
+  int dd_type = DT_F32;
+  float dd_scale = 1.f;
+};
+int vjp_combine(const CombineArgs& a, int rows, int D, cudaStream_t s);
+
+// y[i] += a * x[i]
+int axpy_f32(float* y, const float* x, float a, long long n, cudaStream_t s);
+
+// Weight preparation / gradient assembly for the PARALLEL variant (folded CenterNorm affine).
+struct FoldArgs {
+  int D, hid, heads;
+  const odevit_weights* w;
+  void* w1cat; int w_type;   // [3D+hid, D]
+  void* w1catT;              // [D, 3D+hid] or null
+  float* b1cat;              // [3D+hid]
+  void* w2cat;               // [D, D+hid]
+  void* w2catT;              // [D+hid, D] or null
+  float* b2;                 // [D] (out_proj_b + fc2_b) -- zero if absent
+};
+int fold_weights_parallel(const FoldArgs& a, cudaStream_t s);
+
+struct UnfoldArgs {
+  int D, hid, heads;
+  const odevit_weights* w;
+  const odevit_weight_grads* gw;
+  const float* G1;  // [3D+hid, D]   = sum dz^T xc
+  const float* c1;  // [3D+hid]      = colsum dz
+  const float* G2;  // [D, D+hid]    = sum dd^T [O|h]
+  const float* c2;  // [D]           = colsum dd
+};
+int unfold_grads_parallel(const UnfoldArgs& a, cudaStream_t s);
+
+}  // namespace odevit

@@ -1,0 +1,387 @@
+// Row-wise and element-wise kernels of the hot path: all HBM-bound, one warp per token row,
+// coalesced 128-byte warp accesses, no shared memory (no reuse beyond a row held in registers).
+//
+//   center_rows        CenterNorm / LayerNorm core       ode_transformer_gpt.py:79-83, macaron.py:80-82
+//   softmax_rows       softmax over key positions        nn.MultiheadAttention explicit path (:228)
+//   softmax_bwd_rows   its VJP (+ injected dP for the `attentions` output)
+//   colsum_accum       bias-gradient column sums
+//   vjp_combine        CenterNorm VJP + reverse-mode Runge-Kutta stage combination
+//   fold / unfold      CenterNorm affine folded into the GEMM weights, and the chain rule back
+#include "epilogue.cuh"
+#include "internal.h"
+
+namespace odevit {
+
+namespace {
+
+constexpr int MAX_PER_LANE = 32;  // rows up to 1024 elements are held in registers
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__global__ void __launch_bounds__(256) center_rows_kernel(const float* __restrict__ x, void* xc,
+                                                          int xc_type, float* rstd_out, float eps,
+                                                          int rows, int D) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (long long)row * D;
+  float v[MAX_PER_LANE];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    v[i] = (c < D) ? xr[c] : 0.f;
+    s += v[i];
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float rstd = 1.f;
+  if (rstd_out) {
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_PER_LANE; ++i) {
+      const int c = lane + i * 32;
+      const float d = (c < D) ? v[i] - mean : 0.f;
+      q += d * d;
+    }
+    rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+    if (lane == 0) rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < MAX_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    if (c < D) store_elem(xc, (long long)row * D + c, xc_type, (v[i] - mean) * rstd);
+  }
+}
+
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* p, float* copy_to, long long rows,
+                                                           int n) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* pr = p + row * n;
+  float v[MAX_PER_LANE];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < MAX_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    v[i] = (c < n) ? pr[c] : -INFINITY;
+    mx = fmaxf(mx, v[i]);
+  }
+  mx = warp_max(mx);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    v[i] = (c < n) ? expf(v[i] - mx) : 0.f;
+    s += v[i];
+  }
+  const float inv = 1.f / warp_sum(s);
+#pragma unroll
+  for (int i = 0; i < MAX_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    if (c < n) {
+      const float o = v[i] * inv;
+      pr[c] = o;
+      if (copy_to) copy_to[row * n + c] = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const float* __restrict__ p, float* dp,
+                                                               const float* __restrict__ dpx,
+                                                               long long rows, int n) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* pr = p + row * n;
+  float* dr = dp + row * n;
+  float pv[MAX_PER_LANE], gv[MAX_PER_LANE];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    pv[i] = 0.f;
+    gv[i] = 0.f;
+    if (c < n) {
+      pv[i] = pr[c];
+      gv[i] = dr[c];
+      if (dpx) gv[i] += dpx[row * n + c];
+    }
+    s = fmaf(pv[i], gv[i], s);
+  }
+  s = warp_sum(s);
+#pragma unroll
+  for (int i = 0; i < MAX_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    if (c < n) dr[c] = pv[i] * (gv[i] - s);
+  }
+}
+
+__global__ void __launch_bounds__(128) colsum_kernel(const void* X, int x_type, long long ld, int rows,
+                                                     int cols, int rows_per_block, float* acc) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= cols) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) s += load_elem_rw(X, (long long)r * ld + c, x_type);
+  atomicAdd(acc + c, s);
+}
+
+__global__ void __launch_bounds__(256) vjp_combine_kernel(CombineArgs a, int rows, int D) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const long long base = (long long)row * D;
+  float mu[MAX_PER_LANE];
+  if (a.zsum) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_PER_LANE; ++i) {
+      const int c = lane + i * 32;
+      mu[i] = (c < D) ? a.zsum[base + c] : 0.f;
+      s += mu[i];
+    }
+    const float mean = warp_sum(s) / (float)D;
+#pragma unroll
+    for (int i = 0; i < MAX_PER_LANE; ++i) {
+      const int c = lane + i * 32;
+      mu[i] -= mean;
+      if (a.mu_out && c < D) a.mu_out[base + c] = mu[i];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < MAX_PER_LANE; ++i) mu[i] = 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < MAX_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    if (c >= D) continue;
+    float v = a.coef_mu * mu[i];
+    for (int t = 0; t < a.n_terms; ++t) v = fmaf(a.coef[t], a.term[t][base + c], v);
+    if (a.out_f32) a.out_f32[base + c] = v;
+    if (a.out_dd) store_elem(a.out_dd, base + c, a.dd_type, a.dd_scale * v);
+  }
+}
+
+__global__ void axpy_kernel(float* y, const float* __restrict__ x, float a, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) y[i] = fmaf(a, x[i], y[i]);
+}
+
+// ---- weight folding (PARALLEL variant) -------------------------------------------------------
+// CenterNorm is affine in (x - mean):  n = s*(x-mean)*w + b  with s = D/(D-1)          (:77-83)
+//   n_attn @ W_in^T = (x-mean) @ (s * W_in * diag(w_a))^T + W_in @ b_a
+// so the packed in-proj and fc1 share ONE left operand xc = x - mean and become ONE GEMM over the
+// row-concatenated, column-scaled weight  W1cat = [qs*s*W_in*diag(w_a) ; s*W1*diag(w_m)]  with
+// bias  b1cat = [qs*(W_in b_a + b_in) ; W1 b_m + b_fc1]  (qs = 1/sqrt(d) on the Wq rows: the
+// q*(1/sqrt(d)) of nn.MultiheadAttention).  out_proj and fc2 concatenate along K:
+//   [O | h] @ [Wo | W2]^T.
+__global__ void __launch_bounds__(128) fold_w1_kernel(FoldArgs a, odevit_weights w) {
+  const int D = a.D, hid = a.hid, R = 3 * D + hid;
+  const int j = blockIdx.x;
+  const bool attn = j < 3 * D;
+  const float* Wrow = attn ? w.in_proj_w + (long long)j * D : w.fc1_w + (long long)(j - 3 * D) * D;
+  const float* nw = attn ? w.norm_a_w : w.norm_b_w;
+  const float* nb = attn ? w.norm_a_b : w.norm_b_b;
+  const float* msc = attn ? w.mod_attn_scale : w.mod_mlp_scale;
+  const float* msh = attn ? w.mod_attn_shift : w.mod_mlp_shift;
+  const float* lb = attn ? w.in_proj_b : w.fc1_b;
+  const float s_cn = (float)D / ((float)D - 1.f);
+  const float qs = (j < D) ? rsqrtf((float)(D / a.heads)) : 1.f;
+  float dot = 0.f;
+  for (int i = threadIdx.x; i < D; i += 128) {
+    float we = nw[i], be = nb[i];
+    if (msc) { we *= (1.f + msc[i]); be *= (1.f + msc[i]); }
+    if (msh) be += msh[i];
+    const float wv = Wrow[i];
+    const float f = qs * s_cn * wv * we;
+    store_elem(a.w1cat, (long long)j * D + i, a.w_type, f);
+    if (a.w1catT) store_elem(a.w1catT, (long long)i * R + j, a.w_type, f);
+    dot = fmaf(wv, be, dot);
+  }
+  __shared__ float red[4];
+  dot = warp_sum(dot);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = red[0] + red[1] + red[2] + red[3];
+    if (lb) t += lb[j - (attn ? 0 : 3 * D)];
+    a.b1cat[j] = qs * t;
+  }
+}
+
+__global__ void __launch_bounds__(128) fold_w2_kernel(FoldArgs a, odevit_weights w) {
+  const int D = a.D, hid = a.hid, K2 = D + hid;
+  const int i = blockIdx.x;
+  for (int c = threadIdx.x; c < K2; c += 128) {
+    const float v = (c < D) ? w.out_proj_w[(long long)i * D + c] : w.fc2_w[(long long)i * hid + (c - D)];
+    store_elem(a.w2cat, (long long)i * K2 + c, a.w_type, v);
+    if (a.w2catT) store_elem(a.w2catT, (long long)c * D + i, a.w_type, v);
+  }
+  if (threadIdx.x == 0) {
+    float b = 0.f;
+    if (w.out_proj_b) b += w.out_proj_b[i];
+    if (w.fc2_b) b += w.fc2_b[i];
+    a.b2[i] = b;
+  }
+}
+
+// ---- gradient un-folding ---------------------------------------------------------------------
+//   G1 = sum dz^T xc,  c1 = colsum dz,  G2 = sum dd^T [O|h],  c2 = colsum dd   (over all f-evals)
+//   dW[j,i]  = qs_j * (s*w_eff[i]*G1[j,i] + c1[j]*b_eff[i])
+//   dw[i]    = (1+msc[i]) * sum_j qs_j*s*W[j,i]*G1[j,i]
+//   db[i]    = (1+msc[i]) * sum_j qs_j*W[j,i]*c1[j]
+__global__ void __launch_bounds__(128) unfold_w1_kernel(UnfoldArgs a, odevit_weights w,
+                                                        odevit_weight_grads g) {
+  const int D = a.D, hid = a.hid;
+  const int j = blockIdx.x;
+  const bool attn = j < 3 * D;
+  const int jr = attn ? j : j - 3 * D;
+  float* dW = attn ? g.in_proj_w : g.fc1_w;
+  const float* nw = attn ? w.norm_a_w : w.norm_b_w;
+  const float* nb = attn ? w.norm_a_b : w.norm_b_b;
+  const float* msc = attn ? w.mod_attn_scale : w.mod_mlp_scale;
+  const float* msh = attn ? w.mod_attn_shift : w.mod_mlp_shift;
+  const float s_cn = (float)D / ((float)D - 1.f);
+  const float qs = (j < D) ? rsqrtf((float)(D / a.heads)) : 1.f;
+  const float cj = a.c1[j];
+  if (dW) {
+    for (int i = threadIdx.x; i < D; i += 128) {
+      float we = nw[i], be = nb[i];
+      if (msc) { we *= (1.f + msc[i]); be *= (1.f + msc[i]); }
+      if (msh) be += msh[i];
+      dW[(long long)jr * D + i] += qs * (s_cn * we * a.G1[(long long)j * D + i] + cj * be);
+    }
+  }
+  if (threadIdx.x == 0) {
+    float* db = attn ? g.in_proj_b : g.fc1_b;
+    if (db) db[jr] += qs * cj;
+  }
+  (void)hid;
+}
+
+__global__ void __launch_bounds__(128) unfold_norm_kernel(UnfoldArgs a, odevit_weights w,
+                                                          odevit_weight_grads g) {
+  const int D = a.D, hid = a.hid;
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= D) return;
+  const float s_cn = (float)D / ((float)D - 1.f);
+  const float q = rsqrtf((float)(D / a.heads));
+  float dwa = 0.f, dba = 0.f, dwm = 0.f, dbm = 0.f;
+  for (int j = 0; j < 3 * D; ++j) {
+    const float qs = (j < D) ? q : 1.f;
+    const float wv = qs * w.in_proj_w[(long long)j * D + i];
+    dwa = fmaf(wv, a.G1[(long long)j * D + i], dwa);
+    dba = fmaf(wv, a.c1[j], dba);
+  }
+  for (int j = 0; j < hid; ++j) {
+    const float wv = w.fc1_w[(long long)j * D + i];
+    dwm = fmaf(wv, a.G1[(long long)(3 * D + j) * D + i], dwm);
+    dbm = fmaf(wv, a.c1[3 * D + j], dbm);
+  }
+  const float ma = w.mod_attn_scale ? 1.f + w.mod_attn_scale[i] : 1.f;
+  const float mm = w.mod_mlp_scale ? 1.f + w.mod_mlp_scale[i] : 1.f;
+  if (g.norm_a_w) g.norm_a_w[i] += ma * s_cn * dwa;
+  if (g.norm_a_b) g.norm_a_b[i] += ma * dba;
+  if (g.norm_b_w) g.norm_b_w[i] += mm * s_cn * dwm;
+  if (g.norm_b_b) g.norm_b_b[i] += mm * dbm;
+}
+
+__global__ void __launch_bounds__(128) unfold_w2_kernel(UnfoldArgs a, odevit_weight_grads g) {
+  const int D = a.D, hid = a.hid, K2 = D + hid;
+  const int i = blockIdx.x;
+  for (int c = threadIdx.x; c < K2; c += 128) {
+    const float v = a.G2[(long long)i * K2 + c];
+    if (c < D) { if (g.out_proj_w) g.out_proj_w[(long long)i * D + c] += v; }
+    else if (g.fc2_w) g.fc2_w[(long long)i * hid + (c - D)] += v;
+  }
+  if (threadIdx.x == 0) {
+    if (g.out_proj_b) g.out_proj_b[i] += a.c2[i];
+    if (g.fc2_b) g.fc2_b[i] += a.c2[i];
+  }
+}
+
+}  // namespace
+
+int center_rows(const float* x, void* xc, int xc_type, float* rstd_out, float eps, int rows, int D,
+                cudaStream_t s) {
+  ProfScope prof(KC_CENTER, s);
+  if (D > 32 * MAX_PER_LANE) return set_error(ODEVIT_ERR_UNSUPPORTED, "center_rows: D=%d > 1024", D);
+  center_rows_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, xc, xc_type, rstd_out, eps, rows, D);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int softmax_rows(float* p, float* copy_to, long long rows, int n, cudaStream_t s) {
+  ProfScope prof(KC_SOFTMAX, s);
+  if (n > 32 * MAX_PER_LANE) return set_error(ODEVIT_ERR_UNSUPPORTED, "softmax_rows: N=%d > 1024", n);
+  softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(p, copy_to, rows, n);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int softmax_bwd_rows(const float* p, float* dp, const float* dpx, long long rows, int n, cudaStream_t s) {
+  ProfScope prof(KC_BWD_SOFTMAX, s);
+  if (n > 32 * MAX_PER_LANE) return set_error(ODEVIT_ERR_UNSUPPORTED, "softmax_bwd_rows: N=%d > 1024", n);
+  softmax_bwd_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(p, dp, dpx, rows, n);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int colsum_accum(const void* X, int x_type, long long ld, int rows, int cols, float* acc, cudaStream_t s) {
+  ProfScope prof(KC_BWD_COLSUM, s);
+  const int rpb = 256;
+  dim3 grid((cols + 127) / 128, (rows + rpb - 1) / rpb);
+  colsum_kernel<<<grid, 128, 0, s>>>(X, x_type, ld, rows, cols, rpb, acc);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int vjp_combine(const CombineArgs& a, int rows, int D, cudaStream_t s) {
+  ProfScope prof(KC_COMBINE, s);
+  if (D > 32 * MAX_PER_LANE) return set_error(ODEVIT_ERR_UNSUPPORTED, "vjp_combine: D=%d > 1024", D);
+  vjp_combine_kernel<<<(rows + 7) / 8, 256, 0, s>>>(a, rows, D);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int axpy_f32(float* y, const float* x, float a, long long n, cudaStream_t s) {
+  ProfScope prof(KC_COMBINE, s);
+  const int blocks = (int)((n + 1023) / 1024 < 148 * 8 ? (n + 1023) / 1024 : 148 * 8);
+  axpy_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(y, x, a, n);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int fold_weights_parallel(const FoldArgs& a, cudaStream_t s) {
+  ProfScope prof(KC_WEIGHTS, s);
+  fold_w1_kernel<<<3 * a.D + a.hid, 128, 0, s>>>(a, *a.w);
+  ODV_LAUNCH_CHECK();
+  fold_w2_kernel<<<a.D, 128, 0, s>>>(a, *a.w);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int unfold_grads_parallel(const UnfoldArgs& a, cudaStream_t s) {
+  ProfScope prof(KC_WEIGHTS, s);
+  unfold_w1_kernel<<<3 * a.D + a.hid, 128, 0, s>>>(a, *a.w, *a.gw);
+  ODV_LAUNCH_CHECK();
+  unfold_norm_kernel<<<(a.D + 127) / 128, 128, 0, s>>>(a, *a.w, *a.gw);
+  ODV_LAUNCH_CHECK();
+  unfold_w2_kernel<<<a.D, 128, 0, s>>>(a, *a.gw);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace odevit

@@ -1,0 +1,271 @@
+"""PyTorch-facing operators over the C ABI: one vector-field evaluation and the fixed-grid solve,
+each as a `torch.autograd.Function` whose forward/backward enqueue libodevit.so kernels on the
+current CUDA stream.  PyTorch is plumbing here (device memory, streams, autograd graph edges).
+
+Replaces, for CUDA tensors:
+  * `ViT_ODEFunc.forward(t, x)`                         models/ode_transformer_gpt.py:317-330
+  * `torchdiffeq.odeint(func, y0, t, method=...)`        models/ode_transformer_gpt.py:571-578
+  * autograd through both (backprop-through-solver)      train.py:57-67
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import OdevitError
+
+_vp = ctypes.c_void_p
+
+
+@dataclass(frozen=True)
+class FieldSpec:
+    """Static description of the vector field (everything but the batch)."""
+    dim: int
+    heads: int
+    hidden: int
+    scaler: float
+    variant: int = _lib.FIELD_PARALLEL
+    precision: str = "bf16"
+
+    def desc(self, batch: int, tokens: int) -> _lib.Desc:
+        d = _lib.Desc()
+        d.abi_version = _lib.ABI_VERSION
+        d.batch, d.tokens, d.dim, d.heads, d.hidden = batch, tokens, self.dim, self.heads, self.hidden
+        d.variant = self.variant
+        d.precision = _lib.PRECISIONS[self.precision]
+        d.scaler = float(self.scaler)
+        return d
+
+
+# ---------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------
+def _require_cuda(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise OdevitError(f"{what} is on {t.device}: odevit_b200 runs on CUDA devices only (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise OdevitError(f"{what} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return _vp(t.data_ptr()) if t is not None else None
+
+
+_WS_CACHE: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _workspace(desc: _lib.Desc, kind: int, method: int, device: torch.device):
+    """A cached, 1024-byte aligned device workspace (stream-ordered reuse through torch's allocator)."""
+    n = _lib.lib().odevit_workspace_bytes(ctypes.byref(desc), kind, method)
+    if n == 0:
+        _lib.check(-1, "odevit_workspace_bytes")
+    key = (device.index if device.index is not None else torch.cuda.current_device(), kind)
+    buf = _WS_CACHE.get(key)
+    if buf is None or buf.numel() < n + 1024:
+        _WS_CACHE.pop(key, None)
+        buf = None
+        buf = torch.empty(int(n * 1.05) + 2048, dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = buf
+    base = buf.data_ptr()
+    aligned = (base + 1023) & ~1023
+    return buf, _vp(aligned), buf.numel() - (aligned - base)
+
+
+def free_workspaces() -> None:
+    _WS_CACHE.clear()
+
+
+def _stream() -> _vp:
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _pack_weights(names: Sequence[str], tensors: Sequence[torch.Tensor]):
+    w = _lib.Weights()
+    keep = []
+    for n, t in zip(names, tensors):
+        if t is None:
+            continue
+        t = _require_cuda(t.detach(), f"weight {n}")
+        keep.append(t)
+        setattr(w, n, t.data_ptr())
+    return w, keep
+
+
+def _alloc_grads(names: Sequence[str], tensors: Sequence[torch.Tensor], needs: Sequence[bool]):
+    g = _lib.WeightGrads()
+    out: List[Optional[torch.Tensor]] = []
+    for n, t, need in zip(names, tensors, needs):
+        if t is None or not need or n in _lib.MOD_FIELDS:
+            out.append(None)
+            continue
+        gt = torch.zeros_like(t, dtype=torch.float32, memory_format=torch.contiguous_format)
+        setattr(g, n, gt.data_ptr())
+        out.append(gt)
+    return g, out
+
+
+# ---------------------------------------------------------------------------------------------
+# one field evaluation
+# ---------------------------------------------------------------------------------------------
+class _FieldEval(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, spec: FieldSpec, want_p: bool, names: Tuple[str, ...], *weights):
+        x = _require_cuda(x, "x")
+        B, N, D = x.shape
+        desc = spec.desc(B, N)
+        w, keep = _pack_weights(names, weights)
+        dx = torch.empty_like(x)
+        p = torch.empty(B, spec.heads, N, N, device=x.device, dtype=torch.float32) if want_p else None
+        buf, ws, ws_bytes = _workspace(desc, _lib.WS_FIELD, _lib.EULER, x.device)
+        with torch.cuda.device(x.device):
+            st = _lib.lib().odevit_field_fwd(ctypes.byref(desc), ctypes.byref(w), _ptr(x), _ptr(dx), _ptr(p),
+                                             ws, ws_bytes, _stream())
+        _lib.check(st, "odevit_field_fwd")
+        ctx.spec, ctx.names, ctx.want_p = spec, names, want_p
+        ctx.save_for_backward(x, *[t for t in weights])
+        ctx.set_materialize_grads(False)
+        if want_p:
+            return dx, p
+        return dx, x.new_empty(0)
+
+    @staticmethod
+    def backward(ctx, g_dx, g_p):
+        x, *weights = ctx.saved_tensors
+        spec, names = ctx.spec, ctx.names
+        B, N, D = x.shape
+        desc = spec.desc(B, N)
+        w, keep = _pack_weights(names, weights)
+        needs = ctx.needs_input_grad[4:]
+        gw, gts = _alloc_grads(names, weights, needs)
+        if g_dx is None:
+            g_dx = torch.zeros_like(x)
+        g_dx = _require_cuda(g_dx, "g_dx")
+        if g_p is not None and (not ctx.want_p or g_p.numel() == 0):
+            g_p = None
+        if g_p is not None:
+            g_p = _require_cuda(g_p, "g_p")
+        g_x = torch.empty_like(x)
+        buf, ws, ws_bytes = _workspace(desc, _lib.WS_SOLVE_BWD, _lib.EULER, x.device)
+        with torch.cuda.device(x.device):
+            st = _lib.lib().odevit_field_bwd(ctypes.byref(desc), ctypes.byref(w), _ptr(x), _ptr(g_dx), _ptr(g_p),
+                                             _ptr(g_x), ctypes.byref(gw), ws, ws_bytes, _stream())
+        _lib.check(st, "odevit_field_bwd")
+        return (g_x if ctx.needs_input_grad[0] else None, None, None, None, *gts)
+
+
+def field_eval(x: torch.Tensor, spec: FieldSpec, weights: Dict[str, Optional[torch.Tensor]],
+               want_p: bool = True):
+    """dx, P = f(x).  `weights` maps the odevit_weights field names to fp32 CUDA tensors."""
+    names = tuple(k for k, v in weights.items() if v is not None)
+    dx, p = _FieldEval.apply(x, spec, want_p, names, *[weights[k] for k in names])
+    return dx, (p if want_p else None)
+
+
+# ---------------------------------------------------------------------------------------------
+# the fixed-grid solve
+# ---------------------------------------------------------------------------------------------
+class _OdeSolve(torch.autograd.Function):
+    """(states, final, rows, p_last, p_traj) = solve(x0).
+
+    * `states` [T,B,N,D]: what `odeint` returns;
+    * `final` [B,N,D]: states[-1] as its own output, so a loss on the final state does not make
+      autograd materialise a dense [T,B,N,D] cotangent;
+    * `rows` [Q,B,N,D]: states[row_index] (the control points), same reason;
+    * `p_last` [B,H,N,N]: attention map of the last field evaluation (`block.attentions`);
+    * `p_traj` [E,B,H,N,N]: maps of the last E evaluations (`attention_trajectory`, detached).
+    """
+
+    @staticmethod
+    def forward(ctx, x0, spec: FieldSpec, method: str, t_host: torch.Tensor, row_index: Tuple[int, ...],
+                want_p_last: bool, p_traj_first: Optional[int], names: Tuple[str, ...], *weights):
+        x0 = _require_cuda(x0, "x0")
+        B, N, D = x0.shape
+        T = int(t_host.numel())
+        S = _lib.STAGES[method]
+        desc = spec.desc(B, N)
+        w, keep = _pack_weights(names, weights)
+        t_host = t_host.detach().to("cpu", torch.float32).contiguous()
+        t_c = (ctypes.c_float * T)(*t_host.tolist())
+        states = torch.empty(T, B, N, D, device=x0.device, dtype=torch.float32)
+        final = torch.empty(B, N, D, device=x0.device, dtype=torch.float32)
+        n_evals = (T - 1) * S
+        p_last = (torch.empty(B, spec.heads, N, N, device=x0.device, dtype=torch.float32)
+                  if (want_p_last and n_evals > 0) else None)
+        p_traj = None
+        first = 0
+        if p_traj_first is not None and n_evals > 0:
+            first = max(0, min(int(p_traj_first), n_evals))
+            if n_evals - first > 0:
+                p_traj = torch.empty(n_evals - first, B, spec.heads, N, N, device=x0.device, dtype=torch.float32)
+        buf, ws, ws_bytes = _workspace(desc, _lib.WS_SOLVE_FWD, _lib.METHODS[method], x0.device)
+        with torch.cuda.device(x0.device):
+            st = _lib.lib().odevit_solve_fwd(ctypes.byref(desc), ctypes.byref(w), _lib.METHODS[method], _ptr(x0),
+                                             t_c, T, _ptr(states), _ptr(final), _ptr(p_last), _ptr(p_traj), first,
+                                             ws, ws_bytes, _stream())
+        _lib.check(st, "odevit_solve_fwd")
+        rows = states[list(row_index)] if len(row_index) else x0.new_empty(0)
+        ctx.spec, ctx.method, ctx.names, ctx.row_index = spec, method, names, tuple(row_index)
+        ctx.t_c, ctx.T = t_c, T
+        ctx.has_p_last = p_last is not None
+        ctx.save_for_backward(states, *weights)
+        ctx.set_materialize_grads(False)
+        empty = x0.new_empty(0)
+        out_p_traj = p_traj if p_traj is not None else empty
+        ctx.mark_non_differentiable(out_p_traj)
+        return states, final, rows, (p_last if p_last is not None else empty), out_p_traj
+
+    @staticmethod
+    def backward(ctx, g_states, g_final, g_rows, g_p_last, _g_p_traj):
+        states, *weights = ctx.saved_tensors
+        spec, method, names = ctx.spec, ctx.method, ctx.names
+        T, B, N, D = states.shape
+        desc = spec.desc(B, N)
+        w, keep = _pack_weights(names, weights)
+        needs = ctx.needs_input_grad[8:]
+        gw, gts = _alloc_grads(names, weights, needs)
+        parts, index = [], []
+        if g_final is not None:
+            parts.append(_require_cuda(g_final, "g_final").unsqueeze(0))
+            index.append(T - 1)
+        if g_rows is not None and g_rows.numel() and len(ctx.row_index):
+            parts.append(_require_cuda(g_rows, "g_rows"))
+            index.extend(ctx.row_index)
+        g_rows_all = torch.cat(parts, 0).contiguous() if parts else None
+        idx_c = (ctypes.c_int32 * max(1, len(index)))(*index)
+        if g_states is not None:
+            g_states = _require_cuda(g_states, "g_states")
+        if g_p_last is not None and (not ctx.has_p_last or g_p_last.numel() == 0):
+            g_p_last = None
+        if g_p_last is not None:
+            g_p_last = _require_cuda(g_p_last, "g_p_last")
+        g_x0 = torch.empty(B, N, D, device=states.device, dtype=torch.float32)
+        buf, ws, ws_bytes = _workspace(desc, _lib.WS_SOLVE_BWD, _lib.METHODS[method], states.device)
+        with torch.cuda.device(states.device):
+            st = _lib.lib().odevit_solve_bwd(ctypes.byref(desc), ctypes.byref(w), _lib.METHODS[method], ctx.t_c, T,
+                                             _ptr(states), _ptr(g_states), _ptr(g_rows_all), idx_c, len(index),
+                                             _ptr(g_p_last), _ptr(g_x0), ctypes.byref(gw), ws, ws_bytes, _stream())
+        _lib.check(st, "odevit_solve_bwd")
+        return (g_x0 if ctx.needs_input_grad[0] else None, None, None, None, None, None, None, None, *gts)
+
+
+def ode_solve(x0: torch.Tensor, t: torch.Tensor, spec: FieldSpec, method: str,
+              weights: Dict[str, Optional[torch.Tensor]], row_index: Sequence[int] = (),
+              want_p_last: bool = False, p_traj_first: Optional[int] = None):
+    """Fixed-grid solve of dx/dt = f(x) over the grid `t` (euler | midpoint | rk4 = 3/8 rule).
+
+    Returns dict(states, final, rows, p_last, p_traj); see `_OdeSolve`."""
+    if method not in _lib.METHODS:
+        raise ValueError(f"unsupported solver {method!r}; fixed-grid euler | midpoint | rk4 are built")
+    if t.ndim != 1 or t.numel() < 1:
+        raise ValueError("t must be one dimensional")
+    names = tuple(k for k, v in weights.items() if v is not None)
+    states, final, rows, p_last, p_traj = _OdeSolve.apply(
+        x0, spec, method, t, tuple(int(i) for i in row_index), want_p_last, p_traj_first, names,
+        *[weights[k] for k in names])
+    return {"states": states, "final": final, "rows": rows if len(row_index) else None,
+            "p_last": p_last if p_last.numel() else None, "p_traj": p_traj if p_traj.numel() else None}

@@ -1,0 +1,242 @@
+"""GPU parity tests proper: the CUDA path (through the nn.Module surface -> ops -> C ABI) against
+the golden vectors the unmodified reference produced, and against the oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): fp32 mode max-rel error <= 1e-4 on final state and
+logits; bf16 mode <= 2e-2; identical top-1.  Gradients are held to 2e-3 (fp32 mode): the
+reference's own fp32 autograd differs from its fp64 rerun by ~1e-4 on these cases."""
+import pytest
+import torch
+
+import odevit_oracle as orc
+from _util import Golden, VIT_CASES, max_rel
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_TOL = 2e-2
+GRAD_TOL = 2e-3
+
+
+def _objective(out, attn_w, ctrl_w):
+    obj = out["loss"]
+    if "control_points" in out:
+        obj = obj + ctrl_w * (out["control_points"][:, :, 0] ** 2).mean()
+    if "attentions" in out:
+        a = out["attentions"][:, :, 0, 1:]
+        obj = obj + (a * attn_w[: a.shape[-1]]).sum(-1).mean()
+    if "jasmin_loss" in out:
+        obj = obj + out["jasmin_loss"]
+    return obj
+
+
+def _build(g: Golden, precision: str):
+    import odevit_b200 as ob
+    model = ob.ViTNeuralODE(**g.ctor)
+    model.load_state_dict(g.group("sd"), strict=True)
+    model = model.cuda().train()
+    model.precision = precision
+    return model
+
+
+@pytest.mark.parametrize("name", VIT_CASES)
+def test_vit_golden_fp32(name):
+    g = Golden(name)
+    model = _build(g, "fp32")
+    px = g.get("in/pixel_values").cuda().requires_grad_(True)
+    call = g.call
+    out = model(px, labels=g.get("in/labels").cuda(), **call)
+    want = g.group("out")
+    for key in ("logits", "states", "attentions", "attentions_register_tokens", "control_points",
+                "second_derivative_upper_bound", "logits_dist", "loss"):
+        if key in want:
+            assert out[key].shape == want[key].shape, key
+            assert max_rel(out[key], want[key]) < FP32_TOL, key
+    assert max_rel(out["states"][-1], want["states"][-1]) < FP32_TOL
+    assert out["logits"].argmax(-1).cpu().tolist() == want["logits"].argmax(-1).tolist()
+    if "jasmin_loss" in want:
+        assert float(out["jasmin_loss"]) == pytest.approx(float(want["jasmin_loss"]), rel=1e-3, abs=1e-5)
+        assert not out["jasmin_loss"].requires_grad
+    for key in ("global_upper_bound", "batched_upper_bound", "batched_upper_bound_per_seq"):
+        got = out["finite_difference_upper_bound"][key]
+        assert max_rel(torch.as_tensor(got), want["finite_difference_upper_bound." + key]) < 2e-3, key
+    obj = _objective(out, g.get("in/attn_w").cuda(), g.meta["ctrl_w"])
+    assert float(obj) == pytest.approx(float(want["objective"]), rel=1e-4)
+    obj.backward()
+    grads = g.group("grad")
+    assert max_rel(px.grad, grads["pixel_values"]) < GRAD_TOL
+    for k, p in model.named_parameters():
+        if grads[k].abs().max() > 0:
+            assert p.grad is not None, k
+            assert max_rel(p.grad, grads[k]) < GRAD_TOL, k
+
+
+@pytest.mark.parametrize("name", VIT_CASES)
+def test_vit_golden_bf16(name):
+    g = Golden(name)
+    model = _build(g, "bf16")
+    px = g.get("in/pixel_values").cuda()
+    with torch.no_grad():
+        out = model(px, labels=g.get("in/labels").cuda(), **g.call)
+    want = g.group("out")
+    assert max_rel(out["states"][-1], want["states"][-1]) < BF16_TOL
+    assert max_rel(out["logits"], want["logits"]) < BF16_TOL
+    top2 = want["logits"].topk(2, -1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 4 * BF16_TOL * want["logits"].abs().max()
+    same = out["logits"].argmax(-1).cpu() == want["logits"].argmax(-1)
+    assert bool(same[decided].all())
+
+
+def test_bf16_gradients_close():
+    g = Golden("c10_rk4_T5_B2")
+    model = _build(g, "bf16")
+    px = g.get("in/pixel_values").cuda().requires_grad_(True)
+    out = model(px, labels=g.get("in/labels").cuda(), **g.call)
+    _objective(out, g.get("in/attn_w").cuda(), g.meta["ctrl_w"]).backward()
+    grads = g.group("grad")
+    assert max_rel(px.grad, grads["pixel_values"]) < 0.1
+    for k, p in model.named_parameters():
+        if grads[k].abs().max() > 0:
+            assert max_rel(p.grad, grads[k]) < 0.1, k
+
+
+def test_field_golden_fp32():
+    """ViT_ODEFunc.forward(t, x) against the reference's direct call (fields_d64 / mha)."""
+    import odevit_b200 as ob
+    g = Golden("fields_d64")
+    f = ob.ViT_ODEFunc(dim=64, num_heads=2, mlp_ratio=2.0, emulate_depth=12, time_interval=1.0,
+                       l2_attention=False)
+    f.load_state_dict(g.group("mha/sd"), strict=True)
+    f = f.cuda()
+    x = g.get("mha/x").cuda().requires_grad_(True)
+    dx = f(torch.tensor(0.25), x)
+    assert max_rel(dx, g.get("mha/dx")) < 1e-5
+    assert max_rel(f.block.attentions, g.get("mha/P")) < 1e-5
+    assert len(f.attention_trajectory) == 1 and not f.attention_trajectory[0].requires_grad
+    (dx * g.get("mha/w").cuda()).sum().backward()
+    assert max_rel(x.grad, g.get("mha/grad_x")) < 1e-4
+    for k, p in f.named_parameters():
+        assert max_rel(p.grad, g.get(f"mha/grad/{k}")) < 1e-4, k
+
+
+def test_field_attention_cotangent():
+    """A loss on block.attentions (the L1 attention consumer) back-propagates through the field."""
+    import odevit_b200 as ob
+    g = Golden("fields_d64")
+    sd = g.group("mha/sd")
+    f = ob.ViT_ODEFunc(dim=64, num_heads=2, mlp_ratio=2.0, emulate_depth=12, time_interval=1.0,
+                       l2_attention=False)
+    f.load_state_dict(sd, strict=True)
+    f = f.cuda()
+    x = g.get("mha/x").cuda().requires_grad_(True)
+    wp = torch.randn(2, 2, 19, 19, generator=torch.Generator().manual_seed(5))
+    dx = f(torch.tensor(0.0), x)
+    ((f.block.attentions * wp.cuda()).sum() + 0.1 * dx.sum()).backward()
+    sdr = {("block." + k): v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr = g.get("mha/x").clone().requires_grad_(True)
+    dxr, pr = orc.field_parallel(xr, sdr, 2, 12.0, prefix="block.")
+    ((pr * wp).sum() + 0.1 * dxr.sum()).backward()
+    assert max_rel(x.grad, xr.grad) < 1e-4
+    for k, p in f.named_parameters():
+        assert max_rel(p.grad, sdr["block." + k].grad) < 1e-4, k
+
+
+@pytest.mark.parametrize("solver,T,prec,tol", [("euler", 4, "fp32", FP32_TOL), ("rk4", 3, "fp32", FP32_TOL),
+                                               ("euler", 4, "bf16", BF16_TOL)])
+def test_c100_shape_vs_oracle(solver, T, prec, tol):
+    """224 px / D=768 / H=12 / R=10 (N=207) against the oracle on seeded inputs, small batch."""
+    import odevit_b200 as ob
+    cfg = dict(img_size=224, patch_size=16, num_classes=100, embed_dim=768, num_heads=12, mlp_ratio=1.0,
+               emulate_depth=12, time_interval=1.0, num_eval_steps=T, solver=solver, register_tokens=10)
+    sd = orc.reference_like_init(cfg, 100, seed=3)
+    model = ob.ViTNeuralODE(**cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    model.precision = prec
+    px = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(1234))
+    with torch.no_grad():
+        out = model(px.cuda(), output_hidden_states=True, output_attentions=True, jasmin_k=2)
+        want = orc.vit_ode_forward(sd, cfg, px, output_hidden_states=True, output_attentions=True, jasmin_k=2)
+    assert max_rel(out["states"][-1], want["states"][-1]) < tol
+    assert max_rel(out["logits"], want["logits"]) < tol
+    assert max_rel(out["attentions"], want["attentions"]) < (1e-4 if prec == "fp32" else 5e-2)
+    if prec == "fp32":
+        assert out["logits"].argmax(-1).cpu().tolist() == want["logits"].argmax(-1).tolist()
+
+
+# ---- size-independent properties at BASELINE sizes -------------------------------------------
+
+def _c10_model(T=5, solver="rk4", B=None, prec="fp32"):
+    import odevit_b200 as ob
+    cfg = dict(img_size=32, patch_size=4, num_classes=10, embed_dim=192, num_heads=3, mlp_ratio=4.0,
+               emulate_depth=12, time_interval=1.0, num_eval_steps=T, solver=solver, register_tokens=4)
+    model = ob.ViTNeuralODE(**cfg)
+    model.load_state_dict(orc.reference_like_init(cfg, 10, seed=1), strict=True)
+    model = model.cuda().eval()
+    model.precision = prec
+    return model
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_images_are_independent(prec):
+    """Solving a batch == solving its images one by one (attention never crosses images)."""
+    model = _c10_model(prec=prec)
+    px = torch.randn(64, 3, 32, 32, device="cuda")
+    with torch.no_grad():
+        full = model(px, output_hidden_states=True)["states"]
+        one = model(px[17:18], output_hidden_states=True)["states"]
+        perm = torch.randperm(64, device="cuda")
+        shuf = model(px[perm], output_hidden_states=True)["states"]
+    tol = 1e-5 if prec == "fp32" else 1e-5
+    assert max_rel(full[:, 17:18], one) < tol
+    assert max_rel(shuf, full[:, perm]) < tol
+
+
+def test_grid_composition():
+    """Solving over [t0..t4] == solving [t0..t2] then restarting from that state over [t2..t4]."""
+    import odevit_b200 as ob
+    model = _c10_model()
+    x0 = model.patch_embed(torch.randn(8, 3, 32, 32, device="cuda")).detach()
+    t = torch.tensor([0.0, 0.2, 0.5, 0.7, 1.0])
+    with torch.no_grad():
+        whole = ob.odeint(model.odefunc, x0, t, method="rk4")
+        a = ob.odeint(model.odefunc, x0, t[:3], method="rk4")
+        b = ob.odeint(model.odefunc, a[-1].contiguous(), t[2:], method="rk4")
+    assert torch.equal(whole[0], x0)
+    assert max_rel(a, whole[:3]) < 1e-6
+    assert max_rel(b, whole[2:]) < 1e-6
+    assert len(model.odefunc.attention_trajectory) == (4 + 2 + 2) * 4
+
+
+def test_single_point_grid_and_euler_identity():
+    import odevit_b200 as ob
+    model = _c10_model()
+    x0 = model.patch_embed(torch.randn(2, 3, 32, 32, device="cuda")).detach()
+    with torch.no_grad():
+        s = ob.odeint(model.odefunc, x0, torch.tensor([0.3]), method="euler", record_attention=False)
+        assert s.shape == (1, *x0.shape) and torch.equal(s[0], x0)
+        # one Euler step == x0 + dt * f(x0)
+        s = ob.odeint(model.odefunc, x0, torch.tensor([0.0, 0.125]), method="euler", record_attention=False)
+        dx = model.odefunc(torch.tensor(0.0), x0)
+    assert max_rel(s[1], x0 + 0.125 * dx) < 1e-6
+
+
+def test_solver_order_on_the_real_field():
+    """RK4(3/8) self-convergence on the actual vector field: halving dt cuts the error ~16x, Euler ~2x."""
+    import odevit_b200 as ob
+    model = _c10_model()
+    model.odefunc.scaler = 1.0
+    x0 = model.patch_embed(torch.randn(4, 3, 32, 32, device="cuda")).detach()
+
+    def final(method, steps):
+        with torch.no_grad():
+            return ob.odeint(model.odefunc, x0, torch.linspace(0, 1, steps + 1), method=method,
+                             record_attention=False)[-1].double()
+
+    ref = final("rk4", 64)
+    e_eu = [float((final("euler", n) - ref).abs().max()) for n in (8, 16)]
+    assert 1.6 < e_eu[0] / e_eu[1] < 2.6
+    e_mid = [float((final("midpoint", n) - ref).abs().max()) for n in (4, 8)]
+    assert 3.0 < e_mid[0] / e_mid[1] < 5.5
+    # RK4 errors at these step counts sit near the fp32 floor; only require a clear 4th-order drop
+    e_rk = [float((final("rk4", n) - ref).abs().max()) for n in (1, 2)]
+    assert e_rk[0] / e_rk[1] > 6.0
