@@ -185,16 +185,25 @@ int odevit_field_bwd(const odevit_desc* desc, const odevit_weights* w,
                      float* g_x, const odevit_weight_grads* gw,
                      void* workspace, size_t workspace_bytes, odevit_stream_t stream);
 
-/* Number of kernels the library launched on this thread since the last reset (bench.py's
+/* Number of kernels the library launched (process-wide, all threads) since the last reset (bench.py's
  * gpu_launches claim is counted, not estimated). */
 int64_t odevit_launch_count(void);
 void odevit_reset_launch_count(void);
+
+/* Diagnostic entry (no reference counterpart): the GEMM kernel on its own, for unit parity tests.
+ *   C[M,N] (fp32, row-major) = or += sum_k A(m,k) * B(n,k), bf16 operands.
+ *   mn_major == 0: A is [M,K], B is [N,K] row-major (K contiguous);
+ *   mn_major == 1: A is [K,M], B is [K,N] row-major (the weight-gradient products, split-K).
+ *   engine: 0 = CUDA-core FFMA kernel, 1 = tcgen05/TMA kernel (ODEVIT_ERR_UNSUPPORTED if the shape
+ *   is outside what it covers). */
+int odevit_gemm_bf16(int32_t M, int32_t N, int32_t K, int32_t mn_major, const void* A, const void* B,
+                     float* C, int32_t accumulate, int32_t engine, odevit_stream_t stream);
 
 /* Per-kernel-class device timing for bench.py's roofline line (no reference counterpart).
  * While enabled, each launch is bracketed by a CUDA event pair on its stream (a few microseconds
  * of host time per launch).  odevit_profile_read synchronises on the recorded events, so call it
  * after the work has been enqueued; it returns the summed milliseconds and the launch count of
- * class `kclass` since the last enable, or a negative status.  Thread-local like the counter. */
+ * class `kclass` since the last enable, or a negative status.  Process-wide like the counter. */
 int odevit_profile_enable(int32_t on);
 int odevit_profile_num_classes(void);
 const char* odevit_profile_class_name(int32_t kclass);

@@ -88,6 +88,8 @@ def lib() -> ctypes.CDLL:
                                    ctypes.POINTER(ctypes.c_float), ctypes.c_int32, _vp, _vp, _vp,
                                    ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, _vp, _vp,
                                    ctypes.POINTER(WeightGrads), _vp, ctypes.c_size_t, _vp]
+    L.odevit_gemm_bf16.restype = ctypes.c_int
+    L.odevit_gemm_bf16.argtypes = [ctypes.c_int32] * 4 + [_vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _vp]
     L.odevit_profile_enable.restype = ctypes.c_int
     L.odevit_profile_enable.argtypes = [ctypes.c_int32]
     L.odevit_profile_num_classes.restype = ctypes.c_int
@@ -135,5 +137,5 @@ def profile_read() -> dict:
 DECLARED_SYMBOLS = ("odevit_abi_version", "odevit_build_info", "odevit_last_error_string",
                     "odevit_workspace_bytes", "odevit_field_fwd", "odevit_solve_fwd", "odevit_solve_bwd",
                     "odevit_field_bwd", "odevit_launch_count", "odevit_reset_launch_count",
-                    "odevit_profile_enable", "odevit_profile_num_classes", "odevit_profile_class_name",
+                    "odevit_gemm_bf16", "odevit_profile_enable", "odevit_profile_num_classes", "odevit_profile_class_name",
                     "odevit_profile_read")

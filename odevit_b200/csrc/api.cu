@@ -14,8 +14,10 @@
 //
 // The reverse sweep recomputes each step's stage intermediates from the stored trajectory row
 // (no stage tensor survives the forward) and applies the exact VJP of the unrolled RK step.
+#include <atomic>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 
 #include "internal.h"
 
@@ -27,8 +29,10 @@ namespace odevit {
 // ------------------------------------------------------------------------------------------------
 // thread-local error text + launch counter
 // ------------------------------------------------------------------------------------------------
+// The error text is thread-local; the launch counter and the profiling state are process-wide
+// (PyTorch runs the backward on its own autograd thread, which must be counted too).
 static thread_local char g_err[512] = "ok";
-static thread_local int64_t g_launches = 0;
+static std::atomic<int64_t> g_launches{0};
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -37,19 +41,20 @@ int set_error(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
-void count_launch(int n) { g_launches += n; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---- per-class event timing ------------------------------------------------------------------
 namespace {
 constexpr int kMaxProfPairs = 1 << 16;
 struct ProfState {
+  std::mutex mu;
   bool on = false;
   int used = 0;
   int cap = 0;
   cudaEvent_t* ev = nullptr;  // 2 per pair
   int* cls = nullptr;
 };
-thread_local ProfState g_prof;
+ProfState g_prof;
 const char* const kClassNames[KC_COUNT] = {
     "center_rows", "gemm_in_qkv_fc1", "attn_qk", "softmax", "attn_pv", "gemm_out_rk",
     "bwd_gemm_doh", "bwd_gemm_g2", "bwd_attn", "bwd_softmax", "bwd_gemm_dx", "bwd_gemm_g1",
@@ -59,6 +64,7 @@ const char* const kClassNames[KC_COUNT] = {
 ProfScope::ProfScope(int c, cudaStream_t st) : cls(c), s(st), slot(-1) {
   ProfState& p = g_prof;
   if (!p.on) return;
+  std::lock_guard<std::mutex> lock(p.mu);
   if (p.used >= p.cap) {
     if (p.cap >= kMaxProfPairs) return;
     if (cudaEventCreate(&p.ev[2 * p.cap]) != cudaSuccess || cudaEventCreate(&p.ev[2 * p.cap + 1]) != cudaSuccess) return;
@@ -512,11 +518,30 @@ const char* odevit_build_info(void) {
 
 const char* odevit_last_error_string(void) { return g_err; }
 
-int64_t odevit_launch_count(void) { return g_launches; }
-void odevit_reset_launch_count(void) { g_launches = 0; }
+int64_t odevit_launch_count(void) { return g_launches.load(); }
+void odevit_reset_launch_count(void) { g_launches.store(0); }
+
+int odevit_gemm_bf16(int32_t M, int32_t N, int32_t K, int32_t mn_major, const void* A, const void* B, float* C,
+                     int32_t accumulate, int32_t engine, odevit_stream_t stream) {
+  ODV_TRY(check_device_ptr(A, "A"));
+  ODV_TRY(check_device_ptr(B, "B"));
+  ODV_TRY(check_device_ptr(C, "C"));
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K;
+  g.A = A; g.a_type = DT_BF16;
+  g.B = B; g.b_type = DT_BF16;
+  if (mn_major) { g.a_rs = 1; g.a_cs = M; g.b_rs = 1; g.b_cs = N; }
+  else { g.a_rs = K; g.a_cs = 1; g.b_rs = K; g.b_cs = 1; }
+  g.epi_mode = accumulate ? EPI_ACCUM : EPI_STORE;
+  g.epi.out = C; g.epi.out_type = DT_F32; g.epi.ld_out = N;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (engine == 1) return gemm_tc(g, s);
+  return gemm_simt(g, s);
+}
 
 int odevit_profile_enable(int32_t on) {
   ProfState& p = g_prof;
+  std::lock_guard<std::mutex> lock(p.mu);
   if (on) {
     if (!p.ev) {
       p.ev = new cudaEvent_t[2 * kMaxProfPairs];

@@ -71,4 +71,115 @@ __device__ __forceinline__ void epi_apply(const Epi& e, int m, int n, float acc,
   }
 }
 
+// ---- vectorised form for the tcgen05 kernels: one thread holds 16 consecutive columns
+// [n, n+16) of row m (n % 16 == 0, all 16 in range; row pointers 16-byte aligned). -------------
+__device__ __forceinline__ void store16(void* p, long long idx, int type, const float* v) {
+  if (type == DT_F32) {
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + idx);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p) + idx);
+    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+__device__ __forceinline__ void load16(const void* p, long long idx, int type, float* v) {
+  if (type == DT_F32) {
+    const float4* in = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + idx);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = in[i];
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+  } else {
+    const uint4* in = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p) + idx);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint4 t = in[h];
+      const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+        v[8 * h + 2 * i] = __low2float(b);
+        v[8 * h + 2 * i + 1] = __high2float(b);
+      }
+    }
+  }
+}
+
+template <int EPI, bool ATOMIC>
+__device__ __forceinline__ void epi_chunk16(const Epi& e, int m, int n, float* v) {
+  if constexpr (EPI == EPI_STORE) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = e.alpha * v[j] + (e.bias ? e.bias[n + j] : 0.f);
+    store16(e.out, (long long)m * e.ld_out + n, e.out_type, v);
+  } else if constexpr (EPI == EPI_FWD1) {
+    if (e.bias) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += e.bias[n + j];
+    }
+    if (n < e.split) {
+      store16(e.out, (long long)m * e.ld_out + n, e.out_type, v);
+    } else {
+      const int c = n - e.split;
+      if (e.out3) store16(e.out3, (long long)m * e.ld_out3 + c, e.aux_type, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+      store16(e.out2, (long long)m * e.ld_out2 + c, e.aux_type, v);
+    }
+  } else if constexpr (EPI == EPI_RK) {
+    const long long idx = (long long)m * e.ld_out + n;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = e.alpha * (v[j] + (e.bias ? e.bias[n + j] : 0.f));
+    if (e.k_store) store16(e.k_store, idx, DT_F32, v);
+    float r[16], t[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[j] = e.c_new * v[j];
+    if (e.y) {
+      load16(e.y, idx, DT_F32, t);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = fmaf(e.y_coef, t[j], r[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (e.kin[i]) {
+        load16(e.kin[i], idx, DT_F32, t);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = fmaf(e.c_k[i], t[j], r[j]);
+      }
+    }
+    store16(e.out, idx, DT_F32, r);
+  } else if constexpr (EPI == EPI_BWD3) {
+    if (n < e.split) {
+      store16(e.out, (long long)m * e.ld_out + n, e.out_type, v);
+    } else {
+      const int c = n - e.split;
+      float hp[16];
+      load16(e.aux, (long long)m * e.ld_aux + c, e.aux_type, hp);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] *= gelu_erf_grad(hp[j]);
+      store16(e.out2, (long long)m * e.ld_out2 + c, e.aux_type, v);
+    }
+  } else if constexpr (EPI == EPI_ACCUM) {
+    float* o = reinterpret_cast<float*>(e.out) + (long long)m * e.ld_out + n;
+    if constexpr (ATOMIC) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) atomicAdd(o + j, e.alpha * v[j]);
+    } else {
+      float t[16];
+      load16(o, 0, DT_F32, t);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) t[j] = fmaf(e.alpha, v[j], t[j]);
+      store16(o, 0, DT_F32, t);
+    }
+  }
+}
+
 }  // namespace odevit

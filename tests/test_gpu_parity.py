@@ -131,13 +131,13 @@ def test_field_attention_cotangent():
     wp = torch.randn(2, 2, 19, 19, generator=torch.Generator().manual_seed(5))
     dx = f(torch.tensor(0.0), x)
     ((f.block.attentions * wp.cuda()).sum() + 0.1 * dx.sum()).backward()
-    sdr = {("block." + k): v.clone().requires_grad_(True) for k, v in sd.items()}
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     xr = g.get("mha/x").clone().requires_grad_(True)
     dxr, pr = orc.field_parallel(xr, sdr, 2, 12.0, prefix="block.")
     ((pr * wp).sum() + 0.1 * dxr.sum()).backward()
     assert max_rel(x.grad, xr.grad) < 1e-4
     for k, p in f.named_parameters():
-        assert max_rel(p.grad, sdr["block." + k].grad) < 1e-4, k
+        assert max_rel(p.grad, sdr[k].grad) < 1e-4, k
 
 
 @pytest.mark.parametrize("solver,T,prec,tol", [("euler", 4, "fp32", FP32_TOL), ("rk4", 3, "fp32", FP32_TOL),
