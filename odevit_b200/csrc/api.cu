@@ -318,34 +318,38 @@ int eval_forward(const Plan& p, const WeightBufs& wb, const StageCtx& c, const f
     g.epi.aux_type = p.act;
     ODV_TRY(gemm(p, g, s));
   }
-  const HeadView hv = qkv_view(p);
-  const char* qkv = reinterpret_cast<const char*>(c.qkv);
-  const size_t e = dtype_size(p.act);
-  {  // S = q k^T  (the 1/sqrt(d) is folded into the Wq rows)
-    GemmArgs g;
-    g.M = p.N; g.N = p.N; g.K = p.d;
-    g.A = qkv; g.a_type = p.act; g.a_rs = hv.rs; g.a_cs = 1; g.a_bo = hv.bo; g.a_bi = hv.bi;
-    g.B = qkv + (size_t)D * e; g.b_type = p.act; g.b_rs = hv.rs; g.b_cs = 1; g.b_bo = hv.bo; g.b_bi = hv.bi;
-    g.batch_outer = p.B; g.batch_inner = p.H;
-    g.epi_mode = EPI_STORE;
-    g.epi.out = P; g.epi.out_type = DT_F32; g.epi.ld_out = p.N;
-    g.epi.out_bo = (long long)p.H * p.N * p.N; g.epi.out_bi = (long long)p.N * p.N;
-    g.kclass = KC_ATTN_S;
-    ODV_TRY(gemm_simt(g, s));
-  }
-  ODV_TRY(softmax_rows(P, p_copy, (long long)p.B * p.H * p.N, p.N, s));
-  {  // O = P v  -> columns [h*d, (h+1)*d) of the [O|h] buffer
-    GemmArgs g;
-    g.M = p.N; g.N = p.d; g.K = p.N;
-    g.A = P; g.a_type = DT_F32; g.a_rs = p.N; g.a_cs = 1;
-    g.a_bo = (long long)p.H * p.N * p.N; g.a_bi = (long long)p.N * p.N;
-    g.B = qkv + (size_t)2 * D * e; g.b_type = p.act; g.b_rs = 1; g.b_cs = hv.rs; g.b_bo = hv.bo; g.b_bi = hv.bi;
-    g.batch_outer = p.B; g.batch_inner = p.H;
-    g.epi_mode = EPI_STORE;
-    g.epi.out = c.oh; g.epi.out_type = p.act; g.epi.ld_out = K2;
-    g.epi.out_bo = (long long)p.N * K2; g.epi.out_bi = p.d;
-    g.kclass = KC_ATTN_PV;
-    ODV_TRY(gemm_simt(g, s));
+  if (p.precision == ODEVIT_BF16 && attn_fwd_tc_supports(p.N, D, p.H, p.act, K2)) {
+    ODV_TRY(attn_fwd_tc(c.qkv, c.oh, K2, p_copy, p.B, p.N, p.H, D, s));
+  } else {
+    const HeadView hv = qkv_view(p);
+    const char* qkv = reinterpret_cast<const char*>(c.qkv);
+    const size_t e = dtype_size(p.act);
+    {  // S = q k^T  (the 1/sqrt(d) is folded into the Wq rows)
+      GemmArgs g;
+      g.M = p.N; g.N = p.N; g.K = p.d;
+      g.A = qkv; g.a_type = p.act; g.a_rs = hv.rs; g.a_cs = 1; g.a_bo = hv.bo; g.a_bi = hv.bi;
+      g.B = qkv + (size_t)D * e; g.b_type = p.act; g.b_rs = hv.rs; g.b_cs = 1; g.b_bo = hv.bo; g.b_bi = hv.bi;
+      g.batch_outer = p.B; g.batch_inner = p.H;
+      g.epi_mode = EPI_STORE;
+      g.epi.out = P; g.epi.out_type = DT_F32; g.epi.ld_out = p.N;
+      g.epi.out_bo = (long long)p.H * p.N * p.N; g.epi.out_bi = (long long)p.N * p.N;
+      g.kclass = KC_ATTN_S;
+      ODV_TRY(gemm_simt(g, s));
+    }
+    ODV_TRY(softmax_rows(P, p_copy, (long long)p.B * p.H * p.N, p.N, s));
+    {  // O = P v  -> columns [h*d, (h+1)*d) of the [O|h] buffer
+      GemmArgs g;
+      g.M = p.N; g.N = p.d; g.K = p.N;
+      g.A = P; g.a_type = DT_F32; g.a_rs = p.N; g.a_cs = 1;
+      g.a_bo = (long long)p.H * p.N * p.N; g.a_bi = (long long)p.N * p.N;
+      g.B = qkv + (size_t)2 * D * e; g.b_type = p.act; g.b_rs = 1; g.b_cs = hv.rs; g.b_bo = hv.bo; g.b_bi = hv.bi;
+      g.batch_outer = p.B; g.batch_inner = p.H;
+      g.epi_mode = EPI_STORE;
+      g.epi.out = c.oh; g.epi.out_type = p.act; g.epi.ld_out = K2;
+      g.epi.out_bo = (long long)p.N * K2; g.epi.out_bi = p.d;
+      g.kclass = KC_ATTN_PV;
+      ODV_TRY(gemm_simt(g, s));
+    }
   }
   if (rk) {
     GemmArgs g;

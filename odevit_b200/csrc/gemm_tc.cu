@@ -262,6 +262,21 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64
   return 0;
 }
 
+int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1_elems,
+                      uint64_t ld2_elems, uint32_t b0, uint32_t b1, uint32_t b2) {
+  EncodeFn fn = encode_fn();
+  if (!fn) return set_error(ODEVIT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {ld1_elems * 2, ld2_elems * 2};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(ODEVIT_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 bool gemm_tc_supports(const GemmArgs& g) {
   if (g.a_type != DT_BF16 || g.b_type != DT_BF16) return false;
   if (g.batch_outer * g.batch_inner != 1) return false;

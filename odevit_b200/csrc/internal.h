@@ -138,6 +138,11 @@ int gemm_simt(const GemmArgs& g, cudaStream_t s);
 int gemm_tc(const GemmArgs& g, cudaStream_t s);
 bool gemm_tc_supports(const GemmArgs& g);
 
+// Fused tcgen05 attention forward (attn_tc.cu): qkv [B,N,3D] bf16 -> O into oh[:, h*64..] (bf16),
+// optional fp32 P export.  Covers head dim 64, N <= 256.
+bool attn_fwd_tc_supports(int N, int D, int H, int act_type, long long ld_oh);
+int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, int B, int N, int H, int D, cudaStream_t s);
+
 // ---------------------------------------------------------------------------------------------
 // row-wise / elementwise kernels (odevit_rows.cu)
 // ---------------------------------------------------------------------------------------------
