@@ -58,7 +58,7 @@ ProfState g_prof;
 const char* const kClassNames[KC_COUNT] = {
     "center_rows", "gemm_in_qkv_fc1", "attn_qk", "softmax", "attn_pv", "gemm_out_rk",
     "bwd_gemm_doh", "bwd_gemm_g2", "bwd_attn", "bwd_softmax", "bwd_gemm_dx", "bwd_gemm_g1",
-    "bwd_colsum", "combine", "weights", "fused_attn", "other"};
+    "bwd_colsum", "combine", "weights", "fused_attn", "fused_attn_bwd", "other"};
 }  // namespace
 
 ProfScope::ProfScope(int c, cudaStream_t st) : cls(c), s(st), slot(-1) {
@@ -155,6 +155,7 @@ struct WeightBufs {
 };
 struct StageCtx {
   void *xc, *qkv, *oh, *hpre;
+  float* lse;  // [B,H,N] log2-domain row log-sum-exp of the attention (reverse sweep only)
 };
 
 WeightBufs take_weights(const Plan& p, Arena& a) {
@@ -176,6 +177,7 @@ StageCtx take_ctx(const Plan& p, Arena& a, bool with_hpre) {
   c.qkv = a.take((size_t)p.M * 3 * p.D * e);
   c.oh = a.take((size_t)p.M * (p.D + p.hid) * e);
   c.hpre = with_hpre ? a.take((size_t)p.M * p.hid * e) : nullptr;
+  c.lse = with_hpre ? a.f32((size_t)p.B * p.H * p.N) : nullptr;
   return c;
 }
 
@@ -209,6 +211,7 @@ struct BwdBufs {
   float* zsum;
   float* mu[4];
   float* gy;
+  float *delta, *dq_scratch;
   float *G1, *c1, *G2, *c2;
   size_t acc_bytes;  // G1..c2 are contiguous: one memset
 };
@@ -218,7 +221,7 @@ BwdBufs layout_bwd(const Plan& p, Arena& a, int S) {
   const size_t R = 3 * (size_t)p.D + p.hid, K2 = (size_t)p.D + p.hid;
   BwdBufs b;
   b.w = take_weights(p, a);
-  for (int i = 0; i < 4; ++i) b.ctx[i] = (i < S) ? take_ctx(p, a, true) : StageCtx{nullptr, nullptr, nullptr, nullptr};
+  for (int i = 0; i < 4; ++i) b.ctx[i] = (i < S) ? take_ctx(p, a, true) : StageCtx{nullptr, nullptr, nullptr, nullptr, nullptr};
   b.P = a.f32(p.BHNN);
   b.dP = a.f32(p.BHNN);
   b.u = a.f32(MD);
@@ -229,6 +232,11 @@ BwdBufs layout_bwd(const Plan& p, Arena& a, int S) {
   b.zsum = a.f32(MD);
   for (int i = 0; i < 4; ++i) b.mu[i] = (i >= 1 && i < S) ? a.f32(MD) : nullptr;
   b.gy = a.f32(MD);
+  b.delta = a.f32((size_t)p.B * p.H * p.N);
+  {
+    const size_t n = attn_bwd_tc_scratch_floats(p.B, p.N, p.H);
+    b.dq_scratch = n ? a.f32(n) : nullptr;
+  }
   // accumulators, contiguous (sizes are multiples of 4 bytes; keep them packed for one memset)
   const size_t acc_floats = R * p.D + R + K2 * p.D + p.D;
   float* acc = a.f32(acc_floats);
@@ -319,7 +327,7 @@ int eval_forward(const Plan& p, const WeightBufs& wb, const StageCtx& c, const f
     ODV_TRY(gemm(p, g, s));
   }
   if (p.precision == ODEVIT_BF16 && attn_fwd_tc_supports(p.N, D, p.H, p.act, K2)) {
-    ODV_TRY(attn_fwd_tc(c.qkv, c.oh, K2, p_copy, p.B, p.N, p.H, D, s));
+    ODV_TRY(attn_fwd_tc(c.qkv, c.oh, K2, p_copy, c.lse, p.B, p.N, p.H, D, s));
   } else {
     const HeadView hv = qkv_view(p);
     const char* qkv = reinterpret_cast<const char*>(c.qkv);
@@ -417,58 +425,63 @@ int eval_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b,
   }
   if (need_c2) ODV_TRY(colsum_accum(b.dd, p.act, D, p.M, D, b.c2, s));
 
-  // ---- attention VJP per (image, head); P is recomputed from q, k -----------------------------
-  const HeadView hv = qkv_view(p);
-  const char* qkv = reinterpret_cast<const char*>(c.qkv);
-  const long long pbo = (long long)p.H * p.N * p.N, pbi = (long long)p.N * p.N;
-  auto head_gemm = [&](GemmArgs& g) {
-    g.batch_outer = p.B; g.batch_inner = p.H;
-    g.kclass = KC_BWD_ATTN;
-    return gemm_simt(g, s);
-  };
-  {  // S
-    GemmArgs g;
-    g.M = p.N; g.N = p.N; g.K = p.d;
-    g.A = qkv; g.a_type = p.act; g.a_rs = hv.rs; g.a_cs = 1; g.a_bo = hv.bo; g.a_bi = hv.bi;
-    g.B = qkv + (size_t)D * e; g.b_type = p.act; g.b_rs = hv.rs; g.b_cs = 1; g.b_bo = hv.bo; g.b_bi = hv.bi;
-    g.epi.out = b.P; g.epi.ld_out = p.N; g.epi.out_bo = pbo; g.epi.out_bi = pbi;
-    ODV_TRY(head_gemm(g));
-  }
-  ODV_TRY(softmax_rows(b.P, nullptr, (long long)p.B * p.H * p.N, p.N, s));
-  {  // dP = dO v^T
-    GemmArgs g;
-    g.M = p.N; g.N = p.N; g.K = p.d;
-    g.A = b.dO; g.a_type = p.act; g.a_rs = D; g.a_cs = 1; g.a_bo = (long long)p.N * D; g.a_bi = p.d;
-    g.B = qkv + (size_t)2 * D * e; g.b_type = p.act; g.b_rs = hv.rs; g.b_cs = 1; g.b_bo = hv.bo; g.b_bi = hv.bi;
-    g.epi.out = b.dP; g.epi.ld_out = p.N; g.epi.out_bo = pbo; g.epi.out_bi = pbi;
-    ODV_TRY(head_gemm(g));
-  }
-  ODV_TRY(softmax_bwd_rows(b.P, b.dP, g_p, (long long)p.B * p.H * p.N, p.N, s));
-  {  // dq = dS k      (dq is the cotangent of the already-scaled q: the scale lives in W1cat)
-    GemmArgs g;
-    g.M = p.N; g.N = p.d; g.K = p.N;
-    g.A = b.dP; g.a_type = DT_F32; g.a_rs = p.N; g.a_cs = 1; g.a_bo = pbo; g.a_bi = pbi;
-    g.B = qkv + (size_t)D * e; g.b_type = p.act; g.b_rs = 1; g.b_cs = hv.rs; g.b_bo = hv.bo; g.b_bi = hv.bi;
-    g.epi.out = dz; g.epi.out_type = p.act; g.epi.ld_out = R; g.epi.out_bo = (long long)p.N * R; g.epi.out_bi = p.d;
-    ODV_TRY(head_gemm(g));
-  }
-  {  // dk = dS^T q
-    GemmArgs g;
-    g.M = p.N; g.N = p.d; g.K = p.N;
-    g.A = b.dP; g.a_type = DT_F32; g.a_rs = 1; g.a_cs = p.N; g.a_bo = pbo; g.a_bi = pbi;
-    g.B = qkv; g.b_type = p.act; g.b_rs = 1; g.b_cs = hv.rs; g.b_bo = hv.bo; g.b_bi = hv.bi;
-    g.epi.out = dz + (size_t)D * e; g.epi.out_type = p.act; g.epi.ld_out = R;
-    g.epi.out_bo = (long long)p.N * R; g.epi.out_bi = p.d;
-    ODV_TRY(head_gemm(g));
-  }
-  {  // dv = P^T dO
-    GemmArgs g;
-    g.M = p.N; g.N = p.d; g.K = p.N;
-    g.A = b.P; g.a_type = DT_F32; g.a_rs = 1; g.a_cs = p.N; g.a_bo = pbo; g.a_bi = pbi;
-    g.B = b.dO; g.b_type = p.act; g.b_rs = 1; g.b_cs = D; g.b_bo = (long long)p.N * D; g.b_bi = p.d;
-    g.epi.out = dz + (size_t)2 * D * e; g.epi.out_type = p.act; g.epi.ld_out = R;
-    g.epi.out_bo = (long long)p.N * R; g.epi.out_bi = p.d;
-    ODV_TRY(head_gemm(g));
+  // ---- attention VJP per (image, head) ----------------------------------------------------------
+  if (p.precision == ODEVIT_BF16 && !g_p && c.lse && attn_fwd_tc_supports(p.N, D, p.H, p.act, K2)) {
+    // fused tcgen05 kernel (P recomputed on chip from q, k and the saved row log-sum-exp)
+    ODV_TRY(attn_bwd_tc(c.qkv, b.dO, c.oh, K2, c.lse, b.delta, b.dz, R, b.dq_scratch, p.B, p.N, p.H, D, s));
+  } else {
+    const HeadView hv = qkv_view(p);
+    const char* qkv = reinterpret_cast<const char*>(c.qkv);
+    const long long pbo = (long long)p.H * p.N * p.N, pbi = (long long)p.N * p.N;
+    auto head_gemm = [&](GemmArgs& g) {
+      g.batch_outer = p.B; g.batch_inner = p.H;
+      g.kclass = KC_BWD_ATTN;
+      return gemm_simt(g, s);
+    };
+    {  // S
+      GemmArgs g;
+      g.M = p.N; g.N = p.N; g.K = p.d;
+      g.A = qkv; g.a_type = p.act; g.a_rs = hv.rs; g.a_cs = 1; g.a_bo = hv.bo; g.a_bi = hv.bi;
+      g.B = qkv + (size_t)D * e; g.b_type = p.act; g.b_rs = hv.rs; g.b_cs = 1; g.b_bo = hv.bo; g.b_bi = hv.bi;
+      g.epi.out = b.P; g.epi.ld_out = p.N; g.epi.out_bo = pbo; g.epi.out_bi = pbi;
+      ODV_TRY(head_gemm(g));
+    }
+    ODV_TRY(softmax_rows(b.P, nullptr, (long long)p.B * p.H * p.N, p.N, s));
+    {  // dP = dO v^T
+      GemmArgs g;
+      g.M = p.N; g.N = p.N; g.K = p.d;
+      g.A = b.dO; g.a_type = p.act; g.a_rs = D; g.a_cs = 1; g.a_bo = (long long)p.N * D; g.a_bi = p.d;
+      g.B = qkv + (size_t)2 * D * e; g.b_type = p.act; g.b_rs = hv.rs; g.b_cs = 1; g.b_bo = hv.bo; g.b_bi = hv.bi;
+      g.epi.out = b.dP; g.epi.ld_out = p.N; g.epi.out_bo = pbo; g.epi.out_bi = pbi;
+      ODV_TRY(head_gemm(g));
+    }
+    ODV_TRY(softmax_bwd_rows(b.P, b.dP, g_p, (long long)p.B * p.H * p.N, p.N, s));
+    {  // dq = dS k      (dq is the cotangent of the already-scaled q: the scale lives in W1cat)
+      GemmArgs g;
+      g.M = p.N; g.N = p.d; g.K = p.N;
+      g.A = b.dP; g.a_type = DT_F32; g.a_rs = p.N; g.a_cs = 1; g.a_bo = pbo; g.a_bi = pbi;
+      g.B = qkv + (size_t)D * e; g.b_type = p.act; g.b_rs = 1; g.b_cs = hv.rs; g.b_bo = hv.bo; g.b_bi = hv.bi;
+      g.epi.out = dz; g.epi.out_type = p.act; g.epi.ld_out = R; g.epi.out_bo = (long long)p.N * R; g.epi.out_bi = p.d;
+      ODV_TRY(head_gemm(g));
+    }
+    {  // dk = dS^T q
+      GemmArgs g;
+      g.M = p.N; g.N = p.d; g.K = p.N;
+      g.A = b.dP; g.a_type = DT_F32; g.a_rs = 1; g.a_cs = p.N; g.a_bo = pbo; g.a_bi = pbi;
+      g.B = qkv; g.b_type = p.act; g.b_rs = 1; g.b_cs = hv.rs; g.b_bo = hv.bo; g.b_bi = hv.bi;
+      g.epi.out = dz + (size_t)D * e; g.epi.out_type = p.act; g.epi.ld_out = R;
+      g.epi.out_bo = (long long)p.N * R; g.epi.out_bi = p.d;
+      ODV_TRY(head_gemm(g));
+    }
+    {  // dv = P^T dO
+      GemmArgs g;
+      g.M = p.N; g.N = p.d; g.K = p.N;
+      g.A = b.P; g.a_type = DT_F32; g.a_rs = 1; g.a_cs = p.N; g.a_bo = pbo; g.a_bi = pbi;
+      g.B = b.dO; g.b_type = p.act; g.b_rs = 1; g.b_cs = D; g.b_bo = (long long)p.N * D; g.b_bi = p.d;
+      g.epi.out = dz + (size_t)2 * D * e; g.epi.out_type = p.act; g.epi.ld_out = R;
+      g.epi.out_bo = (long long)p.N * R; g.epi.out_bi = p.d;
+      ODV_TRY(head_gemm(g));
+    }
   }
   {  // zsum = dz @ W1cat          (dL/d xc, before the centring VJP)
     GemmArgs g;

@@ -64,6 +64,7 @@ enum KClass : int {
   KC_COMBINE,      // reverse-mode stage combine / axpy
   KC_WEIGHTS,      // weight fold / gradient unfold
   KC_FUSED_ATTN,   // fused attention (S, softmax, PV in one kernel)
+  KC_FUSED_ATTN_BWD,  // fused attention VJP (delta + dq/dk/dv in one kernel)
   KC_OTHER,
   KC_COUNT
 };
@@ -141,7 +142,12 @@ bool gemm_tc_supports(const GemmArgs& g);
 // Fused tcgen05 attention forward (attn_tc.cu): qkv [B,N,3D] bf16 -> O into oh[:, h*64..] (bf16),
 // optional fp32 P export.  Covers head dim 64, N <= 256.
 bool attn_fwd_tc_supports(int N, int D, int H, int act_type, long long ld_oh);
-int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, int B, int N, int H, int D, cudaStream_t s);
+int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, float* lse_out, int B, int N, int H, int D,
+                cudaStream_t s);
+// Fused attention VJP; needs the forward's lse2 [B,H,N]; writes delta [B,H,N] and dq|dk|dv into dz.
+size_t attn_bwd_tc_scratch_floats(int B, int N, int H);
+int attn_bwd_tc(const void* qkv, const void* dO, const void* oh, long long ld_oh, const float* lse2, float* delta,
+                void* dz, int R, float* dq_scratch, int B, int N, int H, int D, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------
 // row-wise / elementwise kernels (odevit_rows.cu)

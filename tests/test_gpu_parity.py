@@ -163,6 +163,63 @@ def test_c100_shape_vs_oracle(solver, T, prec, tol):
         assert out["logits"].argmax(-1).cpu().tolist() == want["logits"].argmax(-1).tolist()
 
 
+@pytest.mark.parametrize("N,B", [(207, 2), (69, 3), (128, 1), (130, 2), (256, 1)])
+def test_field_bf16_forward_backward_vs_oracle(N, B):
+    """One field evaluation in bf16 mode (tcgen05 GEMMs + fused tcgen05 attention forward/VJP) at
+    D=768, H=12 against the fp32 oracle: token counts on both sides of the 128-row tile edges."""
+    import odevit_b200 as ob
+    torch.manual_seed(5)
+    f = ob.ViT_ODEFunc(dim=768, num_heads=12, mlp_ratio=1.0, emulate_depth=12, time_interval=1.0,
+                       l2_attention=False)
+    with torch.no_grad():
+        for n, p in f.named_parameters():
+            if "norm" in n:
+                p.add_(0.1 * torch.randn_like(p))
+    sd = {k: v.clone() for k, v in f.state_dict().items()}
+    f = f.cuda()
+    f.block.precision = "bf16"
+    x = torch.randn(B, N, 768, generator=torch.Generator().manual_seed(6)) * 2
+    w = torch.randn(B, N, 768, generator=torch.Generator().manual_seed(7))
+    xg = x.cuda().requires_grad_(True)
+    dx = f(torch.tensor(0.0), xg)
+    (dx * w.cuda()).sum().backward()
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr = x.clone().requires_grad_(True)
+    dxr, pr = orc.field_parallel(xr, sdr, 12, 12.0, prefix="block.")
+    (dxr * w).sum().backward()
+    assert max_rel(dx, dxr) < BF16_TOL
+    assert max_rel(f.block.attentions, pr) < 5e-2
+    assert max_rel(xg.grad, xr.grad) < 3e-2
+    for k, p in f.named_parameters():
+        assert max_rel(p.grad, sdr[k].grad) < 3e-2, k
+
+
+def test_c100_shape_training_gradients_bf16():
+    """CE training gradients through the whole solve at the C100 shape (N=207: two key chunks and two
+    query tiles in the fused attention VJP), bf16 mode, against the oracle's autograd."""
+    import odevit_b200 as ob
+    cfg = dict(img_size=224, patch_size=16, num_classes=100, embed_dim=768, num_heads=12, mlp_ratio=1.0,
+               emulate_depth=12, time_interval=1.0, num_eval_steps=4, solver="rk4", register_tokens=10)
+    sd = orc.reference_like_init(cfg, 100, seed=4)
+    model = ob.ViTNeuralODE(**cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    model.precision = "bf16"
+    px = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(1234))
+    lb = torch.tensor([3, 77])
+    out = model(px.cuda(), labels=lb.cuda(), output_attentions=True, output_control_points=True, jasmin_k=2)
+    obj = out["loss"] + 1e-3 * (out["control_points"][:, :, 0] ** 2).mean() + out["attentions"][:, :, 0, 1:].mean()
+    obj.backward()
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    want = orc.vit_ode_forward(sdr, cfg, px, labels=lb, output_attentions=True, output_control_points=True, jasmin_k=2)
+    objr = want["loss"] + 1e-3 * (want["control_points"][:, :, 0] ** 2).mean() + want["attentions"][:, :, 0, 1:].mean()
+    objr.backward()
+    assert max_rel(out["logits"], want["logits"]) < BF16_TOL
+    for k, p in model.named_parameters():
+        if sdr[k].grad is not None and float(sdr[k].grad.abs().max()) > 0:
+            assert max_rel(p.grad, sdr[k].grad) < 0.1, k
+
+
 # ---- size-independent properties at BASELINE sizes -------------------------------------------
 
 def _c10_model(T=5, solver="rk4", B=None, prec="fp32"):
