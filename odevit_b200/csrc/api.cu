@@ -208,7 +208,6 @@ struct BwdBufs {
   float* u;
   float* k[3];
   void *dd, *dO, *dz;
-  float* zsum;
   float* mu[4];
   float* gy;
   float *delta, *dq_scratch;
@@ -229,7 +228,6 @@ BwdBufs layout_bwd(const Plan& p, Arena& a, int S) {
   b.dd = a.take(MD * e);
   b.dO = a.take(MD * e);
   b.dz = a.take((size_t)p.M * R * e);
-  b.zsum = a.f32(MD);
   for (int i = 0; i < 4; ++i) b.mu[i] = (i >= 1 && i < S) ? a.f32(MD) : nullptr;
   b.gy = a.f32(MD);
   b.delta = a.f32((size_t)p.B * p.H * p.N);
@@ -393,10 +391,12 @@ Epi rk_epilogue(const Tableau& tb, int st, float dt, const float* y, float* cons
 }
 
 // VJP of one field evaluation: given dd = scaler * lambda (cotangent of the pre-scaler output, in
-// the activation type), the stage intermediates `c`, produce zsum = dL/d(xc) (fp32, un-centred)
-// and accumulate G1, c1, G2, c2.
+// the activation type) and the stage intermediates `c`, accumulate G1, c1, G2, c2 and deliver
+// mu = J(u)^T lambda = centre_D(dz @ W1cat) through `mu_epi`, the EPI_RK epilogue of the last GEMM
+// (W1cat^T is stored row-centred, so the GEMM yields the centred value directly; the reverse-mode
+// stage combination rides in that epilogue instead of a separate pass over [M, D]).
 int eval_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b, const float* g_p,
-             bool need_c2, cudaStream_t s) {
+             bool need_c2, const Epi& mu_epi, cudaStream_t s) {
   const int D = p.D, hid = p.hid, R = 3 * D + hid, K2 = D + hid;
   const size_t e = dtype_size(p.act);
   char* dz = reinterpret_cast<char*>(b.dz);
@@ -483,13 +483,17 @@ int eval_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b,
       ODV_TRY(head_gemm(g));
     }
   }
-  {  // zsum = dz @ W1cat          (dL/d xc, before the centring VJP)
+  {  // mu = dz @ centred(W1cat), consumed by the caller's stage-combine epilogue
     GemmArgs g;
     g.M = p.M; g.N = D; g.K = R;
     g.A = b.dz; g.a_type = p.act; g.a_rs = R; g.a_cs = 1;
     g.B = wb.w1catT; g.b_type = p.act; g.b_rs = R; g.b_cs = 1;
-    g.epi_mode = EPI_STORE;
-    g.epi.out = b.zsum; g.epi.out_type = DT_F32; g.epi.ld_out = D;
+    g.epi_mode = EPI_RK;
+    g.epi = mu_epi;
+    g.epi.alpha = 1.f;
+    g.epi.bias = nullptr;
+    g.epi.ld_out = D;
+    g.epi.aux_type = p.act;
     g.kclass = KC_BWD_GEMM_DX;
     ODV_TRY(gemm(p, g, s));
   }
@@ -716,14 +720,29 @@ int odevit_solve_bwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
   ODV_CUDA(cudaMemsetAsync(b.G1, 0, b.acc_bytes, s));
 
   // cotangent of trajectory row j = g_states[j] + sum of g_rows whose index is j
+  auto injected_terms = [&](int row, const float** out, int cap) -> int {
+    int n = 0;
+    if (g_states) { if (n < cap) out[n] = g_states + (size_t)row * MD; ++n; }
+    for (int i = 0; i < n_g_rows; ++i)
+      if (g_row_index_host[i] == row) { if (n < cap) out[n] = g_rows + (size_t)i * MD; ++n; }
+    return n;
+  };
   auto inject = [&](int row) -> int {
     if (g_states) ODV_TRY(axpy_f32(b.gy, g_states + (size_t)row * MD, 1.f, (long long)MD, s));
     for (int i = 0; i < n_g_rows; ++i)
       if (g_row_index_host[i] == row) ODV_TRY(axpy_f32(b.gy, g_rows + (size_t)i * MD, 1.f, (long long)MD, s));
     return 0;
   };
+  // dd = scaler * dt * b[S-1] * G : the cotangent entering the last stage of a step
+  auto seed_dd = [&](float dt) -> int {
+    CombineArgs c0;
+    c0.n_terms = 1; c0.term[0] = b.gy; c0.coef[0] = dt * tb->b[S - 1];
+    c0.out_dd = b.dd; c0.dd_type = p.act; c0.dd_scale = p.scaler;
+    return vjp_combine(c0, p.M, p.D, s);
+  };
   ODV_CUDA(cudaMemsetAsync(b.gy, 0, MD * 4, s));
   ODV_TRY(inject(n_grid - 1));
+  if (n_grid >= 2) ODV_TRY(seed_dd(t_grid_host[n_grid - 1] - t_grid_host[n_grid - 2]));
 
   for (int j = n_grid - 2; j >= 0; --j) {
     const float dt = t_grid_host[j + 1] - t_grid_host[j];
@@ -740,41 +759,48 @@ int odevit_solve_bwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
     }
     // (2) reverse through the stages
     //     lambda_st = dt*(b[st]*G + sum_{m>st} a[m][st]*mu_m),  mu_st = J(u_st)^T lambda_st,
-    //     dL/dy = G + sum_st mu_st
-    {
-      CombineArgs c0;
-      c0.n_terms = 1; c0.term[0] = b.gy; c0.coef[0] = dt * tb->b[S - 1];
-      c0.out_dd = b.dd; c0.dd_type = p.act; c0.dd_scale = p.scaler;
-      ODV_TRY(vjp_combine(c0, p.M, p.D, s));
-    }
+    //     dL/dy = G + sum_st mu_st  (+ the cotangents injected at row j)
+    bool dd_seeded = true;
     for (int st = S - 1; st >= 0; --st) {
       const bool last_eval = (j == n_grid - 2 && st == S - 1);
-      ODV_TRY(eval_vjp(p, b.w, b.ctx[st], b, last_eval ? g_p_last : nullptr, need_c2, s));
-      CombineArgs c;
-      c.zsum = b.zsum;
+      Epi e;  // epilogue of the mu GEMM: v = mu_st
+      e.aux_type = p.act;
       if (st > 0) {
-        // store mu_st, form lambda_{st-1} -> dd
-        c.mu_out = b.mu[st];
+        // keep mu_st; dd <- scaler * lambda_{st-1}
+        e.k_store = b.mu[st];
         const int t = st - 1;
-        c.coef_mu = dt * tb->a[st][t];
+        e.c_new = dt * tb->a[st][t];
+        e.y = b.gy; e.y_coef = dt * tb->b[t];
         int n = 0;
-        c.term[n] = b.gy; c.coef[n] = dt * tb->b[t]; ++n;
         for (int m = st + 1; m < S; ++m)
-          if (tb->a[m][t] != 0.f) { c.term[n] = b.mu[m]; c.coef[n] = dt * tb->a[m][t]; ++n; }
-        c.n_terms = n;
-        c.out_dd = b.dd; c.dd_type = p.act; c.dd_scale = p.scaler;
+          if (tb->a[m][t] != 0.f) { e.kin[n] = b.mu[m]; e.c_k[n] = dt * tb->a[m][t]; ++n; }
+        e.out = nullptr;
+        e.out2 = b.dd; e.out2_scale = p.scaler;
       } else {
-        // dL/dy_j = G + mu_0 + sum_{m>=1} mu_m   (in place over G)
-        c.coef_mu = 1.f;
+        // G <- G + mu_0 + sum_{m>=1} mu_m + injected(j);  dd <- seed of step j-1
+        e.c_new = 1.f;
+        e.y = b.gy; e.y_coef = 1.f;
         int n = 0;
-        c.term[n] = b.gy; c.coef[n] = 1.f; ++n;
-        for (int m = 1; m < S; ++m) { c.term[n] = b.mu[m]; c.coef[n] = 1.f; ++n; }
-        c.n_terms = n;
-        c.out_f32 = b.gy;
+        for (int m = 1; m < S; ++m) { e.kin[n] = b.mu[m]; e.c_k[n] = 1.f; ++n; }
+        const float* inj[Epi::kMaxTerms];
+        const int n_inj = injected_terms(j, inj, Epi::kMaxTerms);
+        const bool fits = (n + n_inj <= Epi::kMaxTerms);
+        if (fits) for (int i = 0; i < n_inj; ++i) { e.kin[n] = inj[i]; e.c_k[n] = 1.f; ++n; }
+        e.out = b.gy;
+        if (fits && j > 0) {
+          const float dt_prev = t_grid_host[j] - t_grid_host[j - 1];
+          e.out2 = b.dd; e.out2_scale = p.scaler * dt_prev * tb->b[S - 1];
+        } else {
+          e.out2 = nullptr;
+          dd_seeded = false;
+        }
+        ODV_TRY(eval_vjp(p, b.w, b.ctx[st], b, last_eval ? g_p_last : nullptr, need_c2, e, s));
+        if (!fits) ODV_TRY(inject(j));
+        if (!dd_seeded && j > 0) ODV_TRY(seed_dd(t_grid_host[j] - t_grid_host[j - 1]));
+        continue;
       }
-      ODV_TRY(vjp_combine(c, p.M, p.D, s));
+      ODV_TRY(eval_vjp(p, b.w, b.ctx[st], b, last_eval ? g_p_last : nullptr, need_c2, e, s));
     }
-    ODV_TRY(inject(j));
   }
   ODV_CUDA(cudaMemcpyAsync(g_x0, b.gy, MD * 4, cudaMemcpyDeviceToDevice, s));
   return finish_grads(p, w, gw, b, s);
@@ -803,11 +829,11 @@ int odevit_field_bwd(const odevit_desc* desc, const odevit_weights* w, const flo
     c0.out_dd = b.dd; c0.dd_type = p.act; c0.dd_scale = p.scaler;
     ODV_TRY(vjp_combine(c0, p.M, p.D, s));
   }
-  ODV_TRY(eval_vjp(p, b.w, b.ctx[0], b, g_p, wants_c2(gw), s));
   {
-    CombineArgs c;
-    c.zsum = b.zsum; c.coef_mu = 1.f; c.out_f32 = g_x;
-    ODV_TRY(vjp_combine(c, p.M, p.D, s));
+    Epi e;
+    e.c_new = 1.f;
+    e.out = g_x;
+    ODV_TRY(eval_vjp(p, b.w, b.ctx[0], b, g_p, wants_c2(gw), e, s));
   }
   return finish_grads(p, w, gw, b, s);
 }

@@ -53,9 +53,10 @@ __device__ __forceinline__ void epi_apply(const Epi& e, int m, int n, float acc,
     float r = e.c_new * v;
     if (e.y) r = fmaf(e.y_coef, e.y[idx], r);
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < Epi::kMaxTerms; ++i)
       if (e.kin[i]) r = fmaf(e.c_k[i], e.kin[i][idx], r);
-    reinterpret_cast<float*>(e.out)[idx] = r;
+    if (e.out) reinterpret_cast<float*>(e.out)[idx] = r;
+    if (e.out2) store_elem(e.out2, idx, e.aux_type, e.out2_scale * r);
   } else if constexpr (EPI == EPI_BWD3) {
     if (n < e.split) {
       store_elem(e.out, (long long)m * e.ld_out + n, e.out_type, acc);
@@ -148,14 +149,19 @@ __device__ __forceinline__ void epi_chunk16(const Epi& e, int m, int n, float* v
       for (int j = 0; j < 16; ++j) r[j] = fmaf(e.y_coef, t[j], r[j]);
     }
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < Epi::kMaxTerms; ++i) {
       if (e.kin[i]) {
         load16(e.kin[i], idx, DT_F32, t);
 #pragma unroll
         for (int j = 0; j < 16; ++j) r[j] = fmaf(e.c_k[i], t[j], r[j]);
       }
     }
-    store16(e.out, idx, DT_F32, r);
+    if (e.out) store16(e.out, idx, DT_F32, r);
+    if (e.out2) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] *= e.out2_scale;
+      store16(e.out2, idx, e.aux_type, r);
+    }
   } else if constexpr (EPI == EPI_BWD3) {
     if (n < e.split) {
       store16(e.out, (long long)m * e.ld_out + n, e.out_type, v);

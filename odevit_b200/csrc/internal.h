@@ -90,7 +90,8 @@ enum EpiMode : int {
   EPI_FWD1 = 1,   // n <  split: out[m,n] = acc + bias[n]          (q|k|v)
                   // n >= split: out3[m,n-split] = v (opt), out2[m,n-split] = gelu(v)   (fc1)
   EPI_RK = 2,     // v = alpha*(acc + bias[n]); kstore (opt) = v;
-                  // out[m,n] = y_coef*y[m,n] + c_new*v + sum_i c_k[i]*kin[i][m,n]
+                  // r = y_coef*y[m,n] + c_new*v + sum_i c_k[i]*kin[i][m,n]
+                  // out (opt, fp32) = r;  out2 (opt, aux_type) = out2_scale * r
   EPI_BWD3 = 3,   // n <  split: out[m,n] = acc                    (dO)
                   // n >= split: out2[m,n-split] = acc * gelu'(aux[m,n-split])   (d h_pre)
   EPI_ACCUM = 4   // out[m,n] += alpha*acc   (fp32; atomic when split-K)
@@ -109,8 +110,10 @@ struct Epi {
   long long ld_out3 = 0;
   int aux_type = DT_F32;  // type of out2/out3/aux buffers
   const float* y = nullptr;
-  const float* kin[3] = {nullptr, nullptr, nullptr};
-  float y_coef = 1.f, c_new = 0.f, c_k[3] = {0.f, 0.f, 0.f};
+  static constexpr int kMaxTerms = 6;
+  const float* kin[kMaxTerms] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float y_coef = 1.f, c_new = 0.f, c_k[kMaxTerms] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float out2_scale = 1.f;
   float* k_store = nullptr;
   const void* aux = nullptr;
   long long ld_aux = 0;
@@ -188,7 +191,8 @@ struct FoldArgs {
   int D, hid, heads;
   const odevit_weights* w;
   void* w1cat; int w_type;   // [3D+hid, D]
-  void* w1catT;              // [D, 3D+hid] or null
+  void* w1catT;              // [D, 3D+hid] or null; each W1cat row is CENTRED over D here (so that
+                             // dz @ W1cat directly yields the centring VJP mu = zsum - mean_D zsum)
   float* b1cat;              // [3D+hid]
   void* w2cat;               // [D, D+hid]
   void* w2catT;              // [D+hid, D] or null

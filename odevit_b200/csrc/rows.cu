@@ -137,6 +137,38 @@ __global__ void __launch_bounds__(128) colsum_kernel(const void* X, int x_type, 
   atomicAdd(acc + c, s);
 }
 
+// bf16 fast path: a warp covers 256 columns with one 16-byte load per lane; the 4 warps of a block
+// take interleaved rows of a 128-row panel and meet in shared memory (cols % 8 == 0, ld % 8 == 0).
+__global__ void __launch_bounds__(128) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long long ld,
+                                                          int rows, int cols, float* acc) {
+  __shared__ float part[4][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * 128;
+  const int r1 = min(rows, r0 + 128);
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < cols) {
+#pragma unroll 4
+    for (int r = r0 + warp; r < r1; r += 4) {
+      const uint4 t = *reinterpret_cast<const uint4*>(X + (long long)r * ld + c0);
+      const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+        s[2 * i] += __low2float(b);
+        s[2 * i + 1] += __high2float(b);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) part[warp][lane * 8 + i] = s[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 256; c += 128) {
+    const int col = blockIdx.x * 256 + c;
+    if (col < cols) atomicAdd(acc + col, part[0][c] + part[1][c] + part[2][c] + part[3][c]);
+  }
+}
+
 __global__ void __launch_bounds__(256) vjp_combine_kernel(CombineArgs a, int rows, int D) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -199,7 +231,7 @@ __global__ void __launch_bounds__(128) fold_w1_kernel(FoldArgs a, odevit_weights
   const float* lb = attn ? w.in_proj_b : w.fc1_b;
   const float s_cn = (float)D / ((float)D - 1.f);
   const float qs = (j < D) ? rsqrtf((float)(D / a.heads)) : 1.f;
-  float dot = 0.f;
+  float dot = 0.f, fsum = 0.f;
   for (int i = threadIdx.x; i < D; i += 128) {
     float we = nw[i], be = nb[i];
     if (msc) { we *= (1.f + msc[i]); be *= (1.f + msc[i]); }
@@ -207,17 +239,29 @@ __global__ void __launch_bounds__(128) fold_w1_kernel(FoldArgs a, odevit_weights
     const float wv = Wrow[i];
     const float f = qs * s_cn * wv * we;
     store_elem(a.w1cat, (long long)j * D + i, a.w_type, f);
-    if (a.w1catT) store_elem(a.w1catT, (long long)i * R + j, a.w_type, f);
+    fsum += f;
     dot = fmaf(wv, be, dot);
   }
-  __shared__ float red[4];
+  __shared__ float red[4], red2[4];
   dot = warp_sum(dot);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+  fsum = warp_sum(fsum);
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = dot; red2[threadIdx.x >> 5] = fsum; }
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = red[0] + red[1] + red[2] + red[3];
     if (lb) t += lb[j - (attn ? 0 : 3 * D)];
     a.b1cat[j] = qs * t;
+  }
+  if (a.w1catT) {
+    // the transposed copy feeds dL/dxc = dz @ W1cat followed by the centring VJP (subtract the
+    // row mean over D): fold that subtraction into the weight, row j centred over i
+    const float fmean = (red2[0] + red2[1] + red2[2] + red2[3]) / (float)D;
+    for (int i = threadIdx.x; i < D; i += 128) {
+      float we = nw[i];
+      if (msc) we *= (1.f + msc[i]);
+      const float f = qs * s_cn * Wrow[i] * we;
+      store_elem(a.w1catT, (long long)i * R + j, a.w_type, f - fmean);
+    }
   }
 }
 
@@ -341,6 +385,12 @@ int softmax_bwd_rows(const float* p, float* dp, const float* dpx, long long rows
 
 int colsum_accum(const void* X, int x_type, long long ld, int rows, int cols, float* acc, cudaStream_t s) {
   ProfScope prof(KC_BWD_COLSUM, s);
+  if (x_type == DT_BF16 && cols % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+    dim3 grid((cols + 255) / 256, (rows + 127) / 128);
+    colsum_bf16_kernel<<<grid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(X), ld, rows, cols, acc);
+    ODV_LAUNCH_CHECK();
+    return 0;
+  }
   const int rpb = 256;
   dim3 grid((cols + 127) / 128, (rows + rpb - 1) / rpb);
   colsum_kernel<<<grid, 128, 0, s>>>(X, x_type, ld, rows, cols, rpb, acc);

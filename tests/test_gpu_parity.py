@@ -278,11 +278,14 @@ def test_single_point_grid_and_euler_identity():
 
 
 def test_solver_order_on_the_real_field():
-    """RK4(3/8) self-convergence on the actual vector field: halving dt cuts the error ~16x, Euler ~2x."""
+    """Self-convergence on the actual vector field (scaler 3 keeps the RK4 errors well above the fp32
+    floor): halving dt cuts the Euler error ~2x, midpoint ~4x, RK4 (3/8 rule) ~16x.  Calibrated on the
+    oracle: ratios 1.94 / 3.64 / 12.7 / 13.5 for the same seeded inputs."""
     import odevit_b200 as ob
     model = _c10_model()
-    model.odefunc.scaler = 1.0
-    x0 = model.patch_embed(torch.randn(4, 3, 32, 32, device="cuda")).detach()
+    model.odefunc.scaler = 3.0
+    px = torch.randn(4, 3, 32, 32, generator=torch.Generator().manual_seed(77))
+    x0 = model.patch_embed(px.cuda()).detach()
 
     def final(method, steps):
         with torch.no_grad():
@@ -291,9 +294,8 @@ def test_solver_order_on_the_real_field():
 
     ref = final("rk4", 64)
     e_eu = [float((final("euler", n) - ref).abs().max()) for n in (8, 16)]
-    assert 1.6 < e_eu[0] / e_eu[1] < 2.6
+    assert 1.6 < e_eu[0] / e_eu[1] < 2.4
     e_mid = [float((final("midpoint", n) - ref).abs().max()) for n in (4, 8)]
-    assert 3.0 < e_mid[0] / e_mid[1] < 5.5
-    # RK4 errors at these step counts sit near the fp32 floor; only require a clear 4th-order drop
-    e_rk = [float((final("rk4", n) - ref).abs().max()) for n in (1, 2)]
-    assert e_rk[0] / e_rk[1] > 6.0
+    assert 3.0 < e_mid[0] / e_mid[1] < 4.6
+    e_rk = [float((final("rk4", n) - ref).abs().max()) for n in (1, 2, 4)]
+    assert e_rk[0] / e_rk[1] > 8.0 and e_rk[1] / e_rk[2] > 8.0
