@@ -188,4 +188,186 @@ __device__ __forceinline__ void epi_chunk16(const Epi& e, int m, int n, float* v
   }
 }
 
+
+// ---- float4 form for the tcgen05 GEMM's transposed (coalesced) epilogue: a lane holds 4 consecutive
+// columns [n, n+4) of row m (n % 4 == 0); 8 consecutive lanes cover 128 contiguous bytes of a row.
+__device__ __forceinline__ float4 load4(const void* p, long long idx, int type) {
+  if (type == DT_F32) return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + idx);
+  const uint2 t = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p) + idx);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+  return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+__device__ __forceinline__ void store4(void* p, long long idx, int type, float4 v) {
+  if (type == DT_F32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + idx) = v;
+  } else {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 t;
+    t.x = *reinterpret_cast<const uint32_t*>(&a);
+    t.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p) + idx) = t;
+  }
+}
+__device__ __forceinline__ float4 fma4(float a, float4 x, float4 y) {
+  return make_float4(fmaf(a, x.x, y.x), fmaf(a, x.y, y.y), fmaf(a, x.z, y.z), fmaf(a, x.w, y.w));
+}
+__device__ __forceinline__ float4 scale4(float a, float4 x) { return make_float4(a * x.x, a * x.y, a * x.z, a * x.w); }
+__device__ __forceinline__ float4 add4(float4 x, float4 y) { return make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w); }
+
+// Loads the compiler may not sink towards their first use (asm volatile keeps program order among
+// themselves): the epilogue issues a whole batch of raw loads, then converts / consumes the batch.
+struct Raw4 { uint32_t x, y, z, w; };
+__device__ __forceinline__ Raw4 ldg_raw4(const void* p, long long idx, int type) {
+  Raw4 r;
+  if (type == DT_F32) {
+    asm volatile("ld.global.v4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(reinterpret_cast<const float*>(p) + idx));
+  } else {
+    asm volatile("ld.global.v2.b32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(reinterpret_cast<const __nv_bfloat16*>(p) + idx));
+    r.z = 0; r.w = 0;
+  }
+  return r;
+}
+__device__ __forceinline__ float4 raw_to_float4(const Raw4& r, int type) {
+  if (type == DT_F32) return make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
+  return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                     __uint_as_float(r.y & 0xffff0000u));
+}
+
+// erf-GELU for the bf16 mode's epilogues: erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below
+// the bf16 rounding of the stored value): one MUFU.RCP + one MUFU.EX2 + 8 FMA instead of erff's branches.
+// The exponential exp(-x^2/2) is the Gaussian pdf's, so GELU' gets cdf and pdf from the same evaluation.
+__device__ __forceinline__ void gauss_cdf_pdf(float x, float& cdf, float& pdf) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.f, fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.f));
+  const float ex = exp2f(-0.72134752044448170368f * x * x);  // exp(-x^2/2)
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float half_tail = 0.5f * p * t * ex;  // 0.5 * erfc(|x|/sqrt2)
+  cdf = (x >= 0.f) ? 1.f - half_tail : half_tail;
+  pdf = 0.39894228040143267794f * ex;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float cdf, pdf;
+  gauss_cdf_pdf(x, cdf, pdf);
+  return x * cdf;
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  float cdf, pdf;
+  gauss_cdf_pdf(x, cdf, pdf);
+  return fmaf(x, pdf, cdf);
+}
+
+// The tcgen05 GEMM's epilogue on one lane's share of a 32 x 32 accumulator chunk: 8 float4s, w[i] holding
+// columns [n, n+4) of row m0 + 4*i (rows >= M masked).  All global loads of the chunk are issued
+// before any dependent arithmetic and before every store (8 independent 16-byte loads in flight per
+// lane and operand): the epilogue is latency-bound otherwise.
+template <int EPI, bool ATOMIC>
+__device__ __forceinline__ void epi_rows8(const Epi& e, int m0, int M, int n, float4 (&w)[8]) {
+  bool ok[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ok[i] = (m0 + 4 * i) < M;
+  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+  if constexpr (EPI == EPI_STORE || EPI == EPI_FWD1 || EPI == EPI_RK) {
+    if (e.bias) bias = *reinterpret_cast<const float4*>(e.bias + n);
+  }
+  if constexpr (EPI == EPI_STORE) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (ok[i]) store4(e.out, (long long)(m0 + 4 * i) * e.ld_out + n, e.out_type, fma4(e.alpha, w[i], bias));
+  } else if constexpr (EPI == EPI_FWD1) {
+    if (n < e.split) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (ok[i]) store4(e.out, (long long)(m0 + 4 * i) * e.ld_out + n, e.out_type, add4(w[i], bias));
+    } else {
+      const int c = n - e.split;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (!ok[i]) continue;
+        const float4 v = add4(w[i], bias);
+        if (e.out3) store4(e.out3, (long long)(m0 + 4 * i) * e.ld_out3 + c, e.aux_type, v);
+        store4(e.out2, (long long)(m0 + 4 * i) * e.ld_out2 + c, e.aux_type,
+               make_float4(gelu_fast(v.x), gelu_fast(v.y), gelu_fast(v.z), gelu_fast(v.w)));
+      }
+    }
+  } else if constexpr (EPI == EPI_RK) {
+    float4 r[8];
+    Raw4 t[8];
+    const Raw4 zero = {0u, 0u, 0u, 0u};
+    if (e.y) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] = ok[i] ? ldg_raw4(e.y, (long long)(m0 + 4 * i) * e.ld_out + n, DT_F32) : zero;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      w[i] = scale4(e.alpha, add4(w[i], bias));
+      r[i] = scale4(e.c_new, w[i]);
+    }
+    if (e.y) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = fma4(e.y_coef, raw_to_float4(t[i], DT_F32), r[i]);
+    }
+#pragma unroll
+    for (int k = 0; k < Epi::kMaxTerms; ++k) {
+      if (e.kin[k]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          t[i] = ok[i] ? ldg_raw4(e.kin[k], (long long)(m0 + 4 * i) * e.ld_out + n, DT_F32) : zero;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = fma4(e.c_k[k], raw_to_float4(t[i], DT_F32), r[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (!ok[i]) continue;
+      const long long idx = (long long)(m0 + 4 * i) * e.ld_out + n;
+      if (e.k_store) store4(e.k_store, idx, DT_F32, w[i]);
+      if (e.out) store4(e.out, idx, DT_F32, r[i]);
+      if (e.out2) store4(e.out2, idx, e.aux_type, scale4(e.out2_scale, r[i]));
+    }
+  } else if constexpr (EPI == EPI_BWD3) {
+    if (n < e.split) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (ok[i]) store4(e.out, (long long)(m0 + 4 * i) * e.ld_out + n, e.out_type, w[i]);
+    } else {
+      const int c = n - e.split;
+      Raw4 hr[8];
+      const Raw4 zero = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) hr[i] = ok[i] ? ldg_raw4(e.aux, (long long)(m0 + 4 * i) * e.ld_aux + c, e.aux_type) : zero;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (!ok[i]) continue;
+        const float4 hp = raw_to_float4(hr[i], e.aux_type);
+        float4 v = w[i];
+        v.x *= gelu_grad_fast(hp.x); v.y *= gelu_grad_fast(hp.y);
+        v.z *= gelu_grad_fast(hp.z); v.w *= gelu_grad_fast(hp.w);
+        store4(e.out2, (long long)(m0 + 4 * i) * e.ld_out2 + c, e.aux_type, v);
+      }
+    }
+  } else if constexpr (EPI == EPI_ACCUM) {
+    if constexpr (ATOMIC) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (ok[i])
+          atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (long long)(m0 + 4 * i) * e.ld_out + n),
+                    scale4(e.alpha, w[i]));
+    } else {
+      Raw4 t[8];
+      const Raw4 zero = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] = ok[i] ? ldg_raw4(e.out, (long long)(m0 + 4 * i) * e.ld_out + n, DT_F32) : zero;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (ok[i]) store4(e.out, (long long)(m0 + 4 * i) * e.ld_out + n, DT_F32, fma4(e.alpha, w[i], raw_to_float4(t[i], DT_F32)));
+    }
+  }
+}
+
 }  // namespace odevit

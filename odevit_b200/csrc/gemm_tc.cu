@@ -6,19 +6,27 @@
 // out_proj), and their autograd counterparts, with the CenterNorm affine / GELU / `*scaler` /
 // Runge-Kutta stage combine fused into the epilogues (epilogue.cuh).
 //
-// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
-//   warp 0   TMA producer: cp.async.bulk.tensor 128-byte-swizzled boxes of A and B into a
-//            STAGES-deep shared-memory ring, completion on `full` mbarriers
-//   warp 1   allocates tensor memory; one elected thread issues tcgen05.mma (UMMA 128 x BN x 16,
-//            A and B straight from shared memory through matrix descriptors) and releases ring
-//            slots / publishes accumulators with tcgen05.commit
-//   warps 2-5 epilogue: tcgen05.ld the fp32 accumulator (thread = row, 16 columns at a time),
-//            apply the fused epilogue, vectorised global stores.  Two accumulator buffers in TMEM
-//            let the epilogue of tile i overlap the main loop of tile i+1.
+// Structure: persistent, warp-specialised, 320 threads per CTA; with CG == 2 the two CTAs of a
+// 2-cluster (one SM pair) drive ONE 256 x BN tile through tcgen05.mma.cta_group::2, so that every
+// byte of A and B fetched from L2 / read from shared memory feeds twice the math of the 1-CTA form.
+//   warp 0   TMA producer: 128-byte-swizzled boxes of this CTA's 128 rows of A and its BN/CG rows
+//            of B into a STAGES-deep shared-memory ring; completion bytes are credited to the LEADER
+//            CTA's `full` mbarrier (cp.async.bulk.tensor ... cta_group::2)
+//   warp 1   allocates tensor memory; in the leader CTA one elected thread issues the MMAs
+//            (UMMA 128*CG x BN x 16, operands straight from both CTAs' shared memory through
+//            matrix descriptors), releases ring slots and publishes accumulators with
+//            tcgen05.commit multicast to both CTAs
+//   warps 2-9 epilogue: tcgen05.ld 32 columns of this CTA's 128 accumulator rows (thread = row),
+//            transpose through a swizzled shared-memory scratch so that 8 consecutive lanes hold
+//            128 contiguous bytes of one output row, apply the fused epilogue on float4s with
+//            coalesced global loads / stores.  Two accumulator buffers in TMEM let the epilogue of
+//            tile i overlap the main loop of tile i+1; the peer CTA's epilogue warps release the
+//            buffer with a remote arrive on the leader's `acc_empty` barrier.
 // Operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows], i.e. the
 // transposed products of the weight-gradient GEMMs); out-of-range rows / K are zero-filled by TMA.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "epilogue.cuh"
@@ -30,16 +38,23 @@ namespace odevit {
 namespace {
 
 constexpr int BM = 128, BK = 64;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator buffers
 
-template <int BN>
+template <int CG, int BN>
 struct Cfg {
+  static constexpr int BROWS = BN / CG;  // rows of B this CTA stages
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = BROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 128) ? 6 : 4;
-  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator buffers (256 or 512: powers of two)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STAGES = STAGE_BYTES > 40000 ? 4 : (STAGE_BYTES > 30000 ? 5 : 6);
+  static constexpr int TMEM_COLS = (BN <= 128) ? 256 : 512;  // two accumulator buffers, power of two
+  static constexpr int ACC2 = (BN <= 128) ? 128 : ACC_STRIDE;
+  static constexpr int SCRATCH_BYTES = NUM_EPI_WARPS * 4096;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SCRATCH_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 struct DevArgs {
@@ -48,14 +63,15 @@ struct DevArgs {
   Epi epi;
 };
 
-template <int BN, int EPI, bool A_MN, bool B_MN>
+template <int CG, int BN, int EPI, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ DevArgs g) {
-  using C = Cfg<BN>;
+  using C = Cfg<CG, BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  float* scratch = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::SCRATCH_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + C::STAGES;
   uint64_t* acc_full = bars + 2 * C::STAGES;
@@ -63,6 +79,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+  const int unit = blockIdx.x / CG, num_units = gridDim.x / CG;
+
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
@@ -72,13 +91,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&acc_full[i], 1);
-      ptx::mbar_init(&acc_empty[i], 4);
+      ptx::mbar_init(&acc_empty[i], NUM_EPI_WARPS * CG);
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (CG == 2) ptx::tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+    else ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
+  }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync();
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -89,30 +112,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < total_tiles; tile += num_units) {
         const int nt = tile % g.tiles_n;
         const int mt = (tile / g.tiles_n) % g.tiles_m;
         const int ks = tile / (g.tiles_n * g.tiles_m);
         const int kb0 = ks * g.kb_per_split;
         const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
+        const int m0 = (mt * CG + (int)rank) * BM;
+        const int n0 = nt * BN + (int)rank * C::BROWS;
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
-          ptx::mbar_expect_tx(&full[stage], C::STAGE_BYTES);
-          if constexpr (!A_MN) {
-            ptx::tma_load_2d(sa, &tmA, &full[stage], kb * BK, mt * BM);
-          } else {
+          if constexpr (CG == 1) {
+            ptx::mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+            if constexpr (!A_MN) {
+              ptx::tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i)
-              ptx::tma_load_2d(sa + i * (64 * BK * 2), &tmA, &full[stage], mt * BM + i * 64, kb * BK);
-          }
-          if constexpr (!B_MN) {
-            ptx::tma_load_2d(sb, &tmB, &full[stage], kb * BK, nt * BN);
-          } else {
+              for (int i = 0; i < BM / 64; ++i)
+                ptx::tma_load_2d(sa + i * (64 * BK * 2), &tmA, &full[stage], m0 + i * 64, kb * BK);
+            }
+            if constexpr (!B_MN) {
+              ptx::tma_load_2d(sb, &tmB, &full[stage], kb * BK, n0);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              ptx::tma_load_2d(sb + i * (64 * BK * 2), &tmB, &full[stage], nt * BN + i * 64, kb * BK);
+              for (int i = 0; i < C::BROWS / 64; ++i)
+                ptx::tma_load_2d(sb + i * (64 * BK * 2), &tmB, &full[stage], n0 + i * 64, kb * BK);
+            }
+          } else {
+            // both CTAs' bytes are credited to the leader's barrier, which expects the pair's total
+            if (rank == 0) ptx::mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+            const uint32_t bar = ptx::mapa(&full[stage], 0);
+            if constexpr (!A_MN) {
+              ptx::tma_load_2d_pair(sa, &tmA, bar, kb * BK, m0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BM / 64; ++i)
+                ptx::tma_load_2d_pair(sa + i * (64 * BK * 2), &tmA, bar, m0 + i * 64, kb * BK);
+            }
+            if constexpr (!B_MN) {
+              ptx::tma_load_2d_pair(sb, &tmB, bar, kb * BK, n0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < C::BROWS / 64; ++i)
+                ptx::tma_load_2d_pair(sb + i * (64 * BK * 2), &tmB, bar, n0 + i * 64, kb * BK);
+            }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -120,8 +165,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = ptx::idesc_bf16(BM * CG, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       // K-major: 8-row groups 1024 B apart, one UMMA_K (16 elements) = 32 B along the row.
       // MN-major: 64-wide MN blocks (BK*128 B apart), 8-k-row groups 1024 B apart, UMMA_K = 2 groups.
       constexpr uint32_t A_LBO = A_MN ? BK * 128 : 16, A_SBO = 1024, A_KSTEP = A_MN ? 2048 : 32;
@@ -129,7 +174,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
         const int ks = tile / (g.tiles_n * g.tiles_m);
         const int kb0 = ks * g.kb_per_split;
         const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
@@ -137,7 +182,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t acc_phase = (it >> 1) & 1;
         ptx::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * C::ACC2;
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&full[stage], phase);
           ptx::tc_fence_after();
@@ -147,49 +192,83 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = ptx::smem_desc_sw128(sa + k * A_KSTEP, A_LBO, A_SBO);
             const uint64_t db = ptx::smem_desc_sw128(sb + k * B_KSTEP, B_LBO, B_SBO);
-            ptx::mma_bf16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+            if constexpr (CG == 2) ptx::mma_bf16_ss_pair(d_tmem, da, db, idesc, accum);
+            else ptx::mma_bf16_ss(d_tmem, da, db, idesc, accum);
           }
-          ptx::mma_commit(&empty[stage]);  // ring slot reusable once these MMAs have read it
+          // ring slot reusable (in both CTAs) once these MMAs have read it
+          if constexpr (CG == 2) ptx::mma_commit_pair(&empty[stage], 3);
+          else ptx::mma_commit(&empty[stage]);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::mma_commit(&acc_full[acc]);  // accumulator complete
+        if constexpr (CG == 2) ptx::mma_commit_pair(&acc_full[acc], 3);  // accumulator complete
+        else ptx::mma_commit(&acc_full[acc]);
       }
     }
   } else {
     // ======================================= epilogue =======================================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int ew = warp - 2;
+    const int q = warp & 3;     // TMEM lane quarter this warp may access
+    const int half = ew >> 2;   // which half of the tile's columns
+    constexpr int NCH = BN / 64;  // 32-column chunks per warp
+    float* scr = scratch + ew * 1024;
+    const uint32_t acc_empty_addr0 = ptx::mapa(&acc_empty[0], 0), acc_empty_addr1 = ptx::mapa(&acc_empty[1], 0);
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
       const int nt = tile % g.tiles_n;
       const int mt = (tile / g.tiles_n) % g.tiles_m;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       ptx::mbar_wait(&acc_full[acc], acc_phase);
       ptx::tc_fence_after();
-      const int row = mt * BM + q * 32 + lane;
-      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 2
-      for (int c = 0; c < BN / 16; ++c) {
-        float v[16];
-        ptx::tmem_ld16(taddr + c * 16, v);
+      const int m_base = (mt * CG + (int)rank) * BM + q * 32;
+      const int n_base = nt * BN + half * (BN / 2);
+      const uint32_t taddr = tmem_base + acc * C::ACC2 + half * (BN / 2) + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c) {
+        float v[32];
+        ptx::tmem_ld32(taddr + c * 32, v);
         ptx::tmem_ld_wait();
-        const int n = nt * BN + c * 16;
-        if (row < g.M && n < g.N) {
-          if (g.split_k > 1) epi_chunk16<EPI, true>(g.epi, row, n, v);
-          else epi_chunk16<EPI, false>(g.epi, row, n, v);
+        if (c == NCH - 1) {
+          // every column of this warp's slice is in registers: hand the accumulator back
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 2) ptx::mbar_arrive_cluster(acc ? acc_empty_addr1 : acc_empty_addr0);
+            else ptx::mbar_arrive(&acc_empty[acc]);
+          }
+        }
+        // transpose: lane = row  ->  (row = i*4 + lane/8, 4 columns at (lane%8)*4); 16-byte chunks are
+        // XOR-swizzled by row%8 so both phases are bank-conflict free
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(scr + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int ch = lane & 7;
+        const int n = n_base + c * 32 + ch * 4;
+        float4 w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + (lane >> 3);
+          w[i] = *reinterpret_cast<const float4*>(scr + r * 32 + ((ch ^ (r & 7)) << 2));
+        }
+        __syncwarp();
+        if (n < g.N) {
+          if (g.split_k > 1) epi_rows8<EPI, true>(g.epi, m_base + (lane >> 3), g.M, n, w);
+          else epi_rows8<EPI, false>(g.epi, m_base + (lane >> 3), g.M, n, w);
         }
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
     }
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync();
+  else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (CG == 2) ptx::tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -223,25 +302,94 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int EPI, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const DevArgs& d, int grid, cudaStream_t s) {
-  auto kern = gemm_tc_kernel<BN, EPI, A_MN, B_MN>;
+template <int CG, int BN, int EPI, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const DevArgs& d, int units, cudaStream_t s) {
+  auto kern = gemm_tc_kernel<CG, BN, EPI, A_MN, B_MN>;
+  using C = Cfg<CG, BN>;
   static bool configured = false;
   if (!configured) {
-    ODV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    ODV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
-  kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, s>>>(ta, tb, d);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(units * CG);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ODV_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, d));
   ODV_LAUNCH_CHECK();
   return 0;
 }
 
-template <int BN, int EPI>
-int launch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const DevArgs& d, int grid,
-                 cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch<BN, EPI, false, false>(ta, tb, d, grid, s);
-  if (a_mn && b_mn) return launch<BN, EPI, true, true>(ta, tb, d, grid, s);
-  return set_error(ODEVIT_ERR_UNSUPPORTED, "gemm_tc: mixed operand majors are not instantiated");
+template <int CG, int BN, int EPI>
+int launch_major(bool mn, const CUtensorMap& ta, const CUtensorMap& tb, const DevArgs& d, int units, cudaStream_t s) {
+  if (!mn) return launch<CG, BN, EPI, false, false>(ta, tb, d, units, s);
+  if constexpr ((EPI == EPI_STORE || EPI == EPI_ACCUM) && BN != 192) {
+    return launch<CG, BN, EPI, true, true>(ta, tb, d, units, s);
+  } else {
+    return set_error(ODEVIT_ERR_UNSUPPORTED, "gemm_tc: MN-major operands are built for the store / accumulate epilogues");
+  }
+}
+
+template <int CG, int BN>
+int launch_epi(int epi_mode, bool mn, const CUtensorMap& ta, const CUtensorMap& tb, const DevArgs& d, int units,
+               cudaStream_t s) {
+  switch (epi_mode) {
+    case EPI_STORE: return launch_major<CG, BN, EPI_STORE>(mn, ta, tb, d, units, s);
+    case EPI_FWD1: return launch_major<CG, BN, EPI_FWD1>(mn, ta, tb, d, units, s);
+    case EPI_RK: return launch_major<CG, BN, EPI_RK>(mn, ta, tb, d, units, s);
+    case EPI_BWD3: return launch_major<CG, BN, EPI_BWD3>(mn, ta, tb, d, units, s);
+    case EPI_ACCUM: return launch_major<CG, BN, EPI_ACCUM>(mn, ta, tb, d, units, s);
+    default: return set_error(ODEVIT_ERR_INVALID_ARG, "gemm_tc: bad epilogue %d", epi_mode);
+  }
+}
+
+// Tile shape of one launch: CTA-pair (cg = 2, 256 x bn) unless the problem has a single 128-row
+// panel; bn in {128, 192, 256} picked by a wave-count model (the tile that leaves the fewest idle
+// SM-pairs in the last wave wins; wider tiles win ties: more math per operand byte).
+struct TileChoice {
+  int cg, bn, split_k;
+};
+
+TileChoice choose_tile(const GemmArgs& g, bool mn, int sms) {
+  const char* env = getenv("ODEVIT_GEMM_TILE");  // "<cg>x<bn>", experiments only
+  if (env && !env[0]) env = nullptr;
+  const int num_kb = (g.K + BK - 1) / BK;
+  TileChoice best = {1, 128, 1};
+  double best_cost = 1e30;
+  for (int cg = 2; cg >= 1; --cg) {
+    for (int bn : {256, 192, 128}) {
+      if (cg == 1 && bn != 128) continue;
+      if (mn && bn == 192) continue;
+      if (env && (env[0] - '0' != cg || atoi(env + 2) != bn)) continue;
+      const int units = sms / cg;
+      const long long tiles = (long long)((g.M + BM * cg - 1) / (BM * cg)) * ((g.N + bn - 1) / bn);
+      int sk = 1;
+      if (g.epi_mode == EPI_ACCUM) {
+        // weight-gradient shapes: few output tiles, very long K -> split K across the idle SMs
+        sk = (int)(units / tiles);
+        if (sk > num_kb / 8) sk = num_kb / 8;
+        if (sk < 1) sk = 1;
+      }
+      const int kb_per = (num_kb + sk - 1) / sk;
+      sk = (num_kb + kb_per - 1) / kb_per;
+      const long long waves = (tiles * sk + units - 1) / units;
+      // per-tile time ~ bn * (k blocks + epilogue/fill overhead); rows wasted by a half-empty pair count too
+      double cost = (double)waves * (bn + 64) * (kb_per + 2.0);
+      if (cg == 1) cost *= 1.25;          // half the math per staged byte
+      else if (bn == 128) cost *= 1.08;
+      if (cg == 2 && g.M <= BM) cost *= 2.0;  // second CTA of every pair would idle
+      if (cost < best_cost) { best_cost = cost; best = {cg, bn, sk}; }
+    }
+  }
+  return best;
 }
 
 }  // namespace
@@ -286,6 +434,8 @@ bool gemm_tc_supports(const GemmArgs& g) {
   const bool b_k = (g.b_cs == 1), b_mn = (g.b_rs == 1 && g.b_cs != 1);
   if (!(a_k || a_mn) || !(b_k || b_mn)) return false;
   if ((a_k && !a_mn) != (b_k && !b_mn)) return false;  // both K-major or both MN-major
+  const bool mn = !a_k;
+  if (mn && g.epi_mode != EPI_STORE && g.epi_mode != EPI_ACCUM) return false;
   const long long lda = a_mn ? g.a_cs : g.a_rs, ldb = b_mn ? g.b_cs : g.b_rs;
   if (lda % 8 || ldb % 8) return false;  // TMA: 16-byte global strides
   if ((reinterpret_cast<uintptr_t>(g.A) | reinterpret_cast<uintptr_t>(g.B)) & 15) return false;
@@ -306,42 +456,34 @@ int gemm_tc(const GemmArgs& g, cudaStream_t s) {
   if (!gemm_tc_supports(g)) return set_error(ODEVIT_ERR_UNSUPPORTED, "gemm_tc: unsupported problem");
   ProfScope prof(g.kclass, s);
   const bool mn = (g.a_cs != 1);
-  constexpr int BN = 128;
+  const int sms = num_sms();
+  const TileChoice tc = choose_tile(g, mn, sms);
+  const int cg = tc.cg, bn = tc.bn;
   DevArgs d;
   d.M = g.M; d.N = g.N; d.K = g.K;
-  d.tiles_m = (g.M + BM - 1) / BM;
-  d.tiles_n = (g.N + BN - 1) / BN;
+  d.tiles_m = (g.M + BM * cg - 1) / (BM * cg);
+  d.tiles_n = (g.N + bn - 1) / bn;
   d.num_kb = (g.K + BK - 1) / BK;
-  d.split_k = 1;
-  const int sms = num_sms();
-  if (g.epi_mode == EPI_ACCUM) {
-    // weight-gradient shapes: few output tiles, very long K -> split K across the idle SMs
-    const int tiles = d.tiles_m * d.tiles_n;
-    int sk = sms / tiles;
-    if (sk > d.num_kb / 8) sk = d.num_kb / 8;
-    if (sk > 1) d.split_k = sk;
-  }
+  d.split_k = tc.split_k;
   d.kb_per_split = (d.num_kb + d.split_k - 1) / d.split_k;
   d.split_k = (d.num_kb + d.kb_per_split - 1) / d.kb_per_split;
   d.epi = g.epi;
   CUtensorMap ta, tb;
+  const int brows = bn / cg;
   if (!mn) {
     ODV_TRY(make_tmap_2d_bf16(&ta, g.A, g.K, g.M, g.a_rs, BK, BM));
-    ODV_TRY(make_tmap_2d_bf16(&tb, g.B, g.K, g.N, g.b_rs, BK, BN));
+    ODV_TRY(make_tmap_2d_bf16(&tb, g.B, g.K, g.N, g.b_rs, BK, brows));
   } else {
     ODV_TRY(make_tmap_2d_bf16(&ta, g.A, g.M, g.K, g.a_cs, 64, BK));
     ODV_TRY(make_tmap_2d_bf16(&tb, g.B, g.N, g.K, g.b_cs, 64, BK));
   }
   const int total = d.tiles_m * d.tiles_n * d.split_k;
-  const int grid = total < sms ? total : sms;
-  switch (g.epi_mode) {
-    case EPI_STORE: return launch_major<BN, EPI_STORE>(mn, mn, ta, tb, d, grid, s);
-    case EPI_FWD1: return launch_major<BN, EPI_FWD1>(mn, mn, ta, tb, d, grid, s);
-    case EPI_RK: return launch_major<BN, EPI_RK>(mn, mn, ta, tb, d, grid, s);
-    case EPI_BWD3: return launch_major<BN, EPI_BWD3>(mn, mn, ta, tb, d, grid, s);
-    case EPI_ACCUM: return launch_major<BN, EPI_ACCUM>(mn, mn, ta, tb, d, grid, s);
-    default: return set_error(ODEVIT_ERR_INVALID_ARG, "gemm_tc: bad epilogue %d", g.epi_mode);
-  }
+  const int max_units = sms / cg;
+  const int units = total < max_units ? total : max_units;
+  if (cg == 1) return launch_epi<1, 128>(g.epi_mode, mn, ta, tb, d, units, s);
+  if (bn == 128) return launch_epi<2, 128>(g.epi_mode, mn, ta, tb, d, units, s);
+  if (bn == 192) return launch_epi<2, 192>(g.epi_mode, mn, ta, tb, d, units, s);
+  return launch_epi<2, 256>(g.epi_mode, mn, ta, tb, d, units, s);
 }
 
 }  // namespace odevit
