@@ -294,6 +294,21 @@ def run_ours(args, wl):
                     "frac": achieved / tensor_peak, "traffic": None, "peak_source": peak_src,
                     "avg_launch_us": ms / n * 1e3, "launches": n, "share_of_kernel_time": shares.get(k)}
 
+    # ---- HBM-bound row kernels: algorithmic bytes per launch / measured launch time
+    hbm_peak = float(peaks.get("hbm_gbs", 6500.0))
+    D_, T_ = cfg["embed_dim"], cfg["num_eval_steps"]
+    N_ = (cfg["img_size"] // cfg["patch_size"]) ** 2 + 1 + cfg["register_tokens"]
+    act_b = 2 if args.precision == "bf16" else 4
+    class_bytes = {"center_rows": B * N_ * D_ * (4 + act_b),       # read the fp32 state row, write xc
+                   "fd_curvature": T_ * B * N_ * D_ * 4}           # read the trajectory once
+    roofline_hbm = {}
+    for k, nbytes in class_bytes.items():
+        if k in prof:
+            ms, n = prof[k]
+            gbs = nbytes / (ms / n * 1e-3) / 1e9
+            roofline_hbm[k] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                               "frac": gbs / hbm_peak, "avg_launch_us": ms / n * 1e3, "launches": n}
+
     if rank == 0:
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline and not args.quick:
@@ -318,6 +333,7 @@ def run_ours(args, wl):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,
+            "roofline_hbm": roofline_hbm,
             "kernel_time_shares": shares,
             "kernel_avg_us": {k: round(v[0] / v[1] * 1e3, 2) for k, v in prof.items()},
             "kernel_launches_per_step": {k: v[1] // args.steps for k, v in prof.items()},

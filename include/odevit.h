@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define ODEVIT_ABI_VERSION 1
+#define ODEVIT_ABI_VERSION 2
 
 typedef struct CUstream_st* odevit_stream_t; /* == cudaStream_t */
 
@@ -154,14 +154,24 @@ int odevit_field_fwd(const odevit_desc* desc, const odevit_weights* w,
  *   final_state [B,N,D] or NULL (required when states == NULL);
  *   p_last [B,H,N,N] or NULL: P of the LAST field evaluation (block.attentions after the solve);
  *   p_traj [(n_evals - p_traj_first_eval), B,H,N,N] or NULL: P of every evaluation e >=
- *          p_traj_first_eval, e = step*stages + stage (odefunc.attention_trajectory). */
+ *          p_traj_first_eval, e = step*stages + stage (odefunc.attention_trajectory);
+ *   tape (odevit_tape_bytes() bytes, 1024-aligned) or NULL: when given, the intermediates of every
+ *          field evaluation (centred rows, q|k|v, [O|h], fc1 pre-activation, softmax row log-sums)
+ *          are kept there for odevit_solve_bwd -- what autograd's saved tensors are in the reference
+ *          (train.py:57-67), in bf16 in the bf16 mode. */
 int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t method,
                      const float* x0, const float* t_grid_host, int32_t n_grid,
                      float* states, float* final_state,
                      float* p_last, float* p_traj, int32_t p_traj_first_eval,
+                     void* tape, size_t tape_bytes,
                      void* workspace, size_t workspace_bytes, odevit_stream_t stream);
 
-/* Reverse sweep through the solve (backprop-through-solver semantics, per-step recomputation).
+/* Bytes of the tape of a solve over n_grid points (0 on invalid arguments). */
+size_t odevit_tape_bytes(const odevit_desc* desc, int32_t method, int32_t n_grid);
+
+/* Reverse sweep through the solve (backprop-through-solver semantics).  With `tape` (written by the
+ * forward call of the same desc/method/grid) the stage intermediates are read back; with tape ==
+ * NULL each step is recomputed from its stored trajectory row (no stage tensor is kept).
  *   states [T,B,N,D]: the trajectory odevit_solve_fwd produced (row j = input of step j);
  *   g_states [T,B,N,D] or NULL: cotangent of every trajectory row;
  *   g_rows [n_g_rows,B,N,D] + g_row_index_host [n_g_rows] (HOST ints, may repeat): cotangents of
@@ -175,6 +185,7 @@ int odevit_solve_bwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
                      const float* g_rows, const int32_t* g_row_index_host, int32_t n_g_rows,
                      const float* g_p_last,
                      float* g_x0, const odevit_weight_grads* gw,
+                     const void* tape, size_t tape_bytes,
                      void* workspace, size_t workspace_bytes, odevit_stream_t stream);
 
 /* Vector-Jacobian product of ONE field evaluation (autograd of odevit_field_fwd):
@@ -184,6 +195,15 @@ int odevit_field_bwd(const odevit_desc* desc, const odevit_weights* w,
                      const float* x, const float* g_dx, const float* g_p,
                      float* g_x, const odevit_weight_grads* gw,
                      void* workspace, size_t workspace_bytes, odevit_stream_t stream);
+
+/* Finite-difference curvature of a trajectory in one pass.  Replaces the tensor arithmetic of
+ * ViTNeuralODE.compute_upper_bound_by_fininte_difference (ode_transformer_gpt.py:529-543 with
+ * finite_difference_second_derivative_sequence :458-468):
+ *   per_seq[b,n] = max_j max_d |s[j+2,b,n,d] - 2 s[j+1,b,n,d] + s[j,b,n,d]| / delta_t^2
+ * states [T,B,N,D], T >= 3, D % 4 == 0; per_seq [B,N] out.  The caller applies the scalar prefactor and
+ * the maxima over n and b (tiny). */
+int odevit_fd_curvature(const float* states, int32_t n_grid, int32_t batch, int32_t tokens, int32_t dim,
+                        double delta_t, float* per_seq, odevit_stream_t stream);
 
 /* Number of kernels the library launched (process-wide, all threads) since the last reset (bench.py's
  * gpu_launches claim is counted, not estimated). */

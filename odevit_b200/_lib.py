@@ -13,7 +13,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libodevit.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enums of include/odevit.h
 FIELD_PARALLEL, FIELD_PARALLEL_L2, FIELD_MACARON = 0, 1, 2
@@ -82,12 +82,17 @@ def lib() -> ctypes.CDLL:
     L.odevit_solve_fwd.restype = ctypes.c_int
     L.odevit_solve_fwd.argtypes = [ctypes.POINTER(Desc), ctypes.POINTER(Weights), ctypes.c_int32, _vp,
                                    ctypes.POINTER(ctypes.c_float), ctypes.c_int32, _vp, _vp, _vp, _vp,
-                                   ctypes.c_int32, _vp, ctypes.c_size_t, _vp]
+                                   ctypes.c_int32, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _vp]
+    L.odevit_tape_bytes.restype = ctypes.c_size_t
+    L.odevit_tape_bytes.argtypes = [ctypes.POINTER(Desc), ctypes.c_int32, ctypes.c_int32]
+    L.odevit_fd_curvature.restype = ctypes.c_int
+    L.odevit_fd_curvature.argtypes = [_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                      ctypes.c_double, _vp, _vp]
     L.odevit_solve_bwd.restype = ctypes.c_int
     L.odevit_solve_bwd.argtypes = [ctypes.POINTER(Desc), ctypes.POINTER(Weights), ctypes.c_int32,
                                    ctypes.POINTER(ctypes.c_float), ctypes.c_int32, _vp, _vp, _vp,
                                    ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, _vp, _vp,
-                                   ctypes.POINTER(WeightGrads), _vp, ctypes.c_size_t, _vp]
+                                   ctypes.POINTER(WeightGrads), _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _vp]
     L.odevit_gemm_bf16.restype = ctypes.c_int
     L.odevit_gemm_bf16.argtypes = [ctypes.c_int32] * 4 + [_vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _vp]
     L.odevit_profile_enable.restype = ctypes.c_int
@@ -136,6 +141,6 @@ def profile_read() -> dict:
 
 DECLARED_SYMBOLS = ("odevit_abi_version", "odevit_build_info", "odevit_last_error_string",
                     "odevit_workspace_bytes", "odevit_field_fwd", "odevit_solve_fwd", "odevit_solve_bwd",
-                    "odevit_field_bwd", "odevit_launch_count", "odevit_reset_launch_count",
+                    "odevit_field_bwd", "odevit_tape_bytes", "odevit_fd_curvature", "odevit_launch_count", "odevit_reset_launch_count",
                     "odevit_gemm_bf16", "odevit_profile_enable", "odevit_profile_num_classes", "odevit_profile_class_name",
                     "odevit_profile_read")

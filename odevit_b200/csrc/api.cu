@@ -58,7 +58,7 @@ ProfState g_prof;
 const char* const kClassNames[KC_COUNT] = {
     "center_rows", "gemm_in_qkv_fc1", "attn_qk", "softmax", "attn_pv", "gemm_out_rk",
     "bwd_gemm_doh", "bwd_gemm_g2", "bwd_attn", "bwd_softmax", "bwd_gemm_dx", "bwd_gemm_g1",
-    "bwd_colsum", "combine", "weights", "fused_attn", "fused_attn_bwd", "other"};
+    "bwd_colsum", "combine", "weights", "fused_attn", "fused_attn_bwd", "fd_curvature", "other"};
 }  // namespace
 
 ProfScope::ProfScope(int c, cudaStream_t st) : cls(c), s(st), slot(-1) {
@@ -244,6 +244,19 @@ BwdBufs layout_bwd(const Plan& p, Arena& a, int S) {
   b.c2 = acc ? acc + R * p.D + R + K2 * p.D : nullptr;
   b.acc_bytes = acc_floats * 4;
   return b;
+}
+
+// The tape: one StageCtx per field evaluation e = step*S + stage, written by the forward solve and
+// read by the reverse sweep instead of recomputing the step (HBM is 180 GB: at the C100 bench shape
+// the tape is 3.3 GB).  Layout is a pure function of (plan, n_evals).
+StageCtx tape_ctx(const Plan& p, void* tape, long long e, size_t* total_bytes, long long n_evals) {
+  Arena a0(nullptr);
+  take_ctx(p, a0, true);
+  const size_t per = (a0.off + 1023) & ~size_t(1023);
+  if (total_bytes) *total_bytes = per * (size_t)n_evals;
+  if (!tape) return StageCtx{nullptr, nullptr, nullptr, nullptr, nullptr};
+  Arena a(reinterpret_cast<char*>(tape) + per * (size_t)e);
+  return take_ctx(p, a, true);
 }
 
 int check_ws(const void* ws, size_t have, size_t need) {
@@ -598,7 +611,7 @@ int odevit_profile_read(int32_t kclass, double* total_ms, int64_t* launches) {
 }
 
 size_t odevit_workspace_bytes(const odevit_desc* desc, int32_t ws_kind, int32_t method) {
-  Plan p;
+  Plan p{};
   if (make_plan(desc, &p)) return 0;
   Arena a(nullptr);
   if (ws_kind == ODEVIT_WS_FIELD) {
@@ -613,9 +626,19 @@ size_t odevit_workspace_bytes(const odevit_desc* desc, int32_t ws_kind, int32_t 
   return a.off + 1024;
 }
 
+size_t odevit_tape_bytes(const odevit_desc* desc, int32_t method, int32_t n_grid) {
+  Plan p{};
+  if (make_plan(desc, &p)) return 0;
+  const Tableau* tb = tableau_for(method);
+  if (!tb || n_grid < 1) { set_error(ODEVIT_ERR_INVALID_ARG, "unknown method %d / empty grid", method); return 0; }
+  size_t need = 0;
+  tape_ctx(p, nullptr, 0, &need, (long long)(n_grid - 1) * tb->S);
+  return need;
+}
+
 int odevit_field_fwd(const odevit_desc* desc, const odevit_weights* w, const float* x, float* dx,
                      float* p_out, void* workspace, size_t workspace_bytes, odevit_stream_t stream) {
-  Plan p;
+  Plan p{};
   ODV_TRY(make_plan(desc, &p));
   ODV_TRY(check_weights(p, w));
   ODV_TRY(check_device_ptr(x, "x"));
@@ -635,14 +658,20 @@ int odevit_field_fwd(const odevit_desc* desc, const odevit_weights* w, const flo
 
 int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t method, const float* x0,
                      const float* t_grid_host, int32_t n_grid, float* states, float* final_state,
-                     float* p_last, float* p_traj, int32_t p_traj_first_eval, void* workspace,
-                     size_t workspace_bytes, odevit_stream_t stream) {
-  Plan p;
+                     float* p_last, float* p_traj, int32_t p_traj_first_eval, void* tape, size_t tape_bytes,
+                     void* workspace, size_t workspace_bytes, odevit_stream_t stream) {
+  Plan p{};
   ODV_TRY(make_plan(desc, &p));
   ODV_TRY(check_weights(p, w));
   const Tableau* tb = tableau_for(method);
   if (!tb) return set_error(ODEVIT_ERR_INVALID_ARG, "unknown method %d", method);
   if (!t_grid_host || n_grid < 1) return set_error(ODEVIT_ERR_INVALID_ARG, "t_grid must hold >= 1 point");
+  if (tape) {
+    size_t need = 0;
+    tape_ctx(p, nullptr, 0, &need, (long long)(n_grid - 1) * tb->S);
+    ODV_TRY(check_device_ptr(tape, "tape"));
+    ODV_TRY(check_ws(tape, tape_bytes, need));
+  }
   if (!states && !final_state) return set_error(ODEVIT_ERR_INVALID_ARG, "states and final_state both NULL");
   ODV_TRY(check_device_ptr(x0, "x0"));
   if (states) ODV_TRY(check_device_ptr(states, "states"));
@@ -678,7 +707,8 @@ int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
       float* p_copy = nullptr;
       if (p_traj && e >= p_traj_first_eval) p_copy = p_traj + (size_t)(e - p_traj_first_eval) * p.BHNN;
       else if (p_last && e == n_evals - 1) p_copy = p_last;
-      ODV_TRY(eval_forward(p, f.w, f.ctx, u, f.P, p_copy, &rk, s));
+      const StageCtx ctx = tape ? tape_ctx(p, tape, e, nullptr, n_evals) : f.ctx;
+      ODV_TRY(eval_forward(p, f.w, ctx, u, f.P, p_copy, &rk, s));
       if (p_last && e == n_evals - 1 && p_copy != p_last)
         ODV_CUDA(cudaMemcpyAsync(p_last, p_copy, (size_t)p.BHNN * 4, cudaMemcpyDeviceToDevice, s));
     }
@@ -693,9 +723,9 @@ int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
 int odevit_solve_bwd(const odevit_desc* desc, const odevit_weights* w, int32_t method,
                      const float* t_grid_host, int32_t n_grid, const float* states, const float* g_states,
                      const float* g_rows, const int32_t* g_row_index_host, int32_t n_g_rows,
-                     const float* g_p_last, float* g_x0, const odevit_weight_grads* gw, void* workspace,
-                     size_t workspace_bytes, odevit_stream_t stream) {
-  Plan p;
+                     const float* g_p_last, float* g_x0, const odevit_weight_grads* gw, const void* tape,
+                     size_t tape_bytes, void* workspace, size_t workspace_bytes, odevit_stream_t stream) {
+  Plan p{};
   ODV_TRY(make_plan(desc, &p));
   ODV_TRY(check_weights(p, w));
   const Tableau* tb = tableau_for(method);
@@ -709,6 +739,12 @@ int odevit_solve_bwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
   for (int i = 0; i < n_g_rows; ++i)
     if (g_row_index_host[i] < 0 || g_row_index_host[i] >= n_grid)
       return set_error(ODEVIT_ERR_INVALID_ARG, "g_row_index[%d]=%d outside [0,%d)", i, g_row_index_host[i], n_grid);
+  if (tape) {
+    size_t need = 0;
+    tape_ctx(p, nullptr, 0, &need, (long long)(n_grid - 1) * tb->S);
+    ODV_TRY(check_device_ptr(tape, "tape"));
+    ODV_TRY(check_ws(tape, tape_bytes, need));
+  }
   Arena a(workspace);
   BwdBufs b = layout_bwd(p, a, tb->S);
   ODV_TRY(check_ws(workspace, workspace_bytes, a.off));
@@ -747,8 +783,12 @@ int odevit_solve_bwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
   for (int j = n_grid - 2; j >= 0; --j) {
     const float dt = t_grid_host[j + 1] - t_grid_host[j];
     const float* y = states + (size_t)j * MD;
-    // (1) recompute the stage intermediates of this step (the last stage skips GEMM2)
-    for (int st = 0; st < S; ++st) {
+    // (1) the stage intermediates of this step: read back from the tape when the forward kept one,
+    //     else recomputed from the trajectory row (the last stage skips GEMM2)
+    StageCtx ctx[4];
+    for (int st = 0; st < S; ++st)
+      ctx[st] = tape ? tape_ctx(p, const_cast<void*>(tape), (long long)j * S + st, nullptr, 0) : b.ctx[st];
+    for (int st = 0; st < S && !tape; ++st) {
       const float* u = (st == 0) ? y : b.u;
       if (st < S - 1) {
         Epi rk = rk_epilogue(*tb, st, dt, y, b.k, b.u);
@@ -794,22 +834,32 @@ int odevit_solve_bwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
           e.out2 = nullptr;
           dd_seeded = false;
         }
-        ODV_TRY(eval_vjp(p, b.w, b.ctx[st], b, last_eval ? g_p_last : nullptr, need_c2, e, s));
+        ODV_TRY(eval_vjp(p, b.w, ctx[st], b, last_eval ? g_p_last : nullptr, need_c2, e, s));
         if (!fits) ODV_TRY(inject(j));
         if (!dd_seeded && j > 0) ODV_TRY(seed_dd(t_grid_host[j] - t_grid_host[j - 1]));
         continue;
       }
-      ODV_TRY(eval_vjp(p, b.w, b.ctx[st], b, last_eval ? g_p_last : nullptr, need_c2, e, s));
+      ODV_TRY(eval_vjp(p, b.w, ctx[st], b, last_eval ? g_p_last : nullptr, need_c2, e, s));
     }
   }
   ODV_CUDA(cudaMemcpyAsync(g_x0, b.gy, MD * 4, cudaMemcpyDeviceToDevice, s));
   return finish_grads(p, w, gw, b, s);
 }
 
+int odevit_fd_curvature(const float* states, int32_t n_grid, int32_t batch, int32_t tokens, int32_t dim,
+                        double delta_t, float* per_seq, odevit_stream_t stream) {
+  if (n_grid < 3) return set_error(ODEVIT_ERR_INVALID_ARG, "fd_curvature needs >= 3 grid points, got %d", n_grid);
+  if (batch <= 0 || tokens <= 0 || dim <= 0) return set_error(ODEVIT_ERR_INVALID_ARG, "non-positive dimension");
+  ODV_TRY(check_device_ptr(states, "states"));
+  ODV_TRY(check_device_ptr(per_seq, "per_seq"));
+  return fd_curvature(states, n_grid, (long long)batch * tokens, dim, (float)(delta_t * delta_t), per_seq,
+                      reinterpret_cast<cudaStream_t>(stream));
+}
+
 int odevit_field_bwd(const odevit_desc* desc, const odevit_weights* w, const float* x, const float* g_dx,
                      const float* g_p, float* g_x, const odevit_weight_grads* gw, void* workspace,
                      size_t workspace_bytes, odevit_stream_t stream) {
-  Plan p;
+  Plan p{};
   ODV_TRY(make_plan(desc, &p));
   ODV_TRY(check_weights(p, w));
   if (!gw) return set_error(ODEVIT_ERR_INVALID_ARG, "weight-gradient struct is NULL");

@@ -65,6 +65,7 @@ enum KClass : int {
   KC_WEIGHTS,      // weight fold / gradient unfold
   KC_FUSED_ATTN,   // fused attention (S, softmax, PV in one kernel)
   KC_FUSED_ATTN_BWD,  // fused attention VJP (delta + dq/dk/dv in one kernel)
+  KC_FD_BOUND,        // finite-difference curvature of the trajectory (single pass)
   KC_OTHER,
   KC_COUNT
 };
@@ -182,6 +183,9 @@ struct CombineArgs {
   float dd_scale = 1.f;
 };
 int vjp_combine(const CombineArgs& a, int rows, int D, cudaStream_t s);
+
+// per_seq[r] = max_j max_d |s[j+2,r,d] - 2 s[j+1,r,d] + s[j,r,d]| / dt2   (states [T, rows, D])
+int fd_curvature(const float* states, int T, long long rows, int D, float dt2, float* per_seq, cudaStream_t s);
 
 // y[i] += a * x[i]
 int axpy_f32(float* y, const float* x, float a, long long n, cudaStream_t s);

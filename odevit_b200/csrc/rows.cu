@@ -211,6 +211,56 @@ __global__ void axpy_kernel(float* y, const float* __restrict__ x, float a, long
   for (; i < n; i += stride) y[i] = fmaf(a, x[i], y[i]);
 }
 
+// ---- finite-difference curvature of the trajectory ------------------------------------------
+// compute_upper_bound_by_fininte_difference (ode_transformer_gpt.py:529-543) forms the second
+// difference (s[j+2] - 2 s[j+1] + s[j]) / dt^2 over the whole [T,B,N,D] trajectory, its inf-norm over
+// D and the max over time: in PyTorch that is ~6 full-trajectory passes.  Here one warp owns a token
+// row (b,n), walks the T rows once with a 3-row register window and emits per_seq[b,n]; every state
+// element is read exactly once (algorithmic bytes = T*B*N*D*4).
+template <int CH>  // CH float4 chunks per lane: D <= 128*CH
+__global__ void __launch_bounds__(256) fd_curvature_kernel(const float* __restrict__ states, int T, long long rows,
+                                                           int D, float dt2, float* __restrict__ per_seq) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const long long stride = rows * D;
+  const float* base = states + row * D;
+  float4 w[3][CH];
+  auto load = [&](float4* dst, int j) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int c = (lane + i * 32) * 4;
+      dst[i] = (c < D) ? __ldcs(reinterpret_cast<const float4*>(base + (long long)j * stride + c))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  load(w[0], 0);
+  load(w[1], 1);
+  float mx = 0.f;
+  // the window rotates through the three register rows; unrolled by 3 so the indices stay static
+  auto step = [&](float4* a, float4* b, float4* c, int j) {
+    load(c, j);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      // same association as the reference: (s[j+2] - 2*s[j+1]) + s[j]
+      mx = fmaxf(mx, fabsf((c[i].x - 2.f * b[i].x) + a[i].x));
+      mx = fmaxf(mx, fabsf((c[i].y - 2.f * b[i].y) + a[i].y));
+      mx = fmaxf(mx, fabsf((c[i].z - 2.f * b[i].z) + a[i].z));
+      mx = fmaxf(mx, fabsf((c[i].w - 2.f * b[i].w) + a[i].w));
+    }
+  };
+  int j = 2;
+  for (; j + 2 < T; j += 3) {
+    step(w[0], w[1], w[2], j);
+    step(w[1], w[2], w[0], j + 1);
+    step(w[2], w[0], w[1], j + 2);
+  }
+  if (j < T) { step(w[0], w[1], w[2], j); ++j; }
+  if (j < T) { step(w[1], w[2], w[0], j); ++j; }
+  mx = warp_max(mx);
+  if (lane == 0) per_seq[row] = mx / dt2;
+}
+
 // ---- weight folding (PARALLEL variant) -------------------------------------------------------
 // CenterNorm is affine in (x - mean):  n = s*(x-mean)*w + b  with s = D/(D-1)          (:77-83)
 //   n_attn @ W_in^T = (x-mean) @ (s * W_in * diag(w_a))^T + W_in @ b_a
@@ -315,31 +365,40 @@ __global__ void __launch_bounds__(128) unfold_w1_kernel(UnfoldArgs a, odevit_wei
   (void)hid;
 }
 
+// one block = 128 columns i x a slice of kUnfoldRows rows j of G1; partial sums meet through atomics
+constexpr int kUnfoldRows = 64;
 __global__ void __launch_bounds__(128) unfold_norm_kernel(UnfoldArgs a, odevit_weights w,
                                                           odevit_weight_grads g) {
   const int D = a.D, hid = a.hid;
   const int i = blockIdx.x * 128 + threadIdx.x;
   if (i >= D) return;
+  const int j0 = blockIdx.y * kUnfoldRows;
+  const int j1 = min(3 * D + hid, j0 + kUnfoldRows);
   const float s_cn = (float)D / ((float)D - 1.f);
   const float q = rsqrtf((float)(D / a.heads));
   float dwa = 0.f, dba = 0.f, dwm = 0.f, dbm = 0.f;
-  for (int j = 0; j < 3 * D; ++j) {
-    const float qs = (j < D) ? q : 1.f;
-    const float wv = qs * w.in_proj_w[(long long)j * D + i];
-    dwa = fmaf(wv, a.G1[(long long)j * D + i], dwa);
-    dba = fmaf(wv, a.c1[j], dba);
-  }
-  for (int j = 0; j < hid; ++j) {
-    const float wv = w.fc1_w[(long long)j * D + i];
-    dwm = fmaf(wv, a.G1[(long long)(3 * D + j) * D + i], dwm);
-    dbm = fmaf(wv, a.c1[3 * D + j], dbm);
+  for (int j = j0; j < j1; ++j) {
+    const float g1 = a.G1[(long long)j * D + i], cj = a.c1[j];
+    if (j < 3 * D) {
+      const float wv = ((j < D) ? q : 1.f) * w.in_proj_w[(long long)j * D + i];
+      dwa = fmaf(wv, g1, dwa);
+      dba = fmaf(wv, cj, dba);
+    } else {
+      const float wv = w.fc1_w[(long long)(j - 3 * D) * D + i];
+      dwm = fmaf(wv, g1, dwm);
+      dbm = fmaf(wv, cj, dbm);
+    }
   }
   const float ma = w.mod_attn_scale ? 1.f + w.mod_attn_scale[i] : 1.f;
   const float mm = w.mod_mlp_scale ? 1.f + w.mod_mlp_scale[i] : 1.f;
-  if (g.norm_a_w) g.norm_a_w[i] += ma * s_cn * dwa;
-  if (g.norm_a_b) g.norm_a_b[i] += ma * dba;
-  if (g.norm_b_w) g.norm_b_w[i] += mm * s_cn * dwm;
-  if (g.norm_b_b) g.norm_b_b[i] += mm * dbm;
+  if (j0 < 3 * D) {
+    if (g.norm_a_w) atomicAdd(g.norm_a_w + i, ma * s_cn * dwa);
+    if (g.norm_a_b) atomicAdd(g.norm_a_b + i, ma * dba);
+  }
+  if (j1 > 3 * D) {
+    if (g.norm_b_w) atomicAdd(g.norm_b_w + i, mm * s_cn * dwm);
+    if (g.norm_b_b) atomicAdd(g.norm_b_b + i, mm * dbm);
+  }
 }
 
 __global__ void __launch_bounds__(128) unfold_w2_kernel(UnfoldArgs a, odevit_weight_grads g) {
@@ -414,6 +473,19 @@ int axpy_f32(float* y, const float* x, float a, long long n, cudaStream_t s) {
   return 0;
 }
 
+int fd_curvature(const float* states, int T, long long rows, int D, float dt2, float* per_seq, cudaStream_t s) {
+  ProfScope prof(KC_FD_BOUND, s);
+  if (D % 4 || D > 1024) return set_error(ODEVIT_ERR_UNSUPPORTED, "fd_curvature: D=%d (need D %% 4 == 0, D <= 1024)", D);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  const int ch = (D + 127) / 128;
+  if (ch <= 2) fd_curvature_kernel<2><<<grid, 256, 0, s>>>(states, T, rows, D, dt2, per_seq);
+  else if (ch <= 4) fd_curvature_kernel<4><<<grid, 256, 0, s>>>(states, T, rows, D, dt2, per_seq);
+  else if (ch <= 6) fd_curvature_kernel<6><<<grid, 256, 0, s>>>(states, T, rows, D, dt2, per_seq);
+  else fd_curvature_kernel<8><<<grid, 256, 0, s>>>(states, T, rows, D, dt2, per_seq);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
 int fold_weights_parallel(const FoldArgs& a, cudaStream_t s) {
   ProfScope prof(KC_WEIGHTS, s);
   fold_w1_kernel<<<3 * a.D + a.hid, 128, 0, s>>>(a, *a.w);
@@ -427,7 +499,7 @@ int unfold_grads_parallel(const UnfoldArgs& a, cudaStream_t s) {
   ProfScope prof(KC_WEIGHTS, s);
   unfold_w1_kernel<<<3 * a.D + a.hid, 128, 0, s>>>(a, *a.w, *a.gw);
   ODV_LAUNCH_CHECK();
-  unfold_norm_kernel<<<(a.D + 127) / 128, 128, 0, s>>>(a, *a.w, *a.gw);
+  unfold_norm_kernel<<<dim3((a.D + 127) / 128, (3 * a.D + a.hid + kUnfoldRows - 1) / kUnfoldRows), 128, 0, s>>>(a, *a.w, *a.gw);
   ODV_LAUNCH_CHECK();
   unfold_w2_kernel<<<a.D, 128, 0, s>>>(a, *a.gw);
   ODV_LAUNCH_CHECK();

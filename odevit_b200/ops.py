@@ -10,6 +10,7 @@ Replaces, for CUDA tensors:
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -30,6 +31,7 @@ class FieldSpec:
     scaler: float
     variant: int = _lib.FIELD_PARALLEL
     precision: str = "bf16"
+    backward: str = "auto"   # "tape" | "recompute" | "auto" (tape when it fits TAPE_BUDGET_FRACTION of free HBM)
 
     def desc(self, batch: int, tokens: int) -> _lib.Desc:
         d = _lib.Desc()
@@ -78,6 +80,33 @@ def _workspace(desc: _lib.Desc, kind: int, method: int, device: torch.device):
 
 def free_workspaces() -> None:
     _WS_CACHE.clear()
+
+
+TAPE_BUDGET_FRACTION = float(os.environ.get("ODEVIT_TAPE_FRACTION", "0.5"))
+
+
+def _alloc_tape(desc: _lib.Desc, method: int, n_grid: int, mode: str, device: torch.device):
+    """The forward's record of per-evaluation intermediates for the reverse sweep (what autograd's saved
+    tensors are in the reference), or None -> the reverse sweep recomputes each step."""
+    if mode == "recompute" or n_grid < 2:
+        return None
+    n = int(_lib.lib().odevit_tape_bytes(ctypes.byref(desc), method, n_grid))
+    if n == 0:
+        return None
+    if mode == "auto":
+        free, _total = torch.cuda.mem_get_info(device)
+        reusable = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+        if n > TAPE_BUDGET_FRACTION * (free + reusable):
+            return None
+    return torch.empty(n + 1024, dtype=torch.uint8, device=device)
+
+
+def _aligned(buf: Optional[torch.Tensor]):
+    if buf is None:
+        return None, 0
+    base = buf.data_ptr()
+    al = (base + 1023) & ~1023
+    return _vp(al), buf.numel() - (al - base)
 
 
 def _stream() -> _vp:
@@ -203,11 +232,14 @@ class _OdeSolve(torch.autograd.Function):
             if n_evals - first > 0:
                 p_traj = torch.empty(n_evals - first, B, spec.heads, N, N, device=x0.device, dtype=torch.float32)
         buf, ws, ws_bytes = _workspace(desc, _lib.WS_SOLVE_FWD, _lib.METHODS[method], x0.device)
+        tape = _alloc_tape(desc, _lib.METHODS[method], T, spec.backward, x0.device) if any(ctx.needs_input_grad) else None
+        tape_p, tape_n = _aligned(tape)
         with torch.cuda.device(x0.device):
             st = _lib.lib().odevit_solve_fwd(ctypes.byref(desc), ctypes.byref(w), _lib.METHODS[method], _ptr(x0),
                                              t_c, T, _ptr(states), _ptr(final), _ptr(p_last), _ptr(p_traj), first,
-                                             ws, ws_bytes, _stream())
+                                             tape_p, tape_n, ws, ws_bytes, _stream())
         _lib.check(st, "odevit_solve_fwd")
+        ctx.tape = tape
         rows = states[list(row_index)] if len(row_index) else x0.new_empty(0)
         ctx.spec, ctx.method, ctx.names, ctx.row_index = spec, method, names, tuple(row_index)
         ctx.t_c, ctx.T = t_c, T
@@ -245,11 +277,14 @@ class _OdeSolve(torch.autograd.Function):
             g_p_last = _require_cuda(g_p_last, "g_p_last")
         g_x0 = torch.empty(B, N, D, device=states.device, dtype=torch.float32)
         buf, ws, ws_bytes = _workspace(desc, _lib.WS_SOLVE_BWD, _lib.METHODS[method], states.device)
+        tape_p, tape_n = _aligned(ctx.tape)
         with torch.cuda.device(states.device):
             st = _lib.lib().odevit_solve_bwd(ctypes.byref(desc), ctypes.byref(w), _lib.METHODS[method], ctx.t_c, T,
                                              _ptr(states), _ptr(g_states), _ptr(g_rows_all), idx_c, len(index),
-                                             _ptr(g_p_last), _ptr(g_x0), ctypes.byref(gw), ws, ws_bytes, _stream())
+                                             _ptr(g_p_last), _ptr(g_x0), ctypes.byref(gw), tape_p, tape_n,
+                                             ws, ws_bytes, _stream())
         _lib.check(st, "odevit_solve_bwd")
+        ctx.tape = None
         return (g_x0 if ctx.needs_input_grad[0] else None, None, None, None, None, None, None, None, *gts)
 
 
@@ -269,3 +304,15 @@ def ode_solve(x0: torch.Tensor, t: torch.Tensor, spec: FieldSpec, method: str,
         *[weights[k] for k in names])
     return {"states": states, "final": final, "rows": rows if len(row_index) else None,
             "p_last": p_last if p_last.numel() else None, "p_traj": p_traj if p_traj.numel() else None}
+
+
+def fd_curvature(states: torch.Tensor, delta_t: float) -> torch.Tensor:
+    """per_seq [B,N] = max over time and features of |s[j+2] - 2 s[j+1] + s[j]| / delta_t^2, one pass
+    over the trajectory (ode_transformer_gpt.py:458-468 + the norms/maxima of :529-543)."""
+    states = _require_cuda(states.detach(), "states")
+    T, B, N, D = states.shape
+    out = torch.empty(B, N, device=states.device, dtype=torch.float32)
+    with torch.cuda.device(states.device):
+        st = _lib.lib().odevit_fd_curvature(_ptr(states), T, B, N, D, float(delta_t), _ptr(out), _stream())
+    _lib.check(st, "odevit_fd_curvature")
+    return out

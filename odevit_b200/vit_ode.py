@@ -111,7 +111,8 @@ class ParallelAttentionMLP(nn.Module):
     def field_spec(self, scaler: float) -> ops.FieldSpec:
         hidden = self.mlp.fc1.weight.shape[0]
         return ops.FieldSpec(dim=self.dim, heads=self.num_heads, hidden=hidden, scaler=float(scaler),
-                             variant=_lib.FIELD_PARALLEL, precision=self.precision)
+                             variant=_lib.FIELD_PARALLEL, precision=self.precision,
+                             backward=getattr(self, "backward_mode", "auto"))
 
     def field_weights(self) -> Dict[str, Optional[torch.Tensor]]:
         """odevit_weights field name -> parameter, read at call time."""
@@ -347,10 +348,12 @@ class ViTNeuralODE(nn.Module):
     def compute_upper_bound_by_fininte_difference(self, x, L, N):
         """:529-543"""
         first = (math.e ** L - 1) / (2 * L * N)
-        curv = torch.norm(self.finite_difference_second_derivative_sequence(x, 1 / N), p=float("inf"), dim=-1)
-        per_seq = curv.max(dim=0)[0]
+        if x.shape[0] < 3:
+            raise RuntimeError("finite-difference bound needs a trajectory of at least 3 states "
+                               "(the reference's max() over an empty tensor fails the same way)")
+        per_seq = ops.fd_curvature(x, 1 / N)           # one pass over [T,B,N,D] (odevit_fd_curvature)
         per_batch = per_seq.max(-1)[0]
-        return dict(global_upper_bound=(first * curv.max()).item(), batched_upper_bound=first * per_batch,
+        return dict(global_upper_bound=(first * per_batch.max()).item(), batched_upper_bound=first * per_batch,
                     batched_upper_bound_per_seq=first * per_seq)
 
     def init_space_predictor(self, outher_embedding_dimension):

@@ -58,7 +58,7 @@ def test_vit_golden_fp32(name):
         assert not out["jasmin_loss"].requires_grad
     for key in ("global_upper_bound", "batched_upper_bound", "batched_upper_bound_per_seq"):
         got = out["finite_difference_upper_bound"][key]
-        assert max_rel(torch.as_tensor(got), want["finite_difference_upper_bound." + key]) < 2e-3, key
+        assert max_rel(torch.as_tensor(got), want["finite_difference_upper_bound." + key]) < 1e-3, key
     obj = _objective(out, g.get("in/attn_w").cuda(), g.meta["ctrl_w"])
     assert float(obj) == pytest.approx(float(want["objective"]), rel=1e-4)
     obj.backward()
@@ -299,3 +299,42 @@ def test_solver_order_on_the_real_field():
     assert 3.0 < e_mid[0] / e_mid[1] < 4.6
     e_rk = [float((final("rk4", n) - ref).abs().max()) for n in (1, 2, 4)]
     assert e_rk[0] / e_rk[1] > 8.0 and e_rk[1] / e_rk[2] > 8.0
+
+
+# ---- tape (stored stage intermediates) vs per-step recomputation ----------------------------
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["c10_rk4_T5_B2", "tiny_midpoint_T5_B2", "c10_euler_T13_B2"])
+def test_tape_matches_recompute(name, precision):
+    """The reverse sweep reading the forward's tape and the one recomputing every step from the
+    trajectory row see the same intermediates: gradients agree to accumulation-order noise."""
+    g = Golden(name)
+    grads = {}
+    for mode in ("recompute", "tape"):
+        model = _build(g, precision)
+        model.odefunc.block.backward_mode = mode
+        px = g.get("in/pixel_values").cuda().requires_grad_(True)
+        out = model(px, labels=g.get("in/labels").cuda(), **g.call)
+        _objective(out, g.get("in/attn_w").cuda(), g.meta["ctrl_w"]).backward()
+        grads[mode] = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+        grads[mode]["pixel_values"] = px.grad.clone()
+    assert grads["tape"].keys() == grads["recompute"].keys()
+    # bf16: evaluations whose P is exported normalise before the bf16 rounding of P, the recomputation
+    # (no export) after it -- O differs by bf16 rounding between the two modes
+    tol = 2e-5 if precision == "fp32" else 1e-2
+    for k in grads["tape"]:
+        assert max_rel(grads["tape"][k], grads["recompute"][k]) < tol, k
+
+
+@pytest.mark.parametrize("T,B,N,D", [(3, 2, 5, 64), (4, 1, 69, 192), (7, 3, 17, 768), (24, 2, 207, 768),
+                                     (5, 2, 3, 1024), (6, 2, 9, 132)])
+def test_fd_curvature_matches_reference_formula(T, B, N, D):
+    """odevit_fd_curvature against the tensor arithmetic of ode_transformer_gpt.py:458-468, :529-543."""
+    from odevit_b200 import ops
+    s = torch.randn(T, B, N, D, generator=torch.Generator().manual_seed(T * 100 + D)).cumsum(0)
+    dt = float(T)
+    second = (s[2:] - 2 * s[1:-1] + s[:-2]) / (dt ** 2)
+    want = torch.norm(second, p=float("inf"), dim=-1).max(dim=0)[0]
+    got = ops.fd_curvature(s.cuda(), dt)
+    assert got.shape == (B, N)
+    assert max_rel(got, want) < 1e-6
