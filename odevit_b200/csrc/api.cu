@@ -19,6 +19,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "host.h"
 #include "internal.h"
 
 #define ODEVIT_STR2(x) #x
@@ -104,15 +105,8 @@ const Tableau* tableau_for(int method) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// plan + workspace arena
+// plan + workspace arena (structs in host.h)
 // ------------------------------------------------------------------------------------------------
-struct Plan {
-  int B, N, D, H, hid, d, M;
-  int variant, precision, act;  // act = DType of activation buffers
-  float scaler;
-  long long BHNN;
-};
-
 int make_plan(const odevit_desc* desc, Plan* p) {
   if (!desc) return set_error(ODEVIT_ERR_INVALID_ARG, "desc is NULL");
   if (desc->abi_version != ODEVIT_ABI_VERSION)
@@ -127,36 +121,17 @@ int make_plan(const odevit_desc* desc, Plan* p) {
     return set_error(ODEVIT_ERR_UNSUPPORTED, "dim %d / tokens %d above 1024", p->D, p->N);
   if (p->precision != ODEVIT_FP32 && p->precision != ODEVIT_BF16)
     return set_error(ODEVIT_ERR_INVALID_ARG, "unknown precision %d", p->precision);
-  if (p->variant != ODEVIT_FIELD_PARALLEL)
-    return set_error(ODEVIT_ERR_UNSUPPORTED, "variant %d not built yet", p->variant);
+  if (p->variant != ODEVIT_FIELD_PARALLEL && p->variant != ODEVIT_FIELD_PARALLEL_L2 &&
+      p->variant != ODEVIT_FIELD_MACARON)
+    return set_error(ODEVIT_ERR_INVALID_ARG, "unknown variant %d", p->variant);
   p->d = p->D / p->H;
   p->M = p->B * p->N;
   p->act = (p->precision == ODEVIT_BF16) ? DT_BF16 : DT_F32;
+  // MACARON: the cotangent runs along the fp32 residual chain x -> x1 -> x2 -> x3
+  p->dd_type = (p->variant == ODEVIT_FIELD_MACARON) ? DT_F32 : p->act;
   p->BHNN = (long long)p->B * p->H * p->N * p->N;
   return 0;
 }
-
-struct Arena {
-  char* base;
-  size_t off = 0;
-  explicit Arena(void* b) : base(reinterpret_cast<char*>(b)) {}
-  void* take(size_t bytes) {
-    off = (off + 1023) & ~size_t(1023);
-    void* p = base ? base + off : nullptr;
-    off += bytes;
-    return p;
-  }
-  float* f32(size_t n) { return reinterpret_cast<float*>(take(n * 4)); }
-};
-
-struct WeightBufs {
-  void *w1cat, *w1catT, *w2cat, *w2catT;
-  float *b1cat, *b2;
-};
-struct StageCtx {
-  void *xc, *qkv, *oh, *hpre;
-  float* lse;  // [B,H,N] log2-domain row log-sum-exp of the attention (reverse sweep only)
-};
 
 WeightBufs take_weights(const Plan& p, Arena& a) {
   const size_t e = dtype_size(p.act);
@@ -168,16 +143,29 @@ WeightBufs take_weights(const Plan& p, Arena& a) {
   w.w2catT = a.take(K2 * p.D * e);
   w.b1cat = a.f32(R);
   w.b2 = a.f32(p.D);
+  w.user = nullptr;
   return w;
 }
 StageCtx take_ctx(const Plan& p, Arena& a, bool with_hpre) {
   const size_t e = dtype_size(p.act);
-  StageCtx c;
-  c.xc = a.take((size_t)p.M * p.D * e);
-  c.qkv = a.take((size_t)p.M * 3 * p.D * e);
-  c.oh = a.take((size_t)p.M * (p.D + p.hid) * e);
-  c.hpre = with_hpre ? a.take((size_t)p.M * p.hid * e) : nullptr;
+  const size_t MD = (size_t)p.M * p.D, Mh = (size_t)p.M * p.hid;
+  const bool mac = (p.variant == ODEVIT_FIELD_MACARON);
+  if (mac) with_hpre = true;  // the chain x -> x1 -> x2 is written either way; keep one layout
+  StageCtx c{};
+  c.xc = a.take(MD * e);
+  c.qkv = a.take(3 * MD * e);
+  c.oh = a.take((MD + Mh) * e);
+  c.hpre = with_hpre ? a.take(Mh * e) : nullptr;
   c.lse = with_hpre ? a.f32((size_t)p.B * p.H * p.N) : nullptr;
+  if (mac) {
+    c.x0 = a.f32(MD);
+    c.x1 = a.f32(MD);
+    c.x2 = a.f32(MD);
+    c.n2 = a.take(MD * e);
+    c.n3 = a.take(MD * e);
+    c.hpre3 = a.take(Mh * e);
+    c.h3 = a.take(Mh * e);
+  }
   return c;
 }
 
@@ -188,6 +176,7 @@ struct FwdBufs {
   float* u;
   float* k[3];
   float* ytmp[2];
+  float* sq;
 };
 FwdBufs layout_fwd(const Plan& p, Arena& a, int S) {
   FwdBufs f;
@@ -198,34 +187,22 @@ FwdBufs layout_fwd(const Plan& p, Arena& a, int S) {
   for (int i = 0; i < 3; ++i) f.k[i] = (i < S - 1) ? a.f32((size_t)p.M * p.D) : nullptr;
   f.ytmp[0] = a.f32((size_t)p.M * p.D);
   f.ytmp[1] = a.f32((size_t)p.M * p.D);
+  f.sq = (p.variant == ODEVIT_FIELD_PARALLEL_L2) ? a.f32((size_t)2 * p.B * p.H * p.N) : nullptr;
   return f;
 }
 
-struct BwdBufs {
-  WeightBufs w;
-  StageCtx ctx[4];
-  float *P, *dP;
-  float* u;
-  float* k[3];
-  void *dd, *dO, *dz;
-  float* mu[4];
-  float* gy;
-  float *delta, *dq_scratch;
-  float *G1, *c1, *G2, *c2;
-  size_t acc_bytes;  // G1..c2 are contiguous: one memset
-};
 BwdBufs layout_bwd(const Plan& p, Arena& a, int S) {
   const size_t e = dtype_size(p.act);
   const size_t MD = (size_t)p.M * p.D;
   const size_t R = 3 * (size_t)p.D + p.hid, K2 = (size_t)p.D + p.hid;
   BwdBufs b;
   b.w = take_weights(p, a);
-  for (int i = 0; i < 4; ++i) b.ctx[i] = (i < S) ? take_ctx(p, a, true) : StageCtx{nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int i = 0; i < 4; ++i) b.ctx[i] = (i < S) ? take_ctx(p, a, true) : StageCtx{};
   b.P = a.f32(p.BHNN);
   b.dP = a.f32(p.BHNN);
   b.u = a.f32(MD);
   for (int i = 0; i < 3; ++i) b.k[i] = (i < S - 1) ? a.f32(MD) : nullptr;
-  b.dd = a.take(MD * e);
+  b.dd = a.take(MD * dtype_size(p.dd_type));
   b.dO = a.take(MD * e);
   b.dz = a.take((size_t)p.M * R * e);
   for (int i = 0; i < 4; ++i) b.mu[i] = (i >= 1 && i < S) ? a.f32(MD) : nullptr;
@@ -236,13 +213,18 @@ BwdBufs layout_bwd(const Plan& p, Arena& a, int S) {
     b.dq_scratch = n ? a.f32(n) : nullptr;
   }
   // accumulators, contiguous (sizes are multiples of 4 bytes; keep them packed for one memset)
-  const size_t acc_floats = R * p.D + R + K2 * p.D + p.D;
+  const size_t acc_floats = R * p.D + R + K2 * p.D + 2 * (size_t)p.D;
   float* acc = a.f32(acc_floats);
   b.G1 = acc;
   b.c1 = acc ? acc + R * p.D : nullptr;
   b.G2 = acc ? acc + R * p.D + R : nullptr;
   b.c2 = acc ? acc + R * p.D + R + K2 * p.D : nullptr;
+  b.c3 = acc ? b.c2 + p.D : nullptr;
   b.acc_bytes = acc_floats * 4;
+  const bool mac = (p.variant == ODEVIT_FIELD_MACARON);
+  b.dn = mac ? a.f32(MD) : nullptr;
+  b.ddc = mac ? a.take(MD * e) : nullptr;
+  b.sq = (p.variant == ODEVIT_FIELD_PARALLEL_L2) ? a.f32((size_t)2 * p.B * p.H * p.N) : nullptr;
   return b;
 }
 
@@ -254,7 +236,7 @@ StageCtx tape_ctx(const Plan& p, void* tape, long long e, size_t* total_bytes, l
   take_ctx(p, a0, true);
   const size_t per = (a0.off + 1023) & ~size_t(1023);
   if (total_bytes) *total_bytes = per * (size_t)n_evals;
-  if (!tape) return StageCtx{nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (!tape) return StageCtx{};
   Arena a(reinterpret_cast<char*>(tape) + per * (size_t)e);
   return take_ctx(p, a, true);
 }
@@ -290,24 +272,29 @@ int check_weights(const Plan& p, const odevit_weights* w) {
   if (!w) return set_error(ODEVIT_ERR_INVALID_ARG, "weights is NULL");
   if (!w->norm_a_w || !w->norm_a_b || !w->norm_b_w || !w->norm_b_b || !w->in_proj_w || !w->out_proj_w ||
       !w->fc1_w || !w->fc2_w)
-    return set_error(ODEVIT_ERR_INVALID_ARG, "PARALLEL variant needs norm_a/norm_b/in_proj/out_proj/fc1/fc2 weights");
-  (void)p;
+    return set_error(ODEVIT_ERR_INVALID_ARG, "the field needs norm_a/norm_b/in_proj/out_proj/fc1/fc2 weights");
+  if (p.variant == ODEVIT_FIELD_PARALLEL_L2 && (!w->in_proj_b || !w->out_proj_b))
+    return set_error(ODEVIT_ERR_INVALID_ARG, "PARALLEL_L2 needs in_proj_b ([bq;bk;bv]) and out_proj_b");
+  if (p.variant == ODEVIT_FIELD_MACARON &&
+      (!w->norm_c_w || !w->norm_c_b || !w->in_proj_b || !w->out_proj_b || !w->fc1_b || !w->fc2_b || !w->res_scale))
+    return set_error(ODEVIT_ERR_INVALID_ARG, "MACARON needs norm_c, all four biases and res_scale");
   return check_device_ptr(w->in_proj_w, "weights.in_proj_w");
 }
 
-// ------------------------------------------------------------------------------------------------
-// GEMM dispatch: tcgen05 in bf16 mode where the kernel covers the shape, FFMA otherwise
-// ------------------------------------------------------------------------------------------------
-int gemm(const Plan& p, const GemmArgs& g, cudaStream_t s) {
-  if (p.precision == ODEVIT_BF16 && gemm_tc_supports(g)) return gemm_tc(g, s);
-  return gemm_simt(g, s);
+float q_scale_of(const Plan& p) {
+  // nn.MultiheadAttention scales q by 1/sqrt(d) (folded into the Wq rows); L2SelfAttention applies its
+  // scale to the squared distance instead (ode_transformer_gpt.py:24, :54)
+  return (p.variant == ODEVIT_FIELD_PARALLEL_L2) ? 1.f : 1.f / sqrtf((float)p.d);
 }
 
-int prepare_weights(const Plan& p, const odevit_weights* w, const WeightBufs& wb, cudaStream_t s) {
+int prepare_weights(const Plan& p, const odevit_weights* w, WeightBufs& wb, cudaStream_t s) {
   FoldArgs f;
   f.D = p.D; f.hid = p.hid; f.heads = p.H; f.w = w;
+  f.q_scale = q_scale_of(p);
+  f.fold_norm = (p.variant != ODEVIT_FIELD_MACARON);
   f.w1cat = wb.w1cat; f.w1catT = wb.w1catT; f.w_type = p.act;
   f.b1cat = wb.b1cat; f.w2cat = wb.w2cat; f.w2catT = wb.w2catT; f.b2 = wb.b2;
+  wb.user = w;
   return fold_weights_parallel(f, s);
 }
 
@@ -317,9 +304,148 @@ struct HeadView {
 };
 HeadView qkv_view(const Plan& p) { return {(long long)p.N * 3 * p.D, (long long)p.d, (long long)3 * p.D}; }
 
-// Forward evaluation at stage input `u`.  `rk` (nullable) is the epilogue of GEMM2.
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// GEMM dispatch: tcgen05 in bf16 mode where the kernel covers the shape, FFMA otherwise
+// ------------------------------------------------------------------------------------------------
+int gemm(const Plan& p, const GemmArgs& g, cudaStream_t s) {
+  if (p.precision == ODEVIT_BF16 && gemm_tc_supports(g)) return gemm_tc(g, s);
+  return gemm_simt(g, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention per (image, head): fused tcgen05 kernels in bf16 mode (head dim 64, N <= 256), else
+// batched FFMA products + row kernels.  PARALLEL_L2 swaps the softmax for the L2 weights (:48-56).
+// ------------------------------------------------------------------------------------------------
+int attention_forward(const Plan& p, const void* qkv_v, void* oh, long long ld_oh, float* P, float* p_copy,
+                      float* lse, float* sq, cudaStream_t s) {
+  const int D = p.D;
+  const bool l2 = (p.variant == ODEVIT_FIELD_PARALLEL_L2);
+  if (!l2 && p.precision == ODEVIT_BF16 && attn_fwd_tc_supports(p.N, D, p.H, p.act, ld_oh))
+    return attn_fwd_tc(qkv_v, oh, ld_oh, p_copy, lse, p.B, p.N, p.H, D, s);
+  const HeadView hv = qkv_view(p);
+  const char* qkv = reinterpret_cast<const char*>(qkv_v);
+  const size_t e = dtype_size(p.act);
+  {  // S = q k^T  (MHA: the 1/sqrt(d) is folded into the Wq rows)
+    GemmArgs g;
+    g.M = p.N; g.N = p.N; g.K = p.d;
+    g.A = qkv; g.a_type = p.act; g.a_rs = hv.rs; g.a_cs = 1; g.a_bo = hv.bo; g.a_bi = hv.bi;
+    g.B = qkv + (size_t)D * e; g.b_type = p.act; g.b_rs = hv.rs; g.b_cs = 1; g.b_bo = hv.bo; g.b_bi = hv.bi;
+    g.batch_outer = p.B; g.batch_inner = p.H;
+    g.epi_mode = EPI_STORE;
+    g.epi.out = P; g.epi.out_type = DT_F32; g.epi.ld_out = p.N;
+    g.epi.out_bo = (long long)p.H * p.N * p.N; g.epi.out_bi = (long long)p.N * p.N;
+    g.kclass = KC_ATTN_S;
+    ODV_TRY(gemm_simt(g, s));
+  }
+  if (l2) {
+    if (!sq) return set_error(ODEVIT_ERR_WORKSPACE, "L2 attention: squared-norm scratch missing");
+    ODV_TRY(head_sqnorm(qkv_v, p.act, sq, p.B, p.N, p.H, D, s));
+    ODV_TRY(l2_prob_rows(P, sq, 1.f / sqrtf((float)p.d), p_copy, p.B, p.H, p.N, s));
+  } else {
+    ODV_TRY(softmax_rows(P, p_copy, (long long)p.B * p.H * p.N, p.N, s));
+  }
+  {  // O = P v  -> columns [h*d, (h+1)*d) of the output buffer
+    GemmArgs g;
+    g.M = p.N; g.N = p.d; g.K = p.N;
+    g.A = P; g.a_type = DT_F32; g.a_rs = p.N; g.a_cs = 1;
+    g.a_bo = (long long)p.H * p.N * p.N; g.a_bi = (long long)p.N * p.N;
+    g.B = qkv + (size_t)2 * D * e; g.b_type = p.act; g.b_rs = 1; g.b_cs = hv.rs; g.b_bo = hv.bo; g.b_bi = hv.bi;
+    g.batch_outer = p.B; g.batch_inner = p.H;
+    g.epi_mode = EPI_STORE;
+    g.epi.out = oh; g.epi.out_type = p.act; g.epi.ld_out = ld_oh;
+    g.epi.out_bo = (long long)p.N * ld_oh; g.epi.out_bi = p.d;
+    g.kclass = KC_ATTN_PV;
+    ODV_TRY(gemm_simt(g, s));
+  }
+  return 0;
+}
+
+int attention_vjp(const Plan& p, const void* qkv_v, const void* oh, long long ld_oh, const float* lse, BwdBufs& b,
+                  const float* g_p, void* dz_v, int R, cudaStream_t s) {
+  const int D = p.D;
+  const bool l2 = (p.variant == ODEVIT_FIELD_PARALLEL_L2);
+  const size_t e = dtype_size(p.act);
+  char* dz = reinterpret_cast<char*>(dz_v);
+  if (!l2 && p.precision == ODEVIT_BF16 && !g_p && lse && attn_fwd_tc_supports(p.N, D, p.H, p.act, ld_oh)) {
+    // fused tcgen05 kernel (P recomputed on chip from q, k and the saved row log-sum-exp)
+    return attn_bwd_tc(qkv_v, b.dO, oh, ld_oh, lse, b.delta, dz_v, R, b.dq_scratch, p.B, p.N, p.H, D, s);
+  }
+  const HeadView hv = qkv_view(p);
+  const char* qkv = reinterpret_cast<const char*>(qkv_v);
+  const long long pbo = (long long)p.H * p.N * p.N, pbi = (long long)p.N * p.N;
+  auto head_gemm = [&](GemmArgs& g) {
+    g.batch_outer = p.B; g.batch_inner = p.H;
+    g.kclass = KC_BWD_ATTN;
+    return gemm_simt(g, s);
+  };
+  {  // S
+    GemmArgs g;
+    g.M = p.N; g.N = p.N; g.K = p.d;
+    g.A = qkv; g.a_type = p.act; g.a_rs = hv.rs; g.a_cs = 1; g.a_bo = hv.bo; g.a_bi = hv.bi;
+    g.B = qkv + (size_t)D * e; g.b_type = p.act; g.b_rs = hv.rs; g.b_cs = 1; g.b_bo = hv.bo; g.b_bi = hv.bi;
+    g.epi.out = b.P; g.epi.ld_out = p.N; g.epi.out_bo = pbo; g.epi.out_bi = pbi;
+    ODV_TRY(head_gemm(g));
+  }
+  float ds_coef = 1.f;  // d(q k^T) = ds_coef * ds
+  if (l2) {
+    if (!b.sq) return set_error(ODEVIT_ERR_WORKSPACE, "L2 attention: squared-norm scratch missing");
+    ODV_TRY(head_sqnorm(qkv_v, p.act, b.sq, p.B, p.N, p.H, D, s));
+    ODV_TRY(l2_prob_rows(b.P, b.sq, 1.f / sqrtf((float)p.d), nullptr, p.B, p.H, p.N, s));
+    ds_coef = 2.f / sqrtf((float)p.d);
+  } else {
+    ODV_TRY(softmax_rows(b.P, nullptr, (long long)p.B * p.H * p.N, p.N, s));
+  }
+  {  // dP = dO v^T
+    GemmArgs g;
+    g.M = p.N; g.N = p.N; g.K = p.d;
+    g.A = b.dO; g.a_type = p.act; g.a_rs = D; g.a_cs = 1; g.a_bo = (long long)p.N * D; g.a_bi = p.d;
+    g.B = qkv + (size_t)2 * D * e; g.b_type = p.act; g.b_rs = hv.rs; g.b_cs = 1; g.b_bo = hv.bo; g.b_bi = hv.bi;
+    g.epi.out = b.dP; g.epi.ld_out = p.N; g.epi.out_bo = pbo; g.epi.out_bi = pbi;
+    ODV_TRY(head_gemm(g));
+  }
+  // ds = P o (dP - sum_j P dP): also the L2 weights' VJP w.r.t. -scale*dist^2 (the +1e-8 drops out)
+  ODV_TRY(softmax_bwd_rows(b.P, b.dP, g_p, (long long)p.B * p.H * p.N, p.N, s));
+  {  // dq = ds k      (MHA: dq is the cotangent of the already-scaled q, the scale lives in W1cat)
+    GemmArgs g;
+    g.M = p.N; g.N = p.d; g.K = p.N;
+    g.A = b.dP; g.a_type = DT_F32; g.a_rs = p.N; g.a_cs = 1; g.a_bo = pbo; g.a_bi = pbi;
+    g.B = qkv + (size_t)D * e; g.b_type = p.act; g.b_rs = 1; g.b_cs = hv.rs; g.b_bo = hv.bo; g.b_bi = hv.bi;
+    g.epi.alpha = ds_coef;
+    g.epi.out = dz; g.epi.out_type = p.act; g.epi.ld_out = R; g.epi.out_bo = (long long)p.N * R; g.epi.out_bi = p.d;
+    ODV_TRY(head_gemm(g));
+  }
+  {  // dk = ds^T q
+    GemmArgs g;
+    g.M = p.N; g.N = p.d; g.K = p.N;
+    g.A = b.dP; g.a_type = DT_F32; g.a_rs = 1; g.a_cs = p.N; g.a_bo = pbo; g.a_bi = pbi;
+    g.B = qkv; g.b_type = p.act; g.b_rs = 1; g.b_cs = hv.rs; g.b_bo = hv.bo; g.b_bi = hv.bi;
+    g.epi.alpha = ds_coef;
+    g.epi.out = dz + (size_t)D * e; g.epi.out_type = p.act; g.epi.ld_out = R;
+    g.epi.out_bo = (long long)p.N * R; g.epi.out_bi = p.d;
+    ODV_TRY(head_gemm(g));
+  }
+  {  // dv = P^T dO
+    GemmArgs g;
+    g.M = p.N; g.N = p.d; g.K = p.N;
+    g.A = b.P; g.a_type = DT_F32; g.a_rs = 1; g.a_cs = p.N; g.a_bo = pbo; g.a_bi = pbi;
+    g.B = b.dO; g.b_type = p.act; g.b_rs = 1; g.b_cs = D; g.b_bo = (long long)p.N * D; g.b_bi = p.d;
+    g.epi.out = dz + (size_t)2 * D * e; g.epi.out_type = p.act; g.epi.ld_out = R;
+    g.epi.out_bo = (long long)p.N * R; g.epi.out_bi = p.d;
+    ODV_TRY(head_gemm(g));
+  }
+  // L2: dist^2 = |q|^2 + |k|^2 - 2 q.k -- the squared-norm terms add -ds_coef*rowsum(ds) q, -ds_coef*colsum(ds) k
+  if (l2) ODV_TRY(l2_vjp_fix(b.dP, qkv_v, p.act, dz_v, R, ds_coef, p.B, p.N, p.H, D, s));
+  return 0;
+}
+
+namespace {
+
+// Forward evaluation at stage input `u`.  `rk` (nullable) is the epilogue of the last GEMM.
 int eval_forward(const Plan& p, const WeightBufs& wb, const StageCtx& c, const float* u, float* P,
-                 float* p_copy, const Epi* rk, cudaStream_t s) {
+                 float* p_copy, float* sq, const Epi* rk, cudaStream_t s) {
+  if (p.variant == ODEVIT_FIELD_MACARON) return macaron_forward(p, wb, c, u, P, rk, s);
   const int D = p.D, hid = p.hid, R = 3 * D + hid, K2 = D + hid;
   ODV_TRY(center_rows(u, c.xc, p.act, nullptr, 0.f, p.M, D, s));
   {
@@ -337,39 +463,7 @@ int eval_forward(const Plan& p, const WeightBufs& wb, const StageCtx& c, const f
     g.epi.aux_type = p.act;
     ODV_TRY(gemm(p, g, s));
   }
-  if (p.precision == ODEVIT_BF16 && attn_fwd_tc_supports(p.N, D, p.H, p.act, K2)) {
-    ODV_TRY(attn_fwd_tc(c.qkv, c.oh, K2, p_copy, c.lse, p.B, p.N, p.H, D, s));
-  } else {
-    const HeadView hv = qkv_view(p);
-    const char* qkv = reinterpret_cast<const char*>(c.qkv);
-    const size_t e = dtype_size(p.act);
-    {  // S = q k^T  (the 1/sqrt(d) is folded into the Wq rows)
-      GemmArgs g;
-      g.M = p.N; g.N = p.N; g.K = p.d;
-      g.A = qkv; g.a_type = p.act; g.a_rs = hv.rs; g.a_cs = 1; g.a_bo = hv.bo; g.a_bi = hv.bi;
-      g.B = qkv + (size_t)D * e; g.b_type = p.act; g.b_rs = hv.rs; g.b_cs = 1; g.b_bo = hv.bo; g.b_bi = hv.bi;
-      g.batch_outer = p.B; g.batch_inner = p.H;
-      g.epi_mode = EPI_STORE;
-      g.epi.out = P; g.epi.out_type = DT_F32; g.epi.ld_out = p.N;
-      g.epi.out_bo = (long long)p.H * p.N * p.N; g.epi.out_bi = (long long)p.N * p.N;
-      g.kclass = KC_ATTN_S;
-      ODV_TRY(gemm_simt(g, s));
-    }
-    ODV_TRY(softmax_rows(P, p_copy, (long long)p.B * p.H * p.N, p.N, s));
-    {  // O = P v  -> columns [h*d, (h+1)*d) of the [O|h] buffer
-      GemmArgs g;
-      g.M = p.N; g.N = p.d; g.K = p.N;
-      g.A = P; g.a_type = DT_F32; g.a_rs = p.N; g.a_cs = 1;
-      g.a_bo = (long long)p.H * p.N * p.N; g.a_bi = (long long)p.N * p.N;
-      g.B = qkv + (size_t)2 * D * e; g.b_type = p.act; g.b_rs = 1; g.b_cs = hv.rs; g.b_bo = hv.bo; g.b_bi = hv.bi;
-      g.batch_outer = p.B; g.batch_inner = p.H;
-      g.epi_mode = EPI_STORE;
-      g.epi.out = c.oh; g.epi.out_type = p.act; g.epi.ld_out = K2;
-      g.epi.out_bo = (long long)p.N * K2; g.epi.out_bi = p.d;
-      g.kclass = KC_ATTN_PV;
-      ODV_TRY(gemm_simt(g, s));
-    }
-  }
+  ODV_TRY(attention_forward(p, c.qkv, c.oh, K2, P, p_copy, c.lse, sq, s));
   if (rk) {
     GemmArgs g;
     g.M = p.M; g.N = D; g.K = K2;
@@ -409,7 +503,11 @@ Epi rk_epilogue(const Tableau& tb, int st, float dt, const float* y, float* cons
 // (W1cat^T is stored row-centred, so the GEMM yields the centred value directly; the reverse-mode
 // stage combination rides in that epilogue instead of a separate pass over [M, D]).
 int eval_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b, const float* g_p,
-             bool need_c2, const Epi& mu_epi, cudaStream_t s) {
+             bool need_c2, const odevit_weight_grads* gw, const Epi& mu_epi, cudaStream_t s) {
+  if (p.variant == ODEVIT_FIELD_MACARON) {
+    if (g_p) return set_error(ODEVIT_ERR_UNSUPPORTED, "MACARON has no attention-map output (macaron.py:60-65)");
+    return macaron_vjp(p, wb, c, b, gw, mu_epi, s);
+  }
   const int D = p.D, hid = p.hid, R = 3 * D + hid, K2 = D + hid;
   const size_t e = dtype_size(p.act);
   char* dz = reinterpret_cast<char*>(b.dz);
@@ -439,63 +537,7 @@ int eval_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b,
   if (need_c2) ODV_TRY(colsum_accum(b.dd, p.act, D, p.M, D, b.c2, s));
 
   // ---- attention VJP per (image, head) ----------------------------------------------------------
-  if (p.precision == ODEVIT_BF16 && !g_p && c.lse && attn_fwd_tc_supports(p.N, D, p.H, p.act, K2)) {
-    // fused tcgen05 kernel (P recomputed on chip from q, k and the saved row log-sum-exp)
-    ODV_TRY(attn_bwd_tc(c.qkv, b.dO, c.oh, K2, c.lse, b.delta, b.dz, R, b.dq_scratch, p.B, p.N, p.H, D, s));
-  } else {
-    const HeadView hv = qkv_view(p);
-    const char* qkv = reinterpret_cast<const char*>(c.qkv);
-    const long long pbo = (long long)p.H * p.N * p.N, pbi = (long long)p.N * p.N;
-    auto head_gemm = [&](GemmArgs& g) {
-      g.batch_outer = p.B; g.batch_inner = p.H;
-      g.kclass = KC_BWD_ATTN;
-      return gemm_simt(g, s);
-    };
-    {  // S
-      GemmArgs g;
-      g.M = p.N; g.N = p.N; g.K = p.d;
-      g.A = qkv; g.a_type = p.act; g.a_rs = hv.rs; g.a_cs = 1; g.a_bo = hv.bo; g.a_bi = hv.bi;
-      g.B = qkv + (size_t)D * e; g.b_type = p.act; g.b_rs = hv.rs; g.b_cs = 1; g.b_bo = hv.bo; g.b_bi = hv.bi;
-      g.epi.out = b.P; g.epi.ld_out = p.N; g.epi.out_bo = pbo; g.epi.out_bi = pbi;
-      ODV_TRY(head_gemm(g));
-    }
-    ODV_TRY(softmax_rows(b.P, nullptr, (long long)p.B * p.H * p.N, p.N, s));
-    {  // dP = dO v^T
-      GemmArgs g;
-      g.M = p.N; g.N = p.N; g.K = p.d;
-      g.A = b.dO; g.a_type = p.act; g.a_rs = D; g.a_cs = 1; g.a_bo = (long long)p.N * D; g.a_bi = p.d;
-      g.B = qkv + (size_t)2 * D * e; g.b_type = p.act; g.b_rs = hv.rs; g.b_cs = 1; g.b_bo = hv.bo; g.b_bi = hv.bi;
-      g.epi.out = b.dP; g.epi.ld_out = p.N; g.epi.out_bo = pbo; g.epi.out_bi = pbi;
-      ODV_TRY(head_gemm(g));
-    }
-    ODV_TRY(softmax_bwd_rows(b.P, b.dP, g_p, (long long)p.B * p.H * p.N, p.N, s));
-    {  // dq = dS k      (dq is the cotangent of the already-scaled q: the scale lives in W1cat)
-      GemmArgs g;
-      g.M = p.N; g.N = p.d; g.K = p.N;
-      g.A = b.dP; g.a_type = DT_F32; g.a_rs = p.N; g.a_cs = 1; g.a_bo = pbo; g.a_bi = pbi;
-      g.B = qkv + (size_t)D * e; g.b_type = p.act; g.b_rs = 1; g.b_cs = hv.rs; g.b_bo = hv.bo; g.b_bi = hv.bi;
-      g.epi.out = dz; g.epi.out_type = p.act; g.epi.ld_out = R; g.epi.out_bo = (long long)p.N * R; g.epi.out_bi = p.d;
-      ODV_TRY(head_gemm(g));
-    }
-    {  // dk = dS^T q
-      GemmArgs g;
-      g.M = p.N; g.N = p.d; g.K = p.N;
-      g.A = b.dP; g.a_type = DT_F32; g.a_rs = 1; g.a_cs = p.N; g.a_bo = pbo; g.a_bi = pbi;
-      g.B = qkv; g.b_type = p.act; g.b_rs = 1; g.b_cs = hv.rs; g.b_bo = hv.bo; g.b_bi = hv.bi;
-      g.epi.out = dz + (size_t)D * e; g.epi.out_type = p.act; g.epi.ld_out = R;
-      g.epi.out_bo = (long long)p.N * R; g.epi.out_bi = p.d;
-      ODV_TRY(head_gemm(g));
-    }
-    {  // dv = P^T dO
-      GemmArgs g;
-      g.M = p.N; g.N = p.d; g.K = p.N;
-      g.A = b.P; g.a_type = DT_F32; g.a_rs = 1; g.a_cs = p.N; g.a_bo = pbo; g.a_bi = pbi;
-      g.B = b.dO; g.b_type = p.act; g.b_rs = 1; g.b_cs = D; g.b_bo = (long long)p.N * D; g.b_bi = p.d;
-      g.epi.out = dz + (size_t)2 * D * e; g.epi.out_type = p.act; g.epi.ld_out = R;
-      g.epi.out_bo = (long long)p.N * R; g.epi.out_bi = p.d;
-      ODV_TRY(head_gemm(g));
-    }
-  }
+  ODV_TRY(attention_vjp(p, c.qkv, c.oh, K2, c.lse, b, g_p, b.dz, R, s));
   {  // mu = dz @ centred(W1cat), consumed by the caller's stage-combine epilogue
     GemmArgs g;
     g.M = p.M; g.N = D; g.K = R;
@@ -506,7 +548,7 @@ int eval_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b,
     g.epi.alpha = 1.f;
     g.epi.bias = nullptr;
     g.epi.ld_out = D;
-    g.epi.aux_type = p.act;
+    g.epi.aux_type = p.dd_type;
     g.kclass = KC_BWD_GEMM_DX;
     ODV_TRY(gemm(p, g, s));
   }
@@ -529,6 +571,11 @@ int finish_grads(const Plan& p, const odevit_weights* w, const odevit_weight_gra
   UnfoldArgs u;
   u.D = p.D; u.hid = p.hid; u.heads = p.H; u.w = w; u.gw = gw;
   u.G1 = b.G1; u.c1 = b.c1; u.G2 = b.G2; u.c2 = b.c2;
+  u.q_scale = q_scale_of(p);
+  if (p.variant == ODEVIT_FIELD_MACARON) {
+    u.c3 = b.c3;
+    return unfold_grads_macaron(u, s);
+  }
   return unfold_grads_parallel(u, s);
 }
 
@@ -644,6 +691,8 @@ int odevit_field_fwd(const odevit_desc* desc, const odevit_weights* w, const flo
   ODV_TRY(check_device_ptr(x, "x"));
   ODV_TRY(check_device_ptr(dx, "dx"));
   if (x == dx) return set_error(ODEVIT_ERR_INVALID_ARG, "x and dx may not alias");
+  if (p.variant == ODEVIT_FIELD_MACARON && p_out)
+    return set_error(ODEVIT_ERR_INVALID_ARG, "MACARON exposes no attention map (need_weights=False, macaron.py:60-65)");
   Arena a(workspace);
   FwdBufs f = layout_fwd(p, a, 1);
   ODV_TRY(check_ws(workspace, workspace_bytes, a.off));
@@ -653,7 +702,7 @@ int odevit_field_fwd(const odevit_desc* desc, const odevit_weights* w, const flo
   rk.out = dx;
   rk.y = nullptr;
   rk.c_new = 1.f;
-  return eval_forward(p, f.w, f.ctx, x, f.P, p_out, &rk, s);
+  return eval_forward(p, f.w, f.ctx, x, f.P, p_out, f.sq, &rk, s);
 }
 
 int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t method, const float* x0,
@@ -673,6 +722,8 @@ int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
     ODV_TRY(check_ws(tape, tape_bytes, need));
   }
   if (!states && !final_state) return set_error(ODEVIT_ERR_INVALID_ARG, "states and final_state both NULL");
+  if (p.variant == ODEVIT_FIELD_MACARON && (p_last || p_traj))
+    return set_error(ODEVIT_ERR_INVALID_ARG, "MACARON exposes no attention map (need_weights=False, macaron.py:60-65)");
   ODV_TRY(check_device_ptr(x0, "x0"));
   if (states) ODV_TRY(check_device_ptr(states, "states"));
   for (int j = 0; j + 2 < n_grid; ++j) {
@@ -708,7 +759,7 @@ int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
       if (p_traj && e >= p_traj_first_eval) p_copy = p_traj + (size_t)(e - p_traj_first_eval) * p.BHNN;
       else if (p_last && e == n_evals - 1) p_copy = p_last;
       const StageCtx ctx = tape ? tape_ctx(p, tape, e, nullptr, n_evals) : f.ctx;
-      ODV_TRY(eval_forward(p, f.w, ctx, u, f.P, p_copy, &rk, s));
+      ODV_TRY(eval_forward(p, f.w, ctx, u, f.P, p_copy, f.sq, &rk, s));
       if (p_last && e == n_evals - 1 && p_copy != p_last)
         ODV_CUDA(cudaMemcpyAsync(p_last, p_copy, (size_t)p.BHNN * 4, cudaMemcpyDeviceToDevice, s));
     }
@@ -773,7 +824,7 @@ int odevit_solve_bwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
   auto seed_dd = [&](float dt) -> int {
     CombineArgs c0;
     c0.n_terms = 1; c0.term[0] = b.gy; c0.coef[0] = dt * tb->b[S - 1];
-    c0.out_dd = b.dd; c0.dd_type = p.act; c0.dd_scale = p.scaler;
+    c0.out_dd = b.dd; c0.dd_type = p.dd_type; c0.dd_scale = p.scaler;
     return vjp_combine(c0, p.M, p.D, s);
   };
   ODV_CUDA(cudaMemsetAsync(b.gy, 0, MD * 4, s));
@@ -792,9 +843,9 @@ int odevit_solve_bwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
       const float* u = (st == 0) ? y : b.u;
       if (st < S - 1) {
         Epi rk = rk_epilogue(*tb, st, dt, y, b.k, b.u);
-        ODV_TRY(eval_forward(p, b.w, b.ctx[st], u, b.P, nullptr, &rk, s));
+        ODV_TRY(eval_forward(p, b.w, b.ctx[st], u, b.P, nullptr, b.sq, &rk, s));
       } else {
-        ODV_TRY(eval_forward(p, b.w, b.ctx[st], u, b.P, nullptr, nullptr, s));
+        ODV_TRY(eval_forward(p, b.w, b.ctx[st], u, b.P, nullptr, b.sq, nullptr, s));
       }
     }
     // (2) reverse through the stages
@@ -804,7 +855,7 @@ int odevit_solve_bwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
     for (int st = S - 1; st >= 0; --st) {
       const bool last_eval = (j == n_grid - 2 && st == S - 1);
       Epi e;  // epilogue of the mu GEMM: v = mu_st
-      e.aux_type = p.act;
+      e.aux_type = p.dd_type;
       if (st > 0) {
         // keep mu_st; dd <- scaler * lambda_{st-1}
         e.k_store = b.mu[st];
@@ -834,12 +885,12 @@ int odevit_solve_bwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
           e.out2 = nullptr;
           dd_seeded = false;
         }
-        ODV_TRY(eval_vjp(p, b.w, ctx[st], b, last_eval ? g_p_last : nullptr, need_c2, e, s));
+        ODV_TRY(eval_vjp(p, b.w, ctx[st], b, last_eval ? g_p_last : nullptr, need_c2, gw, e, s));
         if (!fits) ODV_TRY(inject(j));
         if (!dd_seeded && j > 0) ODV_TRY(seed_dd(t_grid_host[j] - t_grid_host[j - 1]));
         continue;
       }
-      ODV_TRY(eval_vjp(p, b.w, ctx[st], b, last_eval ? g_p_last : nullptr, need_c2, e, s));
+      ODV_TRY(eval_vjp(p, b.w, ctx[st], b, last_eval ? g_p_last : nullptr, need_c2, gw, e, s));
     }
   }
   ODV_CUDA(cudaMemcpyAsync(g_x0, b.gy, MD * 4, cudaMemcpyDeviceToDevice, s));
@@ -872,18 +923,18 @@ int odevit_field_bwd(const odevit_desc* desc, const odevit_weights* w, const flo
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   ODV_TRY(prepare_weights(p, w, b.w, s));
   ODV_CUDA(cudaMemsetAsync(b.G1, 0, b.acc_bytes, s));
-  ODV_TRY(eval_forward(p, b.w, b.ctx[0], x, b.P, nullptr, nullptr, s));
+  ODV_TRY(eval_forward(p, b.w, b.ctx[0], x, b.P, nullptr, b.sq, nullptr, s));
   {
     CombineArgs c0;
     c0.n_terms = 1; c0.term[0] = g_dx; c0.coef[0] = 1.f;
-    c0.out_dd = b.dd; c0.dd_type = p.act; c0.dd_scale = p.scaler;
+    c0.out_dd = b.dd; c0.dd_type = p.dd_type; c0.dd_scale = p.scaler;
     ODV_TRY(vjp_combine(c0, p.M, p.D, s));
   }
   {
     Epi e;
     e.c_new = 1.f;
     e.out = g_x;
-    ODV_TRY(eval_vjp(p, b.w, b.ctx[0], b, g_p, wants_c2(gw), e, s));
+    ODV_TRY(eval_vjp(p, b.w, b.ctx[0], b, g_p, wants_c2(gw), gw, e, s));
   }
   return finish_grads(p, w, gw, b, s);
 }

@@ -31,6 +31,7 @@ template <int EPI, bool ATOMIC>
 __device__ __forceinline__ void epi_apply(const Epi& e, int m, int n, float acc, int zo, int zi) {
   if constexpr (EPI == EPI_STORE) {
     float v = e.alpha * acc;
+    if (e.dev_scale) v *= *e.dev_scale;
     if (e.bias) v += e.bias[n];
     const long long idx = (long long)zo * e.out_bo + (long long)zi * e.out_bi + (long long)m * e.ld_out + n;
     store_elem(e.out, idx, e.out_type, v);
@@ -49,6 +50,8 @@ __device__ __forceinline__ void epi_apply(const Epi& e, int m, int n, float acc,
     if (e.bias) v += e.bias[n];
     v *= e.alpha;
     const long long idx = (long long)m * e.ld_out + n;
+    if (e.dev_scale) v *= *e.dev_scale;
+    if (e.resid) v = fmaf(e.resid_coef, e.resid[idx], v);
     if (e.k_store) e.k_store[idx] = v;
     float r = e.c_new * v;
     if (e.y) r = fmaf(e.y_coef, e.y[idx], r);
@@ -63,6 +66,7 @@ __device__ __forceinline__ void epi_apply(const Epi& e, int m, int n, float acc,
     } else {
       const int c = n - e.split;
       const float hp = load_elem_rw(e.aux, (long long)m * e.ld_aux + c, e.aux_type);
+      if (e.dev_scale) acc *= *e.dev_scale;
       store_elem(e.out2, (long long)m * e.ld_out2 + c, e.aux_type, acc * gelu_erf_grad(hp));
     }
   } else if constexpr (EPI == EPI_ACCUM) {
@@ -119,7 +123,7 @@ template <int EPI, bool ATOMIC>
 __device__ __forceinline__ void epi_chunk16(const Epi& e, int m, int n, float* v) {
   if constexpr (EPI == EPI_STORE) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = e.alpha * v[j] + (e.bias ? e.bias[n + j] : 0.f);
+    for (int j = 0; j < 16; ++j) v[j] = e.alpha * (e.dev_scale ? *e.dev_scale : 1.f) * v[j] + (e.bias ? e.bias[n + j] : 0.f);
     store16(e.out, (long long)m * e.ld_out + n, e.out_type, v);
   } else if constexpr (EPI == EPI_FWD1) {
     if (e.bias) {
@@ -139,8 +143,18 @@ __device__ __forceinline__ void epi_chunk16(const Epi& e, int m, int n, float* v
     const long long idx = (long long)m * e.ld_out + n;
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = e.alpha * (v[j] + (e.bias ? e.bias[n + j] : 0.f));
-    if (e.k_store) store16(e.k_store, idx, DT_F32, v);
     float r[16], t[16];
+    if (e.dev_scale) {
+      const float ds = *e.dev_scale;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] *= ds;
+    }
+    if (e.resid) {
+      load16(e.resid, idx, DT_F32, t);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(e.resid_coef, t[j], v[j]);
+    }
+    if (e.k_store) store16(e.k_store, idx, DT_F32, v);
 #pragma unroll
     for (int j = 0; j < 16; ++j) r[j] = e.c_new * v[j];
     if (e.y) {
@@ -169,8 +183,9 @@ __device__ __forceinline__ void epi_chunk16(const Epi& e, int m, int n, float* v
       const int c = n - e.split;
       float hp[16];
       load16(e.aux, (long long)m * e.ld_aux + c, e.aux_type, hp);
+      const float ds = e.dev_scale ? *e.dev_scale : 1.f;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] *= gelu_erf_grad(hp[j]);
+      for (int j = 0; j < 16; ++j) v[j] *= ds * gelu_erf_grad(hp[j]);
       store16(e.out2, (long long)m * e.ld_out2 + c, e.aux_type, v);
     }
   } else if constexpr (EPI == EPI_ACCUM) {
@@ -275,10 +290,14 @@ __device__ __forceinline__ void epi_rows8(const Epi& e, int m0, int M, int n, fl
   if constexpr (EPI == EPI_STORE || EPI == EPI_FWD1 || EPI == EPI_RK) {
     if (e.bias) bias = *reinterpret_cast<const float4*>(e.bias + n);
   }
+  float ds = 1.f;
+  if constexpr (EPI == EPI_STORE || EPI == EPI_RK || EPI == EPI_BWD3) {
+    if (e.dev_scale) ds = *e.dev_scale;
+  }
   if constexpr (EPI == EPI_STORE) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      if (ok[i]) store4(e.out, (long long)(m0 + 4 * i) * e.ld_out + n, e.out_type, fma4(e.alpha, w[i], bias));
+      if (ok[i]) store4(e.out, (long long)(m0 + 4 * i) * e.ld_out + n, e.out_type, fma4(e.alpha * ds, w[i], bias));
   } else if constexpr (EPI == EPI_FWD1) {
     if (n < e.split) {
 #pragma unroll
@@ -303,11 +322,20 @@ __device__ __forceinline__ void epi_rows8(const Epi& e, int m0, int M, int n, fl
 #pragma unroll
       for (int i = 0; i < 8; ++i) t[i] = ok[i] ? ldg_raw4(e.y, (long long)(m0 + 4 * i) * e.ld_out + n, DT_F32) : zero;
     }
+    if (e.resid) {
+      // Macaron tail: v = alpha*ds*(acc+bias) + resid_coef*resid (loads batched like the others)
+      Raw4 q[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      w[i] = scale4(e.alpha, add4(w[i], bias));
-      r[i] = scale4(e.c_new, w[i]);
+      for (int i = 0; i < 8; ++i) q[i] = ok[i] ? ldg_raw4(e.resid, (long long)(m0 + 4 * i) * e.ld_out + n, DT_F32) : zero;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        w[i] = fma4(e.resid_coef, raw_to_float4(q[i], DT_F32), scale4(e.alpha * ds, add4(w[i], bias)));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = scale4(e.alpha * ds, add4(w[i], bias));
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = scale4(e.c_new, w[i]);
     if (e.y) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) r[i] = fma4(e.y_coef, raw_to_float4(t[i], DT_F32), r[i]);
@@ -345,7 +373,7 @@ __device__ __forceinline__ void epi_rows8(const Epi& e, int m0, int M, int n, fl
       for (int i = 0; i < 8; ++i) {
         if (!ok[i]) continue;
         const float4 hp = raw_to_float4(hr[i], e.aux_type);
-        float4 v = w[i];
+        float4 v = scale4(ds, w[i]);
         v.x *= gelu_grad_fast(hp.x); v.y *= gelu_grad_fast(hp.y);
         v.z *= gelu_grad_fast(hp.z); v.w *= gelu_grad_fast(hp.w);
         store4(e.out2, (long long)(m0 + 4 * i) * e.ld_out2 + c, e.aux_type, v);

@@ -118,6 +118,13 @@ struct Epi {
   float* k_store = nullptr;
   const void* aux = nullptr;
   long long ld_aux = 0;
+  // device-resident scalar factor on the accumulator (macaron.py:104 `res_scale`, a learnable [1]
+  // parameter the host must not read back): EPI_STORE / EPI_RK / EPI_BWD3 multiply by *dev_scale
+  const float* dev_scale = nullptr;
+  // EPI_RK: v += resid_coef * resid[m,n] before k_store / the stage combine (the Macaron field
+  // returns scaler * (x2 + half-FFN), macaron.py:118-123, :148)
+  const float* resid = nullptr;
+  float resid_coef = 0.f;
 };
 
 struct GemmArgs {
@@ -193,6 +200,8 @@ int axpy_f32(float* y, const float* x, float a, long long n, cudaStream_t s);
 // Weight preparation / gradient assembly for the PARALLEL variant (folded CenterNorm affine).
 struct FoldArgs {
   int D, hid, heads;
+  float q_scale;   // factor on the Wq rows / bq: 1/sqrt(d) for nn.MultiheadAttention, 1 for L2SelfAttention
+  bool fold_norm;  // fold the CenterNorm affines (PARALLEL*) or copy the weights as they are (MACARON)
   const odevit_weights* w;
   void* w1cat; int w_type;   // [3D+hid, D]
   void* w1catT;              // [D, 3D+hid] or null; each W1cat row is CENTRED over D here (so that
@@ -206,6 +215,8 @@ int fold_weights_parallel(const FoldArgs& a, cudaStream_t s);
 
 struct UnfoldArgs {
   int D, hid, heads;
+  float q_scale;
+  const float* c3 = nullptr;  // MACARON: colsum of the fc2 cotangent (c2 is the out-proj one)
   const odevit_weights* w;
   const odevit_weight_grads* gw;
   const float* G1;  // [3D+hid, D]   = sum dz^T xc
@@ -214,5 +225,41 @@ struct UnfoldArgs {
   const float* c2;  // [D]           = colsum dd
 };
 int unfold_grads_parallel(const UnfoldArgs& a, cudaStream_t s);
+// MACARON (no folded norms; G2/c2/c3 were accumulated WITHOUT res_scale, macaron.py:104):
+//   dW_in += q_scale_row*G1[:3D], dW_fc1 += G1[3D:], dWo += rs*G2[:, :D], dW_fc2 += rs*G2[:, D:],
+//   d res_scale += <Wo, G2[:, :D]> + <bo, c2> + <W2, G2[:, D:]> + <b2, c3>
+int unfold_grads_macaron(const UnfoldArgs& a, cudaStream_t s);
+
+// LayerNorm rows (nn.LayerNorm, eps inside the sqrt; macaron.py:80-82): out = (x-mean)*rstd*w + b
+int ln_rows(const float* x, const float* w, const float* b, void* out, int out_type, float eps, int rows, int D,
+            cudaStream_t s);
+// Its VJP fused with the residual add:  g_out = g_in + dLN(x)^T dn ;  dw += sum dn*xhat ; db += sum dn ;
+// optional dd_out = cast(dd_coef * g_out) (the next GEMM's operand).  g_out may alias g_in.
+struct LnBwdArgs {
+  const float* x = nullptr;
+  const float* dn = nullptr;
+  const float* w = nullptr;
+  const float* g_in = nullptr;
+  float* g_out = nullptr;
+  void* dd_out = nullptr;
+  int dd_type = DT_F32;
+  float dd_coef = 1.f;
+  float* dw = nullptr;
+  float* db = nullptr;
+  float eps = 1e-5f;
+};
+int ln_bwd_rows(const LnBwdArgs& a, int rows, int D, cudaStream_t s);
+// EPI_RK applied to a plain [rows, D] fp32 array v (alpha/bias ignored): the stage combine when the
+// producer of v is not a GEMM.
+int rk_apply_rows(const Epi& e, const float* v, int rows, int D, cudaStream_t s);
+
+// L2SelfAttention pieces (ode_transformer_gpt.py:34-63)
+// sq[0][b,h,i] = |q_i|^2, sq[1][b,h,j] = |k_j|^2 from the packed qkv rows
+int head_sqnorm(const void* qkv, int type, float* sq, int B, int N, int H, int D, cudaStream_t s);
+// S[b,h,i,j] = q_i.k_j in place -> P = exp(-(|q_i|^2+|k_j|^2-2S)*scale) / (rowsum + 1e-8)
+int l2_prob_rows(float* S, const float* sq, float scale, float* copy_to, int B, int H, int N, cudaStream_t s);
+// dq_i -= coef * rowsum_i(ds) * q_i ;  dk_j -= coef * colsum_j(ds) * k_j   (the |q|^2, |k|^2 terms)
+int l2_vjp_fix(const float* ds, const void* qkv, int type, void* dz, int R, float coef, int B, int N, int H, int D,
+               cudaStream_t s);
 
 }  // namespace odevit

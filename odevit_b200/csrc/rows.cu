@@ -261,6 +261,236 @@ __global__ void __launch_bounds__(256) fd_curvature_kernel(const float* __restri
   if (lane == 0) per_seq[row] = mx / dt2;
 }
 
+// ---- LayerNorm rows (MACARON) ---------------------------------------------------------------
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ b, void* out, int out_type,
+                                                      float eps, int rows, int D) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (long long)row * D;
+  float v[MAX_PER_LANE];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    v[i] = (c < D) ? xr[c] : 0.f;
+    s += v[i];
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    const float d = (c < D) ? v[i] - mean : 0.f;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < MAX_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    if (c < D) store_elem(out, (long long)row * D + c, out_type, (v[i] - mean) * rstd * w[c] + b[c]);
+  }
+}
+
+// One warp walks rows row0, row0+stride, ...; the per-column sums for dw / db stay in registers and
+// meet the other warps of the block in shared memory, then one atomic per column and block.
+__global__ void __launch_bounds__(256) ln_bwd_rows_kernel(LnBwdArgs a, int rows, int D) {
+  __shared__ float red[8][32 * MAX_PER_LANE];  // 32 KB: per-warp column partials
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float dwp[MAX_PER_LANE], dbp[MAX_PER_LANE];
+#pragma unroll
+  for (int i = 0; i < MAX_PER_LANE; ++i) { dwp[i] = 0.f; dbp[i] = 0.f; }
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+    const long long base = (long long)row * D;
+    float xh[MAX_PER_LANE], dh[MAX_PER_LANE];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_PER_LANE; ++i) {
+      const int c = lane + i * 32;
+      xh[i] = (c < D) ? a.x[base + c] : 0.f;
+      s += xh[i];
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_PER_LANE; ++i) {
+      const int c = lane + i * 32;
+      xh[i] = (c < D) ? xh[i] - mean : 0.f;
+      q += xh[i] * xh[i];
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + a.eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_PER_LANE; ++i) {
+      const int c = lane + i * 32;
+      xh[i] *= rstd;
+      const float dn = (c < D) ? a.dn[base + c] : 0.f;
+      dwp[i] = fmaf(dn, xh[i], dwp[i]);
+      dbp[i] += dn;
+      dh[i] = (c < D) ? dn * a.w[c] : 0.f;
+      s1 += dh[i];
+      s2 = fmaf(dh[i], xh[i], s2);
+    }
+    s1 = warp_sum(s1) / (float)D;
+    s2 = warp_sum(s2) / (float)D;
+#pragma unroll
+    for (int i = 0; i < MAX_PER_LANE; ++i) {
+      const int c = lane + i * 32;
+      if (c >= D) continue;
+      float g = rstd * (dh[i] - s1 - xh[i] * s2);
+      if (a.g_in) g += a.g_in[base + c];
+      if (a.g_out) a.g_out[base + c] = g;
+      if (a.dd_out) store_elem(a.dd_out, base + c, a.dd_type, a.dd_coef * g);
+    }
+  }
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    float* dst = which ? a.db : a.dw;
+    if (!dst) continue;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < MAX_PER_LANE; ++i) {
+      const int c = lane + i * 32;
+      if (c < D) red[warp][c] = which ? dbp[i] : dwp[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += red[k][c];
+      atomicAdd(dst + c, t);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) rk_apply_kernel(const __grid_constant__ Epi e, const float* __restrict__ v,
+                                                       long long n, int D) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) epi_apply<EPI_RK, false>(e, (int)(i / D), (int)(i % D), v[i], 0, 0);
+}
+
+// ---- L2 attention pieces ---------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_sqnorm_kernel(const void* qkv, int type, float* sq, int B, int N, int H,
+                                                          int D) {
+  // one warp per (token row, head, q|k)
+  const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)B * N * H * 2;
+  if (wid >= total) return;
+  const int which = (int)(wid % 2);
+  const int h = (int)((wid / 2) % H);
+  const long long row = wid / (2 * H);
+  const int d = D / H;
+  const long long base = row * 3 * D + (long long)which * D + (long long)h * d;
+  float s = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float v = load_elem_rw(qkv, base + c, type);
+    s = fmaf(v, v, s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    const long long b = row / N, i = row % N;
+    sq[(long long)which * B * H * N + (b * H + h) * N + i] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) l2_prob_rows_kernel(float* p, const float* __restrict__ sq, float scale,
+                                                           float* copy_to, long long rows, int n) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* pr = p + row * n;
+  const float q2 = sq[row];
+  const float* k2 = sq + rows + (row / n) * n;  // row = (b*H + h)*N + i
+  float v[MAX_PER_LANE];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    v[i] = 0.f;
+    if (c < n) {
+      const float dist2 = q2 + k2[c] - 2.f * pr[c];
+      v[i] = expf(-dist2 * scale);
+    }
+    s += v[i];
+  }
+  const float z = warp_sum(s) + 1e-8f;
+#pragma unroll
+  for (int i = 0; i < MAX_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    if (c < n) {
+      const float o = v[i] / z;
+      pr[c] = o;
+      if (copy_to) copy_to[row * n + c] = o;
+    }
+  }
+}
+
+// one block per (image, head): row / column sums of ds [N,N] into shared memory, then the rank-one fixes
+__global__ void __launch_bounds__(256) l2_vjp_fix_kernel(const float* __restrict__ ds, const void* qkv, int type,
+                                                         void* dz, int R, float coef, int N, int H, int D) {
+  extern __shared__ float sm[];
+  float* rs = sm;
+  float* cs = sm + N;
+  const int bh = blockIdx.x, b = bh / H, h = bh % H, d = D / H;
+  const float* m = ds + (long long)bh * N * N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = warp; i < N; i += 8) {
+    float s = 0.f;
+    for (int j = lane; j < N; j += 32) s += m[(long long)i * N + j];
+    s = warp_sum(s);
+    if (lane == 0) rs[i] = s;
+  }
+  for (int j = threadIdx.x; j < N; j += 256) {
+    float s = 0.f;
+    for (int i = 0; i < N; ++i) s += m[(long long)i * N + j];
+    cs[j] = s;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < N * d; e += 256) {
+    const int i = e / d, c = e % d;
+    const long long row = (long long)b * N + i;
+    const long long qi = row * 3 * D + (long long)h * d + c;
+    const long long zi = row * R + (long long)h * d + c;
+    const float q = load_elem_rw(qkv, qi, type), k = load_elem_rw(qkv, qi + D, type);
+    store_elem(dz, zi, type, load_elem_rw(dz, zi, type) - coef * rs[i] * q);
+    store_elem(dz, zi + D, type, load_elem_rw(dz, zi + D, type) - coef * cs[i] * k);
+  }
+}
+
+// ---- MACARON gradient assembly ------------------------------------------------------------------
+// block = one row i of G2 [D, D+hid]: dWo[i,:] += rs*G2[i,:D], dW2[i,:] += rs*G2[i,D:], biases, and the
+// res_scale gradient <Wo,G2a> + <W2,G2b> + <bo,c2> + <b2,c3> (block partial -> one atomic)
+__global__ void __launch_bounds__(128) unfold_w2_macaron_kernel(UnfoldArgs a, odevit_weights w, odevit_weight_grads g) {
+  const int D = a.D, hid = a.hid, K2 = D + hid;
+  const int i = blockIdx.x;
+  const float rs = *w.res_scale;
+  float dot = 0.f;
+  for (int c = threadIdx.x; c < K2; c += 128) {
+    const float v = a.G2[(long long)i * K2 + c];
+    if (c < D) {
+      if (g.out_proj_w) g.out_proj_w[(long long)i * D + c] += rs * v;
+      dot = fmaf(w.out_proj_w[(long long)i * D + c], v, dot);
+    } else {
+      if (g.fc2_w) g.fc2_w[(long long)i * hid + (c - D)] += rs * v;
+      dot = fmaf(w.fc2_w[(long long)i * hid + (c - D)], v, dot);
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (g.out_proj_b) g.out_proj_b[i] += rs * a.c2[i];
+    if (g.fc2_b) g.fc2_b[i] += rs * a.c3[i];
+    if (w.out_proj_b) dot = fmaf(w.out_proj_b[i], a.c2[i], dot);
+    if (w.fc2_b) dot = fmaf(w.fc2_b[i], a.c3[i], dot);
+  }
+  __shared__ float red[4];
+  dot = warp_sum(dot);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0 && g.res_scale) atomicAdd(g.res_scale, red[0] + red[1] + red[2] + red[3]);
+}
+
 // ---- weight folding (PARALLEL variant) -------------------------------------------------------
 // CenterNorm is affine in (x - mean):  n = s*(x-mean)*w + b  with s = D/(D-1)          (:77-83)
 //   n_attn @ W_in^T = (x-mean) @ (s * W_in * diag(w_a))^T + W_in @ b_a
@@ -279,13 +509,14 @@ __global__ void __launch_bounds__(128) fold_w1_kernel(FoldArgs a, odevit_weights
   const float* msc = attn ? w.mod_attn_scale : w.mod_mlp_scale;
   const float* msh = attn ? w.mod_attn_shift : w.mod_mlp_shift;
   const float* lb = attn ? w.in_proj_b : w.fc1_b;
-  const float s_cn = (float)D / ((float)D - 1.f);
-  const float qs = (j < D) ? rsqrtf((float)(D / a.heads)) : 1.f;
+  const bool fn = a.fold_norm;
+  const float s_cn = fn ? (float)D / ((float)D - 1.f) : 1.f;
+  const float qs = (j < D) ? a.q_scale : 1.f;
   float dot = 0.f, fsum = 0.f;
   for (int i = threadIdx.x; i < D; i += 128) {
-    float we = nw[i], be = nb[i];
-    if (msc) { we *= (1.f + msc[i]); be *= (1.f + msc[i]); }
-    if (msh) be += msh[i];
+    float we = fn ? nw[i] : 1.f, be = fn ? nb[i] : 0.f;
+    if (fn && msc) { we *= (1.f + msc[i]); be *= (1.f + msc[i]); }
+    if (fn && msh) be += msh[i];
     const float wv = Wrow[i];
     const float f = qs * s_cn * wv * we;
     store_elem(a.w1cat, (long long)j * D + i, a.w_type, f);
@@ -305,10 +536,10 @@ __global__ void __launch_bounds__(128) fold_w1_kernel(FoldArgs a, odevit_weights
   if (a.w1catT) {
     // the transposed copy feeds dL/dxc = dz @ W1cat followed by the centring VJP (subtract the
     // row mean over D): fold that subtraction into the weight, row j centred over i
-    const float fmean = (red2[0] + red2[1] + red2[2] + red2[3]) / (float)D;
+    const float fmean = fn ? (red2[0] + red2[1] + red2[2] + red2[3]) / (float)D : 0.f;
     for (int i = threadIdx.x; i < D; i += 128) {
-      float we = nw[i];
-      if (msc) we *= (1.f + msc[i]);
+      float we = fn ? nw[i] : 1.f;
+      if (fn && msc) we *= (1.f + msc[i]);
       const float f = qs * s_cn * Wrow[i] * we;
       store_elem(a.w1catT, (long long)i * R + j, a.w_type, f - fmean);
     }
@@ -347,14 +578,15 @@ __global__ void __launch_bounds__(128) unfold_w1_kernel(UnfoldArgs a, odevit_wei
   const float* nb = attn ? w.norm_a_b : w.norm_b_b;
   const float* msc = attn ? w.mod_attn_scale : w.mod_mlp_scale;
   const float* msh = attn ? w.mod_attn_shift : w.mod_mlp_shift;
-  const float s_cn = (float)D / ((float)D - 1.f);
-  const float qs = (j < D) ? rsqrtf((float)(D / a.heads)) : 1.f;
+  const bool fn = (a.c3 == nullptr);  // MACARON passes c3 and has no folded norms
+  const float s_cn = fn ? (float)D / ((float)D - 1.f) : 1.f;
+  const float qs = (j < D) ? a.q_scale : 1.f;
   const float cj = a.c1[j];
   if (dW) {
     for (int i = threadIdx.x; i < D; i += 128) {
-      float we = nw[i], be = nb[i];
-      if (msc) { we *= (1.f + msc[i]); be *= (1.f + msc[i]); }
-      if (msh) be += msh[i];
+      float we = fn ? nw[i] : 1.f, be = fn ? nb[i] : 0.f;
+      if (fn && msc) { we *= (1.f + msc[i]); be *= (1.f + msc[i]); }
+      if (fn && msh) be += msh[i];
       dW[(long long)jr * D + i] += qs * (s_cn * we * a.G1[(long long)j * D + i] + cj * be);
     }
   }
@@ -375,7 +607,7 @@ __global__ void __launch_bounds__(128) unfold_norm_kernel(UnfoldArgs a, odevit_w
   const int j0 = blockIdx.y * kUnfoldRows;
   const int j1 = min(3 * D + hid, j0 + kUnfoldRows);
   const float s_cn = (float)D / ((float)D - 1.f);
-  const float q = rsqrtf((float)(D / a.heads));
+  const float q = a.q_scale;
   float dwa = 0.f, dba = 0.f, dwm = 0.f, dbm = 0.f;
   for (int j = j0; j < j1; ++j) {
     const float g1 = a.G1[(long long)j * D + i], cj = a.c1[j];
@@ -482,6 +714,69 @@ int fd_curvature(const float* states, int T, long long rows, int D, float dt2, f
   else if (ch <= 4) fd_curvature_kernel<4><<<grid, 256, 0, s>>>(states, T, rows, D, dt2, per_seq);
   else if (ch <= 6) fd_curvature_kernel<6><<<grid, 256, 0, s>>>(states, T, rows, D, dt2, per_seq);
   else fd_curvature_kernel<8><<<grid, 256, 0, s>>>(states, T, rows, D, dt2, per_seq);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int ln_rows(const float* x, const float* w, const float* b, void* out, int out_type, float eps, int rows, int D,
+            cudaStream_t s) {
+  ProfScope prof(KC_CENTER, s);
+  if (D > 32 * MAX_PER_LANE) return set_error(ODEVIT_ERR_UNSUPPORTED, "ln_rows: D=%d > 1024", D);
+  ln_rows_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, w, b, out, out_type, eps, rows, D);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int ln_bwd_rows(const LnBwdArgs& a, int rows, int D, cudaStream_t s) {
+  ProfScope prof(KC_COMBINE, s);
+  if (D > 32 * MAX_PER_LANE) return set_error(ODEVIT_ERR_UNSUPPORTED, "ln_bwd_rows: D=%d > 1024", D);
+  const int blocks = (rows + 7) / 8 < 148 * 4 ? (rows + 7) / 8 : 148 * 4;
+  ln_bwd_rows_kernel<<<blocks, 256, 0, s>>>(a, rows, D);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int rk_apply_rows(const Epi& e, const float* v, int rows, int D, cudaStream_t s) {
+  ProfScope prof(KC_COMBINE, s);
+  Epi e2 = e;
+  e2.alpha = 1.f; e2.bias = nullptr; e2.dev_scale = nullptr; e2.resid = nullptr; e2.ld_out = D;
+  const long long n = (long long)rows * D;
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  rk_apply_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(e2, v, n, D);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int head_sqnorm(const void* qkv, int type, float* sq, int B, int N, int H, int D, cudaStream_t s) {
+  ProfScope prof(KC_SOFTMAX, s);
+  const long long warps = (long long)B * N * H * 2;
+  head_sqnorm_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(qkv, type, sq, B, N, H, D);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int l2_prob_rows(float* S, const float* sq, float scale, float* copy_to, int B, int H, int N, cudaStream_t s) {
+  ProfScope prof(KC_SOFTMAX, s);
+  if (N > 32 * MAX_PER_LANE) return set_error(ODEVIT_ERR_UNSUPPORTED, "l2_prob_rows: N=%d > 1024", N);
+  const long long rows = (long long)B * H * N;
+  l2_prob_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(S, sq, scale, copy_to, rows, N);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int l2_vjp_fix(const float* ds, const void* qkv, int type, void* dz, int R, float coef, int B, int N, int H, int D,
+               cudaStream_t s) {
+  ProfScope prof(KC_BWD_SOFTMAX, s);
+  l2_vjp_fix_kernel<<<B * H, 256, 2 * N * sizeof(float), s>>>(ds, qkv, type, dz, R, coef, N, H, D);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int unfold_grads_macaron(const UnfoldArgs& a, cudaStream_t s) {
+  ProfScope prof(KC_WEIGHTS, s);
+  unfold_w1_kernel<<<3 * a.D + a.hid, 128, 0, s>>>(a, *a.w, *a.gw);
+  ODV_LAUNCH_CHECK();
+  unfold_w2_macaron_kernel<<<a.D, 128, 0, s>>>(a, *a.w, *a.gw);
   ODV_LAUNCH_CHECK();
   return 0;
 }

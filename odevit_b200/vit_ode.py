@@ -79,6 +79,24 @@ class MultiheadSelfAttention(nn.Module):
         self.proj_drop = nn.Dropout(proj_drop)
 
 
+class L2SelfAttention(nn.Module):
+    """Parameter container for ode_transformer_gpt.py:12-63: separate q/k/v/out Linears WITH bias;
+    weights exp(-||q_i - k_j||^2 / sqrt(d)) normalised by (row sum + 1e-8).  The arithmetic runs in
+    libodevit.so (variant PARALLEL_L2)."""
+
+    def __init__(self, dim: int, num_heads: int, attn_drop: float = 0.0, proj_drop: float = 0.0):
+        super().__init__()
+        self.num_heads = num_heads
+        self.head_dim = dim // num_heads
+        self.scale = self.head_dim ** -0.5
+        self.q_proj = nn.Linear(dim, dim)
+        self.k_proj = nn.Linear(dim, dim)
+        self.v_proj = nn.Linear(dim, dim)
+        self.out_proj = nn.Linear(dim, dim)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj_drop = nn.Dropout(proj_drop)
+
+
 def _check_no_dropout(mod: nn.Module, *ps: float) -> None:
     if mod.training and any(p > 0 for p in ps):
         raise NotImplementedError(
@@ -95,12 +113,12 @@ class ParallelAttentionMLP(nn.Module):
         super().__init__()
         self.norm_attn = CenterNorm(dim)
         self.norm_mlp = CenterNorm(dim)
-        if use_l2:
-            raise NotImplementedError(
-                "odevit_b200: the L2SelfAttention variant (ode_transformer_gpt.py:12-63) is not built; "
-                "it is unreachable through the reference's ViTNeuralODE.forward (SURVEY 2.3 quirk 13)")
-        self.attn = MultiheadSelfAttention(dim=dim, num_heads=num_heads, attn_drop=attn_drop,
-                                           proj_drop=proj_drop)
+        self.use_l2 = use_l2
+        if use_l2:      # :259-262
+            self.attn = L2SelfAttention(dim=dim, num_heads=num_heads, attn_drop=attn_drop, proj_drop=proj_drop)
+        else:
+            self.attn = MultiheadSelfAttention(dim=dim, num_heads=num_heads, attn_drop=attn_drop,
+                                               proj_drop=proj_drop)
         self.mlp = MLP(dim=dim, hidden_dim=int(dim * mlp_ratio), drop=mlp_drop)
         self.dim, self.num_heads = dim, num_heads
         self._drops = (attn_drop, proj_drop, mlp_drop)
@@ -111,16 +129,25 @@ class ParallelAttentionMLP(nn.Module):
     def field_spec(self, scaler: float) -> ops.FieldSpec:
         hidden = self.mlp.fc1.weight.shape[0]
         return ops.FieldSpec(dim=self.dim, heads=self.num_heads, hidden=hidden, scaler=float(scaler),
-                             variant=_lib.FIELD_PARALLEL, precision=self.precision,
+                             variant=_lib.FIELD_PARALLEL_L2 if self.use_l2 else _lib.FIELD_PARALLEL,
+                             precision=self.precision,
                              backward=getattr(self, "backward_mode", "auto"))
 
     def field_weights(self) -> Dict[str, Optional[torch.Tensor]]:
         """odevit_weights field name -> parameter, read at call time."""
+        if self.use_l2:
+            a = self.attn   # the ABI takes [Wq; Wk; Wv] stacked like nn.MultiheadAttention's packed weight
+            in_w = torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0)
+            in_b = torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0)
+            out_w, out_b = a.out_proj.weight, a.out_proj.bias
+        else:
+            mha = self.attn.mha
+            in_w, in_b, out_w, out_b = mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias
         w = {
             "norm_a_w": self.norm_attn.weight, "norm_a_b": self.norm_attn.bias,
             "norm_b_w": self.norm_mlp.weight, "norm_b_b": self.norm_mlp.bias,
-            "in_proj_w": self.attn.mha.in_proj_weight, "in_proj_b": self.attn.mha.in_proj_bias,
-            "out_proj_w": self.attn.mha.out_proj.weight, "out_proj_b": self.attn.mha.out_proj.bias,
+            "in_proj_w": in_w, "in_proj_b": in_b,
+            "out_proj_w": out_w, "out_proj_b": out_b,
             "fc1_w": self.mlp.fc1.weight, "fc1_b": self.mlp.fc1.bias,
             "fc2_w": self.mlp.fc2.weight, "fc2_b": self.mlp.fc2.bias,
         }
@@ -167,9 +194,11 @@ def odeint(func: ViT_ODEFunc, y0: torch.Tensor, t: torch.Tensor, *, method: str 
     leaves `func.block.attentions` (last evaluation, differentiable) and extends
     `func.attention_trajectory` (every evaluation, detached) unless `record_attention=False`.
     rtol / atol are ignored by fixed-grid methods; `options` (step_size ...) is not supported."""
-    if not isinstance(func, ViT_ODEFunc):
+    if not (hasattr(func, "block") and hasattr(func.block, "field_spec") and hasattr(func, "scaler")):
         raise TypeError("odevit_b200.odeint integrates odevit_b200 vector-field modules only "
                         "(there is no generic / CPU solver in this package)")
+    if func.block.field_spec(1.0).variant == _lib.FIELD_MACARON:
+        record_attention = False   # macaron.py:60-65: need_weights=False, the block exposes no map
     if options:
         raise NotImplementedError("odeint options (step_size, ...) are not used by the reference and not built")
     _check_no_dropout(func.block, *func.block._drops)
