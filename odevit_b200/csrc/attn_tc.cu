@@ -220,269 +220,467 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 // ================================================================================================
 // Fused attention VJP (bf16 mode, head dim 64, N <= 256).  Per (image b, head h), with the
-// log-sum-exp `lse2` of every row saved by the forward recomputation and
-// delta_i = sum_d dO_id O_id  (== sum_j P_ij dP_ij):
+// log-sum-exp `lse2` of every row saved by the forward and delta_i = sum_d dO_id O_id:
 //     S = q k^T,  P = exp2(S*log2e - lse2),  dP = dO v^T,  dS = P o (dP - delta)
 //     dq = dS k,  dk = dS^T q,  dv = P^T dO
-// One CTA (128 threads, thread = query row) per (b, h).  Keys are processed in chunks of 128
-// (outer loop), queries in tiles of 128 (inner loop):
-//   thread 0   TMA (Q and dO tiles once; K / V chunk per outer iteration), and all MMAs:
-//              S and dP (SS) into TMEM [0,128) / [128,256);
-//   all        S, dP rows from TMEM -> P, dS as bf16 into 128-byte-swizzled shared-memory tiles
-//   thread 0   dQ_tile  = dS K      (A = dS tile K-major,  B = K chunk MN-major)   TMEM [384,448)
-//              dK_chunk += dS^T Q   (A = dS tile MN-major, B = Q tile MN-major)    TMEM [256,320)
-//              dV_chunk += P^T dO   (A = P tile MN-major,  B = dO tile MN-major)   TMEM [320,384)
-//   all        dQ epilogue (thread = query row); with two key chunks the first chunk's partial
-//              goes through an fp32 scratch row that the same thread re-reads on the second;
-//              dK / dV epilogue (thread = key row) after the inner loop.
+// PERSISTENT kernel: one CTA per SM walks the (b, h) items c, c+G, c+2G, ...; everything is in the
+// TRANSPOSED orientation (thread = key row), so that P^T and dS^T are A operands that never leave
+// tensor memory, and the operand tiles of the NEXT item stream in while this one is computed:
+//   warp 8 (one lane)  TMA + all MMAs.  Operand tiles live in three rotating 64 KB sets
+//        {K, Q, V, dO} x 128 rows: item i keeps rows [0,128) in set s0 and rows [128,256) in s1; the
+//        third set receives rows [0,128) of item i+1 at the start of item i, and s0 is refilled with
+//        rows [128,256) of item i+1 as soon as its last reader has retired.
+//        per (key chunk kc, query tile qt):
+//          S^T  = K_kc Q_qt^T,  dP^T = V_kc dO_qt^T                 (SS)  -> TMEM [0,128), [128,256)
+//          dV_kc += P^T dO_qt,  dK_kc += dS^T Q_qt                  (TS: A = bf16 P^T / dS^T in TMEM)
+//          dQ_qt += dS K_kc     (A = dS^T tile in shared memory read MN-major, B = K chunk MN-major)
+//        dK, dV, dQ_0, dQ_1 accumulate in TMEM [256,512): no partial sum ever goes through memory.
+//   warps 0-7          two warpgroups split the query columns of a tile; thread = key row:
+//          P^T, dS^T from S^T, dP^T (per-query lse / delta broadcast from shared memory), packed to
+//          bf16 in registers; dS^T also goes to a 128-byte-swizzled shared-memory tile; after a
+//          barrier among the 256 threads the packed values overwrite S^T / dP^T in place
+//          (tcgen05.st).  Epilogues: dK | dV per key chunk (one warpgroup each), dQ at the item's end.
+//   warps 9-12         lse and delta = <dO_i, O_i> of the NEXT item into shared memory (double
+//          buffered): the only global loads that are not TMA, kept off the compute warps.
 // The cotangent of an exported P (`attentions`, last evaluation only) is not handled here; that
-// single evaluation takes the CUDA-core path (api.cu::eval_vjp).
+// single evaluation takes the CUDA-core path (api.cu::attention_vjp).
 struct AttnBwdArgs {
   int B, N, H, D, R;
-  int n_kc, n_qt;
-  const float* lse2;    // [B,H,N]
-  const float* delta;   // [B,H,N]
-  void* dz;             // [B*N, R] bf16: dq | dk | dv at columns h*64, D + h*64, 2D + h*64
-  float* dq_scratch;    // [B*H, 256, 64] fp32 (used when n_kc == 2)
+  int n_t;                      // 128-row tiles per item: 1 or 2 (keys and queries alike)
+  int items;                    // B * H
+  const float* lse2;            // [B,H,N]
+  const __nv_bfloat16* dO;      // [B*N, D]
+  const __nv_bfloat16* O;       // [B*N, ld_o]
+  long long ld_o;
+  void* dz;                     // [B*N, R] bf16: dq | dk | dv at columns h*64, D + h*64, 2D + h*64
 };
 
 constexpr int BWD_TMEM_COLS = 512;
-constexpr int T_S = 0, T_DP = 128, T_DK = 256, T_DV = 320, T_DQ = 384;
+constexpr int T_ST = 0, T_DPT = 128, T_DK = 256, T_DV = 320, T_DQ = 384;  // T_DQ + 64*qt
+constexpr int BWD_THREADS = 13 * 32;
+constexpr int SLOT = 16384;               // one [128 x 64] bf16 tile
+constexpr int SET = 4 * SLOT;             // {K, Q, V, dO}
+enum { SL_K = 0, SL_Q = 1, SL_V = 2, SL_DO = 3 };
 
-__device__ __forceinline__ void store_bf16x8_sw128(uint8_t* tile, int r, int key, const float* v) {
-  // tile: atoms [128 rows x 64 keys] of 16 KB; 16-byte chunk index XOR (row % 8)
-  uint32_t w[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-    w[j] = *reinterpret_cast<uint32_t*>(&hh);
-  }
-  const int atom = key >> 6, chunk = (key & 63) >> 3;
+__device__ __forceinline__ void store_bf16x8_sw128(uint8_t* tile, int r, int col, const uint32_t* w) {
+  // tile: atoms [128 rows x 64 columns] of 16 KB; 16-byte chunk index XOR (row % 8)
+  const int atom = col >> 6, chunk = (col & 63) >> 3;
   uint4* dst = reinterpret_cast<uint4*>(tile + atom * 16384 + r * 128 + ((chunk ^ (r & 7)) << 4));
   *dst = make_uint4(w[0], w[1], w[2], w[3]);
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
-__global__ void __launch_bounds__(128, 1)
+// This warp's 32 accumulator rows x 64 fp32 columns -> bf16 -> global rows of `stride` elements.
+// Thread = row out of TMEM; a 4 KB staging tile (16-byte chunks XOR-swizzled by row) turns the
+// row-per-thread layout into 128 contiguous bytes per 8 lanes, so every store instruction covers
+// 4 full lines instead of 32 partial ones.
+__device__ __forceinline__ void store_rows_bf16(__nv_bfloat16* g_row0, long long stride, uint32_t t_addr,
+                                                uint8_t* stage, int lane, int rows_valid) {
+  float v[64];
+#pragma unroll
+  for (int c = 0; c < HD / 16; ++c) ptx::tmem_ld16(t_addr + c * 16, v + c * 16);
+  ptx::tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < HD / 8; ++c) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 hh = __floats2bfloat162_rn(v[c * 8 + 2 * j], v[c * 8 + 2 * j + 1]);
+      w[j] = *reinterpret_cast<uint32_t*>(&hh);
+    }
+    *reinterpret_cast<uint4*>(stage + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __syncwarp();
+  const int c = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3);
+    const uint4 val = *reinterpret_cast<const uint4*>(stage + row * 128 + ((c ^ (row & 7)) << 4));
+    if (row < rows_valid) *reinterpret_cast<uint4*>(g_row0 + row * stride + c * 8) = val;
+  }
+  __syncwarp();
+}
+
+#ifdef ATTN_TRACE
+__device__ uint32_t tr[3][100];
+__device__ uint8_t tr_id[3][100];
+__device__ int tr_n[3];
+#define TRC(slot) ((slot) >= 100 ? 2 : ((slot) & 1))
+#define TR(slot) do { if (blockIdx.x == 0 && tr_on && tr_n[TRC(slot)] < 100) { const int _c = TRC(slot); const int _i = tr_n[_c]++; tr[_c][_i] = (uint32_t)clock(); tr_id[_c][_i] = (slot); } } while (0)
+#else
+#define TR(slot) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ AttnBwdArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                 // 2 x 16 KB
-  uint8_t* sDO = sQ + 2 * 16384;      // 2 x 16 KB
-  uint8_t* sK = sDO + 2 * 16384;      // 16 KB
-  uint8_t* sV = sK + 16384;           // 16 KB
-  uint8_t* sP = sV + 16384;           // 32 KB (2 atoms)
-  uint8_t* sDS = sP + 32768;          // 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 32768);
-  uint64_t* bar_qdo = bars;
-  uint64_t* bar_kv = bars + 1;
-  uint64_t* bar_sdp = bars + 2;
-  uint64_t* bar_mma2 = bars + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sSets = smem;                       // 3 sets x 4 slots x 16 KB
+  uint8_t* sDS = sSets + 3 * SET;              // 32 KB: dS^T tile
+  float* sLse = reinterpret_cast<float*>(sDS + 32768);   // [256]
+  float* sDelta = sLse + 256;                             // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
+  uint64_t* bar_full = bars;      // [3] operand set landed
+  uint64_t* bar_sdp = bars + 3;   // S^T / dP^T of an iteration are in TMEM
+  uint64_t* bar_pds = bars + 4;   // P^T / dS^T written (TMEM + shared memory)
+  uint64_t* bar_c = bars + 5;     // the dV / dK / dQ MMAs of an iteration have retired
+  uint64_t* bar_epi = bars + 6;   // accumulators of a key chunk (and dQ at the item's end) read out
+  uint64_t* bar_aux = bars + 7;   // lse / delta of an item are in shared memory
+  uint64_t* bar_item = bars + 8;  // an item is finished by the compute warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+#ifdef ATTN_TRACE
+  if (threadIdx.x == 0 && blockIdx.x == 0) { tr_n[0] = 0; tr_n[1] = 0; tr_n[2] = 0; }
+#endif
 
-  const int warp = threadIdx.x >> 5;
-  const int t = threadIdx.x;
-  const int h = blockIdx.x % a.H;
-  const int b = blockIdx.x / a.H;
-
-  if (t == 0) {
-    ptx::prefetch_tensormap(&tmQKV);
-    ptx::prefetch_tensormap(&tmDO);
-    ptx::mbar_init(bar_qdo, 1);
-    ptx::mbar_init(bar_kv, 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef ATTN_TRACE
+  const bool tr_on = (threadIdx.x == 0) || (warp == 8 && lane == 0) || (warp == 9 && lane == 0);
+#endif
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) ptx::mbar_init(bar_full + i, 1);
     ptx::mbar_init(bar_sdp, 1);
-    ptx::mbar_init(bar_mma2, 1);
+    ptx::mbar_init(bar_pds, 256);
+    ptx::mbar_init(bar_c, 1);
+    ptx::mbar_init(bar_epi, 256);
+    ptx::mbar_init(bar_aux, 128);
+    ptx::mbar_init(bar_item, 256);
     ptx::fence_barrier_init();
   }
-  if (warp == 0) ptx::tmem_alloc(tmem_slot, BWD_TMEM_COLS);
+  if (warp == 8) ptx::tmem_alloc(tmem_slot, BWD_TMEM_COLS);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-
-  if (t == 0) {
-    ptx::mbar_expect_tx(bar_qdo, a.n_qt * 2 * 16384);
-    for (int qt = 0; qt < a.n_qt; ++qt) {
-      ptx::tma_load_3d(sQ + qt * 16384, &tmQKV, bar_qdo, h * HD, qt * 128, b);
-      ptx::tma_load_3d(sDO + qt * 16384, &tmDO, bar_qdo, h * HD, qt * 128, b);
-    }
-  }
-  constexpr float LOG2E = 1.4426950408889634f;
   const int NP = (a.N + 15) / 16 * 16;
-  uint32_t ph_sdp = 0, ph_mma2 = 0;
-  __nv_bfloat16* dz = reinterpret_cast<__nv_bfloat16*>(a.dz);
+  const int nt = a.n_t;
+  const int n_iter = nt * nt;
+  const int n_mine = (a.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  for (int kc = 0; kc < a.n_kc; ++kc) {
-    const int cw = min(128, NP - kc * 128);  // chunk width (multiple of 16)
-    if (t == 0) {
-      ptx::mbar_expect_tx(bar_kv, 2 * 16384);
-      ptx::tma_load_3d(sK, &tmQKV, bar_kv, a.D + h * HD, kc * 128, b);
-      ptx::tma_load_3d(sV, &tmQKV, bar_kv, 2 * a.D + h * HD, kc * 128, b);
+  if (warp == 8) {
+    // =========================== producer: TMA + every MMA ===========================
+    // The whole warp walks the schedule (uniform control flow keeps descriptors in uniform registers);
+    // only the elected lane issues TMA / MMA / commit.  The schedule is flattened over (item, kc, qt):
+    // the descriptors of iteration gi+1 are formed BEFORE waiting for the compute warps of iteration
+    // gi, so that S^T / dP^T of gi+1 are issued back to back with the accumulating MMAs of gi.
+    const bool leader = ptx::elect_one();
+    if (leader) {
+      ptx::prefetch_tensormap(&tmQKV);
+      ptx::prefetch_tensormap(&tmDO);
     }
-    for (int qt = 0; qt < a.n_qt; ++qt) {
-      if (t == 0) {
-        if (kc == 0 && qt == 0) ptx::mbar_wait(bar_qdo, 0);
-        if (qt == 0) ptx::mbar_wait(bar_kv, kc & 1);
-        ptx::tc_fence_after();
-        const uint32_t idesc = ptx::idesc_bf16(128, cw, 0, 0);
-        const uint32_t q_addr = ptx::smem_u32(sQ + qt * 16384), do_addr = ptx::smem_u32(sDO + qt * 16384);
-        const uint32_t k_addr = ptx::smem_u32(sK), v_addr = ptx::smem_u32(sV);
+    uint32_t ph_full[3] = {0, 0, 0};
+    uint32_t n_epi = 0;      // accumulator read-outs the producer has waited for
+    uint32_t n_epi_due = 0;  // read-outs the compute warps will have signalled before the next first-of-chunk C
+    // rows [128*t, 128*t+128) of item `item` -> set `set`
+    auto load_set = [&](int item, int t, int set) {
+      const int hh = item % a.H, bb = item / a.H;
+      uint8_t* base = sSets + set * SET;
+      if (leader) {
+        ptx::mbar_expect_tx(bar_full + set, SET);
+        ptx::tma_load_3d(base + SL_K * SLOT, &tmQKV, bar_full + set, a.D + hh * HD, t * 128, bb);
+        ptx::tma_load_3d(base + SL_Q * SLOT, &tmQKV, bar_full + set, hh * HD, t * 128, bb);
+        ptx::tma_load_3d(base + SL_V * SLOT, &tmQKV, bar_full + set, 2 * a.D + hh * HD, t * 128, bb);
+        ptx::tma_load_3d(base + SL_DO * SLOT, &tmDO, bar_full + set, hh * HD, t * 128, bb);
+      }
+      __syncwarp();
+    };
+    struct Iter {
+      uint64_t dk_k, dq_k, dv_k, ddo_k;   // K-major descriptors (S^T, dP^T)
+      uint64_t ddo_mn, dq_mn, dk_mn;      // MN-major descriptors (dV, dK, dQ)
+      uint32_t id_s, acc_q, acc_k;
+      int nq, nk, qt, it;
+    };
+    // nt == 2: an item holds two sets (rows [0,128) in s0, rows [128,256) in s1), the third one (sf)
+    //          receives rows [0,128) of the next item during iteration 0 and s0 is refilled with its rows
+    //          [128,256) during iteration 3;  (s0, s1, sf) <- (sf, s0, s1) at every item boundary.
+    // nt == 1: an item holds one set; item i lives in set i % 3 and is loaded two items ahead.
+    int s0 = 0, s1 = 1, sf = 2;
+    bool t1_ready = (nt == 1);
+    // describes iteration `it` of the item whose sets are (s0, s1); waits for the operand sets it touches first
+    auto make_iter = [&](int it) {
+      Iter r;
+      const int kc = (nt == 2) ? (it >> 1) : 0, qt = (nt == 2) ? (it & 1) : 0;
+      if (it == 0) {
+        ptx::mbar_wait(bar_full + s0, ph_full[s0]);
+        ph_full[s0] ^= 1;
+        t1_ready = (nt == 1);
+      } else if (!t1_ready) {
+        ptx::mbar_wait(bar_full + s1, ph_full[s1]);
+        ph_full[s1] ^= 1;
+        t1_ready = true;
+      }
+      const int qw = min(128, NP - qt * 128), cw = min(128, NP - kc * 128);  // multiples of 16
+      const uint32_t kset = ptx::smem_u32(sSets + (kc ? s1 : s0) * SET), qset = ptx::smem_u32(sSets + (qt ? s1 : s0) * SET);
+      const uint32_t k_addr = kset + SL_K * SLOT, v_addr = kset + SL_V * SLOT;
+      const uint32_t q_addr = qset + SL_Q * SLOT, do_addr = qset + SL_DO * SLOT;
+      r.dk_k = ptx::smem_desc_sw128(k_addr, 16, 1024);
+      r.dq_k = ptx::smem_desc_sw128(q_addr, 16, 1024);
+      r.dv_k = ptx::smem_desc_sw128(v_addr, 16, 1024);
+      r.ddo_k = ptx::smem_desc_sw128(do_addr, 16, 1024);
+      r.ddo_mn = ptx::smem_desc_sw128(do_addr, 8192, 1024);
+      r.dq_mn = ptx::smem_desc_sw128(q_addr, 8192, 1024);
+      r.dk_mn = ptx::smem_desc_sw128(k_addr, 8192, 1024);
+      r.id_s = ptx::idesc_bf16(128, qw, 0, 0);
+      r.nq = qw / 16; r.nk = cw / 16;
+      r.acc_q = qt > 0 ? 1u : 0u; r.acc_k = kc > 0 ? 1u : 0u;
+      r.qt = qt; r.it = it;
+      return r;
+    };
+    auto issue_a = [&](const Iter& r) {  // S^T = K Q^T, dP^T = V dO^T
+      if (leader) {
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          ptx::mma_bf16_ss(tmem + T_S, ptx::smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                           ptx::smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
+        for (int k = 0; k < HD / 16; ++k) ptx::mma_bf16_ss(tmem + T_ST, r.dk_k + 2 * k, r.dq_k + 2 * k, r.id_s, k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          ptx::mma_bf16_ss(tmem + T_DP, ptx::smem_desc_sw128(do_addr + k * 32, 16, 1024),
-                           ptx::smem_desc_sw128(v_addr + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
+        for (int k = 0; k < HD / 16; ++k) ptx::mma_bf16_ss(tmem + T_DPT, r.dv_k + 2 * k, r.ddo_k + 2 * k, r.id_s, k > 0 ? 1u : 0u);
         ptx::mma_commit(bar_sdp);
       }
-      // ---- this thread's query row: P and dS of the chunk -> shared memory ----
-      const int qrow = qt * 128 + t;
-      float lse = INFINITY, dlt = 0.f;
-      if (qrow < a.N) {
-        const long long si = ((long long)b * a.H + h) * a.N + qrow;
-        lse = a.lse2[si];
-        dlt = a.delta[si];
-      }
-      ptx::mbar_wait(bar_sdp, ph_sdp);
-      ph_sdp ^= 1;
-      ptx::tc_fence_after();
-      for (int c = 0; c < cw / 16; ++c) {
-        float sv[16], dp[16];
-        ptx::tmem_ld16(t_lane + T_S + c * 16, sv);
-        ptx::tmem_ld16(t_lane + T_DP + c * 16, dp);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int key = kc * 128 + c * 16 + j;
-          const float p = (key < a.N) ? exp2f(fmaf(sv[j], LOG2E, -lse)) : 0.f;
-          sv[j] = p;
-          dp[j] = p * (dp[j] - dlt);
+      __syncwarp();
+    };
+    const uint32_t id_ts = ptx::idesc_bf16(128, HD, 0, 1);   // A from TMEM, B MN-major
+    const uint32_t id_dq = ptx::idesc_bf16(128, HD, 1, 1);   // A, B MN-major
+    const uint64_t dds_mn = ptx::smem_desc_sw128(ptx::smem_u32(sDS), 16384, 1024);
+    const int total = n_mine * n_iter;
+    if (n_mine > 0) {
+      load_set(blockIdx.x, 0, s0);
+      if (nt > 1) load_set(blockIdx.x, 1, s1);
+      else if (n_mine > 1) load_set((int)blockIdx.x + (int)gridDim.x, 0, 1);
+      TR(1);
+      Iter cur = make_iter(0);
+      issue_a(cur);
+      int idx = 0;
+      for (int gi = 0; gi < total; ++gi) {
+        // ---- operand prefetch, into sets whose last reader has retired ----
+        if (nt == 1) {
+          if (idx + 2 < n_mine) {
+            if (gi > 0) ptx::mbar_wait(bar_c, (gi - 1) & 1);
+            load_set((int)blockIdx.x + (idx + 2) * (int)gridDim.x, 0, (idx + 2) % 3);   // the set of item idx-1
+          }
+        } else if (idx + 1 < n_mine && (cur.it == 0 || cur.it == 3)) {
+          const int next_item = (int)blockIdx.x + (idx + 1) * (int)gridDim.x;
+          if (gi > 0) ptx::mbar_wait(bar_c, (gi - 1) & 1);   // every accumulating MMA issued so far has retired
+          if (cur.it == 0) load_set(next_item, 0, sf);        // sf: rows [128,256) of the previous item
+          else load_set(next_item, 1, s0);                    // s0: last read by iteration 2
         }
-        store_bf16x8_sw128(sP, t, c * 16, sv);
-        store_bf16x8_sw128(sP, t, c * 16 + 8, sv + 8);
-        store_bf16x8_sw128(sDS, t, c * 16, dp);
-        store_bf16x8_sw128(sDS, t, c * 16 + 8, dp + 8);
-      }
-      ptx::fence_async_shared();
-      ptx::tc_fence_before();
-      __syncthreads();
-      if (t == 0) {
-        ptx::tc_fence_after();
-        const uint32_t ds_addr = ptx::smem_u32(sDS), p_addr = ptx::smem_u32(sP);
-        const uint32_t q_addr = ptx::smem_u32(sQ + qt * 16384), do_addr = ptx::smem_u32(sDO + qt * 16384);
-        const uint32_t k_addr = ptx::smem_u32(sK);
-        // dQ = dS K : contraction over the chunk's keys
-        const uint32_t id_q = ptx::idesc_bf16(128, HD, 0, 1);
-        for (int ks = 0; ks < cw / 16; ++ks)
-          ptx::mma_bf16_ss(tmem + T_DQ,
-                           ptx::smem_desc_sw128(ds_addr + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                           ptx::smem_desc_sw128(k_addr + ks * 2048, 8192, 1024), id_q, ks > 0 ? 1u : 0u);
-        // dK += dS^T Q, dV += P^T dO : contraction over the tile's 128 query rows
-        const uint32_t id_kv = ptx::idesc_bf16(128, HD, 1, 1);
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t acc = (qt > 0 || ks > 0) ? 1u : 0u;
-          ptx::mma_bf16_ss(tmem + T_DK, ptx::smem_desc_sw128(ds_addr + ks * 2048, 16384, 1024),
-                           ptx::smem_desc_sw128(q_addr + ks * 2048, 8192, 1024), id_kv, acc);
-          ptx::mma_bf16_ss(tmem + T_DV, ptx::smem_desc_sw128(p_addr + ks * 2048, 16384, 1024),
-                           ptx::smem_desc_sw128(do_addr + ks * 2048, 8192, 1024), id_kv, acc);
-        }
-        ptx::mma_commit(bar_mma2);
-      }
-      ptx::mbar_wait(bar_mma2, ph_mma2);
-      ph_mma2 ^= 1;
-      ptx::tc_fence_after();
-      // ---- dQ epilogue (thread = query row) ----
-      {
-        float* scr = a.dq_scratch ? a.dq_scratch + ((long long)blockIdx.x * 256 + qrow) * HD : nullptr;
-        const bool last = (kc == a.n_kc - 1);
-#pragma unroll
-        for (int c = 0; c < HD / 16; ++c) {
-          float v[16];
-          ptx::tmem_ld16(t_lane + T_DQ + c * 16, v);
-          ptx::tmem_ld_wait();
-          if (qrow < a.N) {
-            if (kc > 0) {
-              const float4* sp = reinterpret_cast<const float4*>(scr + c * 16);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 x = sp[i];
-                v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
-              }
-            }
-            if (last) {
-              uint32_t w[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                w[j] = *reinterpret_cast<uint32_t*>(&hh);
-              }
-              uint4* o = reinterpret_cast<uint4*>(dz + ((long long)b * a.N + qrow) * a.R + h * HD + c * 16);
-              o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-              o[1] = make_uint4(w[4], w[5], w[6], w[7]);
-            } else {
-              float4* sp = reinterpret_cast<float4*>(scr + c * 16);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) sp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            }
+        // ---- the next iteration's descriptors, before the wait ----
+        const bool has_next = gi + 1 < total;
+        Iter nxt = cur;
+        if (has_next) {
+          if (cur.it == n_iter - 1) {
+            ++idx;
+            if (nt == 1) { s0 = idx % 3; }
+            else { const int t = s0; s0 = sf; sf = s1; s1 = t; }   // (s0, s1, sf) <- (sf, s0, s1)
+            nxt = make_iter(0);
+          } else {
+            nxt = make_iter(cur.it + 1);
           }
         }
+        TR(3);
+        // ---- wait for P^T / dS^T (TMEM) and dS^T (shared memory) of iteration gi ----
+        ptx::mbar_wait(bar_pds, gi & 1);
+        ptx::tc_fence_after();
+        if (cur.qt == 0 && n_epi < n_epi_due) {  // the accumulators of the previous chunk have been read out
+          ptx::mbar_wait(bar_epi, n_epi & 1);
+          ++n_epi;
+          ptx::tc_fence_after();
+        }
+        TR(5);
+        if (leader) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {  // contraction over the tile's queries (16 rows = 2048 B = 128 units)
+            if (ks < cur.nq) {
+              ptx::mma_bf16_ts(tmem + T_DV, tmem + T_ST + ks * 8, cur.ddo_mn + 128 * ks, id_ts, ks > 0 ? 1u : cur.acc_q);
+              ptx::mma_bf16_ts(tmem + T_DK, tmem + T_DPT + ks * 8, cur.dq_mn + 128 * ks, id_ts, ks > 0 ? 1u : cur.acc_q);
+            }
+          }
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)    // contraction over the chunk's keys
+            if (ks < cur.nk)
+              ptx::mma_bf16_ss(tmem + T_DQ + cur.qt * 64, dds_mn + 128 * ks, cur.dk_mn + 128 * ks, id_dq,
+                               ks > 0 ? 1u : cur.acc_k);
+          ptx::mma_commit(bar_c);
+        }
+        __syncwarp();
+        if (cur.qt == nt - 1) ++n_epi_due;  // the compute warps read this chunk's accumulators out next
+        if (has_next) issue_a(nxt);
+        TR(7);
+        cur = nxt;
       }
-      ptx::tc_fence_before();
-      __syncthreads();
     }
-    // ---- dK / dV epilogue of this key chunk (thread = key row) ----
-    {
-      const int key = kc * 128 + t;
+  } else if (warp >= 9) {
+    // =========================== lse / delta loader (128 threads) ===========================
+    // The values of item idx are formed in registers while item idx-1 is being computed and dropped
+    // into the (single) shared-memory buffer the moment that item is finished.
+    const int tl = threadIdx.x - 9 * 32;
+    for (int idx = 0; idx < n_mine; ++idx) {
+      const int item = (int)blockIdx.x + idx * (int)gridDim.x;
+      const int hh = item % a.H, bb = item / a.H;
+      TR(100);
+      float lse[2], dl[2];
 #pragma unroll
-      for (int which = 0; which < 2; ++which) {
-        __nv_bfloat16* dst = dz + ((long long)b * a.N + key) * a.R + (which + 1) * a.D + h * HD;
+      for (int r = 0; r < 2; ++r) {
+        const int q = tl + r * 128;
+        lse[r] = INFINITY;
+        dl[r] = 0.f;
+        if (q < a.N) {
+          lse[r] = a.lse2[(long long)item * a.N + q];
+          const uint4* pd = reinterpret_cast<const uint4*>(a.dO + ((long long)bb * a.N + q) * a.D + hh * HD);
+          const uint4* po = reinterpret_cast<const uint4*>(a.O + ((long long)bb * a.N + q) * a.ld_o + hh * HD);
+          uint4 x[8], y[8];
 #pragma unroll
-        for (int c = 0; c < HD / 16; ++c) {
-          float v[16];
-          ptx::tmem_ld16(t_lane + (which ? T_DV : T_DK) + c * 16, v);
-          ptx::tmem_ld_wait();
-          if (key < a.N) {
-            uint32_t w[8];
+          for (int i = 0; i < 8; ++i) { x[i] = pd[i]; y[i] = po[i]; }
+          float acc = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t xs[4] = {x[i].x, x[i].y, x[i].z, x[i].w}, ys[4] = {y[i].x, y[i].y, y[i].z, y[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162 xb = *reinterpret_cast<const __nv_bfloat162*>(&xs[j]);
+              const __nv_bfloat162 yb = *reinterpret_cast<const __nv_bfloat162*>(&ys[j]);
+              acc = fmaf(__low2float(xb), __low2float(yb), acc);
+              acc = fmaf(__high2float(xb), __high2float(yb), acc);
+            }
+          }
+          dl[r] = acc;
+        }
+      }
+      TR(102);
+      if (idx >= 1) ptx::mbar_wait(bar_item, (idx - 1) & 1);  // the previous item no longer reads the buffer
+      TR(104);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        sLse[tl + r * 128] = lse[r];
+        sDelta[tl + r * 128] = dl[r];
+      }
+      ptx::mbar_arrive(bar_aux);
+    }
+  } else {
+    // =========================== compute warps (thread = key row) ===========================
+    const int wg = warp >> 2, quarter = warp & 3;
+    const int trow = quarter * 32 + lane;  // row inside a 128-row tile / chunk
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    __nv_bfloat16* dz = reinterpret_cast<__nv_bfloat16*>(a.dz);
+    constexpr float LOG2E = 1.4426950408889634f;
+    uint32_t g = 0;  // global iteration counter (phases of bar_sdp / bar_c)
+    for (int idx = 0; idx < n_mine; ++idx) {
+      const int item = (int)blockIdx.x + idx * (int)gridDim.x;
+      const int h = item % a.H, b = item / a.H;
+      const float* lse_s = sLse;
+      const float* dl_s = sDelta;
+      TR(22);
+      ptx::mbar_wait(bar_aux, idx & 1);
+      TR(24);
+      for (int it = 0; it < n_iter; ++it, ++g) {
+        const int kc = it / nt, qt = it - kc * nt;
+        const int qw = min(128, NP - qt * 128);
+        const int nch = qw / 16;
+        const int c_lo = wg ? (nch + 1) / 2 : 0, c_hi = wg ? nch : (nch + 1) / 2;   // this warpgroup's chunks
+        const bool key_ok = (kc * 128 + trow) < a.N;
+        TR(0);
+        ptx::mbar_wait(bar_sdp, g & 1);
+        ptx::tc_fence_after();
+        TR(2);
+        uint32_t pP[4][8], pDS[4][8];
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = c_lo + ci;
+          if (c < c_hi) {
+            float sv[16], dp[16];
+            ptx::tmem_ld16(t_lane + T_ST + c * 16, sv);
+            ptx::tmem_ld16(t_lane + T_DPT + c * 16, dp);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int q = qt * 128 + c * 16 + j;
+              const float p = key_ok ? ex2_fast(fmaf(sv[j], LOG2E, -lse_s[q])) : 0.f;
+              sv[j] = p;
+              dp[j] = p * (dp[j] - dl_s[q]);
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-              w[j] = *reinterpret_cast<uint32_t*>(&hh);
+              __nv_bfloat162 hp = __floats2bfloat162_rn(sv[2 * j], sv[2 * j + 1]);
+              __nv_bfloat162 hd = __floats2bfloat162_rn(dp[2 * j], dp[2 * j + 1]);
+              pP[ci][j] = *reinterpret_cast<uint32_t*>(&hp);
+              pDS[ci][j] = *reinterpret_cast<uint32_t*>(&hd);
             }
-            uint4* o = reinterpret_cast<uint4*>(dst + c * 16);
-            o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-            o[1] = make_uint4(w[4], w[5], w[6], w[7]);
           }
         }
+        // the dS^T tile is single-buffered: the dQ MMA of the previous iteration must have retired
+        TR(4);
+        if (g > 0) ptx::mbar_wait(bar_c, (g - 1) & 1);
+        TR(6);
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = c_lo + ci;
+          if (c < c_hi) {
+            store_bf16x8_sw128(sDS, trow, c * 16, pDS[ci]);
+            store_bf16x8_sw128(sDS, trow, c * 16 + 8, pDS[ci] + 4);
+          }
+        }
+        ptx::tc_fence_before();
+        TR(8);
+        compute_bar_sync();  // every thread has read its S^T / dP^T columns: they may be overwritten
+        ptx::tc_fence_after();
+        TR(10);
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = c_lo + ci;
+          if (c < c_hi) {
+            tmem_st8(t_lane + T_ST + c * 8, pP[ci]);
+            tmem_st8(t_lane + T_DPT + c * 8, pDS[ci]);
+          }
+        }
+        ptx::tmem_st_wait();
+        TR(12);
+        ptx::fence_async_shared();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(bar_pds);
+        TR(14);
+        if (qt == nt - 1) {
+          // ---- dK | dV of this key chunk: warpgroup 0 -> dK, warpgroup 1 -> dV (thread = key row) ----
+          ptx::mbar_wait(bar_c, g & 1);
+          ptx::tc_fence_after();
+          TR(16);
+          // (the dS^T tile is idle here -- every MMA that reads it has retired -- and serves as staging)
+          uint8_t* stage = sDS + warp * 4096;
+          const int key0 = kc * 128 + quarter * 32;  // first of this warp's 32 key rows
+          store_rows_bf16(dz + ((long long)b * a.N + key0) * a.R + (wg + 1) * a.D + h * HD, a.R,
+                          t_lane + (wg ? T_DV : T_DK), stage, lane, a.N - key0);
+          if (kc == nt - 1 && wg < nt) {
+            // ---- dQ: warpgroup qt reads tile qt (thread = query row); every MMA of the item has retired
+            const int q0 = wg * 128 + quarter * 32;
+            store_rows_bf16(dz + ((long long)b * a.N + q0) * a.R + h * HD, a.R, t_lane + T_DQ + wg * 64, stage, lane,
+                            a.N - q0);
+          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(bar_epi);
+          compute_bar_sync();  // staging regions are dS^T rows of other warps in the next iteration
+          TR(18);
+        }
       }
+      TR(20);
+      ptx::mbar_arrive(bar_item);
     }
-    ptx::tc_fence_before();
-    __syncthreads();
   }
-  if (warp == 0) {
+  ptx::tc_fence_before();
+  __syncthreads();
+#ifdef ATTN_TRACE
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int w = 0; w < 3; ++w)
+      for (int i = 0; i < tr_n[w]; ++i) printf("TR %d %d %u\n", w, (int)tr_id[w][i], tr[w][i]);
+  }
+#endif
+  if (warp == 8) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem, BWD_TMEM_COLS);
-  }
-}
-
-// delta[b,h,i] = sum_d dO[i, h*64+d] * O[i, h*64+d]    (one warp per token row, all heads)
-__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, long long ld_do,
-                                                         const __nv_bfloat16* __restrict__ O, long long ld_o,
-                                                         float* __restrict__ delta, int B, int N, int H) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= B * N) return;
-  const int b = row / N, i = row - b * N;
-  for (int h = 0; h < H; ++h) {
-    const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(dO + (long long)row * ld_do + h * HD + lane * 2);
-    const __nv_bfloat162 y = *reinterpret_cast<const __nv_bfloat162*>(O + (long long)row * ld_o + h * HD + lane * 2);
-    float s = __low2float(x) * __low2float(y) + __high2float(x) * __high2float(y);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) delta[((long long)b * H + h) * N + i] = s;
   }
 }
 
@@ -521,33 +719,42 @@ int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, float*
   return 0;
 }
 
-size_t attn_bwd_tc_scratch_floats(int B, int N, int H) { return N > 128 ? (size_t)B * H * 256 * HD : 0; }
+size_t attn_bwd_tc_scratch_floats(int B, int N, int H) {
+  (void)B; (void)N; (void)H;
+  return 0;  // dQ accumulates in tensor memory across key chunks
+}
 
-// qkv [B,N,3D] bf16; dO [B*N, D] bf16; O = oh[:, 0:D] (ld_oh); lse2, delta [B,H,N] fp32 (delta is
-// written here); dz [B*N, R] bf16 receives dq | dk | dv.
+// qkv [B,N,3D] bf16; dO [B*N, D] bf16; O = oh[:, 0:D] (ld_oh); lse2 [B,H,N] fp32; dz [B*N, R] bf16
+// receives dq | dk | dv.  (`delta`, `dq_scratch` are unused: delta is formed in the kernel.)
 int attn_bwd_tc(const void* qkv, const void* dO, const void* oh, long long ld_oh, const float* lse2, float* delta,
                 void* dz, int R, float* dq_scratch, int B, int N, int H, int D, cudaStream_t s) {
+  (void)delta; (void)dq_scratch;
   if (!attn_fwd_tc_supports(N, D, H, DT_BF16, ld_oh) || R % 8)
     return set_error(ODEVIT_ERR_UNSUPPORTED, "attn_bwd_tc: unsupported shape N=%d D=%d H=%d", N, D, H);
   ProfScope prof(KC_FUSED_ATTN_BWD, s);
-  attn_delta_kernel<<<(B * N + 7) / 8, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dO), D,
-                                                     reinterpret_cast<const __nv_bfloat16*>(oh), ld_oh, delta, B, N, H);
-  ODV_LAUNCH_CHECK();
   AttnBwdArgs a;
   a.B = B; a.N = N; a.H = H; a.D = D; a.R = R;
-  a.n_kc = (N + 127) / 128; a.n_qt = (N + 127) / 128;
-  a.lse2 = lse2; a.delta = delta; a.dz = dz; a.dq_scratch = dq_scratch;
-  if (a.n_kc > 1 && !dq_scratch) return set_error(ODEVIT_ERR_WORKSPACE, "attn_bwd_tc: scratch missing");
+  a.n_t = (N + 127) / 128;
+  a.items = B * H;
+  a.lse2 = lse2; a.dz = dz;
+  a.dO = reinterpret_cast<const __nv_bfloat16*>(dO);
+  a.O = reinterpret_cast<const __nv_bfloat16*>(oh);
+  a.ld_o = ld_oh;
   CUtensorMap tqkv, tdo;
   ODV_TRY(make_tmap_3d_bf16(&tqkv, qkv, 3 * D, N, B, 3 * D, (uint64_t)N * 3 * D, HD, 128, 1));
   ODV_TRY(make_tmap_3d_bf16(&tdo, dO, D, N, B, D, (uint64_t)N * D, HD, 128, 1));
-  const int smem = 10 * 16384 + 1024 + 64;
+  const int smem = 3 * SET + 32768 + 2048 + 128;
   static bool configured = false;
+  static int sms = 148;
   if (!configured) {
     ODV_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int dev = 0;
+    ODV_CUDA(cudaGetDevice(&dev));
+    ODV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     configured = true;
   }
-  attn_bwd_tc_kernel<<<B * H, 128, smem, s>>>(tqkv, tdo, a);
+  const int grid = a.items < sms ? a.items : sms;
+  attn_bwd_tc_kernel<<<grid, BWD_THREADS, smem, s>>>(tqkv, tdo, a);
   ODV_LAUNCH_CHECK();
   return 0;
 }
