@@ -225,6 +225,7 @@ int odevit_gemm_bf16(int32_t M, int32_t N, int32_t K, int32_t mn_major, const vo
  * after the work has been enqueued; it returns the summed milliseconds and the launch count of
  * class `kclass` since the last enable, or a negative status.  Process-wide like the counter. */
 int odevit_profile_enable(int32_t on);
+int odevit_profile_reserve(int32_t pairs); /* pre-create event pairs (keeps cudaEventCreate out of timed regions) */
 int odevit_profile_num_classes(void);
 const char* odevit_profile_class_name(int32_t kclass);
 int odevit_profile_read(int32_t kclass, double* total_ms, int64_t* launches);

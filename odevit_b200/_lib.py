@@ -97,6 +97,8 @@ def lib() -> ctypes.CDLL:
     L.odevit_gemm_bf16.argtypes = [ctypes.c_int32] * 4 + [_vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _vp]
     L.odevit_profile_enable.restype = ctypes.c_int
     L.odevit_profile_enable.argtypes = [ctypes.c_int32]
+    L.odevit_profile_reserve.restype = ctypes.c_int
+    L.odevit_profile_reserve.argtypes = [ctypes.c_int32]
     L.odevit_profile_num_classes.restype = ctypes.c_int
     L.odevit_profile_class_name.restype = ctypes.c_char_p
     L.odevit_profile_class_name.argtypes = [ctypes.c_int32]
@@ -127,6 +129,10 @@ def profile_enable(on: bool) -> None:
     check(lib().odevit_profile_enable(1 if on else 0), "odevit_profile_enable")
 
 
+def profile_reserve(pairs: int) -> None:
+    check(lib().odevit_profile_reserve(int(pairs)), "odevit_profile_reserve")
+
+
 def profile_read() -> dict:
     """{class name: (total_ms, launches)} of the launches recorded since profile_enable(True)."""
     L = lib()
@@ -142,5 +148,5 @@ def profile_read() -> dict:
 DECLARED_SYMBOLS = ("odevit_abi_version", "odevit_build_info", "odevit_last_error_string",
                     "odevit_workspace_bytes", "odevit_field_fwd", "odevit_solve_fwd", "odevit_solve_bwd",
                     "odevit_field_bwd", "odevit_tape_bytes", "odevit_fd_curvature", "odevit_launch_count", "odevit_reset_launch_count",
-                    "odevit_gemm_bf16", "odevit_profile_enable", "odevit_profile_num_classes", "odevit_profile_class_name",
+                    "odevit_gemm_bf16", "odevit_profile_enable", "odevit_profile_reserve", "odevit_profile_num_classes", "odevit_profile_class_name",
                     "odevit_profile_read")

@@ -59,7 +59,7 @@ ProfState g_prof;
 const char* const kClassNames[KC_COUNT] = {
     "center_rows", "gemm_in_qkv_fc1", "attn_qk", "softmax", "attn_pv", "gemm_out_rk",
     "bwd_gemm_doh", "bwd_gemm_g2", "bwd_attn", "bwd_softmax", "bwd_gemm_dx", "bwd_gemm_g1",
-    "bwd_colsum", "combine", "weights", "fused_attn", "fused_attn_bwd", "fd_curvature", "other"};
+    "bwd_colsum", "combine", "weights", "fused_attn", "fused_attn_bwd", "fd_curvature", "fused_attn_export", "other"};
 }  // namespace
 
 ProfScope::ProfScope(int c, cudaStream_t st) : cls(c), s(st), slot(-1) {
@@ -633,6 +633,23 @@ int odevit_profile_enable(int32_t on) {
     p.on = true;
   } else {
     p.on = false;
+  }
+  return 0;
+}
+int odevit_profile_reserve(int32_t pairs) {
+  // create the event pairs up front, so that cudaEventCreate never lands inside a timed region
+  ProfState& p = g_prof;
+  std::lock_guard<std::mutex> lock(p.mu);
+  if (!p.ev) {
+    p.ev = new cudaEvent_t[2 * kMaxProfPairs];
+    p.cls = new int[kMaxProfPairs];
+    p.cap = 0;
+  }
+  if (pairs > kMaxProfPairs) pairs = kMaxProfPairs;
+  while (p.cap < pairs) {
+    if (cudaEventCreate(&p.ev[2 * p.cap]) != cudaSuccess || cudaEventCreate(&p.ev[2 * p.cap + 1]) != cudaSuccess)
+      return set_error(ODEVIT_ERR_CUDA, "odevit_profile_reserve: cudaEventCreate failed at pair %d", p.cap);
+    ++p.cap;
   }
   return 0;
 }

@@ -695,7 +695,7 @@ int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, float*
                 cudaStream_t s) {
   if (!attn_fwd_tc_supports(N, D, H, DT_BF16, ld_oh))
     return set_error(ODEVIT_ERR_UNSUPPORTED, "attn_fwd_tc: unsupported shape N=%d D=%d H=%d", N, D, H);
-  ProfScope prof(KC_FUSED_ATTN, s);
+  ProfScope prof(p_out ? KC_FUSED_ATTN_EXPORT : KC_FUSED_ATTN, s);
   AttnArgs a;
   a.B = B; a.N = N; a.H = H; a.D = D;
   a.NP = (N + 15) / 16 * 16;
