@@ -292,6 +292,12 @@ def run_ours(args, wl):
     tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PF sustained"
     cf = class_flops(cfg, B)
+    traffic = {}
+    try:   # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/r01_b_ncu_full.md)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    traffic_ok = (args.workload == "c100" and B == wl["batch"] and args.precision == "bf16")
     total_ms = sum(v[0] for v in prof.values()) or 1.0
     shares = {k: round(v[0] / total_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
     roofline = None
@@ -300,7 +306,8 @@ def run_ours(args, wl):
         k, (ms, n) = max(gemm_classes, key=lambda kv: kv[1][0])
         achieved = cf[k] / (ms / n * 1e-3) / 1e12
         roofline = {"kernel": k, "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                    "frac": achieved / tensor_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / tensor_peak,
+                    "traffic": traffic.get(k) if traffic_ok else None, "peak_source": peak_src,
                     "avg_launch_us": ms / n * 1e3, "launches": n, "share_of_kernel_time": shares.get(k)}
 
     # ---- HBM-bound row kernels: algorithmic bytes per launch / measured launch time
@@ -316,7 +323,8 @@ def run_ours(args, wl):
             ms, n = prof[k]
             gbs = nbytes / (ms / n * 1e-3) / 1e9
             roofline_hbm[k] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                               "frac": gbs / hbm_peak, "avg_launch_us": ms / n * 1e3, "launches": n}
+                               "frac": gbs / hbm_peak, "avg_launch_us": ms / n * 1e3, "launches": n,
+                               "algorithmic_bytes": nbytes, "traffic": traffic.get(k) if traffic_ok else None}
 
     if rank == 0:
         cpu_baseline = None
