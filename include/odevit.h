@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define ODEVIT_ABI_VERSION 2
+#define ODEVIT_ABI_VERSION 3
 
 typedef struct CUstream_st* odevit_stream_t; /* == cudaStream_t */
 
@@ -84,7 +84,17 @@ typedef struct {
   int32_t variant;     /* odevit_variant                                                      */
   int32_t precision;   /* odevit_precision                                                    */
   float scaler;        /* ViT_ODEFunc.scaler (emulate_depth if time_interval == 1 else 1)     */
-  int32_t reserved[7];
+  /* Training-mode dropout (0 = off; PARALLEL / PARALLEL_L2): on the attention map (the returned P is
+   * post-dropout), after out_proj, and after GELU + after fc2 (ode_transformer_gpt.py:56, :61, :196-199,
+   * :217-231).  Masks are re-drawn at every field evaluation from a counter-based generator keyed
+   * by (seed, evaluation index, site, element): the reverse sweep regenerates them, nothing is stored.
+   * Not bit-compatible with PyTorch's Philox stream. */
+  float attn_drop;
+  float proj_drop;
+  float mlp_drop;
+  uint32_t drop_seed_lo;
+  uint32_t drop_seed_hi;
+  int32_t reserved[2];
 } odevit_desc;
 
 /* Weights of the vector field, fp32 device pointers in state_dict layout; unused = NULL.

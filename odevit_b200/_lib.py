@@ -13,7 +13,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libodevit.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # enums of include/odevit.h
 FIELD_PARALLEL, FIELD_PARALLEL_L2, FIELD_MACARON = 0, 1, 2
@@ -37,7 +37,9 @@ class Desc(ctypes.Structure):
     _fields_ = [("abi_version", ctypes.c_int32), ("batch", ctypes.c_int32), ("tokens", ctypes.c_int32),
                 ("dim", ctypes.c_int32), ("heads", ctypes.c_int32), ("hidden", ctypes.c_int32),
                 ("variant", ctypes.c_int32), ("precision", ctypes.c_int32), ("scaler", ctypes.c_float),
-                ("reserved", ctypes.c_int32 * 7)]
+                ("attn_drop", ctypes.c_float), ("proj_drop", ctypes.c_float), ("mlp_drop", ctypes.c_float),
+                ("drop_seed_lo", ctypes.c_uint32), ("drop_seed_hi", ctypes.c_uint32),
+                ("reserved", ctypes.c_int32 * 2)]
 
 
 class Weights(ctypes.Structure):

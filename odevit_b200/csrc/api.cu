@@ -19,6 +19,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "epilogue.cuh"
 #include "host.h"
 #include "internal.h"
 
@@ -129,6 +130,13 @@ int make_plan(const odevit_desc* desc, Plan* p) {
   p->act = (p->precision == ODEVIT_BF16) ? DT_BF16 : DT_F32;
   // MACARON: the cotangent runs along the fp32 residual chain x -> x1 -> x2 -> x3
   p->dd_type = (p->variant == ODEVIT_FIELD_MACARON) ? DT_F32 : p->act;
+  p->p_attn = desc->attn_drop; p->p_proj = desc->proj_drop; p->p_mlp = desc->mlp_drop;
+  p->seed_lo = desc->drop_seed_lo; p->seed_hi = desc->drop_seed_hi;
+  for (float q : {p->p_attn, p->p_proj, p->p_mlp})
+    if (!(q >= 0.f && q < 1.f)) return set_error(ODEVIT_ERR_INVALID_ARG, "dropout probability %g outside [0, 1)", q);
+  p->split_out = (p->p_proj > 0.f || p->p_mlp > 0.f);
+  if (p->variant == ODEVIT_FIELD_MACARON && (p->split_out || p->p_attn > 0.f))
+    return set_error(ODEVIT_ERR_UNSUPPORTED, "dropout > 0 is not built for the MACARON field");
   p->BHNN = (long long)p->B * p->H * p->N * p->N;
   return 0;
 }
@@ -177,6 +185,7 @@ struct FwdBufs {
   float* k[3];
   float* ytmp[2];
   float* sq;
+  float* tmp;
 };
 FwdBufs layout_fwd(const Plan& p, Arena& a, int S) {
   FwdBufs f;
@@ -188,6 +197,7 @@ FwdBufs layout_fwd(const Plan& p, Arena& a, int S) {
   f.ytmp[0] = a.f32((size_t)p.M * p.D);
   f.ytmp[1] = a.f32((size_t)p.M * p.D);
   f.sq = (p.variant == ODEVIT_FIELD_PARALLEL_L2) ? a.f32((size_t)2 * p.B * p.H * p.N) : nullptr;
+  f.tmp = p.split_out ? a.f32((size_t)p.M * p.D) : nullptr;
   return f;
 }
 
@@ -225,6 +235,9 @@ BwdBufs layout_bwd(const Plan& p, Arena& a, int S) {
   b.dn = mac ? a.f32(MD) : nullptr;
   b.ddc = mac ? a.take(MD * e) : nullptr;
   b.sq = (p.variant == ODEVIT_FIELD_PARALLEL_L2) ? a.f32((size_t)2 * p.B * p.H * p.N) : nullptr;
+  b.tmp = p.split_out ? a.f32(MD) : nullptr;
+  b.dd1 = p.split_out ? a.take(MD * e) : nullptr;
+  b.dd2 = p.split_out ? a.take(MD * e) : nullptr;
   return b;
 }
 
@@ -309,6 +322,18 @@ HeadView qkv_view(const Plan& p) { return {(long long)p.N * 3 * p.D, (long long)
 // ------------------------------------------------------------------------------------------------
 // GEMM dispatch: tcgen05 in bf16 mode where the kernel covers the shape, FFMA otherwise
 // ------------------------------------------------------------------------------------------------
+Drop make_drop(const Plan& p, int site, long long e) {
+  Drop d;
+  const float q = (site == DS_ATTN) ? p.p_attn : (site == DS_PROJ) ? p.p_proj : p.p_mlp;
+  if (!(q > 0.f)) return d;
+  const double t = (double)q * 4294967296.0;
+  d.thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+  if (d.thresh == 0) d.thresh = 1;
+  d.scale = 1.f / (1.f - q);
+  d.key = drop_mix(p.seed_lo ^ drop_mix(p.seed_hi ^ 0x632BE5ABu) ^ ((uint32_t)(e * 4 + site + 1) * 0x27D4EB2Fu));
+  return d;
+}
+
 int gemm(const Plan& p, const GemmArgs& g, cudaStream_t s) {
   if (p.precision == ODEVIT_BF16 && gemm_tc_supports(g)) return gemm_tc(g, s);
   return gemm_simt(g, s);
@@ -319,11 +344,11 @@ int gemm(const Plan& p, const GemmArgs& g, cudaStream_t s) {
 // batched FFMA products + row kernels.  PARALLEL_L2 swaps the softmax for the L2 weights (:48-56).
 // ------------------------------------------------------------------------------------------------
 int attention_forward(const Plan& p, const void* qkv_v, void* oh, long long ld_oh, float* P, float* p_copy,
-                      float* lse, float* sq, cudaStream_t s) {
+                      float* lse, float* sq, Drop drop, cudaStream_t s) {
   const int D = p.D;
   const bool l2 = (p.variant == ODEVIT_FIELD_PARALLEL_L2);
   if (!l2 && p.precision == ODEVIT_BF16 && attn_fwd_tc_supports(p.N, D, p.H, p.act, ld_oh))
-    return attn_fwd_tc(qkv_v, oh, ld_oh, p_copy, lse, p.B, p.N, p.H, D, s);
+    return attn_fwd_tc(qkv_v, oh, ld_oh, p_copy, lse, p.B, p.N, p.H, D, drop, s);
   const HeadView hv = qkv_view(p);
   const char* qkv = reinterpret_cast<const char*>(qkv_v);
   const size_t e = dtype_size(p.act);
@@ -342,10 +367,12 @@ int attention_forward(const Plan& p, const void* qkv_v, void* oh, long long ld_o
   if (l2) {
     if (!sq) return set_error(ODEVIT_ERR_WORKSPACE, "L2 attention: squared-norm scratch missing");
     ODV_TRY(head_sqnorm(qkv_v, p.act, sq, p.B, p.N, p.H, D, s));
-    ODV_TRY(l2_prob_rows(P, sq, 1.f / sqrtf((float)p.d), p_copy, p.B, p.H, p.N, s));
+    ODV_TRY(l2_prob_rows(P, sq, 1.f / sqrtf((float)p.d), drop.thresh ? nullptr : p_copy, p.B, p.H, p.N, s));
   } else {
-    ODV_TRY(softmax_rows(P, p_copy, (long long)p.B * p.H * p.N, p.N, s));
+    ODV_TRY(softmax_rows(P, drop.thresh ? nullptr : p_copy, (long long)p.B * p.H * p.N, p.N, s));
   }
+  // attention-map dropout: what the caller sees (p_copy) and what multiplies v are both post-dropout
+  if (drop.thresh) ODV_TRY(drop_inplace_f32(P, p_copy, drop, (long long)p.B * p.H * p.N, p.N, s));
   {  // O = P v  -> columns [h*d, (h+1)*d) of the output buffer
     GemmArgs g;
     g.M = p.N; g.N = p.d; g.K = p.N;
@@ -363,14 +390,14 @@ int attention_forward(const Plan& p, const void* qkv_v, void* oh, long long ld_o
 }
 
 int attention_vjp(const Plan& p, const void* qkv_v, const void* oh, long long ld_oh, const float* lse, BwdBufs& b,
-                  const float* g_p, void* dz_v, int R, cudaStream_t s) {
+                  const float* g_p, void* dz_v, int R, Drop drop, cudaStream_t s) {
   const int D = p.D;
   const bool l2 = (p.variant == ODEVIT_FIELD_PARALLEL_L2);
   const size_t e = dtype_size(p.act);
   char* dz = reinterpret_cast<char*>(dz_v);
   if (!l2 && p.precision == ODEVIT_BF16 && !g_p && lse && attn_fwd_tc_supports(p.N, D, p.H, p.act, ld_oh)) {
     // fused tcgen05 kernel (P recomputed on chip from q, k and the saved row log-sum-exp)
-    return attn_bwd_tc(qkv_v, b.dO, oh, ld_oh, lse, b.delta, dz_v, R, b.dq_scratch, p.B, p.N, p.H, D, s);
+    return attn_bwd_tc(qkv_v, b.dO, oh, ld_oh, lse, b.delta, dz_v, R, b.dq_scratch, p.B, p.N, p.H, D, drop, s);
   }
   const HeadView hv = qkv_view(p);
   const char* qkv = reinterpret_cast<const char*>(qkv_v);
@@ -405,8 +432,15 @@ int attention_vjp(const Plan& p, const void* qkv_v, const void* oh, long long ld
     g.epi.out = b.dP; g.epi.ld_out = p.N; g.epi.out_bo = pbo; g.epi.out_bi = pbi;
     ODV_TRY(head_gemm(g));
   }
+  if (drop.thresh) {
+    // O = drop(P) v and the exported map is drop(P):  cotangent of P = mask o (dO v^T + g_p)
+    if (g_p) ODV_TRY(axpy_f32(b.dP, g_p, 1.f, p.BHNN, s));
+    ODV_TRY(drop_inplace_f32(b.dP, nullptr, drop, (long long)p.B * p.H * p.N, p.N, s));
+    g_p = nullptr;
+  }
   // ds = P o (dP - sum_j P dP): also the L2 weights' VJP w.r.t. -scale*dist^2 (the +1e-8 drops out)
   ODV_TRY(softmax_bwd_rows(b.P, b.dP, g_p, (long long)p.B * p.H * p.N, p.N, s));
+  if (drop.thresh) ODV_TRY(drop_inplace_f32(b.P, nullptr, drop, (long long)p.B * p.H * p.N, p.N, s));  // dv uses drop(P)
   {  // dq = ds k      (MHA: dq is the cotangent of the already-scaled q, the scale lives in W1cat)
     GemmArgs g;
     g.M = p.N; g.N = p.d; g.K = p.N;
@@ -444,7 +478,7 @@ namespace {
 
 // Forward evaluation at stage input `u`.  `rk` (nullable) is the epilogue of the last GEMM.
 int eval_forward(const Plan& p, const WeightBufs& wb, const StageCtx& c, const float* u, float* P,
-                 float* p_copy, float* sq, const Epi* rk, cudaStream_t s) {
+                 float* p_copy, float* sq, float* tmp, long long e, const Epi* rk, cudaStream_t s) {
   if (p.variant == ODEVIT_FIELD_MACARON) return macaron_forward(p, wb, c, u, P, rk, s);
   const int D = p.D, hid = p.hid, R = 3 * D + hid, K2 = D + hid;
   ODV_TRY(center_rows(u, c.xc, p.act, nullptr, 0.f, p.M, D, s));
@@ -461,10 +495,45 @@ int eval_forward(const Plan& p, const WeightBufs& wb, const StageCtx& c, const f
     g.epi.out2 = reinterpret_cast<char*>(c.oh) + (size_t)D * dtype_size(p.act); g.epi.ld_out2 = K2;
     g.epi.out3 = c.hpre; g.epi.ld_out3 = hid;
     g.epi.aux_type = p.act;
+    g.epi.drop = make_drop(p, DS_MLP_H, e);   // dropout after GELU (:196-197)
     ODV_TRY(gemm(p, g, s));
   }
-  ODV_TRY(attention_forward(p, c.qkv, c.oh, K2, P, p_copy, c.lse, sq, s));
-  if (rk) {
+  ODV_TRY(attention_forward(p, c.qkv, c.oh, K2, P, p_copy, c.lse, sq, make_drop(p, DS_ATTN, e), s));
+  if (rk && p.split_out) {
+    // out-proj and fc2 outputs take different dropout masks (:231 proj_drop, :199 mlp drop): two GEMMs,
+    // the first parks scaler * drop(h W2^T) in `tmp`, the second adds it (Epi::resid) before the stage combine
+    const size_t es = dtype_size(p.act);
+    if (!tmp) return set_error(ODEVIT_ERR_WORKSPACE, "dropout: scratch for the split output projection missing");
+    {
+      GemmArgs g;
+      g.M = p.M; g.N = D; g.K = hid;
+      g.A = reinterpret_cast<const char*>(c.oh) + (size_t)D * es; g.a_type = p.act; g.a_rs = K2; g.a_cs = 1;
+      g.B = reinterpret_cast<const char*>(wb.w2cat) + (size_t)D * es; g.b_type = p.act; g.b_rs = K2; g.b_cs = 1;
+      g.epi_mode = EPI_RK;
+      g.kclass = KC_GEMM_OUT;
+      g.epi.alpha = p.scaler;
+      g.epi.c_new = 1.f;
+      g.epi.out = tmp;
+      g.epi.ld_out = D;
+      g.epi.drop = make_drop(p, DS_MLP_OUT, e);
+      ODV_TRY(gemm(p, g, s));
+    }
+    {
+      GemmArgs g;
+      g.M = p.M; g.N = D; g.K = D;
+      g.A = c.oh; g.a_type = p.act; g.a_rs = K2; g.a_cs = 1;
+      g.B = wb.w2cat; g.b_type = p.act; g.b_rs = K2; g.b_cs = 1;
+      g.epi_mode = EPI_RK;
+      g.kclass = KC_GEMM_OUT;
+      g.epi = *rk;
+      g.epi.bias = wb.b2;
+      g.epi.alpha = p.scaler;
+      g.epi.ld_out = D;
+      g.epi.drop = make_drop(p, DS_PROJ, e);
+      g.epi.resid = tmp; g.epi.resid_coef = 1.f;
+      ODV_TRY(gemm(p, g, s));
+    }
+  } else if (rk) {
     GemmArgs g;
     g.M = p.M; g.N = D; g.K = K2;
     g.A = c.oh; g.a_type = p.act; g.a_rs = K2; g.a_cs = 1;
@@ -503,7 +572,7 @@ Epi rk_epilogue(const Tableau& tb, int st, float dt, const float* y, float* cons
 // (W1cat^T is stored row-centred, so the GEMM yields the centred value directly; the reverse-mode
 // stage combination rides in that epilogue instead of a separate pass over [M, D]).
 int eval_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b, const float* g_p,
-             bool need_c2, const odevit_weight_grads* gw, const Epi& mu_epi, cudaStream_t s) {
+             bool need_c2, const odevit_weight_grads* gw, long long ev, const Epi& mu_epi, cudaStream_t s) {
   if (p.variant == ODEVIT_FIELD_MACARON) {
     if (g_p) return set_error(ODEVIT_ERR_UNSUPPORTED, "MACARON has no attention-map output (macaron.py:60-65)");
     return macaron_vjp(p, wb, c, b, gw, mu_epi, s);
@@ -511,6 +580,56 @@ int eval_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b,
   const int D = p.D, hid = p.hid, R = 3 * D + hid, K2 = D + hid;
   const size_t e = dtype_size(p.act);
   char* dz = reinterpret_cast<char*>(b.dz);
+  if (p.split_out) {
+    // the cotangent enters the out-proj branch under the proj mask and the fc2 branch under the mlp-output mask
+    if (gw->fc2_b) return set_error(ODEVIT_ERR_UNSUPPORTED, "dropout with an fc2 bias is not built (the reference has none)");
+    ODV_TRY(drop_pair_rows(b.dd, b.dd1, b.dd2, p.act, make_drop(p, DS_MLP_OUT, ev), make_drop(p, DS_PROJ, ev), p.M, D, s));
+    const char* w2T = reinterpret_cast<const char*>(wb.w2catT);
+    {  // dO = dd2 @ Wo
+      GemmArgs g;
+      g.M = p.M; g.N = D; g.K = D;
+      g.A = b.dd2; g.a_type = p.act; g.a_rs = D; g.a_cs = 1;
+      g.B = w2T; g.b_type = p.act; g.b_rs = D; g.b_cs = 1;
+      g.epi_mode = EPI_STORE;
+      g.kclass = KC_BWD_GEMM_DOH;
+      g.epi.out = b.dO; g.epi.out_type = p.act; g.epi.ld_out = D;
+      ODV_TRY(gemm(p, g, s));
+    }
+    {  // d h_pre = (dd1 @ W2) o mask_h o GELU'
+      GemmArgs g;
+      g.M = p.M; g.N = hid; g.K = D;
+      g.A = b.dd1; g.a_type = p.act; g.a_rs = D; g.a_cs = 1;
+      g.B = w2T + (size_t)D * D * e; g.b_type = p.act; g.b_rs = D; g.b_cs = 1;
+      g.epi_mode = EPI_BWD3;
+      g.kclass = KC_BWD_GEMM_DOH;
+      g.epi.split = 0;
+      g.epi.out2 = dz + (size_t)3 * D * e; g.epi.ld_out2 = R;
+      g.epi.aux = c.hpre; g.epi.ld_aux = hid; g.epi.aux_type = p.act;
+      g.epi.drop = make_drop(p, DS_MLP_H, ev);
+      ODV_TRY(gemm(p, g, s));
+    }
+    {  // G2[:, :D] += dd2^T O
+      GemmArgs g;
+      g.M = D; g.N = D; g.K = p.M;
+      g.A = b.dd2; g.a_type = p.act; g.a_rs = 1; g.a_cs = D;
+      g.B = c.oh; g.b_type = p.act; g.b_rs = 1; g.b_cs = K2;
+      g.epi_mode = EPI_ACCUM;
+      g.epi.out = b.G2; g.epi.ld_out = K2;
+      g.kclass = KC_BWD_GEMM_G2;
+      ODV_TRY(gemm(p, g, s));
+    }
+    {  // G2[:, D:] += dd1^T h   (h as the forward left it: after its dropout)
+      GemmArgs g;
+      g.M = D; g.N = hid; g.K = p.M;
+      g.A = b.dd1; g.a_type = p.act; g.a_rs = 1; g.a_cs = D;
+      g.B = reinterpret_cast<const char*>(c.oh) + (size_t)D * e; g.b_type = p.act; g.b_rs = 1; g.b_cs = K2;
+      g.epi_mode = EPI_ACCUM;
+      g.epi.out = b.G2 + D; g.epi.ld_out = K2;
+      g.kclass = KC_BWD_GEMM_G2;
+      ODV_TRY(gemm(p, g, s));
+    }
+    if (need_c2) ODV_TRY(colsum_accum(b.dd2, p.act, D, p.M, D, b.c2, s));
+  } else {
   {  // d[O|h] = dd @ [Wo|W2];  GELU' on the h half
     GemmArgs g;
     g.M = p.M; g.N = K2; g.K = D;
@@ -535,9 +654,10 @@ int eval_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b,
     ODV_TRY(gemm(p, g, s));
   }
   if (need_c2) ODV_TRY(colsum_accum(b.dd, p.act, D, p.M, D, b.c2, s));
+  }
 
   // ---- attention VJP per (image, head) ----------------------------------------------------------
-  ODV_TRY(attention_vjp(p, c.qkv, c.oh, K2, c.lse, b, g_p, b.dz, R, s));
+  ODV_TRY(attention_vjp(p, c.qkv, c.oh, K2, c.lse, b, g_p, b.dz, R, make_drop(p, DS_ATTN, ev), s));
   {  // mu = dz @ centred(W1cat), consumed by the caller's stage-combine epilogue
     GemmArgs g;
     g.M = p.M; g.N = D; g.K = R;
@@ -719,7 +839,7 @@ int odevit_field_fwd(const odevit_desc* desc, const odevit_weights* w, const flo
   rk.out = dx;
   rk.y = nullptr;
   rk.c_new = 1.f;
-  return eval_forward(p, f.w, f.ctx, x, f.P, p_out, f.sq, &rk, s);
+  return eval_forward(p, f.w, f.ctx, x, f.P, p_out, f.sq, f.tmp, 0, &rk, s);
 }
 
 int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t method, const float* x0,
@@ -776,7 +896,7 @@ int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
       if (p_traj && e >= p_traj_first_eval) p_copy = p_traj + (size_t)(e - p_traj_first_eval) * p.BHNN;
       else if (p_last && e == n_evals - 1) p_copy = p_last;
       const StageCtx ctx = tape ? tape_ctx(p, tape, e, nullptr, n_evals) : f.ctx;
-      ODV_TRY(eval_forward(p, f.w, ctx, u, f.P, p_copy, f.sq, &rk, s));
+      ODV_TRY(eval_forward(p, f.w, ctx, u, f.P, p_copy, f.sq, f.tmp, e, &rk, s));
       if (p_last && e == n_evals - 1 && p_copy != p_last)
         ODV_CUDA(cudaMemcpyAsync(p_last, p_copy, (size_t)p.BHNN * 4, cudaMemcpyDeviceToDevice, s));
     }
@@ -860,9 +980,9 @@ int odevit_solve_bwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
       const float* u = (st == 0) ? y : b.u;
       if (st < S - 1) {
         Epi rk = rk_epilogue(*tb, st, dt, y, b.k, b.u);
-        ODV_TRY(eval_forward(p, b.w, b.ctx[st], u, b.P, nullptr, b.sq, &rk, s));
+        ODV_TRY(eval_forward(p, b.w, b.ctx[st], u, b.P, nullptr, b.sq, b.tmp, (long long)j * S + st, &rk, s));
       } else {
-        ODV_TRY(eval_forward(p, b.w, b.ctx[st], u, b.P, nullptr, b.sq, nullptr, s));
+        ODV_TRY(eval_forward(p, b.w, b.ctx[st], u, b.P, nullptr, b.sq, b.tmp, (long long)j * S + st, nullptr, s));
       }
     }
     // (2) reverse through the stages
@@ -902,12 +1022,12 @@ int odevit_solve_bwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
           e.out2 = nullptr;
           dd_seeded = false;
         }
-        ODV_TRY(eval_vjp(p, b.w, ctx[st], b, last_eval ? g_p_last : nullptr, need_c2, gw, e, s));
+        ODV_TRY(eval_vjp(p, b.w, ctx[st], b, last_eval ? g_p_last : nullptr, need_c2, gw, (long long)j * S + st, e, s));
         if (!fits) ODV_TRY(inject(j));
         if (!dd_seeded && j > 0) ODV_TRY(seed_dd(t_grid_host[j] - t_grid_host[j - 1]));
         continue;
       }
-      ODV_TRY(eval_vjp(p, b.w, ctx[st], b, last_eval ? g_p_last : nullptr, need_c2, gw, e, s));
+      ODV_TRY(eval_vjp(p, b.w, ctx[st], b, last_eval ? g_p_last : nullptr, need_c2, gw, (long long)j * S + st, e, s));
     }
   }
   ODV_CUDA(cudaMemcpyAsync(g_x0, b.gy, MD * 4, cudaMemcpyDeviceToDevice, s));
@@ -940,7 +1060,7 @@ int odevit_field_bwd(const odevit_desc* desc, const odevit_weights* w, const flo
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   ODV_TRY(prepare_weights(p, w, b.w, s));
   ODV_CUDA(cudaMemsetAsync(b.G1, 0, b.acc_bytes, s));
-  ODV_TRY(eval_forward(p, b.w, b.ctx[0], x, b.P, nullptr, b.sq, nullptr, s));
+  ODV_TRY(eval_forward(p, b.w, b.ctx[0], x, b.P, nullptr, b.sq, b.tmp, 0, nullptr, s));
   {
     CombineArgs c0;
     c0.n_terms = 1; c0.term[0] = g_dx; c0.coef[0] = 1.f;
@@ -951,7 +1071,7 @@ int odevit_field_bwd(const odevit_desc* desc, const odevit_weights* w, const flo
     Epi e;
     e.c_new = 1.f;
     e.out = g_x;
-    ODV_TRY(eval_vjp(p, b.w, b.ctx[0], b, g_p, wants_c2(gw), gw, e, s));
+    ODV_TRY(eval_vjp(p, b.w, b.ctx[0], b, g_p, wants_c2(gw), gw, 0, e, s));
   }
   return finish_grads(p, w, gw, b, s);
 }

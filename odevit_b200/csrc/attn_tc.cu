@@ -21,6 +21,7 @@
 // EXPORT variant also writes the normalised fp32 P[b, h, :, :].
 #include <cuda.h>
 
+#include "epilogue.cuh"
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -43,6 +44,7 @@ struct AttnArgs {
   long long ld_oh;
   float* p_out;          // [B, H, N, N] fp32 or null
   float* lse_out;        // [B, H, N] fp32 or null: log2-domain log-sum-exp of each row (for the VJP)
+  Drop drop;             // attention-map dropout (element (b*H+h)*N + i, j); thresh 0 = off
 };
 
 template <bool EXPORT>
@@ -133,6 +135,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     inv = 1.f / sum;
   }
   const int row = mt * BMQ + warp * 32 + lane;
+  const uint32_t drow = (uint32_t)(((long long)b * a.H + h) * a.N + row);   // dropout coordinate of this row
   float* p_row = nullptr;
   if constexpr (EXPORT) {
     if (a.p_out && row < a.N) p_row = a.p_out + (((long long)b * a.H + h) * a.N + row) * a.N;
@@ -147,9 +150,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       float e = (c * 16 + j < a.N) ? exp2f(fmaf(v[j], LOG2E, -mxs)) : 0.f;
       if constexpr (EXPORT) {
         e *= inv;
+        if (a.drop.thresh) e *= drop_factor(a.drop, drow, c * 16 + j);   // the exported map is post-dropout
         if (p_row && c * 16 + j < a.N) p_row[c * 16 + j] = e;
       } else {
         sum += e;
+        if (a.drop.thresh) e *= drop_factor(a.drop, drow, c * 16 + j);
       }
       v[j] = e;
     }
@@ -253,6 +258,7 @@ struct AttnBwdArgs {
   const __nv_bfloat16* O;       // [B*N, ld_o]
   long long ld_o;
   void* dz;                     // [B*N, R] bf16: dq | dk | dv at columns h*64, D + h*64, 2D + h*64
+  Drop drop;                    // the forward's attention-map dropout, regenerated here
 };
 
 constexpr int BWD_TMEM_COLS = 512;
@@ -575,6 +581,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       const int h = item % a.H, b = item / a.H;
       const float* lse_s = sLse;
       const float* dl_s = sDelta;
+      const uint32_t drow0 = (uint32_t)((long long)item * a.N);   // dropout row coordinate of query 0
       TR(22);
       ptx::mbar_wait(bar_aux, idx & 1);
       TR(24);
@@ -601,8 +608,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             for (int j = 0; j < 16; ++j) {
               const int q = qt * 128 + c * 16 + j;
               const float p = key_ok ? ex2_fast(fmaf(sv[j], LOG2E, -lse_s[q])) : 0.f;
-              sv[j] = p;
-              dp[j] = p * (dp[j] - dl_s[q]);
+              if (a.drop.thresh) {
+                // O = drop(P) V:  dV needs drop(P)^T, dS = P o (drop'(dP) - delta)
+                const float f = drop_factor(a.drop, drow0 + q, kc * 128 + trow);
+                sv[j] = p * f;
+                dp[j] = p * (dp[j] * f - dl_s[q]);
+              } else {
+                sv[j] = p;
+                dp[j] = p * (dp[j] - dl_s[q]);
+              }
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -692,7 +706,7 @@ bool attn_fwd_tc_supports(int N, int D, int H, int act_type, long long ld_oh) {
 
 // qkv: [B, N, 3D] bf16 (q | k | v per row); oh: [B*N, ld_oh] bf16; p_out: [B,H,N,N] fp32 or null.
 int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, float* lse_out, int B, int N, int H, int D,
-                cudaStream_t s) {
+                Drop drop, cudaStream_t s) {
   if (!attn_fwd_tc_supports(N, D, H, DT_BF16, ld_oh))
     return set_error(ODEVIT_ERR_UNSUPPORTED, "attn_fwd_tc: unsupported shape N=%d D=%d H=%d", N, D, H);
   ProfScope prof(p_out ? KC_FUSED_ATTN_EXPORT : KC_FUSED_ATTN, s);
@@ -701,6 +715,7 @@ int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, float*
   a.NP = (N + 15) / 16 * 16;
   a.tiles_m = (N + BMQ - 1) / BMQ;
   a.oh = oh; a.ld_oh = ld_oh; a.p_out = p_out; a.lse_out = lse_out;
+  a.drop = drop;
   CUtensorMap tq, tkv;
   ODV_TRY(make_tmap_3d_bf16(&tq, qkv, 3 * D, N, B, 3 * D, (uint64_t)N * 3 * D, HD, BMQ, 1));
   ODV_TRY(make_tmap_3d_bf16(&tkv, qkv, 3 * D, N, B, 3 * D, (uint64_t)N * 3 * D, HD, a.NP, 1));
@@ -727,7 +742,7 @@ size_t attn_bwd_tc_scratch_floats(int B, int N, int H) {
 // qkv [B,N,3D] bf16; dO [B*N, D] bf16; O = oh[:, 0:D] (ld_oh); lse2 [B,H,N] fp32; dz [B*N, R] bf16
 // receives dq | dk | dv.  (`delta`, `dq_scratch` are unused: delta is formed in the kernel.)
 int attn_bwd_tc(const void* qkv, const void* dO, const void* oh, long long ld_oh, const float* lse2, float* delta,
-                void* dz, int R, float* dq_scratch, int B, int N, int H, int D, cudaStream_t s) {
+                void* dz, int R, float* dq_scratch, int B, int N, int H, int D, Drop drop, cudaStream_t s) {
   (void)delta; (void)dq_scratch;
   if (!attn_fwd_tc_supports(N, D, H, DT_BF16, ld_oh) || R % 8)
     return set_error(ODEVIT_ERR_UNSUPPORTED, "attn_bwd_tc: unsupported shape N=%d D=%d H=%d", N, D, H);
@@ -737,6 +752,7 @@ int attn_bwd_tc(const void* qkv, const void* dO, const void* oh, long long ld_oh
   a.n_t = (N + 127) / 128;
   a.items = B * H;
   a.lse2 = lse2; a.dz = dz;
+  a.drop = drop;
   a.dO = reinterpret_cast<const __nv_bfloat16*>(dO);
   a.O = reinterpret_cast<const __nv_bfloat16*>(oh);
   a.ld_o = ld_oh;

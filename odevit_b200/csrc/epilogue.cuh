@@ -27,6 +27,16 @@ __device__ __forceinline__ float load_elem_rw(const void* p, long long idx, int 
   return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[idx]);
 }
 
+// ---- counter-based dropout masks --------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t drop_mix(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+// multiplier of element (r, c): 0 (dropped) or 1/(1-p)
+__device__ __forceinline__ float drop_factor(const Drop& d, uint32_t r, uint32_t c) {
+  return drop_mix((r * 0x9E3779B1U) ^ (c * 0x85EBCA77U) ^ d.key) >= d.thresh ? d.scale : 0.f;
+}
+
 template <int EPI, bool ATOMIC>
 __device__ __forceinline__ void epi_apply(const Epi& e, int m, int n, float acc, int zo, int zi) {
   if constexpr (EPI == EPI_STORE) {
@@ -43,7 +53,9 @@ __device__ __forceinline__ void epi_apply(const Epi& e, int m, int n, float acc,
     } else {
       const int c = n - e.split;
       if (e.out3) store_elem(e.out3, (long long)m * e.ld_out3 + c, e.aux_type, v);
-      store_elem(e.out2, (long long)m * e.ld_out2 + c, e.aux_type, gelu_erf(v));
+      float gv = gelu_erf(v);
+      if (e.drop.thresh) gv *= drop_factor(e.drop, m, c);
+      store_elem(e.out2, (long long)m * e.ld_out2 + c, e.aux_type, gv);
     }
   } else if constexpr (EPI == EPI_RK) {
     float v = acc;
@@ -51,6 +63,7 @@ __device__ __forceinline__ void epi_apply(const Epi& e, int m, int n, float acc,
     v *= e.alpha;
     const long long idx = (long long)m * e.ld_out + n;
     if (e.dev_scale) v *= *e.dev_scale;
+    if (e.drop.thresh) v *= drop_factor(e.drop, m, n);
     if (e.resid) v = fmaf(e.resid_coef, e.resid[idx], v);
     if (e.k_store) e.k_store[idx] = v;
     float r = e.c_new * v;
@@ -67,6 +80,7 @@ __device__ __forceinline__ void epi_apply(const Epi& e, int m, int n, float acc,
       const int c = n - e.split;
       const float hp = load_elem_rw(e.aux, (long long)m * e.ld_aux + c, e.aux_type);
       if (e.dev_scale) acc *= *e.dev_scale;
+      if (e.drop.thresh) acc *= drop_factor(e.drop, m, c);
       store_elem(e.out2, (long long)m * e.ld_out2 + c, e.aux_type, acc * gelu_erf_grad(hp));
     }
   } else if constexpr (EPI == EPI_ACCUM) {
@@ -137,6 +151,10 @@ __device__ __forceinline__ void epi_chunk16(const Epi& e, int m, int n, float* v
       if (e.out3) store16(e.out3, (long long)m * e.ld_out3 + c, e.aux_type, v);
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+      if (e.drop.thresh) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] *= drop_factor(e.drop, m, c + j);
+      }
       store16(e.out2, (long long)m * e.ld_out2 + c, e.aux_type, v);
     }
   } else if constexpr (EPI == EPI_RK) {
@@ -148,6 +166,10 @@ __device__ __forceinline__ void epi_chunk16(const Epi& e, int m, int n, float* v
       const float ds = *e.dev_scale;
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] *= ds;
+    }
+    if (e.drop.thresh) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] *= drop_factor(e.drop, m, n + j);
     }
     if (e.resid) {
       load16(e.resid, idx, DT_F32, t);
@@ -185,7 +207,7 @@ __device__ __forceinline__ void epi_chunk16(const Epi& e, int m, int n, float* v
       load16(e.aux, (long long)m * e.ld_aux + c, e.aux_type, hp);
       const float ds = e.dev_scale ? *e.dev_scale : 1.f;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] *= ds * gelu_erf_grad(hp[j]);
+      for (int j = 0; j < 16; ++j) v[j] *= ds * gelu_erf_grad(hp[j]) * (e.drop.thresh ? drop_factor(e.drop, m, c + j) : 1.f);
       store16(e.out2, (long long)m * e.ld_out2 + c, e.aux_type, v);
     }
   } else if constexpr (EPI == EPI_ACCUM) {
@@ -310,8 +332,13 @@ __device__ __forceinline__ void epi_rows8(const Epi& e, int m0, int M, int n, fl
         if (!ok[i]) continue;
         const float4 v = add4(w[i], bias);
         if (e.out3) store4(e.out3, (long long)(m0 + 4 * i) * e.ld_out3 + c, e.aux_type, v);
-        store4(e.out2, (long long)(m0 + 4 * i) * e.ld_out2 + c, e.aux_type,
-               make_float4(gelu_fast(v.x), gelu_fast(v.y), gelu_fast(v.z), gelu_fast(v.w)));
+        float4 gv = make_float4(gelu_fast(v.x), gelu_fast(v.y), gelu_fast(v.z), gelu_fast(v.w));
+        if (e.drop.thresh) {
+          const uint32_t r = m0 + 4 * i;
+          gv.x *= drop_factor(e.drop, r, c); gv.y *= drop_factor(e.drop, r, c + 1);
+          gv.z *= drop_factor(e.drop, r, c + 2); gv.w *= drop_factor(e.drop, r, c + 3);
+        }
+        store4(e.out2, (long long)(m0 + 4 * i) * e.ld_out2 + c, e.aux_type, gv);
       }
     }
   } else if constexpr (EPI == EPI_RK) {
@@ -322,17 +349,24 @@ __device__ __forceinline__ void epi_rows8(const Epi& e, int m0, int M, int n, fl
 #pragma unroll
       for (int i = 0; i < 8; ++i) t[i] = ok[i] ? ldg_raw4(e.y, (long long)(m0 + 4 * i) * e.ld_out + n, DT_F32) : zero;
     }
-    if (e.resid) {
-      // Macaron tail: v = alpha*ds*(acc+bias) + resid_coef*resid (loads batched like the others)
-      Raw4 q[8];
+    Raw4 q[8];
+    if (e.resid) {   // v = drop(alpha*ds*(acc+bias)) + resid_coef*resid (loads batched like the others)
 #pragma unroll
       for (int i = 0; i < 8; ++i) q[i] = ok[i] ? ldg_raw4(e.resid, (long long)(m0 + 4 * i) * e.ld_out + n, DT_F32) : zero;
+    }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        w[i] = fma4(e.resid_coef, raw_to_float4(q[i], DT_F32), scale4(e.alpha * ds, add4(w[i], bias)));
-    } else {
+    for (int i = 0; i < 8; ++i) w[i] = scale4(e.alpha * ds, add4(w[i], bias));
+    if (e.drop.thresh) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) w[i] = scale4(e.alpha * ds, add4(w[i], bias));
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t r = m0 + 4 * i;
+        w[i].x *= drop_factor(e.drop, r, n); w[i].y *= drop_factor(e.drop, r, n + 1);
+        w[i].z *= drop_factor(e.drop, r, n + 2); w[i].w *= drop_factor(e.drop, r, n + 3);
+      }
+    }
+    if (e.resid) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = fma4(e.resid_coef, raw_to_float4(q[i], DT_F32), w[i]);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) r[i] = scale4(e.c_new, w[i]);
@@ -376,6 +410,11 @@ __device__ __forceinline__ void epi_rows8(const Epi& e, int m0, int M, int n, fl
         float4 v = scale4(ds, w[i]);
         v.x *= gelu_grad_fast(hp.x); v.y *= gelu_grad_fast(hp.y);
         v.z *= gelu_grad_fast(hp.z); v.w *= gelu_grad_fast(hp.w);
+        if (e.drop.thresh) {
+          const uint32_t r = m0 + 4 * i;
+          v.x *= drop_factor(e.drop, r, c); v.y *= drop_factor(e.drop, r, c + 1);
+          v.z *= drop_factor(e.drop, r, c + 2); v.w *= drop_factor(e.drop, r, c + 3);
+        }
         store4(e.out2, (long long)(m0 + 4 * i) * e.ld_out2 + c, e.aux_type, v);
       }
     }

@@ -88,7 +88,7 @@ int macaron_forward(const Plan& p, const WeightBufs& wb, const StageCtx& c, cons
     g.epi.out = c.qkv; g.epi.out_type = p.act; g.epi.ld_out = 3 * D;
     ODV_TRY(gemm(p, g, s));
   }
-  ODV_TRY(attention_forward(p, c.qkv, c.oh, K2, P, nullptr, c.lse, nullptr, s));
+  ODV_TRY(attention_forward(p, c.qkv, c.oh, K2, P, nullptr, c.lse, nullptr, Drop{}, s));
   {
     Epi e;
     e.bias = w->out_proj_b; e.alpha = 1.f; e.dev_scale = w->res_scale;
@@ -210,7 +210,7 @@ int macaron_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs&
     ODV_TRY(gemm(p, gm, s));
   }
   ODV_TRY(colsum_accum(b.ddc, p.act, D, p.M, D, b.c2, s));
-  ODV_TRY(attention_vjp(p, c.qkv, c.oh, K2, c.lse, b, nullptr, b.dz, R, s));  // dq|dk|dv -> dz[:, :3D] (ld R)
+  ODV_TRY(attention_vjp(p, c.qkv, c.oh, K2, c.lse, b, nullptr, b.dz, R, Drop{}, s));  // dq|dk|dv -> dz[:, :3D] (ld R)
   {  // dn2 = dz[:, :3D] @ W_in (q rows scaled)
     GemmArgs gm;
     gm.M = p.M; gm.N = D; gm.K = 3 * D;

@@ -11,7 +11,13 @@ struct Plan {
   int dd_type;                  // DType of the cotangent buffer entering a field VJP
   float scaler;
   long long BHNN;
+  // training-mode dropout (0 = off) and the per-call seed of the mask generator
+  float p_attn, p_proj, p_mlp;
+  uint32_t seed_lo, seed_hi;
+  bool split_out;   // proj / mlp dropout on: out-proj and fc2 run as two GEMMs (their outputs take different masks)
 };
+// mask of dropout site `site` in field evaluation `e` (e = step * stages + stage)
+Drop make_drop(const Plan& p, int site, long long e);
 
 struct Arena {
   char* base;
@@ -63,6 +69,8 @@ struct BwdBufs {
   float* dn;    // [M,D] fp32: cotangent of a LayerNorm output
   void* ddc;    // [M,D] act: cast/scaled copy of the running cotangent (GEMM operand)
   float* sq;    // [2,B,H,N] fp32: |q|^2, |k|^2 per head (L2 attention)
+  float* tmp;   // [M,D] fp32: masked fc2 output waiting for the out-proj GEMM (split_out)
+  void *dd1, *dd2;  // [M,D] act: the cotangent under the fc2-output / out-proj-output masks (split_out)
 };
 
 // GEMM dispatch: tcgen05 in bf16 mode where the kernel covers the problem, FFMA otherwise.
@@ -71,10 +79,10 @@ int gemm(const Plan& p, const GemmArgs& g, cudaStream_t s);
 // softmax(q k^T) v per (image, head) from the packed qkv buffer into oh[:, h*d ...] (leading dim ld_oh).
 // P: [B,H,N,N] fp32 scratch (unfused path); p_copy: optional export; lse: optional row log-sum-exp.
 int attention_forward(const Plan& p, const void* qkv, void* oh, long long ld_oh, float* P, float* p_copy,
-                      float* lse, float* sq, cudaStream_t s);
+                      float* lse, float* sq, Drop drop, cudaStream_t s);
 // Its VJP: dO [M,D] (act) -> dq|dk|dv into dz (leading dim R, act).  g_p: optional cotangent of P.
 int attention_vjp(const Plan& p, const void* qkv, const void* oh, long long ld_oh, const float* lse, BwdBufs& b,
-                  const float* g_p, void* dz, int R, cudaStream_t s);
+                  const float* g_p, void* dz, int R, Drop drop, cudaStream_t s);
 
 // MACARON field (field_macaron.cu)
 int macaron_forward(const Plan& p, const WeightBufs& wb, const StageCtx& c, const float* u, float* P,

@@ -99,6 +99,15 @@ enum EpiMode : int {
   EPI_ACCUM = 4   // out[m,n] += alpha*acc   (fp32; atomic when split-K)
 };
 
+// One dropout site of one field evaluation: element (r, c) is kept iff hash(key, r, c) >= thresh and then
+// multiplied by scale = 1/(1-p).  thresh == 0: no dropout.
+struct Drop {
+  uint32_t key = 0;
+  uint32_t thresh = 0;
+  float scale = 1.f;
+};
+enum DropSite : int { DS_ATTN = 0, DS_PROJ = 1, DS_MLP_H = 2, DS_MLP_OUT = 3 };
+
 struct Epi {
   float alpha = 1.f;
   const float* bias = nullptr;
@@ -126,6 +135,8 @@ struct Epi {
   // returns scaler * (x2 + half-FFN), macaron.py:118-123, :148)
   const float* resid = nullptr;
   float resid_coef = 0.f;
+  // dropout on the epilogue's value: EPI_FWD1 after GELU, EPI_RK on v (before resid), EPI_BWD3 on d h
+  Drop drop;
 };
 
 struct GemmArgs {
@@ -155,11 +166,11 @@ bool gemm_tc_supports(const GemmArgs& g);
 // optional fp32 P export.  Covers head dim 64, N <= 256.
 bool attn_fwd_tc_supports(int N, int D, int H, int act_type, long long ld_oh);
 int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, float* lse_out, int B, int N, int H, int D,
-                cudaStream_t s);
+                Drop drop, cudaStream_t s);
 // Fused attention VJP; needs the forward's lse2 [B,H,N]; writes delta [B,H,N] and dq|dk|dv into dz.
 size_t attn_bwd_tc_scratch_floats(int B, int N, int H);
 int attn_bwd_tc(const void* qkv, const void* dO, const void* oh, long long ld_oh, const float* lse2, float* delta,
-                void* dz, int R, float* dq_scratch, int B, int N, int H, int D, cudaStream_t s);
+                void* dz, int R, float* dq_scratch, int B, int N, int H, int D, Drop drop, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------
 // row-wise / elementwise kernels (odevit_rows.cu)
@@ -194,6 +205,12 @@ int vjp_combine(const CombineArgs& a, int rows, int D, cudaStream_t s);
 
 // per_seq[r] = max_j max_d |s[j+2,r,d] - 2 s[j+1,r,d] + s[j,r,d]| / dt2   (states [T, rows, D])
 int fd_curvature(const float* states, int T, long long rows, int D, float dt2, float* per_seq, cudaStream_t s);
+
+// out1 = x o mask(d1), out2 = x o mask(d2)  (x, out*: [rows, D] of type `type`; the two masked copies of
+// the cotangent that enter the fc2 and the out-proj branch when their output dropouts differ)
+int drop_pair_rows(const void* x, void* out1, void* out2, int type, Drop d1, Drop d2, int rows, int D, cudaStream_t s);
+// p[r, c] = keep(r, c) ? p[r, c] * scale : 0   (fp32 [rows, n]; the attention map of the CUDA-core path)
+int drop_inplace_f32(float* p, float* copy_to, Drop d, long long rows, int n, cudaStream_t s);
 
 // y[i] += a * x[i]
 int axpy_f32(float* y, const float* x, float a, long long n, cudaStream_t s);

@@ -205,6 +205,28 @@ __global__ void __launch_bounds__(256) vjp_combine_kernel(CombineArgs a, int row
   }
 }
 
+__global__ void __launch_bounds__(256) drop_pair_kernel(const void* x, void* out1, void* out2, int type, Drop d1,
+                                                        Drop d2, long long n, int D) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const uint32_t r = (uint32_t)(i / D), c = (uint32_t)(i % D);
+    const float v = load_elem_rw(x, i, type);
+    store_elem(out1, i, type, d1.thresh ? v * drop_factor(d1, r, c) : v);
+    store_elem(out2, i, type, d2.thresh ? v * drop_factor(d2, r, c) : v);
+  }
+}
+
+__global__ void __launch_bounds__(256) drop_inplace_kernel(float* p, float* copy_to, Drop d, long long total, int n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const float v = p[i] * drop_factor(d, (uint32_t)(i / n), (uint32_t)(i % n));
+    p[i] = v;
+    if (copy_to) copy_to[i] = v;
+  }
+}
+
 __global__ void axpy_kernel(float* y, const float* __restrict__ x, float a, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -693,6 +715,24 @@ int vjp_combine(const CombineArgs& a, int rows, int D, cudaStream_t s) {
   ProfScope prof(KC_COMBINE, s);
   if (D > 32 * MAX_PER_LANE) return set_error(ODEVIT_ERR_UNSUPPORTED, "vjp_combine: D=%d > 1024", D);
   vjp_combine_kernel<<<(rows + 7) / 8, 256, 0, s>>>(a, rows, D);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int drop_pair_rows(const void* x, void* out1, void* out2, int type, Drop d1, Drop d2, int rows, int D, cudaStream_t s) {
+  ProfScope prof(KC_COMBINE, s);
+  const long long n = (long long)rows * D;
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  drop_pair_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(x, out1, out2, type, d1, d2, n, D);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int drop_inplace_f32(float* p, float* copy_to, Drop d, long long rows, int n, cudaStream_t s) {
+  ProfScope prof(KC_SOFTMAX, s);
+  const long long total = rows * n;
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  drop_inplace_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(p, copy_to, d, total, n);
   ODV_LAUNCH_CHECK();
   return 0;
 }

@@ -32,6 +32,11 @@ class FieldSpec:
     variant: int = _lib.FIELD_PARALLEL
     precision: str = "bf16"
     backward: str = "auto"   # "tape" | "recompute" | "auto" (tape when it fits TAPE_BUDGET_FRACTION of free HBM)
+    # training-mode dropout (0 = off); masks come from a counter-based generator keyed by `seed`
+    attn_drop: float = 0.0
+    proj_drop: float = 0.0
+    mlp_drop: float = 0.0
+    seed: int = 0
 
     def desc(self, batch: int, tokens: int) -> _lib.Desc:
         d = _lib.Desc()
@@ -40,7 +45,20 @@ class FieldSpec:
         d.variant = self.variant
         d.precision = _lib.PRECISIONS[self.precision]
         d.scaler = float(self.scaler)
+        d.attn_drop, d.proj_drop, d.mlp_drop = float(self.attn_drop), float(self.proj_drop), float(self.mlp_drop)
+        d.drop_seed_lo, d.drop_seed_hi = self.seed & 0xFFFFFFFF, (self.seed >> 32) & 0xFFFFFFFF
         return d
+
+    @property
+    def has_dropout(self) -> bool:
+        return self.attn_drop > 0 or self.proj_drop > 0 or self.mlp_drop > 0
+
+
+def draw_seed() -> int:
+    """A fresh 64-bit mask seed from PyTorch's default CPU generator (so `torch.manual_seed` makes
+    dropout reproducible, as it does in the reference)."""
+    hi, lo = torch.randint(0, 2 ** 31 - 1, (2,)).tolist()
+    return (int(hi) << 32) | int(lo)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -98,10 +98,11 @@ class L2SelfAttention(nn.Module):
 
 
 def _check_no_dropout(mod: nn.Module, *ps: float) -> None:
+    """Variants whose kernels have no dropout (Macaron)."""
     if mod.training and any(p > 0 for p in ps):
         raise NotImplementedError(
-            "odevit_b200: dropout > 0 in training mode is not built yet (the reference re-samples "
-            "dropout at every field evaluation; SURVEY 2.3 quirk 16). Use p=0 or .eval().")
+            "odevit_b200: dropout > 0 in training mode is not built for this field (the reference "
+            "re-samples dropout at every field evaluation; SURVEY 2.3 quirk 16). Use p=0 or .eval().")
 
 
 class ParallelAttentionMLP(nn.Module):
@@ -128,10 +129,16 @@ class ParallelAttentionMLP(nn.Module):
     # -- what the kernels consume --------------------------------------------------------------
     def field_spec(self, scaler: float) -> ops.FieldSpec:
         hidden = self.mlp.fc1.weight.shape[0]
+        # dropout is live in training mode only; every call draws a fresh seed, and inside a solve the
+        # masks are re-drawn at every field evaluation from (seed, evaluation index) -- SURVEY 2.3 quirk 16
+        attn_drop, proj_drop, mlp_drop = self._drops if self.training else (0.0, 0.0, 0.0)
+        seed = ops.draw_seed() if (attn_drop > 0 or proj_drop > 0 or mlp_drop > 0) else 0
         return ops.FieldSpec(dim=self.dim, heads=self.num_heads, hidden=hidden, scaler=float(scaler),
                              variant=_lib.FIELD_PARALLEL_L2 if self.use_l2 else _lib.FIELD_PARALLEL,
                              precision=self.precision,
-                             backward=getattr(self, "backward_mode", "auto"))
+                             backward=getattr(self, "backward_mode", "auto"),
+                             attn_drop=float(attn_drop), proj_drop=float(proj_drop), mlp_drop=float(mlp_drop),
+                             seed=seed)
 
     def field_weights(self) -> Dict[str, Optional[torch.Tensor]]:
         """odevit_weights field name -> parameter, read at call time."""
@@ -158,7 +165,6 @@ class ParallelAttentionMLP(nn.Module):
         return w
 
     def forward(self, x: torch.Tensor, t: Optional[torch.Tensor] = None) -> torch.Tensor:
-        _check_no_dropout(self, *self._drops)
         dx, self.attentions = ops.field_eval(x, self.field_spec(1.0), self.field_weights(), want_p=True)
         return dx
 
@@ -177,7 +183,6 @@ class ViT_ODEFunc(nn.Module):
         self.scaler = float(emulate_depth) if time_interval == 1.0 else 1.0
 
     def forward(self, t: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-        _check_no_dropout(self.block, *self.block._drops)
         dx, p = ops.field_eval(x, self.block.field_spec(self.scaler), self.block.field_weights(), want_p=True)
         self.block.attentions = p
         if not hasattr(self, "attention_trajectory"):
@@ -197,11 +202,12 @@ def odeint(func: ViT_ODEFunc, y0: torch.Tensor, t: torch.Tensor, *, method: str 
     if not (hasattr(func, "block") and hasattr(func.block, "field_spec") and hasattr(func, "scaler")):
         raise TypeError("odevit_b200.odeint integrates odevit_b200 vector-field modules only "
                         "(there is no generic / CPU solver in this package)")
-    if func.block.field_spec(1.0).variant == _lib.FIELD_MACARON:
+    if hasattr(func.block, "res_scale"):   # the Macaron block
         record_attention = False   # macaron.py:60-65: need_weights=False, the block exposes no map
     if options:
         raise NotImplementedError("odeint options (step_size, ...) are not used by the reference and not built")
-    _check_no_dropout(func.block, *func.block._drops)
+    if hasattr(func.block, "res_scale"):
+        _check_no_dropout(func.block, *func.block._drops)
     res = ops.ode_solve(y0, t, func.block.field_spec(func.scaler), method, func.block.field_weights(),
                         want_p_last=record_attention, p_traj_first=0 if record_attention else None)
     if record_attention:
@@ -396,7 +402,6 @@ class ViTNeuralODE(nn.Module):
         """:548-645.  Same output dict; the attention maps are exported only for the evaluations a
         caller can observe (last one for `attentions`, the JaSMin window, all on request)."""
         block = self.odefunc.block
-        _check_no_dropout(block, *block._drops)
         R = self.patch_embed.num_register_tokens
         tokens = self.patch_embed(pixel_values)
         if t_grid is None:
