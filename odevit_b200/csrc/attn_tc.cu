@@ -47,7 +47,7 @@ struct AttnArgs {
   Drop drop;             // attention-map dropout (element (b*H+h)*N + i, j); thresh 0 = off
 };
 
-template <bool EXPORT>
+template <bool EXPORT, bool DROP>
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const __grid_constant__ AttnArgs a) {
@@ -150,11 +150,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       float e = (c * 16 + j < a.N) ? exp2f(fmaf(v[j], LOG2E, -mxs)) : 0.f;
       if constexpr (EXPORT) {
         e *= inv;
-        if (a.drop.thresh) e *= drop_factor(a.drop, drow, c * 16 + j);   // the exported map is post-dropout
+        if constexpr (DROP) e *= drop_factor(a.drop, drow, c * 16 + j);   // the exported map is post-dropout
         if (p_row && c * 16 + j < a.N) p_row[c * 16 + j] = e;
       } else {
         sum += e;
-        if (a.drop.thresh) e *= drop_factor(a.drop, drow, c * 16 + j);
+        if constexpr (DROP) e *= drop_factor(a.drop, drow, c * 16 + j);
       }
       v[j] = e;
     }
@@ -327,6 +327,7 @@ __device__ int tr_n[3];
 #define TR(slot) do { } while (0)
 #endif
 
+template <bool DROP>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ AttnBwdArgs a) {
@@ -608,7 +609,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             for (int j = 0; j < 16; ++j) {
               const int q = qt * 128 + c * 16 + j;
               const float p = key_ok ? ex2_fast(fmaf(sv[j], LOG2E, -lse_s[q])) : 0.f;
-              if (a.drop.thresh) {
+              if constexpr (DROP) {
                 // O = drop(P) V:  dV needs drop(P)^T, dS = P o (drop'(dP) - delta)
                 const float f = drop_factor(a.drop, drow0 + q, kc * 128 + trow);
                 sv[j] = p * f;
@@ -724,12 +725,19 @@ int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, float*
   static bool configured = false;
   if (!configured) {
     const int max_smem = BMQ * HD * 2 + 2 * 256 * HD * 2 + 1024 + 64;
-    ODV_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    ODV_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    ODV_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    ODV_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    ODV_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    ODV_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;
   }
-  if (p_out) attn_fwd_tc_kernel<true><<<grid, 128, smem, s>>>(tq, tkv, a);
-  else attn_fwd_tc_kernel<false><<<grid, 128, smem, s>>>(tq, tkv, a);
+  if (drop.thresh) {
+    if (p_out) attn_fwd_tc_kernel<true, true><<<grid, 128, smem, s>>>(tq, tkv, a);
+    else attn_fwd_tc_kernel<false, true><<<grid, 128, smem, s>>>(tq, tkv, a);
+  } else {
+    if (p_out) attn_fwd_tc_kernel<true, false><<<grid, 128, smem, s>>>(tq, tkv, a);
+    else attn_fwd_tc_kernel<false, false><<<grid, 128, smem, s>>>(tq, tkv, a);
+  }
   ODV_LAUNCH_CHECK();
   return 0;
 }
@@ -763,14 +771,16 @@ int attn_bwd_tc(const void* qkv, const void* dO, const void* oh, long long ld_oh
   static bool configured = false;
   static int sms = 148;
   if (!configured) {
-    ODV_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ODV_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ODV_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int dev = 0;
     ODV_CUDA(cudaGetDevice(&dev));
     ODV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     configured = true;
   }
   const int grid = a.items < sms ? a.items : sms;
-  attn_bwd_tc_kernel<<<grid, BWD_THREADS, smem, s>>>(tqkv, tdo, a);
+  if (drop.thresh) attn_bwd_tc_kernel<true><<<grid, BWD_THREADS, smem, s>>>(tqkv, tdo, a);
+  else attn_bwd_tc_kernel<false><<<grid, BWD_THREADS, smem, s>>>(tqkv, tdo, a);
   ODV_LAUNCH_CHECK();
   return 0;
 }

@@ -39,13 +39,13 @@ __device__ __forceinline__ float drop_factor(const Drop& d, uint32_t r, uint32_t
 
 template <int EPI, bool ATOMIC>
 __device__ __forceinline__ void epi_apply(const Epi& e, int m, int n, float acc, int zo, int zi) {
-  if constexpr (EPI == EPI_STORE) {
+  if constexpr ((EPI & 7) == EPI_STORE) {
     float v = e.alpha * acc;
     if (e.dev_scale) v *= *e.dev_scale;
     if (e.bias) v += e.bias[n];
     const long long idx = (long long)zo * e.out_bo + (long long)zi * e.out_bi + (long long)m * e.ld_out + n;
     store_elem(e.out, idx, e.out_type, v);
-  } else if constexpr (EPI == EPI_FWD1) {
+  } else if constexpr ((EPI & 7) == EPI_FWD1) {
     float v = acc;
     if (e.bias) v += e.bias[n];
     if (n < e.split) {
@@ -54,16 +54,16 @@ __device__ __forceinline__ void epi_apply(const Epi& e, int m, int n, float acc,
       const int c = n - e.split;
       if (e.out3) store_elem(e.out3, (long long)m * e.ld_out3 + c, e.aux_type, v);
       float gv = gelu_erf(v);
-      if (e.drop.thresh) gv *= drop_factor(e.drop, m, c);
+      if constexpr ((EPI & EPI_DROP) != 0) gv *= drop_factor(e.drop, m, c);
       store_elem(e.out2, (long long)m * e.ld_out2 + c, e.aux_type, gv);
     }
-  } else if constexpr (EPI == EPI_RK) {
+  } else if constexpr ((EPI & 7) == EPI_RK) {
     float v = acc;
     if (e.bias) v += e.bias[n];
     v *= e.alpha;
     const long long idx = (long long)m * e.ld_out + n;
     if (e.dev_scale) v *= *e.dev_scale;
-    if (e.drop.thresh) v *= drop_factor(e.drop, m, n);
+    if constexpr ((EPI & EPI_DROP) != 0) v *= drop_factor(e.drop, m, n);
     if (e.resid) v = fmaf(e.resid_coef, e.resid[idx], v);
     if (e.k_store) e.k_store[idx] = v;
     float r = e.c_new * v;
@@ -73,17 +73,17 @@ __device__ __forceinline__ void epi_apply(const Epi& e, int m, int n, float acc,
       if (e.kin[i]) r = fmaf(e.c_k[i], e.kin[i][idx], r);
     if (e.out) reinterpret_cast<float*>(e.out)[idx] = r;
     if (e.out2) store_elem(e.out2, idx, e.aux_type, e.out2_scale * r);
-  } else if constexpr (EPI == EPI_BWD3) {
+  } else if constexpr ((EPI & 7) == EPI_BWD3) {
     if (n < e.split) {
       store_elem(e.out, (long long)m * e.ld_out + n, e.out_type, acc);
     } else {
       const int c = n - e.split;
       const float hp = load_elem_rw(e.aux, (long long)m * e.ld_aux + c, e.aux_type);
       if (e.dev_scale) acc *= *e.dev_scale;
-      if (e.drop.thresh) acc *= drop_factor(e.drop, m, c);
+      if constexpr ((EPI & EPI_DROP) != 0) acc *= drop_factor(e.drop, m, c);
       store_elem(e.out2, (long long)m * e.ld_out2 + c, e.aux_type, acc * gelu_erf_grad(hp));
     }
-  } else if constexpr (EPI == EPI_ACCUM) {
+  } else if constexpr ((EPI & 7) == EPI_ACCUM) {
     float* o = reinterpret_cast<float*>(e.out) + (long long)m * e.ld_out + n;
     if constexpr (ATOMIC) atomicAdd(o, e.alpha * acc);
     else *o += e.alpha * acc;
@@ -135,11 +135,11 @@ __device__ __forceinline__ void load16(const void* p, long long idx, int type, f
 
 template <int EPI, bool ATOMIC>
 __device__ __forceinline__ void epi_chunk16(const Epi& e, int m, int n, float* v) {
-  if constexpr (EPI == EPI_STORE) {
+  if constexpr ((EPI & 7) == EPI_STORE) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = e.alpha * (e.dev_scale ? *e.dev_scale : 1.f) * v[j] + (e.bias ? e.bias[n + j] : 0.f);
     store16(e.out, (long long)m * e.ld_out + n, e.out_type, v);
-  } else if constexpr (EPI == EPI_FWD1) {
+  } else if constexpr ((EPI & 7) == EPI_FWD1) {
     if (e.bias) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] += e.bias[n + j];
@@ -151,13 +151,13 @@ __device__ __forceinline__ void epi_chunk16(const Epi& e, int m, int n, float* v
       if (e.out3) store16(e.out3, (long long)m * e.ld_out3 + c, e.aux_type, v);
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
-      if (e.drop.thresh) {
+      if constexpr ((EPI & EPI_DROP) != 0) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] *= drop_factor(e.drop, m, c + j);
       }
       store16(e.out2, (long long)m * e.ld_out2 + c, e.aux_type, v);
     }
-  } else if constexpr (EPI == EPI_RK) {
+  } else if constexpr ((EPI & 7) == EPI_RK) {
     const long long idx = (long long)m * e.ld_out + n;
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = e.alpha * (v[j] + (e.bias ? e.bias[n + j] : 0.f));
@@ -167,7 +167,7 @@ __device__ __forceinline__ void epi_chunk16(const Epi& e, int m, int n, float* v
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] *= ds;
     }
-    if (e.drop.thresh) {
+    if constexpr ((EPI & EPI_DROP) != 0) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] *= drop_factor(e.drop, m, n + j);
     }
@@ -198,7 +198,7 @@ __device__ __forceinline__ void epi_chunk16(const Epi& e, int m, int n, float* v
       for (int j = 0; j < 16; ++j) r[j] *= e.out2_scale;
       store16(e.out2, idx, e.aux_type, r);
     }
-  } else if constexpr (EPI == EPI_BWD3) {
+  } else if constexpr ((EPI & 7) == EPI_BWD3) {
     if (n < e.split) {
       store16(e.out, (long long)m * e.ld_out + n, e.out_type, v);
     } else {
@@ -207,10 +207,10 @@ __device__ __forceinline__ void epi_chunk16(const Epi& e, int m, int n, float* v
       load16(e.aux, (long long)m * e.ld_aux + c, e.aux_type, hp);
       const float ds = e.dev_scale ? *e.dev_scale : 1.f;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] *= ds * gelu_erf_grad(hp[j]) * (e.drop.thresh ? drop_factor(e.drop, m, c + j) : 1.f);
+      for (int j = 0; j < 16; ++j) v[j] *= ds * gelu_erf_grad(hp[j]) * ((EPI & EPI_DROP) != 0 ? drop_factor(e.drop, m, c + j) : 1.f);
       store16(e.out2, (long long)m * e.ld_out2 + c, e.aux_type, v);
     }
-  } else if constexpr (EPI == EPI_ACCUM) {
+  } else if constexpr ((EPI & 7) == EPI_ACCUM) {
     float* o = reinterpret_cast<float*>(e.out) + (long long)m * e.ld_out + n;
     if constexpr (ATOMIC) {
 #pragma unroll
@@ -309,18 +309,18 @@ __device__ __forceinline__ void epi_rows8(const Epi& e, int m0, int M, int n, fl
 #pragma unroll
   for (int i = 0; i < 8; ++i) ok[i] = (m0 + 4 * i) < M;
   float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-  if constexpr (EPI == EPI_STORE || EPI == EPI_FWD1 || EPI == EPI_RK) {
+  if constexpr ((EPI & 7) == EPI_STORE || (EPI & 7) == EPI_FWD1 || (EPI & 7) == EPI_RK) {
     if (e.bias) bias = *reinterpret_cast<const float4*>(e.bias + n);
   }
   float ds = 1.f;
-  if constexpr (EPI == EPI_STORE || EPI == EPI_RK || EPI == EPI_BWD3) {
+  if constexpr ((EPI & 7) == EPI_STORE || (EPI & 7) == EPI_RK || (EPI & 7) == EPI_BWD3) {
     if (e.dev_scale) ds = *e.dev_scale;
   }
-  if constexpr (EPI == EPI_STORE) {
+  if constexpr ((EPI & 7) == EPI_STORE) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       if (ok[i]) store4(e.out, (long long)(m0 + 4 * i) * e.ld_out + n, e.out_type, fma4(e.alpha * ds, w[i], bias));
-  } else if constexpr (EPI == EPI_FWD1) {
+  } else if constexpr ((EPI & 7) == EPI_FWD1) {
     if (n < e.split) {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -333,7 +333,7 @@ __device__ __forceinline__ void epi_rows8(const Epi& e, int m0, int M, int n, fl
         const float4 v = add4(w[i], bias);
         if (e.out3) store4(e.out3, (long long)(m0 + 4 * i) * e.ld_out3 + c, e.aux_type, v);
         float4 gv = make_float4(gelu_fast(v.x), gelu_fast(v.y), gelu_fast(v.z), gelu_fast(v.w));
-        if (e.drop.thresh) {
+        if constexpr ((EPI & EPI_DROP) != 0) {
           const uint32_t r = m0 + 4 * i;
           gv.x *= drop_factor(e.drop, r, c); gv.y *= drop_factor(e.drop, r, c + 1);
           gv.z *= drop_factor(e.drop, r, c + 2); gv.w *= drop_factor(e.drop, r, c + 3);
@@ -341,7 +341,7 @@ __device__ __forceinline__ void epi_rows8(const Epi& e, int m0, int M, int n, fl
         store4(e.out2, (long long)(m0 + 4 * i) * e.ld_out2 + c, e.aux_type, gv);
       }
     }
-  } else if constexpr (EPI == EPI_RK) {
+  } else if constexpr ((EPI & 7) == EPI_RK) {
     float4 r[8];
     Raw4 t[8];
     const Raw4 zero = {0u, 0u, 0u, 0u};
@@ -356,7 +356,7 @@ __device__ __forceinline__ void epi_rows8(const Epi& e, int m0, int M, int n, fl
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) w[i] = scale4(e.alpha * ds, add4(w[i], bias));
-    if (e.drop.thresh) {
+    if constexpr ((EPI & EPI_DROP) != 0) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint32_t r = m0 + 4 * i;
@@ -392,7 +392,7 @@ __device__ __forceinline__ void epi_rows8(const Epi& e, int m0, int M, int n, fl
       if (e.out) store4(e.out, idx, DT_F32, r[i]);
       if (e.out2) store4(e.out2, idx, e.aux_type, scale4(e.out2_scale, r[i]));
     }
-  } else if constexpr (EPI == EPI_BWD3) {
+  } else if constexpr ((EPI & 7) == EPI_BWD3) {
     if (n < e.split) {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -410,7 +410,7 @@ __device__ __forceinline__ void epi_rows8(const Epi& e, int m0, int M, int n, fl
         float4 v = scale4(ds, w[i]);
         v.x *= gelu_grad_fast(hp.x); v.y *= gelu_grad_fast(hp.y);
         v.z *= gelu_grad_fast(hp.z); v.w *= gelu_grad_fast(hp.w);
-        if (e.drop.thresh) {
+        if constexpr ((EPI & EPI_DROP) != 0) {
           const uint32_t r = m0 + 4 * i;
           v.x *= drop_factor(e.drop, r, c); v.y *= drop_factor(e.drop, r, c + 1);
           v.z *= drop_factor(e.drop, r, c + 2); v.w *= drop_factor(e.drop, r, c + 3);
@@ -418,7 +418,7 @@ __device__ __forceinline__ void epi_rows8(const Epi& e, int m0, int M, int n, fl
         store4(e.out2, (long long)(m0 + 4 * i) * e.ld_out2 + c, e.aux_type, v);
       }
     }
-  } else if constexpr (EPI == EPI_ACCUM) {
+  } else if constexpr ((EPI & 7) == EPI_ACCUM) {
     if constexpr (ATOMIC) {
 #pragma unroll
       for (int i = 0; i < 8; ++i)

@@ -103,9 +103,18 @@ int gemm_simt(const GemmArgs& g, cudaStream_t s) {
     return set_error(ODEVIT_ERR_UNSUPPORTED, "gemm_simt: grid too large");
   switch (g.epi_mode) {
     case EPI_STORE: gemm_simt_kernel<EPI_STORE><<<grid, 256, 0, s>>>(g); break;
-    case EPI_FWD1: gemm_simt_kernel<EPI_FWD1><<<grid, 256, 0, s>>>(g); break;
-    case EPI_RK: gemm_simt_kernel<EPI_RK><<<grid, 256, 0, s>>>(g); break;
-    case EPI_BWD3: gemm_simt_kernel<EPI_BWD3><<<grid, 256, 0, s>>>(g); break;
+    case EPI_FWD1:
+      if (g.epi.drop.thresh) gemm_simt_kernel<EPI_FWD1 | EPI_DROP><<<grid, 256, 0, s>>>(g);
+      else gemm_simt_kernel<EPI_FWD1><<<grid, 256, 0, s>>>(g);
+      break;
+    case EPI_RK:
+      if (g.epi.drop.thresh) gemm_simt_kernel<EPI_RK | EPI_DROP><<<grid, 256, 0, s>>>(g);
+      else gemm_simt_kernel<EPI_RK><<<grid, 256, 0, s>>>(g);
+      break;
+    case EPI_BWD3:
+      if (g.epi.drop.thresh) gemm_simt_kernel<EPI_BWD3 | EPI_DROP><<<grid, 256, 0, s>>>(g);
+      else gemm_simt_kernel<EPI_BWD3><<<grid, 256, 0, s>>>(g);
+      break;
     case EPI_ACCUM: gemm_simt_kernel<EPI_ACCUM><<<grid, 256, 0, s>>>(g); break;
     default: return set_error(ODEVIT_ERR_INVALID_ARG, "gemm_simt: bad epilogue %d", g.epi_mode);
   }

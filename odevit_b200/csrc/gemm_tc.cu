@@ -343,9 +343,15 @@ int launch_epi(int epi_mode, bool mn, const CUtensorMap& ta, const CUtensorMap& 
                cudaStream_t s) {
   switch (epi_mode) {
     case EPI_STORE: return launch_major<CG, BN, EPI_STORE>(mn, ta, tb, d, units, s);
-    case EPI_FWD1: return launch_major<CG, BN, EPI_FWD1>(mn, ta, tb, d, units, s);
-    case EPI_RK: return launch_major<CG, BN, EPI_RK>(mn, ta, tb, d, units, s);
-    case EPI_BWD3: return launch_major<CG, BN, EPI_BWD3>(mn, ta, tb, d, units, s);
+    case EPI_FWD1:
+      if (d.epi.drop.thresh) return launch_major<CG, BN, EPI_FWD1 | EPI_DROP>(mn, ta, tb, d, units, s);
+      return launch_major<CG, BN, EPI_FWD1>(mn, ta, tb, d, units, s);
+    case EPI_RK:
+      if (d.epi.drop.thresh) return launch_major<CG, BN, EPI_RK | EPI_DROP>(mn, ta, tb, d, units, s);
+      return launch_major<CG, BN, EPI_RK>(mn, ta, tb, d, units, s);
+    case EPI_BWD3:
+      if (d.epi.drop.thresh) return launch_major<CG, BN, EPI_BWD3 | EPI_DROP>(mn, ta, tb, d, units, s);
+      return launch_major<CG, BN, EPI_BWD3>(mn, ta, tb, d, units, s);
     case EPI_ACCUM: return launch_major<CG, BN, EPI_ACCUM>(mn, ta, tb, d, units, s);
     default: return set_error(ODEVIT_ERR_INVALID_ARG, "gemm_tc: bad epilogue %d", epi_mode);
   }

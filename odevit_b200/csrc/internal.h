@@ -96,7 +96,9 @@ enum EpiMode : int {
                   // out (opt, fp32) = r;  out2 (opt, aux_type) = out2_scale * r
   EPI_BWD3 = 3,   // n <  split: out[m,n] = acc                    (dO)
                   // n >= split: out2[m,n-split] = acc * gelu'(aux[m,n-split])   (d h_pre)
-  EPI_ACCUM = 4   // out[m,n] += alpha*acc   (fp32; atomic when split-K)
+  EPI_ACCUM = 4,  // out[m,n] += alpha*acc   (fp32; atomic when split-K)
+  // template-only flag: the epilogue applies Epi::drop (kernels without it carry no mask code at all)
+  EPI_DROP = 8
 };
 
 // One dropout site of one field evaluation: element (r, c) is kept iff hash(key, r, c) >= thresh and then

@@ -101,6 +101,7 @@ def free_workspaces() -> None:
 
 
 TAPE_BUDGET_FRACTION = float(os.environ.get("ODEVIT_TAPE_FRACTION", "0.5"))
+_TAPE_FITS: Dict[Tuple[Optional[int], int], bool] = {}
 
 
 def _alloc_tape(desc: _lib.Desc, method: int, n_grid: int, mode: str, device: torch.device):
@@ -112,11 +113,21 @@ def _alloc_tape(desc: _lib.Desc, method: int, n_grid: int, mode: str, device: to
     if n == 0:
         return None
     if mode == "auto":
-        free, _total = torch.cuda.mem_get_info(device)
-        reusable = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
-        if n > TAPE_BUDGET_FRACTION * (free + reusable):
+        key = (device.index, n)
+        ok = _TAPE_FITS.get(key)
+        if ok is None:   # decided once per (device, size): the driver query is not free
+            free, _total = torch.cuda.mem_get_info(device)
+            reusable = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+            ok = _TAPE_FITS[key] = bool(n <= TAPE_BUDGET_FRACTION * (free + reusable))
+        if not ok:
             return None
-    return torch.empty(n + 1024, dtype=torch.uint8, device=device)
+    try:
+        return torch.empty(n + 1024, dtype=torch.uint8, device=device)
+    except torch.OutOfMemoryError:
+        if mode == "tape":
+            raise
+        _TAPE_FITS[(device.index, n)] = False
+        return None
 
 
 def _aligned(buf: Optional[torch.Tensor]):
@@ -144,15 +155,23 @@ def _pack_weights(names: Sequence[str], tensors: Sequence[torch.Tensor]):
 
 
 def _alloc_grads(names: Sequence[str], tensors: Sequence[torch.Tensor], needs: Sequence[bool]):
+    """Zero-filled gradient accumulators: ONE flat buffer (one memset) carved into per-weight views."""
     g = _lib.WeightGrads()
-    out: List[Optional[torch.Tensor]] = []
-    for n, t, need in zip(names, tensors, needs):
-        if t is None or not need or n in _lib.MOD_FIELDS:
-            out.append(None)
+    want = [(t is not None and need and n not in _lib.MOD_FIELDS) for n, t, need in zip(names, tensors, needs)]
+    sizes = [((t.numel() + 63) // 64) * 64 if w else 0 for t, w in zip(tensors, want)]   # 256-byte aligned views
+    out: List[Optional[torch.Tensor]] = [None] * len(want)
+    if not any(want):
+        return g, out
+    dev = next(t for t, w in zip(tensors, want) if w).device
+    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+    off = 0
+    for i, (n, t, w) in enumerate(zip(names, tensors, want)):
+        if not w:
             continue
-        gt = torch.zeros_like(t, dtype=torch.float32, memory_format=torch.contiguous_format)
+        gt = flat[off:off + t.numel()].view(t.shape)
+        off += sizes[i]
         setattr(g, n, gt.data_ptr())
-        out.append(gt)
+        out[i] = gt
     return g, out
 
 
@@ -334,3 +353,63 @@ def fd_curvature(states: torch.Tensor, delta_t: float) -> torch.Tensor:
         st = _lib.lib().odevit_fd_curvature(_ptr(states), T, B, N, D, float(delta_t), _ptr(out), _stream())
     _lib.check(st, "odevit_fd_curvature")
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# patch projection (row (f1) of SURVEY section 8: the caller just before the hot path)
+# ---------------------------------------------------------------------------------------------
+def _gemm_bf16(M: int, N: int, K: int, mn_major: int, A: torch.Tensor, B: torch.Tensor, C: torch.Tensor) -> None:
+    """C[M,N] (fp32) = A . B^T on the tcgen05 GEMM (FFMA kernel for shapes it does not cover)."""
+    L = _lib.lib()
+    with torch.cuda.device(C.device):
+        st = L.odevit_gemm_bf16(M, N, K, mn_major, _ptr(A), _ptr(B), _ptr(C), 0, 1, _stream())
+        if st == -4:   # ODEVIT_ERR_UNSUPPORTED
+            st = L.odevit_gemm_bf16(M, N, K, mn_major, _ptr(A), _ptr(B), _ptr(C), 0, 0, _stream())
+    _lib.check(st, "odevit_gemm_bf16")
+
+
+class _PatchProj(torch.autograd.Function):
+    """`Conv2d(kernel = stride = patch)` (ode_transformer_gpt.py:137, :157) as im2col (one permuting
+    cast) + one bf16 GEMM with fp32 accumulation; weight / input gradients are GEMMs of the same kernel."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, patch: int):
+        x = _require_cuda(x, "pixel_values")
+        Bn, C, H, W = x.shape
+        g_h, g_w = H // patch, W // patch
+        M, K, D = Bn * g_h * g_w, C * patch * patch, weight.shape[0]
+        a = torch.empty(Bn, g_h, g_w, C, patch, patch, dtype=torch.bfloat16, device=x.device)
+        a.copy_(x.view(Bn, C, g_h, patch, g_w, patch).permute(0, 2, 4, 1, 3, 5))
+        w = weight.detach().reshape(D, K).to(torch.bfloat16)
+        out = torch.empty(M, D, dtype=torch.float32, device=x.device)
+        _gemm_bf16(M, D, K, 0, a, w, out)
+        if bias is not None:
+            out += bias.detach()
+        ctx.save_for_backward(a, w)
+        ctx.shape = (Bn, C, H, W, patch, tuple(weight.shape), bias is not None)
+        return out.view(Bn, g_h * g_w, D)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        a, w = ctx.saved_tensors
+        Bn, C, H, W, patch, w_shape, has_bias = ctx.shape
+        g_h, g_w = H // patch, W // patch
+        M, K, D = Bn * g_h * g_w, C * patch * patch, w_shape[0]
+        gy = g_out.reshape(M, D).to(torch.bfloat16).contiguous()
+        g_x = g_w_ = g_b = None
+        if ctx.needs_input_grad[1]:
+            g_w_ = torch.empty(D, K, dtype=torch.float32, device=gy.device)
+            _gemm_bf16(D, K, M, 1, gy, a.view(M, K), g_w_)       # dW[d,k] = sum_m gy[m,d] a[m,k]
+            g_w_ = g_w_.view(w_shape)
+        if has_bias and ctx.needs_input_grad[2]:
+            g_b = g_out.reshape(M, D).sum(0)
+        if ctx.needs_input_grad[0]:
+            cols = torch.empty(M, K, dtype=torch.float32, device=gy.device)
+            _gemm_bf16(M, K, D, 0, gy, w.t().contiguous(), cols)  # dA = gy @ W
+            g_x = cols.view(Bn, g_h, g_w, C, patch, patch).permute(0, 3, 1, 4, 2, 5).reshape(Bn, C, H, W)
+        return g_x, g_w_, g_b, None
+
+
+def patch_project(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], patch: int) -> torch.Tensor:
+    """[B, C, H, W] -> [B, (H/p)(W/p), D] patch tokens (before cls / register / positional assembly)."""
+    return _PatchProj.apply(x, weight, bias, patch)

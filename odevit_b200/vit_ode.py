@@ -248,7 +248,13 @@ class PatchEmbed(nn.Module):
             nn.init.trunc_normal_(self.dist_token, std=0.02)
 
     def forward(self, x: torch.Tensor, learn_ivp: bool = False) -> torch.Tensor:
-        x = self.proj(x).flatten(2).transpose(1, 2)
+        p = self.proj.kernel_size[0]
+        if (getattr(self, "precision", "fp32") == "bf16" and x.is_cuda and x.dtype == torch.float32
+                and x.shape[-1] % p == 0 and x.shape[-2] % p == 0):
+            # bf16 mode: im2col + tcgen05 GEMM (ops.patch_project) instead of cuDNN's TF32 convolution
+            x = ops.patch_project(x, self.proj.weight, self.proj.bias, p)
+        else:
+            x = self.proj(x).flatten(2).transpose(1, 2)
         B = x.shape[0]
         parts = [self.cls_token.expand(B, -1, -1)]
         if self.add_distillation_token:
@@ -298,6 +304,7 @@ class ViTNeuralODE(nn.Module):
         self.time_interval = time_interval
         self.num_eval_steps = num_eval_steps
         self.t_grid = torch.linspace(0.0, time_interval, num_eval_steps)  # plain attribute, not a buffer
+        self.patch_embed.precision = self.odefunc.block.precision
         self.apply(self._spectral_init)
 
     # -- precision switch (not in the reference) -------------------------------------------------
@@ -310,6 +317,7 @@ class ViTNeuralODE(nn.Module):
         if value not in _lib.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
         self.odefunc.block.precision = value
+        self.patch_embed.precision = value
 
     @property
     def device(self):

@@ -210,3 +210,32 @@ def test_time_modulation_matches_composition():
         assert max_rel(p.grad, sdr[k].grad) < 1e-4, k
     ob.attach_time_modulation(f.block, None)
     assert max_rel(f(torch.tensor(0.3), x.detach()), g.get("mha/dx")) < 1e-5
+
+
+# ---- patch projection as a GEMM (bf16 mode) ------------------------------------------------------
+
+@pytest.mark.parametrize("img,patch,D,B", [(32, 4, 192, 5), (224, 16, 768, 2), (16, 4, 64, 3)])
+def test_patch_project_matches_conv(img, patch, D, B):
+    """ops.patch_project (im2col + bf16 tensor-core GEMM) against Conv2d(kernel=stride=patch) in fp32,
+    forward and all three gradients, at bf16 tolerance."""
+    from odevit_b200 import ops
+    torch.manual_seed(1)
+    conv = torch.nn.Conv2d(3, D, kernel_size=patch, stride=patch).cuda()
+    x = torch.randn(B, 3, img, img, device="cuda", requires_grad=True)
+    w = torch.randn(B, (img // patch) ** 2, D, device="cuda")
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = conv(x).flatten(2).transpose(1, 2)
+        (ref * w).sum().backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = True
+    gx, gw, gb = x.grad.clone(), conv.weight.grad.clone(), conv.bias.grad.clone()
+    x.grad = None
+    conv.zero_grad()
+    got = ops.patch_project(x, conv.weight, conv.bias, patch)
+    (got * w).sum().backward()
+    assert got.shape == ref.shape
+    assert max_rel(got, ref) < 1e-2
+    assert max_rel(x.grad, gx) < 2e-2
+    assert max_rel(conv.weight.grad, gw) < 2e-2
+    assert max_rel(conv.bias.grad, gb) < 1e-4
