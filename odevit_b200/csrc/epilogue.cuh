@@ -349,24 +349,29 @@ __device__ __forceinline__ void epi_rows8(const Epi& e, int m0, int M, int n, fl
 #pragma unroll
       for (int i = 0; i < 8; ++i) t[i] = ok[i] ? ldg_raw4(e.y, (long long)(m0 + 4 * i) * e.ld_out + n, DT_F32) : zero;
     }
-    Raw4 q[8];
+    auto mask_rows = [&]() {
+      if constexpr ((EPI & EPI_DROP) != 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t rr = m0 + 4 * i;
+          w[i].x *= drop_factor(e.drop, rr, n); w[i].y *= drop_factor(e.drop, rr, n + 1);
+          w[i].z *= drop_factor(e.drop, rr, n + 2); w[i].w *= drop_factor(e.drop, rr, n + 3);
+        }
+      }
+    };
     if (e.resid) {   // v = drop(alpha*ds*(acc+bias)) + resid_coef*resid (loads batched like the others)
+      Raw4 q[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) q[i] = ok[i] ? ldg_raw4(e.resid, (long long)(m0 + 4 * i) * e.ld_out + n, DT_F32) : zero;
-    }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) w[i] = scale4(e.alpha * ds, add4(w[i], bias));
-    if constexpr ((EPI & EPI_DROP) != 0) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t r = m0 + 4 * i;
-        w[i].x *= drop_factor(e.drop, r, n); w[i].y *= drop_factor(e.drop, r, n + 1);
-        w[i].z *= drop_factor(e.drop, r, n + 2); w[i].w *= drop_factor(e.drop, r, n + 3);
-      }
-    }
-    if (e.resid) {
+      for (int i = 0; i < 8; ++i) w[i] = scale4(e.alpha * ds, add4(w[i], bias));
+      mask_rows();
 #pragma unroll
       for (int i = 0; i < 8; ++i) w[i] = fma4(e.resid_coef, raw_to_float4(q[i], DT_F32), w[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = scale4(e.alpha * ds, add4(w[i], bias));
+      mask_rows();
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) r[i] = scale4(e.c_new, w[i]);
