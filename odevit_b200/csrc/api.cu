@@ -60,7 +60,7 @@ ProfState g_prof;
 const char* const kClassNames[KC_COUNT] = {
     "center_rows", "gemm_in_qkv_fc1", "attn_qk", "softmax", "attn_pv", "gemm_out_rk",
     "bwd_gemm_doh", "bwd_gemm_g2", "bwd_attn", "bwd_softmax", "bwd_gemm_dx", "bwd_gemm_g1",
-    "bwd_colsum", "combine", "weights", "fused_attn", "fused_attn_bwd", "fd_curvature", "fused_attn_export", "other"};
+    "bwd_colsum", "combine", "weights", "fused_attn", "fused_attn_bwd", "fd_curvature", "fused_attn_export", "resident_solve", "other"};
 }  // namespace
 
 ProfScope::ProfScope(int c, cudaStream_t st) : cls(c), s(st), slot(-1) {
@@ -186,6 +186,7 @@ struct FwdBufs {
   float* ytmp[2];
   float* sq;
   float* tmp;
+  float* kbuf;
 };
 FwdBufs layout_fwd(const Plan& p, Arena& a, int S) {
   FwdBufs f;
@@ -198,6 +199,7 @@ FwdBufs layout_fwd(const Plan& p, Arena& a, int S) {
   f.ytmp[1] = a.f32((size_t)p.M * p.D);
   f.sq = (p.variant == ODEVIT_FIELD_PARALLEL_L2) ? a.f32((size_t)2 * p.B * p.H * p.N) : nullptr;
   f.tmp = p.split_out ? a.f32((size_t)p.M * p.D) : nullptr;
+  f.kbuf = (S > 1 && solve_resident_shape_ok(p)) ? a.f32(solve_resident_scratch_floats(p)) : nullptr;
   return f;
 }
 
@@ -880,6 +882,10 @@ int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
   if (states) {
     ODV_CUDA(cudaMemcpyAsync(states, x0, MD * 4, cudaMemcpyDeviceToDevice, s));
     y = states;
+  }
+  if (solve_resident_supports(p, n_grid, p_traj != nullptr, tape != nullptr) && (tb->S == 1 || f.kbuf)) {
+    // small-token shapes: the whole solve of an image in one persistent CTA, state resident on the chip
+    return solve_resident(p, f.w, tb->S, tb->a, tb->b, x0, t_grid_host, n_grid, states, final_state, p_last, f.kbuf, s);
   }
   const int S = tb->S;
   const long long n_evals = (long long)(n_grid - 1) * S;

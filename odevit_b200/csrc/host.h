@@ -84,6 +84,15 @@ int attention_forward(const Plan& p, const void* qkv, void* oh, long long ld_oh,
 int attention_vjp(const Plan& p, const void* qkv, const void* oh, long long ld_oh, const float* lse, BwdBufs& b,
                   const float* g_p, void* dz, int R, Drop drop, cudaStream_t s);
 
+// On-chip-state solver for small-token shapes (solve_resident.cu): one persistent CTA per image runs
+// every step of the solve with the ODE state in shared memory.  Inference, PARALLEL field, bf16 mode.
+bool solve_resident_shape_ok(const Plan& p);
+bool solve_resident_supports(const Plan& p, int n_grid, bool wants_p_traj, bool has_tape);
+size_t solve_resident_scratch_floats(const Plan& p);
+int solve_resident(const Plan& p, const WeightBufs& wb, int S, const float (*ta)[4], const float* tbv, const float* x0,
+                   const float* t_host, int n_grid, float* states, float* final_state, float* p_last, float* kbuf,
+                   cudaStream_t s);
+
 // MACARON field (field_macaron.cu)
 int macaron_forward(const Plan& p, const WeightBufs& wb, const StageCtx& c, const float* u, float* P,
                     const Epi* rk, cudaStream_t s);

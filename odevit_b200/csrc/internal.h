@@ -67,6 +67,7 @@ enum KClass : int {
   KC_FUSED_ATTN_BWD,  // fused attention VJP (delta + dq/dk/dv in one kernel)
   KC_FD_BOUND,        // finite-difference curvature of the trajectory (single pass)
   KC_FUSED_ATTN_EXPORT,  // fused attention forward that also writes the fp32 attention map
+  KC_RESIDENT,        // on-chip-state solver: the whole solve of an image in one persistent CTA
   KC_OTHER,
   KC_COUNT
 };

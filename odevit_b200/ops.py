@@ -248,7 +248,7 @@ class _OdeSolve(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x0, spec: FieldSpec, method: str, t_host: torch.Tensor, row_index: Tuple[int, ...],
-                want_p_last: bool, p_traj_first: Optional[int], names: Tuple[str, ...], *weights):
+                want_p_last: bool, p_traj_first: Optional[int], names: Tuple[str, ...], track: bool, *weights):
         x0 = _require_cuda(x0, "x0")
         B, N, D = x0.shape
         T = int(t_host.numel())
@@ -269,7 +269,9 @@ class _OdeSolve(torch.autograd.Function):
             if n_evals - first > 0:
                 p_traj = torch.empty(n_evals - first, B, spec.heads, N, N, device=x0.device, dtype=torch.float32)
         buf, ws, ws_bytes = _workspace(desc, _lib.WS_SOLVE_FWD, _lib.METHODS[method], x0.device)
-        tape = _alloc_tape(desc, _lib.METHODS[method], T, spec.backward, x0.device) if any(ctx.needs_input_grad) else None
+        # `track`: a backward pass can follow (grad mode on and something requires grad); decided by the
+        # caller, because inside forward() grad mode is always off and needs_input_grad ignores no_grad()
+        tape = _alloc_tape(desc, _lib.METHODS[method], T, spec.backward, x0.device) if track else None
         tape_p, tape_n = _aligned(tape)
         with torch.cuda.device(x0.device):
             st = _lib.lib().odevit_solve_fwd(ctypes.byref(desc), ctypes.byref(w), _lib.METHODS[method], _ptr(x0),
@@ -295,7 +297,7 @@ class _OdeSolve(torch.autograd.Function):
         T, B, N, D = states.shape
         desc = spec.desc(B, N)
         w, keep = _pack_weights(names, weights)
-        needs = ctx.needs_input_grad[8:]
+        needs = ctx.needs_input_grad[9:]
         gw, gts = _alloc_grads(names, weights, needs)
         parts, index = [], []
         if g_final is not None:
@@ -322,7 +324,7 @@ class _OdeSolve(torch.autograd.Function):
                                              ws, ws_bytes, _stream())
         _lib.check(st, "odevit_solve_bwd")
         ctx.tape = None
-        return (g_x0 if ctx.needs_input_grad[0] else None, None, None, None, None, None, None, None, *gts)
+        return (g_x0 if ctx.needs_input_grad[0] else None, None, None, None, None, None, None, None, None, *gts)
 
 
 def ode_solve(x0: torch.Tensor, t: torch.Tensor, spec: FieldSpec, method: str,
@@ -336,8 +338,9 @@ def ode_solve(x0: torch.Tensor, t: torch.Tensor, spec: FieldSpec, method: str,
     if t.ndim != 1 or t.numel() < 1:
         raise ValueError("t must be one dimensional")
     names = tuple(k for k, v in weights.items() if v is not None)
+    track = torch.is_grad_enabled() and (x0.requires_grad or any(weights[k].requires_grad for k in names))
     states, final, rows, p_last, p_traj = _OdeSolve.apply(
-        x0, spec, method, t, tuple(int(i) for i in row_index), want_p_last, p_traj_first, names,
+        x0, spec, method, t, tuple(int(i) for i in row_index), want_p_last, p_traj_first, names, track,
         *[weights[k] for k in names])
     return {"states": states, "final": final, "rows": rows if len(row_index) else None,
             "p_last": p_last if p_last.numel() else None, "p_traj": p_traj if p_traj.numel() else None}

@@ -1,0 +1,82 @@
+"""The on-chip-state solver (csrc/solve_resident.cu: one persistent CTA per image, ODE state resident in
+shared memory across every solver step) against the multi-kernel path and the oracle: same module call,
+the path is picked by the library (ODEVIT_RESIDENT=0 switches it off)."""
+import os
+
+import pytest
+import torch
+
+import odevit_oracle as orc
+from _util import max_rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(cfg, seed=1):
+    import odevit_b200 as ob
+    model = ob.ViTNeuralODE(**cfg)
+    sd = orc.reference_like_init(cfg, cfg["num_classes"], seed=seed)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    model.precision = "bf16"
+    return model, sd
+
+
+def _run(model, px, resident, **kw):
+    import odevit_b200 as ob
+    os.environ["ODEVIT_RESIDENT"] = "1" if resident else "0"
+    try:
+        ob.reset_launch_count()
+        with torch.no_grad():
+            out = model(px, output_hidden_states=True, **kw)
+        torch.cuda.synchronize()
+        return out, ob.launch_count()
+    finally:
+        os.environ.pop("ODEVIT_RESIDENT", None)
+
+
+C10 = dict(img_size=32, patch_size=4, num_classes=10, embed_dim=192, num_heads=3, mlp_ratio=4.0, emulate_depth=12,
+           time_interval=1.0, num_eval_steps=5, solver="rk4", register_tokens=4)
+
+
+@pytest.mark.parametrize("solver,T,B", [("euler", 5, 3), ("rk4", 4, 3), ("midpoint", 3, 2), ("rk4", 5, 200), ("euler", 9, 331)])
+def test_resident_matches_multikernel_and_oracle_c10(solver, T, B):
+    cfg = dict(C10, solver=solver, num_eval_steps=T)
+    model, sd = _model(cfg)
+    px = torch.randn(B, 3, 32, 32, generator=torch.Generator().manual_seed(1234))
+    a, n_a = _run(model, px.cuda(), True)
+    b, n_b = _run(model, px.cuda(), False)
+    assert n_a < n_b          # a handful of launches instead of 4 per evaluation
+    assert max_rel(a["states"], b["states"]) < 1e-2
+    assert max_rel(a["logits"], b["logits"]) < 1e-2
+    if B <= 3:
+        want = orc.vit_ode_forward(sd, cfg, px, output_hidden_states=True)
+        assert max_rel(a["states"][-1], want["states"][-1]) < 2e-2
+        assert max_rel(a["logits"], want["logits"]) < 2e-2
+        assert max_rel(a["states"], want["states"]) < 2e-2
+
+
+def test_resident_exports_last_attention_map():
+    cfg = dict(C10, solver="euler", num_eval_steps=4)
+    model, sd = _model(cfg, seed=2)
+    px = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(9))
+    _run(model, px.cuda(), True)
+    p_res = model.odefunc.block.attentions.clone()
+    _run(model, px.cuda(), False)
+    p_ref = model.odefunc.block.attentions.clone()
+    assert p_res.shape == (2, 3, 69, 69)
+    assert max_rel(p_res, p_ref) < 5e-2
+    assert max_rel(p_res.sum(-1), torch.ones(2, 3, 69)) < 1e-3
+
+
+@pytest.mark.parametrize("D,H,ratio,img,patch,R", [(64, 1, 2.0, 16, 4, 2), (128, 2, 4.0, 32, 4, 0), (256, 4, 1.0, 32, 4, 4)])
+def test_resident_other_small_shapes(D, H, ratio, img, patch, R):
+    cfg = dict(img_size=img, patch_size=patch, num_classes=7, embed_dim=D, num_heads=H, mlp_ratio=ratio, emulate_depth=12,
+               time_interval=1.0, num_eval_steps=4, solver="rk4", register_tokens=R)
+    model, sd = _model(cfg, seed=4)
+    px = torch.randn(5, 3, img, img, generator=torch.Generator().manual_seed(3))
+    a, _ = _run(model, px.cuda(), True)
+    b, _ = _run(model, px.cuda(), False)
+    assert max_rel(a["states"], b["states"]) < 1e-2
+    want = orc.vit_ode_forward(sd, cfg, px, output_hidden_states=True)
+    assert max_rel(a["states"][-1], want["states"][-1]) < 2e-2
