@@ -33,6 +33,7 @@
 //                            max / sum, CenterNorm mean) are exchanged through shared memory between the
 //                            four warps of a quadrant (named barrier 1+q).  Quadrants without rows idle.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 
@@ -63,22 +64,34 @@ int num_sms() {
 __host__ __device__ constexpr int res_threads(bool full) { return full ? 576 : 512; }
 __host__ __device__ constexpr int res_producer(bool full) { return full ? 16 : 3; }
 __host__ __device__ constexpr int res_loader(bool full) { return full ? 17 : 7; }
-constexpr int NU = 10;                               // weight-ring stages of one 8 KB unit
+constexpr int NU = 10;                               // weight-ring slots of 8 KB
 constexpr int T_R0 = 0, T_O = 128, T_R1 = 192;
 constexpr int kMaxGrid = 129;                        // grid points carried in the kernel parameters
-constexpr int kMaxJobs = 64, kMaxTiles = 240;
+constexpr int kMaxJobs = 64, kMaxAllocs = 112;
+constexpr int NB = 8;                                // barrier pairs of the weight ring (>= allocations in flight)
 
 enum JobKind : uint8_t { JOB_QKV = 0, JOB_S = 1, JOB_PV = 2, JOB_FC = 3, JOB_F = 4 };
 
-// The job list of one evaluation and the weight tiles it consumes, in issue order.
+// The job list of one evaluation and the weight ALLOCATIONS it consumes, in issue order.  An allocation is
+// one B operand of a run of 4 MMAs (one 64-wide k-atom): `size` consecutive 8 KB ring slots, each filled by
+// one [64 x 64] TMA box:
+//   kind 0  rows {q, k, v} of head `arg` of W1cat, k-atom ka   -> [192 x 64], N = 192 into R0
+//   kind 1  fc1 rows of hidden chunk `arg`, k-atom ka          -> [128 x 64], N = 128 into HB
+//   kind 2  W2cat k-atom starting at column `arg`              -> [D x 64],   N = D   into R1
+// The slot offsets come from a host-side walk of the ring (an allocation never wraps; every evaluation
+// starts at slot 0, so the pattern repeats); `back` = how many allocations before this one the latest
+// allocation is whose slots (or barrier pair) it reuses: the loader waits for that one's release.
+struct Alloc {
+  uint16_t arg;
+  uint8_t kind, ka, off, size, back, pad;
+};
 struct Sched {
-  int n_jobs, n_tiles;
+  int n_jobs, n_allocs;
   uint8_t kind[kMaxJobs];
   uint8_t arg[kMaxJobs];     // head or hidden chunk
   int8_t dep[kMaxJobs];      // job of this evaluation whose compute phase must be done first; -1: the
                              // previous evaluation's F (or the image's initial phase)
-  uint16_t tile[kMaxTiles];  // bit 15 clear: 64 rows of W1cat from row (v & 0x7fff);  set: 64 columns
-                             // (one k-atom) of W2cat from column (v & 0x7fff)
+  Alloc alloc[kMaxAllocs];
 };
 
 struct ResArgs {
@@ -162,17 +175,27 @@ __device__ __forceinline__ void lds16(const float* p, float* b) {
     b[4 * j] = f.x; b[4 * j + 1] = f.y; b[4 * j + 2] = f.z; b[4 * j + 3] = f.w;
   }
 }
-// GELU(x) = x Phi(x) with Phi = 1/2 + 1/2 tanh(x (c0 + c1 x^2 + c2 x^4)), coefficients fitted to the erf form
-// (|formula error| <= 2.6e-5 over the reals; x^2 clamped where the quartic would turn) and ONE MUFU.TANH
-// (max relative error 2^-11 on tanh): 7 FP32 instructions per element instead of two MUFU + 14.
-__device__ __forceinline__ float gelu_tanh(float x) {
-  const float x2 = fminf(x * x, 49.f);
-  float p = fmaf(-0.000351516788525385f, x2, 0.037005646025752466f);
-  p = fmaf(p, x2, 0.7975078842819603f);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * p));
-  const float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
+// Two GELUs at once in half precision (11-bit significand, finer than the bf16 the tile stores):
+// GELU(x) = hx + hx tanh(x (c0 + c1 x^2)), hx = x/2, coefficients fitted to the erf form (|formula error|
+// <= 2.8e-4 absolute over the reals), ONE MUFU.TANH per pair.  x^2 overflowing to inf gives tanh = +-1, the
+// right limit.  Returns the pair packed as bf16x2 (low half = first argument).
+__device__ __forceinline__ uint32_t gelu2_bf16(float x0, float x1) {
+  const __half2 x = __floats2half2_rn(x0, x1);
+  const __half2 x2 = __hmul2(x, x);
+  const __half2 p = __hfma2(x2, __float2half2_rn(0.034700893432451876f), __float2half2_rn(0.8001570785469041f));
+  const __half2 u = __hmul2(x, p);
+  uint32_t ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
+  const __half2 t = *reinterpret_cast<const __half2*>(&ti);
+  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+  const float2 g = __half22float2(__hfma2(hx, t, hx));
+  const __nv_bfloat162 o = __floats2bfloat162_rn(g.x, g.y);
+  return *reinterpret_cast<const uint32_t*>(&o);
+}
+// 8 consecutive bf16 columns (4 packed words) of row r of a K-major SWIZZLE_128B tile
+__device__ __forceinline__ void st_tile8w(uint8_t* atom0, int atom_bytes, int r, int col, const uint32_t* w) {
+  const int atom = col >> 6, chunk = (col & 63) >> 3;
+  *reinterpret_cast<uint4*>(atom0 + atom * atom_bytes + r * 128 + ((chunk ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -222,6 +245,14 @@ __device__ __forceinline__ void commit_pred(uint32_t bar_addr, uint32_t lead) {
       : "r"(bar_addr), "r"(lead)
       : "memory");
 }
+// shared memory -> global memory through the bulk-copy engine (16-byte aligned, size a multiple of 16)
+__device__ __forceinline__ void bulk_store(float* gdst, const float* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ptx::smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // the four warps of token-row quadrant q
 __device__ __forceinline__ void quad_sync(int q) { asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory"); }
 
@@ -256,11 +287,11 @@ solve_resident_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
   float* sB2 = reinterpret_cast<float*>(smem + L.off_b2);
   float* sEx = reinterpret_cast<float*>(smem + L.off_ex);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
-  uint64_t* bar_full = bars;              // [NU] weight unit landed
-  uint64_t* bar_free = bars + NU;         // [NU] the MMAs that read the stage have retired
-  uint64_t* bar_mma = bars + 2 * NU;      // [2] the MMA group of job (parity of the job counter) has retired
-  uint64_t* bar_cmp = bars + 2 * NU + 2;  // [2] the compute phase (parity of the phase counter) is finished
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NU + 4);
+  uint64_t* bar_full = bars;              // [NB] the boxes of a weight allocation landed
+  uint64_t* bar_free = bars + NB;         // [NB] the MMAs that read the allocation have retired
+  uint64_t* bar_mma = bars + 2 * NB;      // [2] the MMA group of job (parity of the job counter) has retired
+  uint64_t* bar_cmp = bars + 2 * NB + 2;  // [2] the compute phase (parity of the phase counter) is finished
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NB + 4);
 
   constexpr int RES_THREADS = res_threads(FULL), PRODUCER = res_producer(FULL), LOADER = res_loader(FULL);
   const int warp = threadIdx.x >> 5;
@@ -277,7 +308,7 @@ solve_resident_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
   const int n_quads = (N + 31) >> 5;           // token-row quadrants that hold rows
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NU; ++i) { ptx::mbar_init(bar_full + i, 1); ptx::mbar_init(bar_free + i, 1); }
+    for (int i = 0; i < NB; ++i) { ptx::mbar_init(bar_full + i, 1); ptx::mbar_init(bar_free + i, 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_mma + i, 1); ptx::mbar_init(bar_cmp + i, n_quads * 128); }
     ptx::fence_barrier_init();
   }
@@ -302,28 +333,33 @@ solve_resident_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     // Every lane runs the same instruction stream; the tcgen05 instructions carry the election as a
     // predicate, so the warp never diverges and needs no __syncwarp.
     const uint32_t lead = ptx::elect_one() ? 1u : 0u;
-    int c_stage = 0, c_round = 0;             // consume cursor: ring stage, passes over the ring
+    uint32_t cg = 0;                          // allocations consumed (global count: barrier pair and phase)
+    int ci = 0;                               // ... and the index of the next one in the evaluation's list
+    const int n_allocs = a.sc.n_allocs;
     uint32_t waited = 0;                      // compute phases consumed
     uint32_t gm = 0;                          // MMA groups committed
-    const int UPT = D / 64;                   // units per tile
+    const int UPT = D / 64;                   // k-atoms of the model dimension
     // K-major SWIZZLE_128B descriptors differ only in their 14-bit address field: desc(addr) = DESC0 + (addr >> 4)
     const uint64_t DESC0 = ptx::smem_desc_sw128(0, 16, 1024);
     const uint32_t ring_lo = ptx::smem_u32(sRing) >> 4;
     const uint32_t full0 = ptx::smem_u32(bar_full), free0 = ptx::smem_u32(bar_free);
-    const uint32_t id_n64 = ptx::idesc_bf16(128, 64, 0, 0);
+    const uint32_t id_qkv = ptx::idesc_bf16(128, 192, 0, 0), id_fc1 = ptx::idesc_bf16(128, 128, 0, 0);
+    const uint32_t id_out = ptx::idesc_bf16(128, D, 0, 0);
 
-    // one ring unit [64 x 64]: D[128 x 64] (+)= A[128 x 64] (descriptor address field a_lo) * unit^T
-    auto unit_mma = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t acc_first) {
-      const uint32_t fb = full0 + c_stage * 8;
-      for (uint32_t spins = 0; !mbar_try_wait_addr(fb, (uint32_t)(c_round & 1));)
+    // the next weight allocation [N x 64]: D[128 x N] (+)= A[128 x 64] (descriptor address field a_lo) * alloc^T
+    auto alloc_mma = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t idesc, uint32_t acc_first) {
+      const uint32_t b = cg & (NB - 1);
+      const uint32_t fb = full0 + b * 8;
+      for (uint32_t spins = 0; !mbar_try_wait_addr(fb, (cg / NB) & 1);)
         if (++spins > (1u << 24)) __trap();   // a protocol bug must surface as a launch failure, never as a hung GPU
-      const uint64_t da = DESC0 + a_lo, db = DESC0 + (ring_lo + c_stage * 512);
-      mma_ss_pred(d_tmem, da, db, id_n64, acc_first, lead);
-      mma_ss_pred(d_tmem, da + 2, db + 2, id_n64, 1u, lead);
-      mma_ss_pred(d_tmem, da + 4, db + 4, id_n64, 1u, lead);
-      mma_ss_pred(d_tmem, da + 6, db + 6, id_n64, 1u, lead);
-      commit_pred(free0 + c_stage * 8, lead);
-      if (++c_stage == NU) { c_stage = 0; ++c_round; }
+      const uint64_t da = DESC0 + a_lo, db = DESC0 + (ring_lo + (uint32_t)a.sc.alloc[ci].off * 512);
+      mma_ss_pred(d_tmem, da, db, idesc, acc_first, lead);
+      mma_ss_pred(d_tmem, da + 2, db + 2, idesc, 1u, lead);
+      mma_ss_pred(d_tmem, da + 4, db + 4, idesc, 1u, lead);
+      mma_ss_pred(d_tmem, da + 6, db + 6, idesc, 1u, lead);
+      commit_pred(free0 + b * 8, lead);
+      ++cg;
+      if (++ci == n_allocs) ci = 0;
     };
     // all compute phases up to and including `phase` are finished
     auto need = [&](uint32_t phase) {
@@ -339,13 +375,13 @@ solve_resident_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     const uint32_t id_s = ptx::idesc_bf16(128, NK, 0, 0);
     const uint32_t id_pv = ptx::idesc_bf16(128, 64, 0, 1);
     uint32_t r1_acc = 0;                      // 0: the next MMAs into R1 start a new field output
-    // D[128 x 64] = xc[128 x D] * tile[64 x D]^T, one unit per 64-wide k-atom
-    auto mma_xc_tile = [&](uint32_t d_tmem) {
-      for (int sub = 0; sub < UPT; ++sub) unit_mma(d_tmem, xc_lo + sub * atom_lo, sub > 0 ? 1u : 0u);
+    // D[128 x N] = xc[128 x D] * W^T over the k-atoms of the model dimension (q|k|v of a head, or an fc1 chunk)
+    auto mma_xc = [&](uint32_t d_tmem, uint32_t idesc) {
+      for (int ka = 0; ka < UPT; ++ka) alloc_mma(d_tmem, xc_lo + ka * atom_lo, idesc, ka > 0 ? 1u : 0u);
     };
-    // OUT[128 x D] += A[128 x 64] (one 64-column atom, address field a_lo) * tile[D x 64]^T, one unit per 64 output columns
+    // OUT[128 x D] += A[128 x 64] (one 64-column atom, address field a_lo) * W2cat k-atom [D x 64]^T
     auto mma_into_out = [&](uint32_t a_lo) {
-      for (int sub = 0; sub < UPT; ++sub) unit_mma(tmem + T_R1 + sub * 64, a_lo, r1_acc);
+      alloc_mma(tmem + T_R1, a_lo, id_out, r1_acc);
       r1_acc = 1u;
     };
 
@@ -364,7 +400,7 @@ solve_resident_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
           RTR(1, j * 4 + 1);
           if (kind == JOB_QKV) {
             if (arg > 0) mma_into_out(q_lo);                         // O of the previous head (in the q tile)
-            for (int m = 0; m < 3; ++m) mma_xc_tile(tmem + T_R0 + m * 64);
+            mma_xc(tmem + T_R0, id_qkv);
           } else if (kind == JOB_S) {
             const uint64_t da = DESC0 + q_lo, db = DESC0 + k_lo;
 #pragma unroll
@@ -376,7 +412,7 @@ solve_resident_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
           } else if (kind == JOB_FC) {
             if (arg > 0)
               for (int m = 0; m < 2; ++m) mma_into_out(g_lo + m * atom_lo);      // fc2 of the previous chunk
-            for (int m = 0; m < 2; ++m) mma_xc_tile(tmem + T_HB + m * 64);
+            mma_xc(tmem + T_HB, id_fc1);
           } else {  // JOB_F
             mma_into_out(q_lo);                                      // O of the last head
             for (int m = 0; m < 2; ++m) mma_into_out(g_lo + m * atom_lo);
@@ -389,32 +425,33 @@ solve_resident_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     }
   } else if (warp == LOADER) {
     // ======================= loader: streams the weight units of every evaluation through the ring =======================
-    // The ring moves UNITS: one [64 x 64] bf16 box (8 KB).  A tile of the job list is D/64 consecutive units
-    // (the k-atoms of 64 W1cat rows, or the 64-row blocks of one W2cat k-atom), so a stage is refilled as
-    // soon as its 4 MMAs retire and NU units are in flight whatever the job boundaries are.
+    // Walks the evaluation's allocation list (struct Alloc) over and over: NU slots of 8 KB, up to NB
+    // allocations in flight, each refilled as soon as the 4 MMAs that read its predecessor retire.
     const bool leader = ptx::elect_one();
     if (leader) { ptx::prefetch_tensormap(&tmW1); ptx::prefetch_tensormap(&tmW2); }
-    const int tiles_per_eval = a.sc.n_tiles;
-    const int UPT = D / 64;
-    const uint32_t total_units = (uint32_t)n_mine * n_evals * tiles_per_eval * UPT;
-    int l_stage = 0, l_round = 0, l_tile = 0, l_sub = 0;   // ring stage, passes over the ring, tile, unit in tile
-    uint32_t tv = a.sc.tile[0];
-    for (uint32_t u = 0; u < total_units; ++u) {
-      if (l_round > 0) ptx::mbar_wait(bar_free + l_stage, (uint32_t)((l_round - 1) & 1));
+    const int n_allocs = a.sc.n_allocs;
+    const uint32_t total = (uint32_t)n_mine * n_evals * n_allocs;
+    int li = 0;
+    for (uint32_t g = 0; g < total; ++g) {
+      const Alloc al = a.sc.alloc[li];
+      if (g >= al.back) {   // the allocation whose slots / barrier pair this one reuses has been released
+        const uint32_t w = g - al.back;
+        ptx::mbar_wait(bar_free + (w & (NB - 1)), (w / NB) & 1);
+      }
       if (leader) {
-        uint8_t* dst = sRing + l_stage * 8192;
-        const int off = (int)(tv & 0x7fffu);
-        ptx::mbar_expect_tx(bar_full + l_stage, 8192);
-        if (!(tv & 0x8000u)) ptx::tma_load_2d(dst, &tmW1, bar_full + l_stage, l_sub * 64, off);
-        else ptx::tma_load_2d(dst, &tmW2, bar_full + l_stage, off, l_sub * 64);
+        uint64_t* fb = bar_full + (g & (NB - 1));
+        uint8_t* dst = sRing + (int)al.off * 8192;
+        ptx::mbar_expect_tx(fb, (uint32_t)al.size * 8192);
+        if (al.kind == 0) {
+          for (int m = 0; m < 3; ++m) ptx::tma_load_2d(dst + m * 8192, &tmW1, fb, al.ka * 64, m * D + al.arg * 64);
+        } else if (al.kind == 1) {
+          for (int m = 0; m < 2; ++m) ptx::tma_load_2d(dst + m * 8192, &tmW1, fb, al.ka * 64, 3 * D + al.arg * 128 + m * 64);
+        } else {
+          for (int nb = 0; nb < (int)al.size; ++nb) ptx::tma_load_2d(dst + nb * 8192, &tmW2, fb, al.arg, nb * 64);
+        }
       }
       __syncwarp();
-      if (++l_sub == UPT) {
-        l_sub = 0;
-        if (++l_tile == tiles_per_eval) l_tile = 0;
-        tv = a.sc.tile[l_tile];
-      }
-      if (++l_stage == NU) { l_stage = 0; ++l_round; }
+      if (++li == n_allocs) li = 0;
     }
   } else if (warp < 16 && (warp & 3) < n_quads) {
     // ======================= compute warps: thread = (token row, column quarter) =======================
@@ -469,7 +506,8 @@ solve_resident_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       const int img = (int)blockIdx.x + idx * (int)gridDim.x;
       // ---- x0 -> resident state, first xc ----
       {
-        quad_sync(q);   // the previous image's last mean exchange has been read by every warp of the quadrant
+        if (cw == 0) bulk_wait_read();   // the previous image's last row stores have read the state
+        quad_sync(q);   // ... and its last mean exchange has been read by every warp of the quadrant
         float part = 0.f;
         const float* src = a_param.x0 + ((size_t)img * N + (row_ok ? r : 0)) * D + cw * DQ;
 #pragma unroll 1
@@ -504,6 +542,7 @@ solve_resident_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
           RTR(0, j * 4 + 0);
           wait_mma();
           RTR(0, j * 4 + 1);
+          if (j == 0 && cw == 0) bulk_wait_read();   // the row stores of the previous step have read the state
           if (kind == JOB_FC) {
             // ---- fc1 chunk -> bias -> GELU -> bf16 tile: 32 of the 128 columns ----
             const float* bias = sB1 + 3 * D + arg * 128 + cw * 32;
@@ -514,11 +553,12 @@ solve_resident_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
               float bv[16];
               lds16(bias + g * 16, bv);
               ptx::tmem_ld_wait();
+              uint32_t w[8];
 #pragma unroll
-              for (int jj = 0; jj < 16; ++jj) v[jj] = gelu_tanh(v[jj] + bv[jj]);
+              for (int jj = 0; jj < 8; ++jj) w[jj] = gelu2_bf16(v[2 * jj] + bv[2 * jj], v[2 * jj + 1] + bv[2 * jj + 1]);
               if (row_ok) {
-                st_tile8(sG, L.xc_atom, r, cw * 32 + g * 16, v);
-                st_tile8(sG, L.xc_atom, r, cw * 32 + g * 16 + 8, v + 8);
+                st_tile8w(sG, L.xc_atom, r, cw * 32 + g * 16, w);
+                st_tile8w(sG, L.xc_atom, r, cw * 32 + g * 16 + 8, w + 4);
               }
             }
           } else if (kind == JOB_QKV) {
@@ -651,25 +691,25 @@ solve_resident_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
                 for (int jj = 0; jj < 4; ++jj)
                   reinterpret_cast<float4*>(yrow + col0)[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
               }
-              if (srow) {
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
-                  reinterpret_cast<float4*>(srow + col0)[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
-              }
-              if (frow) {
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
-                  reinterpret_cast<float4*>(frow + col0)[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
-              }
               tmem_st16f(t_lane + T_R1 + col0, v);
             }
             centre_from_r1(part);
+            // The updated state row is complete in shared memory (all four column shares, ordered by the
+            // quadrant barrier inside centre_from_r1): one thread per row hands it to the bulk-copy engine.
+            // Per-lane stores of 64 bytes at a 768-byte stride cost ~4600 LSU cycles per step here.
+            if (cw == 0 && row_ok && (srow || frow)) {
+              ptx::fence_async_shared();
+              if (srow) bulk_store(srow, yrow, (uint32_t)D * 4);
+              if (frow) bulk_store(frow, yrow, (uint32_t)D * 4);
+              bulk_commit();
+            }
           }
           done();
           RTR(0, j * 4 + 2);
         }
       }
     }
+    if (cw == 0) bulk_wait_all();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -684,35 +724,58 @@ solve_resident_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
   }
 }
 
-// Job list of one evaluation: per head [Q_h, MLP jobs, S_h, PV_h, MLP jobs], the C hidden chunks spread
+// Job list of one evaluation: per head [Q_h, MLP jobs, S_h, MLP jobs, PV_h], the C hidden chunks spread
 // evenly over the 2H gaps, then F.  Adjacent jobs of one chain serialise (the second group waits for the
-// first's compute phase); the only such pairs left are S_h -> PV_h (a short MMA) when C >= 2H.
-void build_sched(int D, int H, int C, Sched& sc) {
-  int nj = 0, nt = 0, last_a = -1, last_b = -1, c = 0;
+// first's compute phase): with C >= 2H only PV_h -> Q_{h+1} is left (measured 3 % faster than S_h -> PV_h).
+bool build_sched(int D, int H, int C, Sched& sc) {
+  int nj = 0, na = 0, last_a = -1, last_b = -1, c = 0;
+  const int U = D / 64;
   auto push = [&](uint8_t kind, int arg, int dep) { sc.kind[nj] = kind; sc.arg[nj] = (uint8_t)arg; sc.dep[nj] = (int8_t)dep; return nj++; };
-  auto w1 = [&](int row0) { sc.tile[nt++] = (uint16_t)row0; };
-  auto w2 = [&](int col0) { sc.tile[nt++] = (uint16_t)(0x8000 | col0); };
+  auto add = [&](int kind, int ka, int arg, int size) {
+    if (na < kMaxAllocs) sc.alloc[na] = Alloc{(uint16_t)arg, (uint8_t)kind, (uint8_t)ka, 0, (uint8_t)size, 0, 0};
+    ++na;
+  };
+  auto w2 = [&](int col0) { add(2, 0, col0, U); };
   auto mlp_jobs = [&](int slot) {
     const int upto = (slot + 1) * C / (2 * H);
     for (; c < upto; ++c) {
       if (c > 0) { w2(D + (c - 1) * 128); w2(D + (c - 1) * 128 + 64); }
-      w1(3 * D + c * 128); w1(3 * D + c * 128 + 64);
+      for (int ka = 0; ka < U; ++ka) add(1, ka, c, 2);
       last_b = push(JOB_FC, c, last_b);
     }
   };
   for (int h = 0; h < H; ++h) {
     if (h > 0) w2((h - 1) * 64);
-    w1(h * 64); w1(D + h * 64); w1(2 * D + h * 64);
+    for (int ka = 0; ka < U; ++ka) add(0, ka, h, 3);
     last_a = push(JOB_QKV, h, last_a);
     mlp_jobs(2 * h);
     last_a = push(JOB_S, h, last_a);
-    last_a = push(JOB_PV, h, last_a);
     mlp_jobs(2 * h + 1);
+    last_a = push(JOB_PV, h, last_a);
   }
   w2((H - 1) * 64); w2(D + (C - 1) * 128); w2(D + (C - 1) * 128 + 64);
   push(JOB_F, 0, nj - 1);
   sc.n_jobs = nj;
-  sc.n_tiles = nt;
+  sc.n_allocs = na;
+  if (na > kMaxAllocs) return false;
+  // ring walk: no allocation wraps; every evaluation starts at slot 0
+  int pos = 0;
+  for (int i = 0; i < na; ++i) {
+    if (pos + sc.alloc[i].size > NU) pos = 0;
+    sc.alloc[i].off = (uint8_t)pos;
+    pos += sc.alloc[i].size;
+  }
+  // steady state (allocation i of an evaluation, the previous evaluation before it): distance to the latest
+  // older allocation that overlaps its slots, capped by the reuse distance of the barrier pair
+  for (int i = 0; i < na; ++i) {
+    int back = NB;
+    for (int d = 1; d < NB; ++d) {
+      const Alloc& o = sc.alloc[((i - d) % na + na) % na];
+      if (o.off < sc.alloc[i].off + sc.alloc[i].size && sc.alloc[i].off < o.off + o.size) { back = d; break; }
+    }
+    sc.alloc[i].back = (uint8_t)back;
+  }
+  return true;
 }
 
 }  // namespace
@@ -726,7 +789,7 @@ size_t solve_resident_scratch_floats(const Plan& p) {
 bool solve_resident_shape_ok(const Plan& p) {
   if (p.variant != ODEVIT_FIELD_PARALLEL || p.precision != ODEVIT_BF16) return false;
   if (p.d != 64 || p.D % 64 || p.D > 192 || p.hid % 128 || p.hid < 128 || p.N > 128 || p.N < 1) return false;
-  if (3 * p.H + p.hid / 128 + 1 > kMaxJobs || 4 * p.H + 4 * (p.hid / 128) > kMaxTiles || 3 * p.D + p.hid > 0x7fff) return false;
+  if (3 * p.H + p.hid / 128 + 1 > kMaxJobs || 4 * p.H + 5 * (p.hid / 128) > kMaxAllocs || 3 * p.D + p.hid > 0x7fff) return false;
   const int RA = (p.N + 15) / 16 * 16;
   return smem_layout(RA, p.N, p.D, p.hid).total <= 227 * 1024;
 }
@@ -755,7 +818,7 @@ int solve_resident(const Plan& p, const WeightBufs& wb, int S, const float (*ta)
   }
   a.x0 = x0; a.states = states; a.final_state = final_state; a.p_last = p_last;
   a.b1cat = wb.b1cat; a.b2 = wb.b2; a.kbuf = kbuf;
-  build_sched(p.D, p.H, p.hid / 128, a.sc);
+  if (!build_sched(p.D, p.H, p.hid / 128, a.sc)) return set_error(ODEVIT_ERR_INVALID_ARG, "resident solver: allocation list too long");
   const int R = 3 * p.D + p.hid, K2 = p.D + p.hid;
   CUtensorMap t1, t2;
   ODV_TRY(make_tmap_2d_bf16(&t1, wb.w1cat, p.D, R, p.D, 64, 64));

@@ -69,14 +69,18 @@ def test_resident_exports_last_attention_map():
     assert max_rel(p_res.sum(-1), torch.ones(2, 3, 69)) < 1e-3
 
 
-@pytest.mark.parametrize("D,H,ratio,img,patch,R", [(64, 1, 2.0, 16, 4, 2), (128, 2, 4.0, 32, 4, 0), (256, 4, 1.0, 32, 4, 4)])
+@pytest.mark.parametrize("D,H,ratio,img,patch,R", [(64, 1, 2.0, 16, 4, 2), (128, 2, 4.0, 32, 4, 0), (192, 3, 2.0, 32, 4, 0),
+                                                  (64, 1, 2.0, 40, 4, 11), (256, 4, 1.0, 32, 4, 4)])
 def test_resident_other_small_shapes(D, H, ratio, img, patch, R):
     cfg = dict(img_size=img, patch_size=patch, num_classes=7, embed_dim=D, num_heads=H, mlp_ratio=ratio, emulate_depth=12,
                time_interval=1.0, num_eval_steps=4, solver="rk4", register_tokens=R)
     model, sd = _model(cfg, seed=4)
     px = torch.randn(5, 3, img, img, generator=torch.Generator().manual_seed(3))
-    a, _ = _run(model, px.cuda(), True)
-    b, _ = _run(model, px.cuda(), False)
+    a, n_a = _run(model, px.cuda(), True)
+    b, n_b = _run(model, px.cuda(), False)
+    # D <= 192 (tensor-memory budget: 192 + D + 128 columns) runs on the chip-resident path, the 17-warp variant
+    # when more than 96 tokens need the fourth row quadrant; D = 256 stays on the multi-kernel path
+    assert (n_a < n_b) == (D <= 192)
     assert max_rel(a["states"], b["states"]) < 1e-2
     want = orc.vit_ode_forward(sd, cfg, px, output_hidden_states=True)
     assert max_rel(a["states"][-1], want["states"][-1]) < 2e-2

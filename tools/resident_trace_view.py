@@ -1,3 +1,6 @@
+"""Formats the `RTR <class> <job> <event> <clock>` lines a -DRES_TRACE build of csrc/solve_resident.cu prints
+(class 0 = compute thread 0, 1 = MMA-issuing warp; events: 0 job start, 1 dependency met / MMA group retired,
+2 group committed / compute phase done).  See tools/resident_probe.py."""
 import sys
 rows=[l.split() for l in open(sys.argv[1] if len(sys.argv)>1 else 'gpurun_out/rtrace.log') if l.startswith('RTR')]
 names="Q0 c0 S0 PV0 c1 Q1 c2 S1 PV1 c3 Q2 c4 S2 PV2 c5 F".split()
