@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define ODEVIT_ABI_VERSION 3
+#define ODEVIT_ABI_VERSION 4
 
 typedef struct CUstream_st* odevit_stream_t; /* == cudaStream_t */
 
@@ -214,6 +214,16 @@ int odevit_field_bwd(const odevit_desc* desc, const odevit_weights* w,
  * the maxima over n and b (tiny). */
 int odevit_fd_curvature(const float* states, int32_t n_grid, int32_t batch, int32_t tokens, int32_t dim,
                         double delta_t, float* per_seq, odevit_stream_t stream);
+
+/* JaSMin statistic of exported attention maps in one pass.  Replaces the sort-based tensor arithmetic of
+ * ViTNeuralODE.jasmin_loss / g_k (ode_transformer_gpt.py:419-456; the reference calls it on detached maps,
+ * :614-618): for each [tokens x tokens] slice (evaluation, image, head) of p_maps
+ *   out[slice] = max over query rows of log(g_1 / (g_k + 1e-12) + 1e-12)        (k = 0: log(g_1 + 1e-12))
+ * with g_j = x_(j) (1 - x_(j) + x_(j+1)), x_(j) the j-th largest entry of the row after clamp to
+ * [1e-12, 1] and renormalisation by (row sum + 1e-12).  The caller takes the means over heads, images and
+ * evaluations (tiny).  1 <= tokens <= 1024, 0 <= k <= tokens. */
+int odevit_jasmin_rowmax(const float* p_maps, int64_t n_slices, int32_t tokens, int32_t k, float* out,
+                         odevit_stream_t stream);
 
 /* Number of kernels the library launched (process-wide, all threads) since the last reset (bench.py's
  * gpu_launches claim is counted, not estimated). */

@@ -13,7 +13,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libodevit.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # enums of include/odevit.h
 FIELD_PARALLEL, FIELD_PARALLEL_L2, FIELD_MACARON = 0, 1, 2
@@ -87,6 +87,8 @@ def lib() -> ctypes.CDLL:
                                    ctypes.c_int32, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _vp]
     L.odevit_tape_bytes.restype = ctypes.c_size_t
     L.odevit_tape_bytes.argtypes = [ctypes.POINTER(Desc), ctypes.c_int32, ctypes.c_int32]
+    L.odevit_jasmin_rowmax.restype = ctypes.c_int
+    L.odevit_jasmin_rowmax.argtypes = [_vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _vp, _vp]
     L.odevit_fd_curvature.restype = ctypes.c_int
     L.odevit_fd_curvature.argtypes = [_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                       ctypes.c_double, _vp, _vp]
@@ -149,6 +151,6 @@ def profile_read() -> dict:
 
 DECLARED_SYMBOLS = ("odevit_abi_version", "odevit_build_info", "odevit_last_error_string",
                     "odevit_workspace_bytes", "odevit_field_fwd", "odevit_solve_fwd", "odevit_solve_bwd",
-                    "odevit_field_bwd", "odevit_tape_bytes", "odevit_fd_curvature", "odevit_launch_count", "odevit_reset_launch_count",
+                    "odevit_field_bwd", "odevit_tape_bytes", "odevit_fd_curvature", "odevit_jasmin_rowmax", "odevit_launch_count", "odevit_reset_launch_count",
                     "odevit_gemm_bf16", "odevit_profile_enable", "odevit_profile_reserve", "odevit_profile_num_classes", "odevit_profile_class_name",
                     "odevit_profile_read")

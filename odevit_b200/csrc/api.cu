@@ -1050,6 +1050,15 @@ int odevit_fd_curvature(const float* states, int32_t n_grid, int32_t batch, int3
                       reinterpret_cast<cudaStream_t>(stream));
 }
 
+int odevit_jasmin_rowmax(const float* p_maps, int64_t n_slices, int32_t tokens, int32_t k, float* out,
+                         odevit_stream_t stream) {
+  if (n_slices < 0 || tokens <= 0) return set_error(ODEVIT_ERR_INVALID_ARG, "non-positive dimension");
+  if (n_slices == 0) return 0;
+  ODV_TRY(check_device_ptr(p_maps, "p_maps"));
+  ODV_TRY(check_device_ptr(out, "out"));
+  return jasmin_rowmax(p_maps, n_slices, tokens, k, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int odevit_field_bwd(const odevit_desc* desc, const odevit_weights* w, const float* x, const float* g_dx,
                      const float* g_p, float* g_x, const odevit_weight_grads* gw, void* workspace,
                      size_t workspace_bytes, odevit_stream_t stream) {

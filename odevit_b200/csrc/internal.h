@@ -208,6 +208,8 @@ int vjp_combine(const CombineArgs& a, int rows, int D, cudaStream_t s);
 
 // per_seq[r] = max_j max_d |s[j+2,r,d] - 2 s[j+1,r,d] + s[j,r,d]| / dt2   (states [T, rows, D])
 int fd_curvature(const float* states, int T, long long rows, int D, float dt2, float* per_seq, cudaStream_t s);
+// per [N x N] attention-map slice: max over rows of the JaSMin row value (rows.cu)
+int jasmin_rowmax(const float* P, long long n_slices, int N, int k, float* out, cudaStream_t s);
 
 // out1 = x o mask(d1), out2 = x o mask(d2)  (x, out*: [rows, D] of type `type`; the two masked copies of
 // the cotangent that enter the fc2 and the out-proj branch when their output dropouts differ)

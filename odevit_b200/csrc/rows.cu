@@ -239,6 +239,70 @@ __global__ void axpy_kernel(float* y, const float* __restrict__ x, float a, long
 // D and the max over time: in PyTorch that is ~6 full-trajectory passes.  Here one warp owns a token
 // row (b,n), walks the T rows once with a 3-row register window and emits per_seq[b,n]; every state
 // element is read exactly once (algorithmic bytes = T*B*N*D*4).
+// JaSMin statistic of exported attention maps (ode_transformer_gpt.py:419-456, detached by the reference):
+// one CTA per map slice (evaluation, image, head), 8 warps over its N query rows.  Per row: clamp to
+// [1e-12, 1], renormalise by (sum + 1e-12), the k+1 largest entries by repeated warp arg-max over a
+// shared-memory copy of the row (one instance removed per round, so ties keep their multiplicity, as in
+// the reference's sort), g_j = x_(j) (1 - x_(j) + x_(j+1)), row value log(g_1 / (g_k + 1e-12) + 1e-12)
+// (k = 0: log(g_1 + 1e-12)); the CTA writes the maximum over the rows.
+__global__ void __launch_bounds__(256) jasmin_rowmax_kernel(const float* __restrict__ P, int N, int k, float* __restrict__ out) {
+  extern __shared__ float jas_rows[];
+  __shared__ float warp_best[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* row = jas_rows + warp * N;
+  const float* base = P + (size_t)blockIdx.x * N * N;
+  const int need = (k == 0) ? 2 : k + 1;
+  float best = -INFINITY;
+  for (int r = warp; r < N; r += 8) {
+    const float* src = base + (size_t)r * N;
+    float sum = 0.f;
+    for (int c = lane; c < N; c += 32) {
+      const float v = fminf(fmaxf(src[c], 1e-12f), 1.f);
+      row[c] = v;
+      sum += v;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float den = sum + 1e-12f;
+    __syncwarp();
+    float x1 = 0.f, x2 = 0.f, xk = 0.f, xk1 = 0.f;
+    for (int t = 1; t <= need && t <= N; ++t) {
+      float m = -INFINITY;
+      int mi = 0x7fffffff;
+      for (int c = lane; c < N; c += 32) {
+        const float v = row[c];
+        if (v > m) { m = v; mi = c; }
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+      }
+      if (lane == 0) row[mi] = -INFINITY;
+      __syncwarp();
+      const float x = m / den;
+      if (t == 1) x1 = x;
+      if (t == 2) x2 = x;
+      if (t == k) xk = x;
+      if (t == k + 1) xk1 = x;
+    }
+    const float g1 = x1 * (1.f - x1 + x2);
+    float v;
+    if (k == 0) v = logf(g1 + 1e-12f);
+    else v = logf(g1 / (xk * (1.f - xk + xk1) + 1e-12f) + 1e-12f);
+    best = fmaxf(best, v);
+    __syncwarp();
+  }
+  if (lane == 0) warp_best[warp] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = warp_best[0];
+    for (int w = 1; w < 8; ++w) b = fmaxf(b, warp_best[w]);
+    out[blockIdx.x] = b;
+  }
+}
+
 template <int CH>  // CH float4 chunks per lane: D <= 128*CH
 __global__ void __launch_bounds__(256) fd_curvature_kernel(const float* __restrict__ states, int T, long long rows,
                                                            int D, float dt2, float* __restrict__ per_seq) {
@@ -741,6 +805,16 @@ int axpy_f32(float* y, const float* x, float a, long long n, cudaStream_t s) {
   ProfScope prof(KC_COMBINE, s);
   const int blocks = (int)((n + 1023) / 1024 < 148 * 8 ? (n + 1023) / 1024 : 148 * 8);
   axpy_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(y, x, a, n);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int jasmin_rowmax(const float* P, long long n_slices, int N, int k, float* out, cudaStream_t s) {
+  ProfScope prof(KC_FD_BOUND, s);
+  if (N < 1 || N > 1024 || k < 0 || k > N)
+    return set_error(ODEVIT_ERR_UNSUPPORTED, "jasmin_rowmax: tokens=%d k=%d (need 1 <= tokens <= 1024, 0 <= k <= tokens)", N, k);
+  if (n_slices <= 0) return 0;
+  jasmin_rowmax_kernel<<<(unsigned)n_slices, 256, (size_t)8 * N * sizeof(float), s>>>(P, N, k, out);
   ODV_LAUNCH_CHECK();
   return 0;
 }

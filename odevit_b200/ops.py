@@ -358,6 +358,21 @@ def fd_curvature(states: torch.Tensor, delta_t: float) -> torch.Tensor:
     return out
 
 
+def jasmin_rowmax(p_maps: torch.Tensor, k: int) -> torch.Tensor:
+    """[..., N, N] attention maps -> [...] max over query rows of the JaSMin row value
+    log(g_1 / (g_k + 1e-12) + 1e-12) (ode_transformer_gpt.py:419-456), one pass, no sort."""
+    p_maps = _require_cuda(p_maps.detach(), "p_maps").contiguous()
+    N = p_maps.shape[-1]
+    if p_maps.shape[-2] != N:
+        raise ValueError("attention maps must be square in their last two dimensions")
+    lead = p_maps.shape[:-2]
+    out = torch.empty(lead, device=p_maps.device, dtype=torch.float32)
+    with torch.cuda.device(p_maps.device):
+        st = _lib.lib().odevit_jasmin_rowmax(_ptr(p_maps), out.numel(), N, int(k), _ptr(out), _stream())
+    _lib.check(st, "odevit_jasmin_rowmax")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # patch projection (row (f1) of SURVEY section 8: the caller just before the hot path)
 # ---------------------------------------------------------------------------------------------

@@ -453,8 +453,12 @@ class ViTNeuralODE(nn.Module):
             out["attentions"] = p_last[:, :, :-R, :-R]
             out["attentions_register_tokens"] = p_last[:, :, -R:, :]
             window = int(self.num_eval_steps * 0.85)
-            maps = list(p_traj.unbind(0)) if p_traj is not None else []
-            out["jasmin_loss"] = self.jasmin_loss(maps[-window:], k=jasmin_k, reduction="mean")
+            # :614-618 -- the reference sorts every row of every map of the window; same statistic from one
+            # pass over the exported maps (odevit_jasmin_rowmax), means over heads / images / maps here
+            if p_traj is None or p_traj.shape[0] == 0:
+                out["jasmin_loss"] = self.jasmin_loss([], k=jasmin_k, reduction="mean")
+            else:
+                out["jasmin_loss"] = ops.jasmin_rowmax(p_traj[-window:], jasmin_k).mean(dim=2).mean(dim=1).mean()
         if self.add_distillation_token:
             out["logits_dist"] = self.dist_head(final[:, 1])
         if labels is not None:

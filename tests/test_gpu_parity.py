@@ -338,3 +338,38 @@ def test_fd_curvature_matches_reference_formula(T, B, N, D):
     got = ops.fd_curvature(s.cuda(), dt)
     assert got.shape == (B, N)
     assert max_rel(got, want) < 1e-6
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, 10])
+def test_jasmin_rowmax_matches_reference_formula(k):
+    """odevit_jasmin_rowmax against the reference's sort-based jasmin_loss (ode_transformer_gpt.py:419-456,
+    restated in the oracle), incl. rows with tied maxima, zeros (clamped to 1e-12) and un-normalised rows."""
+    import odevit_b200 as ob
+    from odevit_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    E, B, H, N = 3, 2, 3, 37
+    P = torch.softmax(4.0 * torch.randn(E, B, H, N, N, generator=g), dim=-1)
+    P[0, 0, 0, 0] = 0.0
+    P[0, 0, 0, 0, 3] = 0.5
+    P[0, 0, 0, 0, 9] = 0.5                # tie of the two largest
+    P[1, 1, 2, 5] *= 0.7                   # row not summing to one
+    P[2, 0, 1, 7, :20] = 0.0               # zeros -> clamp
+    got = ops.jasmin_rowmax(P.cuda(), k).cpu()
+
+    def g_k(p, kk):
+        s, _ = torch.sort(p, dim=-1, descending=True)
+        x_k = s[..., kk - 1]
+        x_k1 = s[..., kk] if kk < p.size(-1) else torch.zeros_like(x_k)
+        return x_k * (1 - x_k + x_k1)
+    Pc = torch.clamp(P.double(), min=1e-12, max=1.0)
+    Pc = Pc / (Pc.sum(dim=-1, keepdim=True) + 1e-12)
+    g1 = g_k(Pc, 1)
+    want = torch.log(g1 + 1e-12) if k == 0 else torch.log(g1 / (g_k(Pc, k) + 1e-12) + 1e-12)
+    want = want.max(dim=-1).values
+    assert got.shape == (E, B, H)
+    assert torch.allclose(got.double(), want, rtol=1e-4, atol=2e-5)
+    # and through the module: the same scalar the reference's list-of-maps loop gives
+    model = ob.ViTNeuralODE(img_size=16, patch_size=4, num_classes=5, embed_dim=64, num_heads=1, mlp_ratio=2.0,
+                            emulate_depth=12, time_interval=1.0, num_eval_steps=4, solver="euler", register_tokens=2)
+    ref = model.jasmin_loss([p for p in P], k=k, reduction="mean")
+    assert float(got.mean(dim=2).mean(dim=1).mean()) == pytest.approx(float(ref), rel=1e-4, abs=2e-5)
