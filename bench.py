@@ -269,17 +269,41 @@ def run_ours(args, wl):
     prof = {k: (v[0] / max(1, args.repeats), v[1] // max(1, args.repeats)) for k, v in _lib.profile_read().items()}
     _lib.profile_enable(False)
 
-    # ---- end to end: host buffers in, loss out, every step
-    def e2e_step():
-        px = px_h.to(dev, non_blocking=True)
-        lb = lb_h.to(dev, non_blocking=True)
-        return float(step(px, lb).item())
+    # ---- end to end: host buffers in, loss out, every step.  Every step's inputs are copied from pinned host
+    # memory inside the timed region; the copy of step k+1 is enqueued on a side stream before step k computes
+    # (odevit_b200.dp.HostBatchPrefetcher), and the loss is read back (a host sync) every step.
+    from odevit_b200.dp import HostBatchPrefetcher
+    feeder = HostBatchPrefetcher(dev)
+
+    def e2e_region(k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        feeder.submit(px_h, lb_h)
+        for i in range(k):
+            slot, (px, lb) = feeder.take()
+            if i + 1 < k:
+                feeder.submit(px_h, lb_h)
+            loss = step(px, lb)
+            feeder.release(slot)
+            float(loss.item())
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / k
+
+    def timed_e2e(k):
+        vals = [e2e_region(k) for _ in range(max(1, args.repeats))]
+        repeats_log["e2e"] = [round(v, 3) for v in vals]
+        return sorted(vals)[len(vals) // 2]
 
     if args.quick:
         ms_e2e = float("nan")
     else:
-        e2e_step()
-        ms_e2e = timed(e2e_step, args.steps, "e2e")
+        e2e_region(1)
+        ms_e2e = timed_e2e(args.steps)
     clocks = sampler.result()
 
     # ---- kernel-only forward (inference) of the same batch: field evaluations per second

@@ -66,3 +66,45 @@ def shard_batch(n_items: int, rank: int, world: int) -> slice:
     base, rem = divmod(n_items, world)
     start = rank * base + min(rank, rem)
     return slice(start, start + base + (1 if rank < rem else 0))
+
+
+class HostBatchPrefetcher:
+    """Feeds host (pinned) batches to the device one step ahead: the copy of step k+1's inputs runs on a
+    side stream while step k computes, into the buffer set step k-1 used (two sets).  `submit(*tensors)`
+    enqueues a copy; `take()` makes the compute stream wait for the oldest submitted copy and returns its
+    device tensors.  The reference's data path is a DataLoader with pin_memory (its YAML sets
+    `pin_memory: True`, experiment_vit_edo.yaml collator.train) followed by `.to(device)` in the loop
+    (train.py:40-45): same bytes, overlapped."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self._sets = [None, None]
+        self._ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        self._queue: List[int] = []
+        self._next = 0
+
+    def submit(self, *host_tensors: torch.Tensor) -> None:
+        i = self._next
+        self._next ^= 1
+        if i in self._queue:
+            raise RuntimeError("HostBatchPrefetcher: both buffer sets are in flight; take() one first")
+        if self._sets[i] is None or any(d.shape != h.shape or d.dtype != h.dtype for d, h in zip(self._sets[i], host_tensors)):
+            self._sets[i] = [torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in host_tensors]
+        else:
+            self.stream.wait_event(self._consumed[i])     # the step that read this set has been enqueued and finished
+        with torch.cuda.stream(self.stream):
+            for d, h in zip(self._sets[i], host_tensors):
+                d.copy_(h, non_blocking=True)
+            self._ready[i].record(self.stream)
+        self._queue.append(i)
+
+    def take(self):
+        i = self._queue.pop(0)
+        torch.cuda.current_stream(self.device).wait_event(self._ready[i])
+        return i, self._sets[i]
+
+    def release(self, i: int) -> None:
+        """Call after the work reading buffer set `i` has been enqueued on the compute stream."""
+        self._consumed[i].record(torch.cuda.current_stream(self.device))

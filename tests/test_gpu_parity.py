@@ -373,3 +373,23 @@ def test_jasmin_rowmax_matches_reference_formula(k):
                             emulate_depth=12, time_interval=1.0, num_eval_steps=4, solver="euler", register_tokens=2)
     ref = model.jasmin_loss([p for p in P], k=k, reduction="mean")
     assert float(got.mean(dim=2).mean(dim=1).mean()) == pytest.approx(float(ref), rel=1e-4, abs=2e-5)
+
+
+def test_host_batch_prefetcher_round_trip():
+    """odevit_b200.dp.HostBatchPrefetcher: batches come out in submission order with the submitted values,
+    two in flight, buffer sets reused."""
+    from odevit_b200.dp import HostBatchPrefetcher
+    dev = torch.device("cuda", 0)
+    feeder = HostBatchPrefetcher(dev)
+    hosts = [(torch.full((4, 3, 8, 8), float(i)).pin_memory(), torch.full((4,), i, dtype=torch.long).pin_memory()) for i in range(5)]
+    feeder.submit(*hosts[0])
+    seen = []
+    for i in range(5):
+        slot, (px, lb) = feeder.take()
+        if i + 1 < 5:
+            feeder.submit(*hosts[i + 1])
+        seen.append((float(px.mean()), int(lb[0])))
+        feeder.release(slot)
+    assert seen == [(float(i), i) for i in range(5)]
+    with pytest.raises(RuntimeError):
+        feeder.submit(*hosts[0]); feeder.submit(*hosts[1]); feeder.submit(*hosts[2])
