@@ -62,6 +62,37 @@ __global__ void __launch_bounds__(256) center_rows_kernel(const float* __restric
   }
 }
 
+// x - mean(x) -> bf16, D a multiple of 128: 16-byte loads, 8-byte stores (the CenterNorm prologue of every
+// bf16 field evaluation; the affine and D/(D-1) live in the folded weights)
+template <int CH>
+__global__ void __launch_bounds__(256) center_rows_bf16_vec_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xc,
+                                                                   int rows, int D) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
+  const int n4 = D >> 2;
+  float4 v[CH];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int c = lane + i * 32;
+    v[i] = (c < n4) ? __ldg(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) / (float)D;
+  uint2* out = reinterpret_cast<uint2*>(xc + (long long)row * D);
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int c = lane + i * 32;
+    if (c < n4) {
+      const __nv_bfloat162 a = __floats2bfloat162_rn(v[i].x - mean, v[i].y - mean);
+      const __nv_bfloat162 b = __floats2bfloat162_rn(v[i].z - mean, v[i].w - mean);
+      out[c] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) softmax_rows_kernel(float* p, float* copy_to, long long rows,
                                                            int n) {
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -739,7 +770,17 @@ int center_rows(const float* x, void* xc, int xc_type, float* rstd_out, float ep
                 cudaStream_t s) {
   ProfScope prof(KC_CENTER, s);
   if (D > 32 * MAX_PER_LANE) return set_error(ODEVIT_ERR_UNSUPPORTED, "center_rows: D=%d > 1024", D);
-  center_rows_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, xc, xc_type, rstd_out, eps, rows, D);
+  if (xc_type == DT_BF16 && !rstd_out && D % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(xc) & 7) == 0) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(xc);
+    const int ch = (D / 4 + 31) / 32;
+    if (ch <= 2) center_rows_bf16_vec_kernel<2><<<(rows + 7) / 8, 256, 0, s>>>(x, o, rows, D);
+    else if (ch <= 4) center_rows_bf16_vec_kernel<4><<<(rows + 7) / 8, 256, 0, s>>>(x, o, rows, D);
+    else if (ch <= 6) center_rows_bf16_vec_kernel<6><<<(rows + 7) / 8, 256, 0, s>>>(x, o, rows, D);
+    else center_rows_bf16_vec_kernel<8><<<(rows + 7) / 8, 256, 0, s>>>(x, o, rows, D);
+  } else {
+    center_rows_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, xc, xc_type, rstd_out, eps, rows, D);
+  }
   ODV_LAUNCH_CHECK();
   return 0;
 }
