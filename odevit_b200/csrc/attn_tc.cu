@@ -37,6 +37,12 @@ constexpr int BMQ = 128;      // query rows per CTA
 constexpr int O_COL = 128;    // TMEM column of the O accumulator
 constexpr int TMEM_COLS = 256;
 
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct AttnArgs {
   int B, N, H, NP, tiles_m;
   int D;                 // embed dim (column offsets of k, v inside the packed row)
@@ -109,28 +115,44 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   ptx::mbar_wait(bar_s, 0);
   ptx::tc_fence_after();
   const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  const int n_chunks = a.NP / 16;
+  // a warp whose 32 query rows all lie past N (the last tile of an image) skips the passes: its P rows stay
+  // whatever S left there and only feed O rows that are never stored
+  const int n_chunks = (mt * BMQ + warp * 32 < a.N) ? a.NP / 16 : 0;
   constexpr float LOG2E = 1.4426950408889634f;
+  // Tensor-memory loads are issued several chunks at a time and waited for once: with one row per thread
+  // and two warps per scheduler, a load / wait round trip per 16 columns left the passes latency-bound.
   float mx = -INFINITY;
-  for (int c = 0; c < n_chunks; ++c) {
-    float v[16];
-    ptx::tmem_ld16(t_row + c * 16, v);
+  for (int c0 = 0; c0 < n_chunks; c0 += 4) {
+    float v[4][16];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (c0 + u < n_chunks) ptx::tmem_ld16(t_row + (c0 + u) * 16, v[u]);
     ptx::tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (c * 16 + j < a.N) mx = fmaxf(mx, v[j]);
+    for (int u = 0; u < 4; ++u)
+      if (c0 + u < n_chunks) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if ((c0 + u) * 16 + j < a.N) mx = fmaxf(mx, v[u][j]);
+      }
   }
   const float mxs = mx * LOG2E;
   float sum = 0.f;
   float inv = 1.f;
   if constexpr (EXPORT) {
-    for (int c = 0; c < n_chunks; ++c) {
-      float v[16];
-      ptx::tmem_ld16(t_row + c * 16, v);
+    for (int c0 = 0; c0 < n_chunks; c0 += 4) {
+      float v[4][16];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c0 + u < n_chunks) ptx::tmem_ld16(t_row + (c0 + u) * 16, v[u]);
       ptx::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (c * 16 + j < a.N) sum += exp2f(fmaf(v[j], LOG2E, -mxs));
+      for (int u = 0; u < 4; ++u)
+        if (c0 + u < n_chunks) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if ((c0 + u) * 16 + j < a.N) sum += ex2_fast(fmaf(v[u][j], LOG2E, -mxs));
+        }
     }
     inv = 1.f / sum;
   }
@@ -140,34 +162,42 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if constexpr (EXPORT) {
     if (a.p_out && row < a.N) p_row = a.p_out + (((long long)b * a.H + h) * a.N + row) * a.N;
   }
-  for (int c = 0; c < n_chunks; ++c) {
-    float v[16];
-    ptx::tmem_ld16(t_row + c * 16, v);
+  for (int c0 = 0; c0 < n_chunks; c0 += 2) {
+    float v[2][16];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (c0 + u < n_chunks) ptx::tmem_ld16(t_row + (c0 + u) * 16, v[u]);
     ptx::tmem_ld_wait();
-    uint32_t packed[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float e = (c * 16 + j < a.N) ? exp2f(fmaf(v[j], LOG2E, -mxs)) : 0.f;
-      if constexpr (EXPORT) {
-        e *= inv;
-        if constexpr (DROP) e *= drop_factor(a.drop, drow, c * 16 + j);   // the exported map is post-dropout
-        if (p_row && c * 16 + j < a.N) p_row[c * 16 + j] = e;
-      } else {
-        sum += e;
-        if constexpr (DROP) e *= drop_factor(a.drop, drow, c * 16 + j);
+    for (int u = 0; u < 2; ++u) {
+      const int c = c0 + u;
+      if (c < n_chunks) {
+        uint32_t packed[8];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float e = (c * 16 + j < a.N) ? ex2_fast(fmaf(v[u][j], LOG2E, -mxs)) : 0.f;
+          if constexpr (EXPORT) {
+            e *= inv;
+            if constexpr (DROP) e *= drop_factor(a.drop, drow, c * 16 + j);   // the exported map is post-dropout
+            if (p_row && c * 16 + j < a.N) p_row[c * 16 + j] = e;
+          } else {
+            sum += e;
+            if constexpr (DROP) e *= drop_factor(a.drop, drow, c * 16 + j);
+          }
+          v[u][j] = e;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          __nv_bfloat162 hh = __floats2bfloat162_rn(v[u][2 * j], v[u][2 * j + 1]);
+          packed[j] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        // P chunk c (16 keys = 8 packed columns) lands on columns this thread has already consumed
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(t_row + c * 8),
+                     "r"(packed[0]), "r"(packed[1]), "r"(packed[2]), "r"(packed[3]), "r"(packed[4]), "r"(packed[5]),
+                     "r"(packed[6]), "r"(packed[7])
+                     : "memory");
       }
-      v[j] = e;
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-      packed[j] = *reinterpret_cast<uint32_t*>(&hh);
-    }
-    // P chunk c (16 keys = 8 packed columns) lands on columns this thread has already consumed
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(t_row + c * 8),
-                 "r"(packed[0]), "r"(packed[1]), "r"(packed[2]), "r"(packed[3]), "r"(packed[4]), "r"(packed[5]),
-                 "r"(packed[6]), "r"(packed[7])
-                 : "memory");
   }
   if constexpr (!EXPORT) inv = 1.f / sum;
   if (a.lse_out && row < a.N) a.lse_out[((long long)b * a.H + h) * a.N + row] = mxs + log2f(sum);
@@ -182,7 +212,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     ptx::tc_fence_after();
     const uint32_t idesc2 = ptx::idesc_bf16(BMQ, HD, 0, 1);
     const uint32_t v_addr = ptx::smem_u32(sV);
-    for (int k = 0; k < n_chunks; ++k) {
+    for (int k = 0; k < a.NP / 16; ++k) {
       const uint64_t dv = ptx::smem_desc_sw128(v_addr + k * 2048, 8192, 1024);
       ptx::mma_bf16_ts(tmem + O_COL, tmem + k * 8, dv, idesc2, k > 0 ? 1u : 0u);
     }
@@ -280,11 +310,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                : "memory");
 }
 __device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ float ex2_fast(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 // This warp's 32 accumulator rows x 64 fp32 columns -> bf16 -> global rows of `stride` elements.
 // Thread = row out of TMEM; a 4 KB staging tile (16-byte chunks XOR-swizzled by row) turns the
