@@ -21,6 +21,8 @@
 // EXPORT variant also writes the normalised fp32 P[b, h, :, :].
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "epilogue.cuh"
 #include "internal.h"
 #include "ptx.cuh"
@@ -52,6 +54,124 @@ struct AttnArgs {
   float* lse_out;        // [B, H, N] fp32 or null: log2-domain log-sum-exp of each row (for the VJP)
   Drop drop;             // attention-map dropout (element (b*H+h)*N + i, j); thresh 0 = off
 };
+
+// Softmax of this thread's query row straight from tensor memory (S at t_row, n_chunks 16-column chunks; 0 for a
+// warp without valid rows), un-normalised exp packed to bf16 IN PLACE over the consumed S columns; EXPORT also
+// writes the normalised fp32 row.  Returns 1 / row sum (what the O epilogue needs; 1 in EXPORT mode's P).
+template <bool EXPORT, bool DROP>
+__device__ __forceinline__ float attn_softmax_row(const AttnArgs& a, uint32_t t_row, int n_chunks, int b, int h, int row) {
+  constexpr float LOG2E = 1.4426950408889634f;
+  // Tensor-memory loads are issued several chunks at a time and waited for once, and the row max / row sum run
+  // as four independent chains: with one row per thread and two warps per scheduler, a load / wait round trip
+  // per 16 columns and one 208-long dependent FMNMX / FADD chain per pass left the passes latency-bound.
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  for (int c0 = 0; c0 < n_chunks; c0 += 4) {
+    float v[4][16];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (c0 + u < n_chunks) ptx::tmem_ld16(t_row + (c0 + u) * 16, v[u]);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (c0 + u < n_chunks) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if ((c0 + u) * 16 + j < a.N) m4[j & 3] = fmaxf(m4[j & 3], v[u][j]);
+      }
+  }
+  const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+  const float mxs = mx * LOG2E;
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
+  float inv = 1.f;
+  if constexpr (EXPORT) {
+    for (int c0 = 0; c0 < n_chunks; c0 += 4) {
+      float v[4][16];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c0 + u < n_chunks) ptx::tmem_ld16(t_row + (c0 + u) * 16, v[u]);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c0 + u < n_chunks) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if ((c0 + u) * 16 + j < a.N) s4[j & 3] += ex2_fast(fmaf(v[u][j], LOG2E, -mxs));
+        }
+    }
+    inv = 1.f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+  }
+  const uint32_t drow = (uint32_t)(((long long)b * a.H + h) * a.N + row);   // dropout coordinate of this row
+  float* p_row = nullptr;
+  if constexpr (EXPORT) {
+    if (a.p_out && row < a.N) p_row = a.p_out + (((long long)b * a.H + h) * a.N + row) * a.N;
+  }
+  for (int c0 = 0; c0 < n_chunks; c0 += 2) {
+    float v[2][16];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (c0 + u < n_chunks) ptx::tmem_ld16(t_row + (c0 + u) * 16, v[u]);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int c = c0 + u;
+      if (c < n_chunks) {
+        uint32_t packed[8];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float e = (c * 16 + j < a.N) ? ex2_fast(fmaf(v[u][j], LOG2E, -mxs)) : 0.f;
+          if constexpr (EXPORT) {
+            e *= inv;
+            if constexpr (DROP) e *= drop_factor(a.drop, drow, c * 16 + j);   // the exported map is post-dropout
+            if (p_row && c * 16 + j < a.N) p_row[c * 16 + j] = e;
+          } else {
+            s4[j & 3] += e;
+            if constexpr (DROP) e *= drop_factor(a.drop, drow, c * 16 + j);
+          }
+          v[u][j] = e;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          __nv_bfloat162 hh = __floats2bfloat162_rn(v[u][2 * j], v[u][2 * j + 1]);
+          packed[j] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        // P chunk c (16 keys = 8 packed columns) lands on columns this thread has already consumed
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(t_row + c * 8),
+                     "r"(packed[0]), "r"(packed[1]), "r"(packed[2]), "r"(packed[3]), "r"(packed[4]), "r"(packed[5]),
+                     "r"(packed[6]), "r"(packed[7])
+                     : "memory");
+      }
+    }
+  }
+  const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  if constexpr (!EXPORT) inv = 1.f / sum;
+  if (a.lse_out && row < a.N) a.lse_out[((long long)b * a.H + h) * a.N + row] = mxs + log2f(sum);
+  return inv;
+}
+
+// O row (tensor memory, columns t_o ..+64) * inv -> bf16 -> columns [h*64, h*64+64) of the [O | h] buffer
+template <bool EXPORT>
+__device__ __forceinline__ void attn_store_o_row(const AttnArgs& a, uint32_t t_o, int b, int h, int row, float inv) {
+  __nv_bfloat16* o_ptr = reinterpret_cast<__nv_bfloat16*>(a.oh) + ((long long)b * a.N + row) * a.ld_oh + h * HD;
+#pragma unroll
+  for (int c = 0; c < HD / 16; ++c) {
+    float v[16];
+    ptx::tmem_ld16(t_o + c * 16, v);
+    ptx::tmem_ld_wait();
+    if (row < a.N) {
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float s0 = EXPORT ? v[2 * j] : v[2 * j] * inv;
+        const float s1 = EXPORT ? v[2 * j + 1] : v[2 * j + 1] * inv;
+        __nv_bfloat162 hh = __floats2bfloat162_rn(s0, s1);
+        w[j] = *reinterpret_cast<uint32_t*>(&hh);
+      }
+      uint4* o = reinterpret_cast<uint4*>(o_ptr + c * 16);
+      o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+  }
+}
 
 template <bool EXPORT, bool DROP>
 __global__ void __launch_bounds__(128, 2)
@@ -118,89 +238,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   // a warp whose 32 query rows all lie past N (the last tile of an image) skips the passes: its P rows stay
   // whatever S left there and only feed O rows that are never stored
   const int n_chunks = (mt * BMQ + warp * 32 < a.N) ? a.NP / 16 : 0;
-  constexpr float LOG2E = 1.4426950408889634f;
-  // Tensor-memory loads are issued several chunks at a time and waited for once: with one row per thread
-  // and two warps per scheduler, a load / wait round trip per 16 columns left the passes latency-bound.
-  float mx = -INFINITY;
-  for (int c0 = 0; c0 < n_chunks; c0 += 4) {
-    float v[4][16];
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (c0 + u < n_chunks) ptx::tmem_ld16(t_row + (c0 + u) * 16, v[u]);
-    ptx::tmem_ld_wait();
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (c0 + u < n_chunks) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if ((c0 + u) * 16 + j < a.N) mx = fmaxf(mx, v[u][j]);
-      }
-  }
-  const float mxs = mx * LOG2E;
-  float sum = 0.f;
-  float inv = 1.f;
-  if constexpr (EXPORT) {
-    for (int c0 = 0; c0 < n_chunks; c0 += 4) {
-      float v[4][16];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (c0 + u < n_chunks) ptx::tmem_ld16(t_row + (c0 + u) * 16, v[u]);
-      ptx::tmem_ld_wait();
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (c0 + u < n_chunks) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if ((c0 + u) * 16 + j < a.N) sum += ex2_fast(fmaf(v[u][j], LOG2E, -mxs));
-        }
-    }
-    inv = 1.f / sum;
-  }
   const int row = mt * BMQ + warp * 32 + lane;
-  const uint32_t drow = (uint32_t)(((long long)b * a.H + h) * a.N + row);   // dropout coordinate of this row
-  float* p_row = nullptr;
-  if constexpr (EXPORT) {
-    if (a.p_out && row < a.N) p_row = a.p_out + (((long long)b * a.H + h) * a.N + row) * a.N;
-  }
-  for (int c0 = 0; c0 < n_chunks; c0 += 2) {
-    float v[2][16];
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-      if (c0 + u < n_chunks) ptx::tmem_ld16(t_row + (c0 + u) * 16, v[u]);
-    ptx::tmem_ld_wait();
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int c = c0 + u;
-      if (c < n_chunks) {
-        uint32_t packed[8];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float e = (c * 16 + j < a.N) ? ex2_fast(fmaf(v[u][j], LOG2E, -mxs)) : 0.f;
-          if constexpr (EXPORT) {
-            e *= inv;
-            if constexpr (DROP) e *= drop_factor(a.drop, drow, c * 16 + j);   // the exported map is post-dropout
-            if (p_row && c * 16 + j < a.N) p_row[c * 16 + j] = e;
-          } else {
-            sum += e;
-            if constexpr (DROP) e *= drop_factor(a.drop, drow, c * 16 + j);
-          }
-          v[u][j] = e;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          __nv_bfloat162 hh = __floats2bfloat162_rn(v[u][2 * j], v[u][2 * j + 1]);
-          packed[j] = *reinterpret_cast<uint32_t*>(&hh);
-        }
-        // P chunk c (16 keys = 8 packed columns) lands on columns this thread has already consumed
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(t_row + c * 8),
-                     "r"(packed[0]), "r"(packed[1]), "r"(packed[2]), "r"(packed[3]), "r"(packed[4]), "r"(packed[5]),
-                     "r"(packed[6]), "r"(packed[7])
-                     : "memory");
-      }
-    }
-  }
-  if constexpr (!EXPORT) inv = 1.f / sum;
-  if (a.lse_out && row < a.N) a.lse_out[((long long)b * a.H + h) * a.N + row] = mxs + log2f(sum);
+  const float inv = attn_softmax_row<EXPORT, DROP>(a, t_row, n_chunks, b, h, row);
   ptx::tmem_st_wait();
   ptx::tc_fence_before();
   __syncthreads();
@@ -222,28 +261,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   // ---- epilogue: O row / sum -> bf16 ----
   ptx::mbar_wait(bar_o, 0);
   ptx::tc_fence_after();
-  {
-    __nv_bfloat16* o_ptr = reinterpret_cast<__nv_bfloat16*>(a.oh) + ((long long)b * a.N + row) * a.ld_oh + h * HD;
-#pragma unroll
-    for (int c = 0; c < HD / 16; ++c) {
-      float v[16];
-      ptx::tmem_ld16(t_row + O_COL + c * 16, v);
-      ptx::tmem_ld_wait();
-      if (row < a.N) {
-        uint32_t w[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float s0 = EXPORT ? v[2 * j] : v[2 * j] * inv;
-          const float s1 = EXPORT ? v[2 * j + 1] : v[2 * j + 1] * inv;
-          __nv_bfloat162 hh = __floats2bfloat162_rn(s0, s1);
-          w[j] = *reinterpret_cast<uint32_t*>(&hh);
-        }
-        uint4* o = reinterpret_cast<uint4*>(o_ptr + c * 16);
-        o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-        o[1] = make_uint4(w[4], w[5], w[6], w[7]);
-      }
-    }
-  }
+  attn_store_o_row<EXPORT>(a, t_row + O_COL, b, h, row, inv);
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -252,6 +270,143 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Persistent ping-pong variant of the forward: one CTA per SM walks the (query tile, image, head) units
+// c, c+G, c+2G, ...; two softmax warpgroups own one tensor-memory slot each (unit parity) and alternate, a
+// producer warp streams Q / K / V of the units through a ring of shared-memory stages (three when they fit:
+// loads run a full unit ahead) and issues both MMAs of every unit, S of unit u+1 BEFORE P.V of unit u, so
+// the tensor core, the TMA engine and the two warpgroups overlap.  What a CTA-per-unit launch serialises for
+// every unit (launch, TMEM allocation, barrier setup, the TMA round trip) is paid once per SM here.
+//   warp 8         TMA + MMA issue (predicated on the elected lane)
+//   warps 0-3      slot 0: units 0, 2, 4, ... of this CTA      (thread = query row, quadrant = warp & 3)
+//   warps 4-7      slot 1: units 1, 3, 5, ...
+constexpr int PP_THREADS = 288;
+constexpr int PP_MAX_STAGES = 3;
+
+template <bool EXPORT, bool DROP>
+__global__ void __launch_bounds__(PP_THREADS, 1)
+attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                   const __grid_constant__ AttnArgs a, int n_stages) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int kv_bytes = a.NP * HD * 2;
+  const int stage_bytes = BMQ * HD * 2 + 2 * kv_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + n_stages * stage_bytes);
+  uint64_t* bar_qk = bars;                         // [stage] Q and K landed
+  uint64_t* bar_v = bars + PP_MAX_STAGES;          // [stage] V landed
+  uint64_t* bar_free = bars + 2 * PP_MAX_STAGES;   // [stage] P.V of the stage's unit has retired
+  uint64_t* bar_s = bars + 3 * PP_MAX_STAGES;      // [slot] S is in tensor memory
+  uint64_t* bar_p = bar_s + 2;                     // [slot] P is packed (128 arrivals)
+  uint64_t* bar_o = bar_s + 4;                     // [slot] O is in tensor memory
+  uint64_t* bar_epi = bar_s + 6;                   // [slot] the epilogue has read O (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int items = a.B * a.H;
+  const int n_units = items * a.tiles_m;
+  const int n_mine = (n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tmQ);
+    ptx::prefetch_tensormap(&tmKV);
+    for (int i = 0; i < PP_MAX_STAGES; ++i) { ptx::mbar_init(bar_qk + i, 1); ptx::mbar_init(bar_v + i, 1); ptx::mbar_init(bar_free + i, 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_s + i, 1); ptx::mbar_init(bar_p + i, 128); ptx::mbar_init(bar_o + i, 1); ptx::mbar_init(bar_epi + i, 128); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 8) ptx::tmem_alloc(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // unit i of this CTA: all first tiles come before all second tiles, so every CTA gets both kinds
+  auto decode = [&](int i, int& b, int& h, int& mt) {
+    const int idx = (int)blockIdx.x + i * (int)gridDim.x;
+    mt = idx / items;
+    const int item = idx - mt * items;
+    h = item % a.H;
+    b = item / a.H;
+  };
+
+  if (warp == 8) {
+    const bool leader = ptx::elect_one();
+    const uint32_t lead = leader ? 1u : 0u;
+    const uint32_t idesc1 = ptx::idesc_bf16(BMQ, a.NP, 0, 0);
+    const uint32_t idesc2 = ptx::idesc_bf16(BMQ, HD, 0, 1);
+    const uint64_t DESC0 = ptx::smem_desc_sw128(0, 16, 1024);
+    const uint32_t smem0 = ptx::smem_u32(smem);
+    int loaded = 0;
+    auto issue_load = [&](int i) {
+      const int st = i % n_stages;
+      if (i >= n_stages) ptx::mbar_wait(bar_free + st, (uint32_t)((i / n_stages - 1) & 1));
+      if (leader) {
+        int b, h, mt;
+        decode(i, b, h, mt);
+        uint8_t* q = smem + st * stage_bytes;
+        ptx::mbar_expect_tx(bar_qk + st, BMQ * HD * 2 + kv_bytes);
+        ptx::tma_load_3d(q, &tmQ, bar_qk + st, h * HD, mt * BMQ, b);
+        ptx::tma_load_3d(q + BMQ * HD * 2, &tmKV, bar_qk + st, a.D + h * HD, 0, b);
+        ptx::mbar_expect_tx(bar_v + st, kv_bytes);
+        ptx::tma_load_3d(q + BMQ * HD * 2 + kv_bytes, &tmKV, bar_v + st, 2 * a.D + h * HD, 0, b);
+      }
+      __syncwarp();
+    };
+    // P.V of unit v, then the refill of the oldest free stage
+    auto finish = [&](int v) {
+      const int sv = v & 1, stv = v % n_stages;
+      ptx::mbar_wait(bar_p + sv, (uint32_t)((v >> 1) & 1));
+      ptx::mbar_wait(bar_v + stv, (uint32_t)((v / n_stages) & 1));
+      ptx::tc_fence_after();
+      const uint32_t v_addr = smem0 + stv * stage_bytes + BMQ * HD * 2 + kv_bytes;
+      const uint32_t t = tmem + sv * 256;
+      for (int k = 0; k < a.NP / 16; ++k)
+        ptx::mma_ts_pred(t + O_COL, t + k * 8, ptx::smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc2, k > 0 ? 1u : 0u, lead);
+      ptx::commit_pred(ptx::smem_u32(bar_o + sv), lead);
+      ptx::commit_pred(ptx::smem_u32(bar_free + stv), lead);
+      if (loaded < n_mine) { issue_load(loaded); ++loaded; }
+    };
+    for (; loaded < n_stages && loaded < n_mine; ++loaded) issue_load(loaded);
+    for (int u = 0; u < n_mine; ++u) {
+      const int sl = u & 1, st = u % n_stages;
+      ptx::mbar_wait(bar_qk + st, (uint32_t)((u / n_stages) & 1));
+      if (u >= 2) ptx::mbar_wait(bar_epi + sl, (uint32_t)(((u >> 1) - 1) & 1));   // the slot's previous O has been read
+      ptx::tc_fence_after();
+      const uint64_t dq = DESC0 + ((smem0 + st * stage_bytes) >> 4), dk = dq + ((BMQ * HD * 2) >> 4);
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k) ptx::mma_ss_pred(tmem + sl * 256, dq + 2 * k, dk + 2 * k, idesc1, k > 0 ? 1u : 0u, lead);
+      ptx::commit_pred(ptx::smem_u32(bar_s + sl), lead);
+      if (u >= 1) finish(u - 1);
+    }
+    if (n_mine > 0) finish(n_mine - 1);
+  } else {
+    const int wg = warp >> 2, quarter = warp & 3;
+    const uint32_t t_row = tmem + wg * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+    for (int u = wg; u < n_mine; u += 2) {
+      const uint32_t ph = (uint32_t)((u >> 1) & 1);
+      int b, h, mt;
+      decode(u, b, h, mt);
+      const int row = mt * BMQ + quarter * 32 + lane;
+      const int n_chunks = (mt * BMQ + quarter * 32 < a.N) ? a.NP / 16 : 0;
+      ptx::mbar_wait(bar_s + wg, ph);
+      ptx::tc_fence_after();
+      const float inv = attn_softmax_row<EXPORT, DROP>(a, t_row, n_chunks, b, h, row);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar_p + wg);
+      ptx::mbar_wait(bar_o + wg, ph);
+      ptx::tc_fence_after();
+      attn_store_o_row<EXPORT>(a, t_row + O_COL, b, h, row, inv);
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar_epi + wg);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
 
 // ================================================================================================
 // Fused attention VJP (bf16 mode, head dim 64, N <= 256).  Per (image b, head h), with the
@@ -745,6 +900,40 @@ int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, float*
   CUtensorMap tq, tkv;
   ODV_TRY(make_tmap_3d_bf16(&tq, qkv, 3 * D, N, B, 3 * D, (uint64_t)N * 3 * D, HD, BMQ, 1));
   ODV_TRY(make_tmap_3d_bf16(&tkv, qkv, 3 * D, N, B, 3 * D, (uint64_t)N * 3 * D, HD, a.NP, 1));
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  const int n_units = B * H * a.tiles_m;
+  const char* env = getenv("ODEVIT_ATTN_PERSIST");
+  if (!(env && env[0] == '0') && n_units >= 2 * sms && !p_out) {
+    // enough units for every SM to pipeline: the persistent ping-pong kernel (the exporting variant is bound
+    // by its row stores and measured slower there: it stays CTA-per-unit)
+    const int stage_bytes = BMQ * HD * 2 + 2 * a.NP * HD * 2;
+    const int n_stages = (PP_MAX_STAGES * stage_bytes + 2048 <= 227 * 1024) ? PP_MAX_STAGES : 2;
+    const int smem_pp = n_stages * stage_bytes + 1024 + 256;
+    static bool configured_pp = false;
+    if (!configured_pp) {
+      const int max_smem = 227 * 1024;
+      ODV_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      ODV_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      ODV_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      ODV_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      configured_pp = true;
+    }
+    const int grid_pp = n_units < sms ? n_units : sms;
+    if (drop.thresh) {
+      if (p_out) attn_fwd_pp_kernel<true, true><<<grid_pp, PP_THREADS, smem_pp, s>>>(tq, tkv, a, n_stages);
+      else attn_fwd_pp_kernel<false, true><<<grid_pp, PP_THREADS, smem_pp, s>>>(tq, tkv, a, n_stages);
+    } else {
+      if (p_out) attn_fwd_pp_kernel<true, false><<<grid_pp, PP_THREADS, smem_pp, s>>>(tq, tkv, a, n_stages);
+      else attn_fwd_pp_kernel<false, false><<<grid_pp, PP_THREADS, smem_pp, s>>>(tq, tkv, a, n_stages);
+    }
+    ODV_LAUNCH_CHECK();
+    return 0;
+  }
   const int smem = BMQ * HD * 2 + 2 * a.NP * HD * 2 + 1024 + 64;
   const int grid = B * H * a.tiles_m;
   static bool configured = false;

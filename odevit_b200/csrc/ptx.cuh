@@ -219,6 +219,50 @@ __device__ __forceinline__ void mma_commit_pair(uint64_t* bar, uint16_t cta_mask
       : "memory");
 }
 
+// ---- branch-free issue (the issuing warp stays converged: every lane runs the same stream) ----------
+__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// tcgen05 instructions predicated on the elected lane (no branch: the issuing warp stays converged)
+__device__ __forceinline__ void mma_ss_pred(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate,
+                                            uint32_t lead) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts_pred(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate,
+                                            uint32_t lead) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void commit_pred(uint32_t bar_addr, uint32_t lead) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      :
+      : "r"(bar_addr), "r"(lead)
+      : "memory");
+}
 // ---- descriptors ------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_128B canonical layouts (rows of 128 bytes, 8-row
 // groups of 1024 bytes, 16-byte chunks XOR-swizzled by row%8 -- exactly what a TMA box with

@@ -202,49 +202,6 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar_addr, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, P1;\n\t}"
-      : "=r"(ok)
-      : "r"(bar_addr), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// tcgen05 instructions predicated on the elected lane (no branch: the issuing warp stays converged)
-__device__ __forceinline__ void mma_ss_pred(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate,
-                                            uint32_t lead) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      :
-      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(lead)
-      : "memory");
-}
-__device__ __forceinline__ void mma_ts_pred(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate,
-                                            uint32_t lead) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      :
-      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(lead)
-      : "memory");
-}
-__device__ __forceinline__ void commit_pred(uint32_t bar_addr, uint32_t lead) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %1, 0;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-      :
-      : "r"(bar_addr), "r"(lead)
-      : "memory");
-}
 // shared memory -> global memory through the bulk-copy engine (16-byte aligned, size a multiple of 16)
 __device__ __forceinline__ void bulk_store(float* gdst, const float* ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ptx::smem_u32(ssrc)), "r"(bytes)
@@ -350,14 +307,14 @@ solve_resident_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     auto alloc_mma = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t idesc, uint32_t acc_first) {
       const uint32_t b = cg & (NB - 1);
       const uint32_t fb = full0 + b * 8;
-      for (uint32_t spins = 0; !mbar_try_wait_addr(fb, (cg / NB) & 1);)
+      for (uint32_t spins = 0; !ptx::mbar_try_wait_addr(fb, (cg / NB) & 1);)
         if (++spins > (1u << 24)) __trap();   // a protocol bug must surface as a launch failure, never as a hung GPU
       const uint64_t da = DESC0 + a_lo, db = DESC0 + (ring_lo + (uint32_t)a.sc.alloc[ci].off * 512);
-      mma_ss_pred(d_tmem, da, db, idesc, acc_first, lead);
-      mma_ss_pred(d_tmem, da + 2, db + 2, idesc, 1u, lead);
-      mma_ss_pred(d_tmem, da + 4, db + 4, idesc, 1u, lead);
-      mma_ss_pred(d_tmem, da + 6, db + 6, idesc, 1u, lead);
-      commit_pred(free0 + b * 8, lead);
+      ptx::mma_ss_pred(d_tmem, da, db, idesc, acc_first, lead);
+      ptx::mma_ss_pred(d_tmem, da + 2, db + 2, idesc, 1u, lead);
+      ptx::mma_ss_pred(d_tmem, da + 4, db + 4, idesc, 1u, lead);
+      ptx::mma_ss_pred(d_tmem, da + 6, db + 6, idesc, 1u, lead);
+      ptx::commit_pred(free0 + b * 8, lead);
       ++cg;
       if (++ci == n_allocs) ci = 0;
     };
@@ -404,10 +361,10 @@ solve_resident_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
           } else if (kind == JOB_S) {
             const uint64_t da = DESC0 + q_lo, db = DESC0 + k_lo;
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) mma_ss_pred(tmem + T_R0, da + 2 * kk, db + 2 * kk, id_s, kk > 0 ? 1u : 0u, lead);
+            for (int kk = 0; kk < 4; ++kk) ptx::mma_ss_pred(tmem + T_R0, da + 2 * kk, db + 2 * kk, id_s, kk > 0 ? 1u : 0u, lead);
           } else if (kind == JOB_PV) {
             for (int ks = 0; ks < NK / 16; ++ks)
-              mma_ts_pred(tmem + T_O, tmem + T_R0 + ks * 8, ptx::smem_desc_sw128(v_addr + ks * 2048, 8192, 1024), id_pv,
+              ptx::mma_ts_pred(tmem + T_O, tmem + T_R0 + ks * 8, ptx::smem_desc_sw128(v_addr + ks * 2048, 8192, 1024), id_pv,
                           ks > 0 ? 1u : 0u, lead);
           } else if (kind == JOB_FC) {
             if (arg > 0)
@@ -417,7 +374,7 @@ solve_resident_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
             mma_into_out(q_lo);                                      // O of the last head
             for (int m = 0; m < 2; ++m) mma_into_out(g_lo + m * atom_lo);
           }
-          commit_pred(ptx::smem_u32(bar_mma + (int)(gm & 1)), lead);
+          ptx::commit_pred(ptx::smem_u32(bar_mma + (int)(gm & 1)), lead);
           ++gm;
           RTR(1, j * 4 + 2);
         }

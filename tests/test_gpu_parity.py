@@ -4,6 +4,8 @@ the golden vectors the unmodified reference produced, and against the oracle on 
 Tolerances (BASELINE.json north_star): fp32 mode max-rel error <= 1e-4 on final state and
 logits; bf16 mode <= 2e-2; identical top-1.  Gradients are held to 2e-3 (fp32 mode): the
 reference's own fp32 autograd differs from its fp64 rerun by ~1e-4 on these cases."""
+import os
+
 import pytest
 import torch
 
@@ -393,3 +395,40 @@ def test_host_batch_prefetcher_round_trip():
     assert seen == [(float(i), i) for i in range(5)]
     with pytest.raises(RuntimeError):
         feeder.submit(*hosts[0]); feeder.submit(*hosts[1]); feeder.submit(*hosts[2])
+
+
+@pytest.mark.parametrize("N_img,R,B", [(224, 10, 32), (32, 4, 128), (224, 10, 3)])
+def test_attention_forward_persistent_equals_per_unit_kernel(N_img, R, B):
+    """The persistent ping-pong attention forward (attn_fwd_pp_kernel: one CTA per SM, two tensor-memory slots,
+    staged Q/K/V ring) against the CTA-per-unit kernel (ODEVIT_ATTN_PERSIST=0): same arithmetic in the same order,
+    so the module's outputs must be bitwise identical, with and without the exported maps, in training too
+    (the row log-sum-exp feeds the VJP).  The last case has too few units and takes the per-unit kernel anyway."""
+    import odevit_b200 as ob
+    patch = 16 if N_img == 224 else 4
+    cfg = dict(img_size=N_img, patch_size=patch, num_classes=10, embed_dim=768 if N_img == 224 else 192,
+               num_heads=12 if N_img == 224 else 3, mlp_ratio=1.0, emulate_depth=12, time_interval=1.0, num_eval_steps=3,
+               solver="euler", register_tokens=R)
+    torch.manual_seed(3)
+    model = ob.ViTNeuralODE(**cfg).cuda().train()
+    model.precision = "bf16"
+    px = torch.randn(B, 3, N_img, N_img, generator=torch.Generator().manual_seed(8)).cuda()
+    lb = torch.randint(0, 10, (B,), generator=torch.Generator().manual_seed(9)).cuda()
+
+    def run(persist):
+        os.environ["ODEVIT_ATTN_PERSIST"] = "1" if persist else "0"
+        try:
+            model.zero_grad(set_to_none=True)
+            out = model(px, labels=lb, output_hidden_states=True, output_attentions=True, jasmin_k=2)
+            out["loss"].backward()
+            torch.cuda.synchronize()
+            g = torch.cat([p.grad.flatten() for p in model.parameters() if p.grad is not None])
+            return out["states"].clone(), out["attentions"].clone(), out["jasmin_loss"].clone(), g.clone()
+        finally:
+            os.environ.pop("ODEVIT_ATTN_PERSIST", None)
+    a = run(True)
+    b = run(False)
+    for x, y in zip(a[:3], b[:3]):
+        assert torch.equal(x, y)
+    # the weight-gradient GEMMs accumulate split-K partials with fp32 atomics: not bitwise reproducible run to run
+    assert max_rel(a[3], b[3]) < 1e-3
+    assert torch.isfinite(a[0]).all() and torch.isfinite(a[3]).all()
