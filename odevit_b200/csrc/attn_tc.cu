@@ -74,9 +74,14 @@ __device__ __forceinline__ float attn_softmax_row(const AttnArgs& a, uint32_t t_
 #pragma unroll
     for (int u = 0; u < 4; ++u)
       if (c0 + u < n_chunks) {
+        if ((c0 + u + 1) * 16 <= a.N) {   // every column of the chunk is a key: no per-element predicate
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if ((c0 + u) * 16 + j < a.N) m4[j & 3] = fmaxf(m4[j & 3], v[u][j]);
+          for (int j = 0; j < 16; ++j) m4[j & 3] = fmaxf(m4[j & 3], v[u][j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if ((c0 + u) * 16 + j < a.N) m4[j & 3] = fmaxf(m4[j & 3], v[u][j]);
+        }
       }
   }
   const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
@@ -116,13 +121,15 @@ __device__ __forceinline__ float attn_softmax_row(const AttnArgs& a, uint32_t t_
       const int c = c0 + u;
       if (c < n_chunks) {
         uint32_t packed[8];
+        const bool full = (c + 1) * 16 <= a.N;   // every column of the chunk is a key
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float e = (c * 16 + j < a.N) ? ex2_fast(fmaf(v[u][j], LOG2E, -mxs)) : 0.f;
+          float e = ex2_fast(fmaf(v[u][j], LOG2E, -mxs));
+          if (!full) e = (c * 16 + j < a.N) ? e : 0.f;
           if constexpr (EXPORT) {
             e *= inv;
             if constexpr (DROP) e *= drop_factor(a.drop, drow, c * 16 + j);   // the exported map is post-dropout
-            if (p_row && c * 16 + j < a.N) p_row[c * 16 + j] = e;
+            if (p_row && (full || c * 16 + j < a.N)) p_row[c * 16 + j] = e;
           } else {
             s4[j & 3] += e;
             if constexpr (DROP) e *= drop_factor(a.drop, drow, c * 16 + j);
