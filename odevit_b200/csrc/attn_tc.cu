@@ -791,19 +791,28 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             float sv[16], dp[16];
             ptx::tmem_ld16(t_lane + T_ST + c * 16, sv);
             ptx::tmem_ld16(t_lane + T_DPT + c * 16, dp);
+            // per-query lse / delta of the chunk: 16-byte broadcast loads (the row offset is a multiple of 16 floats)
+            float lsq[16], dlq[16];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 l4 = reinterpret_cast<const float4*>(lse_s + qt * 128 + c * 16)[j4];
+              const float4 d4 = reinterpret_cast<const float4*>(dl_s + qt * 128 + c * 16)[j4];
+              lsq[4 * j4] = l4.x; lsq[4 * j4 + 1] = l4.y; lsq[4 * j4 + 2] = l4.z; lsq[4 * j4 + 3] = l4.w;
+              dlq[4 * j4] = d4.x; dlq[4 * j4 + 1] = d4.y; dlq[4 * j4 + 2] = d4.z; dlq[4 * j4 + 3] = d4.w;
+            }
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int q = qt * 128 + c * 16 + j;
-              const float p = key_ok ? ex2_fast(fmaf(sv[j], LOG2E, -lse_s[q])) : 0.f;
+              const float p = key_ok ? ex2_fast(fmaf(sv[j], LOG2E, -lsq[j])) : 0.f;
               if constexpr (DROP) {
                 // O = drop(P) V:  dV needs drop(P)^T, dS = P o (drop'(dP) - delta)
                 const float f = drop_factor(a.drop, drow0 + q, kc * 128 + trow);
                 sv[j] = p * f;
-                dp[j] = p * (dp[j] * f - dl_s[q]);
+                dp[j] = p * (dp[j] * f - dlq[j]);
               } else {
                 sv[j] = p;
-                dp[j] = p * (dp[j] - dl_s[q]);
+                dp[j] = p * (dp[j] - dlq[j]);
               }
             }
 #pragma unroll
