@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define ODEVIT_ABI_VERSION 4
+#define ODEVIT_ABI_VERSION 5
 
 typedef struct CUstream_st* odevit_stream_t; /* == cudaStream_t */
 
@@ -138,7 +138,8 @@ typedef struct {
 typedef enum {
   ODEVIT_WS_FIELD = 0,     /* odevit_field_fwd                                                 */
   ODEVIT_WS_SOLVE_FWD = 1, /* odevit_solve_fwd                                                 */
-  ODEVIT_WS_SOLVE_BWD = 2  /* odevit_solve_bwd                                                 */
+  ODEVIT_WS_SOLVE_BWD = 2, /* odevit_solve_bwd                                                 */
+  ODEVIT_WS_ENCODER_FWD = 3 /* odevit_encoder_fwd (method ignored)                             */
 } odevit_ws_kind;
 
 /* ABI / build identification. */
@@ -214,6 +215,23 @@ int odevit_field_bwd(const odevit_desc* desc, const odevit_weights* w,
  * the maxima over n and b (tiny). */
 int odevit_fd_curvature(const float* states, int32_t n_grid, int32_t batch, int32_t tokens, int32_t dim,
                         double delta_t, float* per_seq, odevit_stream_t stream);
+
+/* Pre-LayerNorm transformer encoder stack, forward only, no tape: the frozen TEACHER of the distillation
+ * step.  Replaces `self.teacher(**inputs, output_hidden_states=True, output_attentions=True)` under
+ * torch.no_grad() (loss_trainer.py:318-321; a HF ViTModel encoder: ViTLayer = x + MHA(LN x), x + MLP(LN x))
+ * from the embedding output on.  desc: batch, tokens, dim, heads, hidden, precision (variant ignored,
+ * dropout must be 0).  layers[l] uses norm_a_* (LayerNorm before attention), norm_b_* (before the MLP),
+ * in_proj_w/b = [Wq; Wk; Wv] / [bq; bk; bv] packed [3D, D] / [3D], out_proj_w/b, fc1_w/b, fc2_w/b.
+ *   x0 [B,N,D] fp32 in;  hidden [L,B,N,D] fp32 out: the output of every layer (HF's hidden_states[1:]);
+ *   p_out: attention maps, p_mode 0 none | 1 last layer only [B,H,N,N] | 2 all layers [L,B,H,N,N].
+ * wcache (odevit_encoder_cache_bytes) holds the activation-typed weight copies: pass wcache_valid = 0 whenever the
+ * weights changed since the last call with this cache, 1 to reuse them (a frozen teacher: every call but the
+ * first).  Workspace kind ODEVIT_WS_ENCODER_FWD. */
+size_t odevit_encoder_cache_bytes(const odevit_desc* desc, int32_t n_layers);
+int odevit_encoder_fwd(const odevit_desc* desc, const odevit_weights* layers, int32_t n_layers, float ln_eps,
+                       const float* x0, float* hidden, float* p_out, int32_t p_mode, void* wcache,
+                       size_t wcache_bytes, int32_t wcache_valid, void* workspace, size_t workspace_bytes,
+                       odevit_stream_t stream);
 
 /* JaSMin statistic of exported attention maps in one pass.  Replaces the sort-based tensor arithmetic of
  * ViTNeuralODE.jasmin_loss / g_k (ode_transformer_gpt.py:419-456; the reference calls it on detached maps,

@@ -13,13 +13,13 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libodevit.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # enums of include/odevit.h
 FIELD_PARALLEL, FIELD_PARALLEL_L2, FIELD_MACARON = 0, 1, 2
 FP32, BF16 = 0, 1
 EULER, MIDPOINT, RK4_38 = 0, 1, 2
-WS_FIELD, WS_SOLVE_FWD, WS_SOLVE_BWD = 0, 1, 2
+WS_FIELD, WS_SOLVE_FWD, WS_SOLVE_BWD, WS_ENCODER_FWD = 0, 1, 2, 3
 
 METHODS = {"euler": EULER, "midpoint": MIDPOINT, "rk4": RK4_38}
 STAGES = {"euler": 1, "midpoint": 2, "rk4": 4}
@@ -87,6 +87,11 @@ def lib() -> ctypes.CDLL:
                                    ctypes.c_int32, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _vp]
     L.odevit_tape_bytes.restype = ctypes.c_size_t
     L.odevit_tape_bytes.argtypes = [ctypes.POINTER(Desc), ctypes.c_int32, ctypes.c_int32]
+    L.odevit_encoder_cache_bytes.restype = ctypes.c_size_t
+    L.odevit_encoder_cache_bytes.argtypes = [ctypes.POINTER(Desc), ctypes.c_int32]
+    L.odevit_encoder_fwd.restype = ctypes.c_int
+    L.odevit_encoder_fwd.argtypes = [ctypes.POINTER(Desc), ctypes.POINTER(Weights), ctypes.c_int32, ctypes.c_float, _vp, _vp, _vp,
+                                     ctypes.c_int32, _vp, ctypes.c_size_t, ctypes.c_int32, _vp, ctypes.c_size_t, _vp]
     L.odevit_jasmin_rowmax.restype = ctypes.c_int
     L.odevit_jasmin_rowmax.argtypes = [_vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _vp, _vp]
     L.odevit_fd_curvature.restype = ctypes.c_int
@@ -151,6 +156,6 @@ def profile_read() -> dict:
 
 DECLARED_SYMBOLS = ("odevit_abi_version", "odevit_build_info", "odevit_last_error_string",
                     "odevit_workspace_bytes", "odevit_field_fwd", "odevit_solve_fwd", "odevit_solve_bwd",
-                    "odevit_field_bwd", "odevit_tape_bytes", "odevit_fd_curvature", "odevit_jasmin_rowmax", "odevit_launch_count", "odevit_reset_launch_count",
+                    "odevit_field_bwd", "odevit_tape_bytes", "odevit_fd_curvature", "odevit_jasmin_rowmax", "odevit_encoder_cache_bytes", "odevit_encoder_fwd", "odevit_launch_count", "odevit_reset_launch_count",
                     "odevit_gemm_bf16", "odevit_profile_enable", "odevit_profile_reserve", "odevit_profile_num_classes", "odevit_profile_class_name",
                     "odevit_profile_read")

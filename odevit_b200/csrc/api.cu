@@ -796,12 +796,54 @@ int odevit_profile_read(int32_t kclass, double* total_ms, int64_t* launches) {
   return 0;
 }
 
+// ---- encoder stack (the distillation teacher): workspace and prepared-weight cache layouts ----
+namespace odevit {
+namespace {
+struct EncBufs {
+  StageCtx ctx;
+  float* P;
+};
+EncBufs layout_encoder(const Plan& p, Arena& a) {
+  const size_t e = dtype_size(p.act);
+  const size_t MD = (size_t)p.M * p.D, Mh = (size_t)p.M * p.hid;
+  EncBufs b{};
+  b.ctx.xc = a.take(MD * e);
+  b.ctx.qkv = a.take(3 * MD * e);
+  b.ctx.oh = a.take((MD + Mh) * e);
+  b.ctx.x1 = a.f32(MD);
+  b.P = a.f32((size_t)p.BHNN);
+  return b;
+}
+// activation-typed [3D+hid, D] and [D, D+hid] blocks + fp32 biases per layer, no transposes (forward only)
+WeightBufs take_encoder_weights(const Plan& p, Arena& a) {
+  const size_t e = dtype_size(p.act);
+  const size_t R = 3 * (size_t)p.D + p.hid, K2 = (size_t)p.D + p.hid;
+  WeightBufs w{};
+  w.w1cat = a.take(R * p.D * e);
+  w.w2cat = a.take(K2 * p.D * e);
+  w.b1cat = a.f32(R);
+  w.b2 = a.f32(p.D);
+  return w;
+}
+int encoder_plan(const odevit_desc* desc, Plan* p) {
+  ODV_TRY(make_plan(desc, p));
+  p->variant = ODEVIT_FIELD_MACARON;   // the four weight blocks unfolded, biases on
+  p->dd_type = DT_F32;
+  if (p->split_out || p->p_attn > 0.f) return set_error(ODEVIT_ERR_UNSUPPORTED, "the encoder stack is inference-only: dropout must be 0");
+  return 0;
+}
+}  // namespace
+}  // namespace odevit
+
 size_t odevit_workspace_bytes(const odevit_desc* desc, int32_t ws_kind, int32_t method) {
   Plan p{};
   if (make_plan(desc, &p)) return 0;
   Arena a(nullptr);
   if (ws_kind == ODEVIT_WS_FIELD) {
     layout_fwd(p, a, 1);
+  } else if (ws_kind == ODEVIT_WS_ENCODER_FWD) {
+    if (encoder_plan(desc, &p)) return 0;
+    layout_encoder(p, a);
   } else {
     const Tableau* tb = tableau_for(method);
     if (!tb) { set_error(ODEVIT_ERR_INVALID_ARG, "unknown method %d", method); return 0; }
@@ -1048,6 +1090,49 @@ int odevit_fd_curvature(const float* states, int32_t n_grid, int32_t batch, int3
   ODV_TRY(check_device_ptr(per_seq, "per_seq"));
   return fd_curvature(states, n_grid, (long long)batch * tokens, dim, (float)(delta_t * delta_t), per_seq,
                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t odevit_encoder_cache_bytes(const odevit_desc* desc, int32_t n_layers) {
+  Plan p{};
+  if (encoder_plan(desc, &p) || n_layers < 1) return 0;
+  Arena a(nullptr);
+  for (int l = 0; l < n_layers; ++l) take_encoder_weights(p, a);
+  return a.off + 1024;
+}
+
+int odevit_encoder_fwd(const odevit_desc* desc, const odevit_weights* layers, int32_t n_layers, float ln_eps,
+                       const float* x0, float* hidden, float* p_out, int32_t p_mode, void* wcache,
+                       size_t wcache_bytes, int32_t wcache_valid, void* workspace, size_t workspace_bytes,
+                       odevit_stream_t stream) {
+  Plan p{};
+  ODV_TRY(encoder_plan(desc, &p));
+  if (!layers || n_layers < 1 || n_layers > 64) return set_error(ODEVIT_ERR_INVALID_ARG, "encoder: 1 <= n_layers <= 64 and a layer array");
+  if (p_mode < 0 || p_mode > 2) return set_error(ODEVIT_ERR_INVALID_ARG, "encoder: p_mode %d (0 none, 1 last layer, 2 all)", p_mode);
+  if (p_mode && !p_out) return set_error(ODEVIT_ERR_INVALID_ARG, "encoder: p_mode %d without p_out", p_mode);
+  ODV_TRY(check_device_ptr(x0, "x0"));
+  ODV_TRY(check_device_ptr(hidden, "hidden"));
+  if (p_out) ODV_TRY(check_device_ptr(p_out, "p_out"));
+  for (int l = 0; l < n_layers; ++l) {
+    const odevit_weights& w = layers[l];
+    if (!w.norm_a_w || !w.norm_a_b || !w.norm_b_w || !w.norm_b_b || !w.in_proj_w || !w.in_proj_b || !w.out_proj_w ||
+        !w.out_proj_b || !w.fc1_w || !w.fc1_b || !w.fc2_w || !w.fc2_b)
+      return set_error(ODEVIT_ERR_INVALID_ARG, "encoder layer %d: norm_a, norm_b, in_proj, out_proj, fc1, fc2 with biases are required", l);
+    ODV_TRY(check_device_ptr(w.in_proj_w, "layers[].in_proj_w"));
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  Arena ca(wcache);
+  WeightBufs wbs[64];
+  for (int l = 0; l < n_layers; ++l) {
+    wbs[l] = take_encoder_weights(p, ca);
+    wbs[l].user = &layers[l];
+  }
+  ODV_TRY(check_ws(wcache, wcache_bytes, ca.off));
+  if (!wcache_valid)
+    for (int l = 0; l < n_layers; ++l) ODV_TRY(prepare_weights(p, &layers[l], wbs[l], s));
+  Arena a(workspace);
+  EncBufs b = layout_encoder(p, a);
+  ODV_TRY(check_ws(workspace, workspace_bytes, a.off));
+  return encoder_forward(p, wbs, n_layers, ln_eps, x0, hidden, p_out, p_mode, b.ctx, b.P, s);
 }
 
 int odevit_jasmin_rowmax(const float* p_maps, int64_t n_slices, int32_t tokens, int32_t k, float* out,

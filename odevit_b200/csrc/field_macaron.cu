@@ -108,6 +108,63 @@ int macaron_forward(const Plan& p, const WeightBufs& wb, const StageCtx& c, cons
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pre-LayerNorm transformer encoder stack, forward only: the frozen TEACHER of the distillation step
+// (loss_trainer.py:318-321 calls a HF ViT with output_hidden_states / output_attentions; SURVEY
+// section 8 row (f)3).  Per layer l, on the fp32 residual stream:
+//     x' = x  + MHA(LN_a x)                 (q/k/v/out Linears with bias, softmax(q k^T / sqrt(d)) v)
+//     x  = x' + fc2(GELU_erf(fc1(LN_b x')))
+// built from the Macaron field's pieces: LayerNorm row kernel, one GEMM per projection with the bias /
+// GELU / residual in its epilogue, the fused attention kernel.  hidden[l] receives every layer's output
+// (it IS the residual stream: layer l+1 reads hidden[l]); p_out the attention maps of the layers asked for.
+// ------------------------------------------------------------------------------------------------
+int encoder_forward(const Plan& p, const WeightBufs* layers, int n_layers, float ln_eps, const float* x0, float* hidden,
+                    float* p_out, int p_mode, const StageCtx& c, float* P_scratch, cudaStream_t s) {
+  const int D = p.D, hid = p.hid, K2 = D + hid;
+  const size_t MD = (size_t)p.M * D;
+  void* h1 = off(c.oh, D, p.act);  // [O | h] rows of K2
+  const float* x = x0;
+  for (int l = 0; l < n_layers; ++l) {
+    const WeightBufs& wb = layers[l];
+    const odevit_weights* w = wb.user;
+    float* x_out = hidden + (size_t)l * MD;
+    float* p_copy = nullptr;
+    if (p_out && (p_mode == 2 || (p_mode == 1 && l == n_layers - 1)))
+      p_copy = p_out + (p_mode == 2 ? (size_t)l * (size_t)p.BHNN : 0);
+    // ---- attention block ----
+    ODV_TRY(ln_rows(x, w->norm_a_w, w->norm_a_b, c.xc, p.act, ln_eps, p.M, D, s));
+    {
+      GemmArgs g;
+      g.M = p.M; g.N = 3 * D; g.K = D;
+      g.A = c.xc; g.a_type = p.act; g.a_rs = D; g.a_cs = 1;
+      g.B = wb.w1cat; g.b_type = p.act; g.b_rs = D; g.b_cs = 1;
+      g.epi_mode = EPI_STORE;
+      g.kclass = KC_GEMM_IN;
+      g.epi.bias = wb.b1cat;
+      g.epi.out = c.qkv; g.epi.out_type = p.act; g.epi.ld_out = 3 * D;
+      ODV_TRY(gemm(p, g, s));
+    }
+    ODV_TRY(attention_forward(p, c.qkv, c.oh, K2, P_scratch, p_copy, nullptr, nullptr, Drop{}, s));
+    {
+      Epi e;
+      e.bias = w->out_proj_b; e.alpha = 1.f;
+      e.c_new = 1.f; e.y = x; e.y_coef = 1.f; e.out = c.x1;
+      ODV_TRY(proj_down(p, c.oh, K2, D, wb.w2cat, K2, e, s));
+    }
+    // ---- MLP block ----
+    ODV_TRY(ln_rows(c.x1, w->norm_b_w, w->norm_b_b, c.xc, p.act, ln_eps, p.M, D, s));
+    ODV_TRY(ffn_up(p, wb, c.xc, h1, K2, nullptr, s));
+    {
+      Epi e;
+      e.bias = w->fc2_b; e.alpha = 1.f;
+      e.c_new = 1.f; e.y = c.x1; e.y_coef = 1.f; e.out = x_out;
+      ODV_TRY(proj_down(p, h1, K2, hid, off(wb.w2cat, D, p.act), K2, e, s));
+    }
+    x = x_out;
+  }
+  return 0;
+}
+
 namespace {
 
 // One half-FFN branch of the VJP.  In: b.ddc = cast(1/2 g) [M,D] (act).  Out: b.dn = cotangent of

@@ -99,4 +99,8 @@ int macaron_forward(const Plan& p, const WeightBufs& wb, const StageCtx& c, cons
 int macaron_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b,
                 const odevit_weight_grads* gw, const Epi& mu_epi, cudaStream_t s);
 
+// Pre-LN encoder stack, forward only (field_macaron.cu): the distillation teacher
+int encoder_forward(const Plan& p, const WeightBufs* layers, int n_layers, float ln_eps, const float* x0, float* hidden,
+                    float* p_out, int p_mode, const StageCtx& c, float* P_scratch, cudaStream_t s);
+
 }  // namespace odevit

@@ -358,6 +358,63 @@ def fd_curvature(states: torch.Tensor, delta_t: float) -> torch.Tensor:
     return out
 
 
+class EncoderWeights:
+    """The weights of a pre-LayerNorm encoder stack as the C ABI takes them (one odevit_weights per layer) plus
+    the library's prepared (activation-typed) copies.  `layers` is a list of dicts with the fp32 CUDA tensors
+    norm_a_w/b, norm_b_w/b, in_proj_w [3D,D], in_proj_b [3D], out_proj_w/b, fc1_w/b, fc2_w/b.  Call
+    `invalidate()` after changing any of them (a frozen teacher never does)."""
+
+    def __init__(self, layers: Sequence[Dict[str, torch.Tensor]]):
+        self.n_layers = len(layers)
+        self._keep = []
+        self.array = (_lib.Weights * self.n_layers)()
+        for i, lw in enumerate(layers):
+            for n, t in lw.items():
+                t = _require_cuda(t.detach(), f"layer {i} weight {n}").contiguous().float()
+                self._keep.append(t)
+                setattr(self.array[i], n, t.data_ptr())
+        self.cache: Optional[torch.Tensor] = None
+        self.cache_key = None
+
+    def invalidate(self) -> None:
+        self.cache_key = None
+
+
+def encoder_forward(x0: torch.Tensor, weights: EncoderWeights, heads: int, hidden: int, ln_eps: float,
+                    precision: str = "bf16", attention_maps: str = "last"):
+    """hidden [L,B,N,D], maps = pre-LN encoder stack on x0 [B,N,D] (odevit_encoder_fwd): HF ViT's encoder, no grad.
+    attention_maps: "none" | "last" ([B,H,N,N]) | "all" ([L,B,H,N,N])."""
+    x0 = _require_cuda(x0.detach(), "x0").contiguous().float()
+    B, N, D = x0.shape
+    L = weights.n_layers
+    desc = _lib.Desc(_lib.ABI_VERSION, B, N, D, heads, hidden, _lib.FIELD_MACARON, _lib.PRECISIONS[precision], 1.0)
+    p_mode = {"none": 0, "last": 1, "all": 2}[attention_maps]
+    hidden_out = torch.empty(L, B, N, D, device=x0.device, dtype=torch.float32)
+    maps = None
+    if p_mode == 1:
+        maps = torch.empty(B, heads, N, N, device=x0.device, dtype=torch.float32)
+    elif p_mode == 2:
+        maps = torch.empty(L, B, heads, N, N, device=x0.device, dtype=torch.float32)
+    with torch.cuda.device(x0.device):
+        need = _lib.lib().odevit_encoder_cache_bytes(ctypes.byref(desc), L)
+        if need == 0:
+            _lib.check(-1, "odevit_encoder_cache_bytes")
+        key = (D, heads, hidden, precision, x0.device)
+        valid = int(weights.cache is not None and weights.cache_key == key)
+        if weights.cache is None or weights.cache.numel() < need + 1024:
+            weights.cache = torch.empty(need + 2048, dtype=torch.uint8, device=x0.device)
+            valid = 0
+        cbase = weights.cache.data_ptr()
+        caligned = (cbase + 1023) & ~1023
+        keep, ws, ws_bytes = _workspace(desc, _lib.WS_ENCODER_FWD, 0, x0.device)
+        st = _lib.lib().odevit_encoder_fwd(ctypes.byref(desc), weights.array, L, float(ln_eps), _ptr(x0), _ptr(hidden_out),
+                                           _ptr(maps), p_mode, _vp(caligned), weights.cache.numel() - (caligned - cbase), valid,
+                                           ws, ws_bytes, _stream())
+    _lib.check(st, "odevit_encoder_fwd")
+    weights.cache_key = key
+    return hidden_out, maps
+
+
 def jasmin_rowmax(p_maps: torch.Tensor, k: int) -> torch.Tensor:
     """[..., N, N] attention maps -> [...] max over query rows of the JaSMin row value
     log(g_1 / (g_k + 1e-12) + 1e-12) (ode_transformer_gpt.py:419-456), one pass, no sort."""

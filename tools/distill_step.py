@@ -57,11 +57,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--ratio", type=float, default=4.0)
     ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--teacher", default="library", choices=["library", "hf"],
+                    help="library: odevit_b200.ViTTeacher (encoder through libodevit.so, same precision mode); hf: the wrapped HF model in eager fp32 PyTorch, as the reference runs it")
     a = ap.parse_args()
     from transformers import ViTConfig, ViTForImageClassification
     dev = torch.device("cuda", 0)
     torch.manual_seed(1)
     teacher = ViTForImageClassification(ViTConfig(num_labels=100, attn_implementation="eager")).to(dev).eval()
+    if a.teacher == "library":
+        teacher = ob.ViTTeacher(teacher, precision=a.precision, attention_maps="last")
     cfg = dict(img_size=224, patch_size=16, num_classes=100, embed_dim=768, num_heads=12, mlp_ratio=a.ratio, emulate_depth=12,
                time_interval=1.0, num_eval_steps=36, solver="euler", register_tokens=10)
     torch.manual_seed(0)
@@ -109,7 +113,7 @@ def main():
         step(record=True)
     nfe = cfg["num_eval_steps"] - 1
     print(json.dumps({
-        "config": 3, "workload": f"distillation step: ViT-B/16 teacher (eager PyTorch, no grad) + ODE-ViT student r={a.ratio} "
+        "config": 3, "teacher": a.teacher, "workload": f"distillation step: ViT-B/16 teacher ({'odevit_b200.ViTTeacher' if a.teacher == 'library' else 'eager fp32 PyTorch'}, no grad) + ODE-ViT student r={a.ratio} "
         f"(N=207, Euler T=36), MSE full path + L1 attention mass + JaSMin k=2, batch {B}",
         "precision": a.precision, "ms_per_step": ms, "img_per_s": B / ms * 1e3, "student_field_evals_per_s": B * nfe / ms * 1e3,
         "loss": float(loss), "split_ms": {k: round(v / 3, 3) for k, v in split.items()},
