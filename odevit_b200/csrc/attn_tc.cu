@@ -59,7 +59,8 @@ struct AttnArgs {
 // warp without valid rows), un-normalised exp packed to bf16 IN PLACE over the consumed S columns; EXPORT also
 // writes the normalised fp32 row.  Returns 1 / row sum (what the O epilogue needs; 1 in EXPORT mode's P).
 template <bool EXPORT, bool DROP>
-__device__ __forceinline__ float attn_softmax_row(const AttnArgs& a, uint32_t t_row, int n_chunks, int b, int h, int row) {
+__device__ __forceinline__ float attn_softmax_row(const AttnArgs& a, uint32_t t_row, int n_chunks, int b, int h, int row,
+                                                  float* stage = nullptr) {
   constexpr float LOG2E = 1.4426950408889634f;
   // Tensor-memory loads are issued several chunks at a time and waited for once, and the row max / row sum run
   // as four independent chains: with one row per thread and two warps per scheduler, a load / wait round trip
@@ -106,9 +107,14 @@ __device__ __forceinline__ float attn_softmax_row(const AttnArgs& a, uint32_t t_
     inv = 1.f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
   }
   const uint32_t drow = (uint32_t)(((long long)b * a.H + h) * a.N + row);   // dropout coordinate of this row
-  float* p_row = nullptr;
+  // EXPORT: the normalised map leaves through a per-warp staging tile [32 rows][32 columns] in shared memory, so
+  // that a store instruction writes 128 contiguous bytes of ONE row (a thread owns a row: storing from registers
+  // scatters every instruction over 32 rows, 8x the memory transactions)
+  const int lane = threadIdx.x & 31;
+  const int row0 = row - lane;                     // first row of this warp
+  float* p_base = nullptr;
   if constexpr (EXPORT) {
-    if (a.p_out && row < a.N) p_row = a.p_out + (((long long)b * a.H + h) * a.N + row) * a.N;
+    if (a.p_out) p_base = a.p_out + ((long long)b * a.H + h) * a.N * a.N;
   }
   for (int c0 = 0; c0 < n_chunks; c0 += 2) {
     float v[2][16];
@@ -129,7 +135,7 @@ __device__ __forceinline__ float attn_softmax_row(const AttnArgs& a, uint32_t t_
           if constexpr (EXPORT) {
             e *= inv;
             if constexpr (DROP) e *= drop_factor(a.drop, drow, c * 16 + j);   // the exported map is post-dropout
-            if (p_row && (full || c * 16 + j < a.N)) p_row[c * 16 + j] = e;
+            stage[lane * 33 + u * 16 + j] = e;
           } else {
             s4[j & 3] += e;
             if constexpr (DROP) e *= drop_factor(a.drop, drow, c * 16 + j);
@@ -147,6 +153,16 @@ __device__ __forceinline__ float attn_softmax_row(const AttnArgs& a, uint32_t t_
                      "r"(packed[6]), "r"(packed[7])
                      : "memory");
       }
+    }
+    if constexpr (EXPORT) {
+      __syncwarp();
+      const int col = c0 * 16 + lane;
+      if (p_base && col < a.N && (c0 + (lane >> 4)) < n_chunks) {
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr)
+          if (row0 + rr < a.N) p_base[(long long)(row0 + rr) * a.N + col] = stage[rr * 33 + lane];
+      }
+      __syncwarp();
     }
   }
   const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
@@ -246,7 +262,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   // whatever S left there and only feed O rows that are never stored
   const int n_chunks = (mt * BMQ + warp * 32 < a.N) ? a.NP / 16 : 0;
   const int row = mt * BMQ + warp * 32 + lane;
-  const float inv = attn_softmax_row<EXPORT, DROP>(a, t_row, n_chunks, b, h, row);
+  float* stage = EXPORT ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 64) + warp * (32 * 33) : nullptr;
+  const float inv = attn_softmax_row<EXPORT, DROP>(a, t_row, n_chunks, b, h, row, stage);
   ptx::tmem_st_wait();
   ptx::tc_fence_before();
   __syncthreads();
@@ -934,19 +951,12 @@ int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, float*
     if (!configured_pp) {
       const int max_smem = 227 * 1024;
       ODV_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-      ODV_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
       ODV_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-      ODV_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
       configured_pp = true;
     }
     const int grid_pp = n_units < sms ? n_units : sms;
-    if (drop.thresh) {
-      if (p_out) attn_fwd_pp_kernel<true, true><<<grid_pp, PP_THREADS, smem_pp, s>>>(tq, tkv, a, n_stages);
-      else attn_fwd_pp_kernel<false, true><<<grid_pp, PP_THREADS, smem_pp, s>>>(tq, tkv, a, n_stages);
-    } else {
-      if (p_out) attn_fwd_pp_kernel<true, false><<<grid_pp, PP_THREADS, smem_pp, s>>>(tq, tkv, a, n_stages);
-      else attn_fwd_pp_kernel<false, false><<<grid_pp, PP_THREADS, smem_pp, s>>>(tq, tkv, a, n_stages);
-    }
+    if (drop.thresh) attn_fwd_pp_kernel<false, true><<<grid_pp, PP_THREADS, smem_pp, s>>>(tq, tkv, a, n_stages);
+    else attn_fwd_pp_kernel<false, false><<<grid_pp, PP_THREADS, smem_pp, s>>>(tq, tkv, a, n_stages);
     ODV_LAUNCH_CHECK();
     return 0;
   }
@@ -954,18 +964,19 @@ int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, float*
   const int grid = B * H * a.tiles_m;
   static bool configured = false;
   if (!configured) {
-    const int max_smem = BMQ * HD * 2 + 2 * 256 * HD * 2 + 1024 + 64;
+    const int max_smem = BMQ * HD * 2 + 2 * 256 * HD * 2 + 1024 + 64 + 4 * 32 * 33 * 4;
     ODV_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     ODV_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     ODV_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     ODV_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;
   }
+  const int smem_x = smem + 4 * 32 * 33 * 4;   // + the export staging tiles
   if (drop.thresh) {
-    if (p_out) attn_fwd_tc_kernel<true, true><<<grid, 128, smem, s>>>(tq, tkv, a);
+    if (p_out) attn_fwd_tc_kernel<true, true><<<grid, 128, smem_x, s>>>(tq, tkv, a);
     else attn_fwd_tc_kernel<false, true><<<grid, 128, smem, s>>>(tq, tkv, a);
   } else {
-    if (p_out) attn_fwd_tc_kernel<true, false><<<grid, 128, smem, s>>>(tq, tkv, a);
+    if (p_out) attn_fwd_tc_kernel<true, false><<<grid, 128, smem_x, s>>>(tq, tkv, a);
     else attn_fwd_tc_kernel<false, false><<<grid, 128, smem, s>>>(tq, tkv, a);
   }
   ODV_LAUNCH_CHECK();
