@@ -401,6 +401,15 @@ int attention_vjp(const Plan& p, const void* qkv_v, const void* oh, long long ld
     // fused tcgen05 kernel (P recomputed on chip from q, k and the saved row log-sum-exp)
     return attn_bwd_tc(qkv_v, b.dO, oh, ld_oh, lse, b.delta, dz_v, R, b.dq_scratch, p.B, p.N, p.H, D, drop, s);
   }
+  if (!l2 && p.precision == ODEVIT_BF16 && g_p && lse && !drop.thresh && b.P && b.delta &&
+      attn_fwd_tc_supports(p.N, D, p.H, p.act, ld_oh)) {
+    // a cotangent on the exported map (the `attentions` output, last evaluation): its row term
+    // sum_j P_ij g_ij needs the normalised map once -- re-exported by the forward kernel (which rewrites O with
+    // the very same values) -- then the fused kernel adds g to dP on the fly
+    ODV_TRY(attn_fwd_tc(qkv_v, const_cast<void*>(oh), ld_oh, b.P, nullptr, p.B, p.N, p.H, D, Drop{}, s));
+    ODV_TRY(rowdot_rows(b.P, g_p, b.delta, (long long)p.B * p.H * p.N, p.N, s));
+    return attn_bwd_tc(qkv_v, b.dO, oh, ld_oh, lse, b.delta, dz_v, R, b.dq_scratch, p.B, p.N, p.H, D, drop, s, g_p, b.delta);
+  }
   const HeadView hv = qkv_view(p);
   const char* qkv = reinterpret_cast<const char*>(qkv_v);
   const long long pbo = (long long)p.H * p.N * p.N, pbi = (long long)p.N * p.N;

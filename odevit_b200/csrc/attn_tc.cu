@@ -468,6 +468,10 @@ struct AttnBwdArgs {
   long long ld_o;
   void* dz;                     // [B*N, R] bf16: dq | dk | dv at columns h*64, D + h*64, 2D + h*64
   Drop drop;                    // the forward's attention-map dropout, regenerated here
+  // cotangent of the EXPORTED map (the `attentions` output of the last evaluation): dS = P o (dP + gp - delta),
+  // delta = <dO, O> + dext with dext[b,h,i] = sum_j P_ij gp_ij formed beforehand (rows.cu::rowdot_rows)
+  const float* gp;              // [B,H,N,N] fp32 or null
+  const float* dext;            // [B,H,N] fp32 or null
 };
 
 constexpr int BWD_TMEM_COLS = 512;
@@ -531,7 +535,7 @@ __device__ int tr_n[3];
 #define TR(slot) do { } while (0)
 #endif
 
-template <bool DROP>
+template <bool DROP, bool GP>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ AttnBwdArgs a) {
@@ -761,6 +765,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             }
           }
           dl[r] = acc;
+          if constexpr (GP) dl[r] += a.dext[(long long)item * a.N + q];
         }
       }
       TR(102);
@@ -810,6 +815,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             ptx::tmem_ld16(t_lane + T_DPT + c * 16, dp);
             // per-query lse / delta of the chunk: 16-byte broadcast loads (the row offset is a multiple of 16 floats)
             float lsq[16], dlq[16];
+            float gq[GP ? 16 : 1];
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               const float4 l4 = reinterpret_cast<const float4*>(lse_s + qt * 128 + c * 16)[j4];
@@ -817,10 +823,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
               lsq[4 * j4] = l4.x; lsq[4 * j4 + 1] = l4.y; lsq[4 * j4 + 2] = l4.z; lsq[4 * j4 + 3] = l4.w;
               dlq[4 * j4] = d4.x; dlq[4 * j4 + 1] = d4.y; dlq[4 * j4 + 2] = d4.z; dlq[4 * j4 + 3] = d4.w;
             }
+            if constexpr (GP) {
+              // + the cotangent of the exported map, read transposed: lanes = consecutive keys of query row q
+              const int key = kc * 128 + trow;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int q = qt * 128 + c * 16 + j;
+                gq[j] = (key_ok && q < a.N) ? __ldg(a.gp + ((long long)item * a.N + q) * a.N + key) : 0.f;
+              }
+            }
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int q = qt * 128 + c * 16 + j;
+              if constexpr (GP) dp[j] += gq[j];
               const float p = key_ok ? ex2_fast(fmaf(sv[j], LOG2E, -lsq[j])) : 0.f;
               if constexpr (DROP) {
                 // O = drop(P) V:  dV needs drop(P)^T, dS = P o (drop'(dP) - delta)
@@ -991,8 +1007,11 @@ size_t attn_bwd_tc_scratch_floats(int B, int N, int H) {
 // qkv [B,N,3D] bf16; dO [B*N, D] bf16; O = oh[:, 0:D] (ld_oh); lse2 [B,H,N] fp32; dz [B*N, R] bf16
 // receives dq | dk | dv.  (`delta`, `dq_scratch` are unused: delta is formed in the kernel.)
 int attn_bwd_tc(const void* qkv, const void* dO, const void* oh, long long ld_oh, const float* lse2, float* delta,
-                void* dz, int R, float* dq_scratch, int B, int N, int H, int D, Drop drop, cudaStream_t s) {
+                void* dz, int R, float* dq_scratch, int B, int N, int H, int D, Drop drop, cudaStream_t s, const float* gp,
+                const float* dext) {
   (void)delta; (void)dq_scratch;
+  if ((gp != nullptr) != (dext != nullptr) || (gp && drop.thresh))
+    return set_error(ODEVIT_ERR_INVALID_ARG, "attn_bwd_tc: map cotangent needs its row dots and no dropout");
   if (!attn_fwd_tc_supports(N, D, H, DT_BF16, ld_oh) || R % 8)
     return set_error(ODEVIT_ERR_UNSUPPORTED, "attn_bwd_tc: unsupported shape N=%d D=%d H=%d", N, D, H);
   ProfScope prof(KC_FUSED_ATTN_BWD, s);
@@ -1002,6 +1021,7 @@ int attn_bwd_tc(const void* qkv, const void* dO, const void* oh, long long ld_oh
   a.items = B * H;
   a.lse2 = lse2; a.dz = dz;
   a.drop = drop;
+  a.gp = gp; a.dext = dext;
   a.dO = reinterpret_cast<const __nv_bfloat16*>(dO);
   a.O = reinterpret_cast<const __nv_bfloat16*>(oh);
   a.ld_o = ld_oh;
@@ -1012,16 +1032,18 @@ int attn_bwd_tc(const void* qkv, const void* dO, const void* oh, long long ld_oh
   static bool configured = false;
   static int sms = 148;
   if (!configured) {
-    ODV_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    ODV_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ODV_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ODV_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ODV_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int dev = 0;
     ODV_CUDA(cudaGetDevice(&dev));
     ODV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     configured = true;
   }
   const int grid = a.items < sms ? a.items : sms;
-  if (drop.thresh) attn_bwd_tc_kernel<true><<<grid, BWD_THREADS, smem, s>>>(tqkv, tdo, a);
-  else attn_bwd_tc_kernel<false><<<grid, BWD_THREADS, smem, s>>>(tqkv, tdo, a);
+  if (gp) attn_bwd_tc_kernel<false, true><<<grid, BWD_THREADS, smem, s>>>(tqkv, tdo, a);
+  else if (drop.thresh) attn_bwd_tc_kernel<true, false><<<grid, BWD_THREADS, smem, s>>>(tqkv, tdo, a);
+  else attn_bwd_tc_kernel<false, false><<<grid, BWD_THREADS, smem, s>>>(tqkv, tdo, a);
   ODV_LAUNCH_CHECK();
   return 0;
 }

@@ -173,7 +173,8 @@ int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, float*
 // Fused attention VJP; needs the forward's lse2 [B,H,N]; writes delta [B,H,N] and dq|dk|dv into dz.
 size_t attn_bwd_tc_scratch_floats(int B, int N, int H);
 int attn_bwd_tc(const void* qkv, const void* dO, const void* oh, long long ld_oh, const float* lse2, float* delta,
-                void* dz, int R, float* dq_scratch, int B, int N, int H, int D, Drop drop, cudaStream_t s);
+                void* dz, int R, float* dq_scratch, int B, int N, int H, int D, Drop drop, cudaStream_t s, const float* gp = nullptr,
+                const float* dext = nullptr);
 
 // ---------------------------------------------------------------------------------------------
 // row-wise / elementwise kernels (odevit_rows.cu)
@@ -209,6 +210,8 @@ int vjp_combine(const CombineArgs& a, int rows, int D, cudaStream_t s);
 // per_seq[r] = max_j max_d |s[j+2,r,d] - 2 s[j+1,r,d] + s[j,r,d]| / dt2   (states [T, rows, D])
 int fd_curvature(const float* states, int T, long long rows, int D, float dt2, float* per_seq, cudaStream_t s);
 // per [N x N] attention-map slice: max over rows of the JaSMin row value (rows.cu)
+// out[row] = sum_j P[row, j] * G[row, j]   (rows.cu)
+int rowdot_rows(const float* P, const float* G, float* out, long long rows, int n, cudaStream_t s);
 int jasmin_rowmax(const float* P, long long n_slices, int N, int k, float* out, cudaStream_t s);
 
 // out1 = x o mask(d1), out2 = x o mask(d2)  (x, out*: [rows, D] of type `type`; the two masked copies of

@@ -270,6 +270,21 @@ __global__ void axpy_kernel(float* y, const float* __restrict__ x, float a, long
 // D and the max over time: in PyTorch that is ~6 full-trajectory passes.  Here one warp owns a token
 // row (b,n), walks the T rows once with a 3-row register window and emits per_seq[b,n]; every state
 // element is read exactly once (algorithmic bytes = T*B*N*D*4).
+// out[row] = <P[row, :], G[row, :]>: the part of the softmax VJP's row term that comes from a cotangent on
+// the exported attention map (warp per row)
+__global__ void __launch_bounds__(256) rowdot_rows_kernel(const float* __restrict__ P, const float* __restrict__ G,
+                                                          float* __restrict__ out, long long rows, int n) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* p = P + row * n;
+  const float* g = G + row * n;
+  float acc = 0.f;
+  for (int c = lane; c < n; c += 32) acc = fmaf(p[c], g[c], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc;
+}
+
 // JaSMin statistic of exported attention maps (ode_transformer_gpt.py:419-456, detached by the reference):
 // one CTA per map slice (evaluation, image, head), 8 warps over its N query rows.  Per row: clamp to
 // [1e-12, 1], renormalise by (sum + 1e-12), the k+1 largest entries by repeated warp arg-max over a
@@ -846,6 +861,13 @@ int axpy_f32(float* y, const float* x, float a, long long n, cudaStream_t s) {
   ProfScope prof(KC_COMBINE, s);
   const int blocks = (int)((n + 1023) / 1024 < 148 * 8 ? (n + 1023) / 1024 : 148 * 8);
   axpy_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(y, x, a, n);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int rowdot_rows(const float* P, const float* G, float* out, long long rows, int n, cudaStream_t s) {
+  ProfScope prof(KC_BWD_SOFTMAX, s);
+  rowdot_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(P, G, out, rows, n);
   ODV_LAUNCH_CHECK();
   return 0;
 }

@@ -432,3 +432,31 @@ def test_attention_forward_persistent_equals_per_unit_kernel(N_img, R, B):
     # the weight-gradient GEMMs accumulate split-K partials with fp32 atomics: not bitwise reproducible run to run
     assert max_rel(a[3], b[3]) < 1e-3
     assert torch.isfinite(a[0]).all() and torch.isfinite(a[3]).all()
+
+
+@pytest.mark.parametrize("N,B", [(69, 3), (128, 2), (207, 2)])
+def test_field_attention_cotangent_bf16_fused(N, B):
+    """bf16 mode, head dim 64: a cotangent on block.attentions ALONE (no dx term) runs the fused attention VJP with
+    the map cotangent added to dP on the fly (attn_bwd_tc_kernel<false, true>: dS = P o (dP + g - delta), the row
+    term sum_j P_ij g_ij from rowdot_rows) -- against the oracle's autograd in fp64-clean fp32."""
+    import odevit_b200 as ob
+    D, H = 192, 3
+    torch.manual_seed(11)
+    f = ob.ViT_ODEFunc(dim=D, num_heads=H, mlp_ratio=2.0, emulate_depth=12, time_interval=1.0, l2_attention=False)
+    sd = {k: v.clone() for k, v in f.state_dict().items()}
+    f = f.cuda()
+    f.block.precision = "bf16"
+    x0 = torch.randn(B, N, D, generator=torch.Generator().manual_seed(12))
+    wp = torch.randn(B, H, N, N, generator=torch.Generator().manual_seed(13))
+    x = x0.clone().cuda().requires_grad_(True)
+    dx = f(torch.tensor(0.0), x)
+    (f.block.attentions * wp.cuda()).sum().backward()
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr = x0.clone().requires_grad_(True)
+    dxr, pr = orc.field_parallel(xr, sdr, H, 12.0, prefix="block.")
+    (pr * wp).sum().backward()
+    assert max_rel(f.block.attentions, pr) < 5e-2
+    assert max_rel(x.grad, xr.grad) < 5e-2
+    for k, p in f.named_parameters():
+        if sdr[k].grad is not None and float(sdr[k].grad.abs().max()) > 0:
+            assert p.grad is not None and max_rel(p.grad, sdr[k].grad) < 5e-2, k

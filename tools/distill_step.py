@@ -47,6 +47,8 @@ def distillation_loss(student_out, teacher_out, lambda_param=0.5):
     attn_t = teacher_out["attentions"][-1][:, :, 0, 1:]                                 # :169-171
     attn_s = student_out["attentions"][:, :, 0, 1:]
     l1 = (extract_mass(attn_s, 0.5) - extract_mass(attn_t, 0.7)).abs().sum() * lambda_param      # :174-183
+    if os.environ.get("DISTILL_NO_L1"):   # diagnosis: how much of the backward is the cotangent on `attentions`
+        l1 = l1.detach()
     return (mse + l1) * lambda_param + student_out["jasmin_loss"]                       # :297, :345-346
 
 
