@@ -1,0 +1,69 @@
+"""CUDA-graph replay of a whole training step (forward, backward, gradient clipping, optimizer).
+
+At CIFAR shapes the step is host-bound: ~300 kernel launches of 5-10 us each are enqueued through Python and
+ctypes at ~8 ms per step while the GPU needs ~2 ms.  libodevit never allocates, never synchronises and reads its
+weights at call time from fixed parameter storage, so the step can be captured once into a CUDA graph (static
+input buffers, torch.cuda.graph's private memory pool for the tape and the autograd intermediates) and replayed
+with one launch.  Eager and replayed steps run the same kernels on the same data: results are identical up to
+the fp32 atomics of the weight-gradient accumulation.
+
+    stepper = GraphedTrainStep(model, optimizer, example_inputs=(px, labels), clip=1.0)
+    for px, labels in loader:
+        loss = stepper(px, labels)          # device tensor; .item() it when you need the number
+
+Restrictions: fixed input shapes; no data-dependent Python control flow in the step (the reference's step has
+none: train.py:40-67); dropout masks are keyed by a per-call seed drawn on the host, so a captured step would
+replay the SAME masks -- models with dropout > 0 are refused; the optimizer must be capturable
+(`torch.optim.AdamW(..., fused=True, capturable=True)`)."""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence
+
+import torch
+from torch import nn
+
+
+class GraphedTrainStep:
+    def __init__(self, model: nn.Module, optimizer: torch.optim.Optimizer, example_inputs: Sequence[torch.Tensor],
+                 clip: Optional[float] = 1.0, loss_fn: Optional[Callable] = None, warmup: int = 3,
+                 grad_hook: Optional[Callable[[], None]] = None):
+        """loss_fn(model, *inputs) -> scalar loss (default: model(px, labels=labels)["loss"]); grad_hook runs
+        between backward and clipping (e.g. the data-parallel FlatGradAllReduce: NCCL collectives are capturable)."""
+        for m in model.modules():
+            drops = getattr(m, "_drops", None)       # (attn_drop, proj_drop, mlp_drop) of the ODE blocks
+            if drops is not None and any(float(d) > 0.0 for d in drops) and model.training:
+                raise ValueError("GraphedTrainStep: dropout > 0 would replay one mask set every step")
+        self.model, self.opt, self.clip = model, optimizer, clip
+        self.loss_fn = loss_fn or (lambda m, px, lb: m(px, labels=lb)["loss"])
+        self.grad_hook = grad_hook
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.static_in = [t.clone() for t in example_inputs]
+        # warm-up on a side stream (lazy initialisations, workspace growth, optimizer state) as torch prescribes
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._eager_step()
+        torch.cuda.current_stream().wait_stream(s)
+        self.graph = torch.cuda.CUDAGraph()
+        self.opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._eager_step(zero=False)
+
+    def _eager_step(self, zero: bool = True) -> torch.Tensor:
+        if zero:
+            self.opt.zero_grad(set_to_none=True)
+        loss = self.loss_fn(self.model, *self.static_in)
+        loss.backward()
+        if self.grad_hook is not None:
+            self.grad_hook()
+        if self.clip is not None:
+            torch.nn.utils.clip_grad_norm_(self.params, self.clip, foreach=True)
+        self.opt.step()
+        return loss.detach()
+
+    def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
+        for dst, src in zip(self.static_in, inputs):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.static_loss

@@ -396,7 +396,11 @@ class ViTNeuralODE(nn.Module):
                                "(the reference's max() over an empty tensor fails the same way)")
         per_seq = ops.fd_curvature(x, 1 / N)           # one pass over [T,B,N,D] (odevit_fd_curvature)
         per_batch = per_seq.max(-1)[0]
-        return dict(global_upper_bound=(first * per_batch.max()).item(), batched_upper_bound=first * per_batch,
+        g = first * per_batch.max()
+        # the reference returns a Python float here (:541), i.e. one host sync per forward; inside a CUDA-graph
+        # capture (odevit_b200.graphs) a sync is illegal and the 0-d tensor is returned instead
+        g = g if torch.cuda.is_current_stream_capturing() else g.item()
+        return dict(global_upper_bound=g, batched_upper_bound=first * per_batch,
                     batched_upper_bound_per_seq=first * per_seq)
 
     def init_space_predictor(self, outher_embedding_dimension):

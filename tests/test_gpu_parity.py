@@ -460,3 +460,41 @@ def test_field_attention_cotangent_bf16_fused(N, B):
     for k, p in f.named_parameters():
         if sdr[k].grad is not None and float(sdr[k].grad.abs().max()) > 0:
             assert p.grad is not None and max_rel(p.grad, sdr[k].grad) < 5e-2, k
+
+
+def test_graphed_train_step_matches_eager():
+    """odevit_b200.graphs.GraphedTrainStep: the captured step (forward, backward, clipping, AdamW) replays to the
+    same losses as eager launches from the same initial weights (libodevit is capture-safe: no allocation, no sync)."""
+    import odevit_b200 as ob
+    from odevit_b200.graphs import GraphedTrainStep
+    cfg = dict(img_size=32, patch_size=4, num_classes=10, embed_dim=192, num_heads=3, mlp_ratio=4.0, emulate_depth=12,
+               time_interval=1.0, num_eval_steps=4, solver="rk4", register_tokens=4)
+    sd = orc.reference_like_init(cfg, 10, seed=1)
+    px = torch.randn(6, 3, 32, 32, generator=torch.Generator().manual_seed(1)).cuda()
+    lb = torch.randint(0, 10, (6,), generator=torch.Generator().manual_seed(2)).cuda()
+
+    def build():
+        m = ob.ViTNeuralODE(**cfg)
+        m.load_state_dict(sd, strict=True)
+        m = m.cuda().train()
+        m.precision = "bf16"
+        ps = [p for p in m.parameters() if p.requires_grad]
+        return m, ps, torch.optim.AdamW(ps, lr=1e-4, weight_decay=5e-2, fused=True, capturable=True)
+    m1, p1, o1 = build()
+    eager = []
+    for _ in range(6):
+        o1.zero_grad(set_to_none=True)
+        loss = m1(px, labels=lb)["loss"]
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(p1, 1.0, foreach=True)
+        o1.step()
+        eager.append(float(loss))
+    m2, p2, o2 = build()
+    stepper = GraphedTrainStep(m2, o2, (px, lb), clip=1.0, warmup=2)      # 2 warm-up steps (capture records, it does not run)
+    replayed = [float(stepper(px, lb)) for _ in range(3)]                  # steps 3, 4, 5
+    assert all(x == x and abs(x) < 1e3 for x in eager + replayed) and len(set(eager)) == len(eager)   # finite, and the weights move
+    for a, b in zip(eager[2:5], replayed):
+        assert a == pytest.approx(b, rel=2e-2)
+    with pytest.raises(ValueError):
+        m3 = ob.ViTNeuralODE(**dict(cfg, attn_drop=0.1)).cuda().train()
+        GraphedTrainStep(m3, torch.optim.AdamW(m3.parameters(), fused=True, capturable=True), (px, lb))
