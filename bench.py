@@ -201,7 +201,7 @@ def run_ours(args, wl):
     model = ob.ViTNeuralODE(**cfg).to(dev).train()      # the reference's own init (:494-513), dropout 0
     model.precision = args.precision
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=5e-2, fused=True)
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=5e-2, fused=True, capturable=True)
     reducer = FlatGradAllReduce(params)
 
     px_h, lb_h = synthetic_batch(cfg, B, seed_off=rank)
@@ -249,6 +249,24 @@ def run_ours(args, wl):
     import gc
     for _ in range(args.warmup):
         step(px_d, lb_d)
+    # The timed steps replay ONE CUDA graph of the whole step (forward, backward, all-reduce, clipping, AdamW):
+    # ~1200 launches per step leave sub-microsecond gaps that a replay closes.  Same kernels, same work; the
+    # per-class roofline region below stays eager (it brackets every launch with events).
+    stepper, launch_mode, graph_launches = None, "eager", 0
+    if not args.no_graph and not args.quick:
+        try:
+            from odevit_b200.graphs import GraphedTrainStep
+            ob.reset_launch_count()
+            stepper = GraphedTrainStep(model, opt, (px_d, lb_d), clip=1.0, warmup=1,
+                                       grad_hook=(reducer if world > 1 and not os.environ.get("ODEVIT_BENCH_SKIP_ALLREDUCE") else None))
+            graph_launches = ob.launch_count() // 2       # one warm-up step + the captured one
+            launch_mode = "cuda_graph_replay"
+        except Exception as e:  # noqa: BLE001
+            stepper, launch_mode = None, f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+            torch.cuda.synchronize()
+
+    def fast_step(px, lb):
+        return stepper(px, lb) if stepper is not None else step(px, lb)
     # per-class event pairs are created here, outside the timed region (cudaEventCreate can stall)
     ob.reset_launch_count()
     step(px_d, lb_d)
@@ -260,8 +278,10 @@ def run_ours(args, wl):
     sampler.start()
     # ---- device-resident number ("value"): K steps, no per-class event pairs in the stream
     ob.reset_launch_count()
-    ms_step = timed(lambda: step(px_d, lb_d), args.steps, "value")
+    ms_step = timed(lambda: fast_step(px_d, lb_d), args.steps, "value")
     launches = ob.launch_count() // max(1, args.repeats)     # per timed region of K steps
+    if stepper is not None:
+        launches = graph_launches * args.steps                # kernel nodes replayed (counted while capturing)
     # ---- the same K steps once more with an event pair around every launch (2 x ~1200 event records per
     # step cost ~4 % of the step): per-class kernel times for the roofline lines, in their own timed region
     _lib.profile_enable(True)
@@ -284,7 +304,7 @@ def run_ours(args, wl):
             slot, (px, lb) = feeder.take()
             if i + 1 < k:
                 feeder.submit(px_h, lb_h)
-            loss = step(px, lb)
+            loss = fast_step(px, lb)
             feeder.release(slot)
             float(loss.item())
         e1.record()
@@ -396,7 +416,7 @@ def run_ours(args, wl):
             "inference_field_evals_per_sec": world * B * nfe / (ms_inf * 1e-3),
             "e2e": {"value": ips_e2e, "unit": "img/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": px_h.numel() * 4 + lb_h.numel() * 8, "d2h_bytes_per_step": 4},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "launch_mode": launch_mode,
             "clocks": clocks,
             "roofline": roofline,
             "roofline_tensor": roofline_tensor,
@@ -424,6 +444,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--repeats", type=int, default=3,
                     help="timed regions of K steps each; the median one is reported, all are listed")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph replay of the step")
     ap.add_argument("--quick", action="store_true",
                     help="profiling helper (ncu launch lists): only the device-resident timed region, any warm-up count; "
                          "its JSON line is not a bench value")
