@@ -26,16 +26,28 @@ from torch import nn
 class GraphedTrainStep:
     def __init__(self, model: nn.Module, optimizer: torch.optim.Optimizer, example_inputs: Sequence[torch.Tensor],
                  clip: Optional[float] = 1.0, loss_fn: Optional[Callable] = None, warmup: int = 3,
-                 grad_hook: Optional[Callable[[], None]] = None):
+                 grad_hook: Optional[Callable[[], None]] = None, capture_optimizer: bool = True):
         """loss_fn(model, *inputs) -> scalar loss (default: model(px, labels=labels)["loss"]); grad_hook runs
-        between backward and clipping (e.g. the data-parallel FlatGradAllReduce: NCCL collectives are capturable)."""
+        between backward and clipping (the data-parallel FlatGradAllReduce).  capture_optimizer=False captures
+        forward + backward only and runs grad_hook / clipping / optimizer.step() eagerly after each replay (a
+        few dozen launches): required with a grad_hook that issues NCCL collectives -- capturing them hung a
+        2-GPU run here -- and it lifts the `capturable=True` requirement on the optimizer."""
         for m in model.modules():
             drops = getattr(m, "_drops", None)       # (attn_drop, proj_drop, mlp_drop) of the ODE blocks
             if drops is not None and any(float(d) > 0.0 for d in drops) and model.training:
                 raise ValueError("GraphedTrainStep: dropout > 0 would replay one mask set every step")
+        # `block.attentions` (ode_transformer_gpt.py:276) keeps the last forward's map WITH its autograd graph, hence
+        # the AccumulateGrad nodes of earlier eager steps on the legacy stream: a capture must not depend on that stream
+        for m in model.modules():
+            t = getattr(m, "attentions", None)
+            if torch.is_tensor(t) and t.grad_fn is not None:
+                m.attentions = t.detach()
         self.model, self.opt, self.clip = model, optimizer, clip
         self.loss_fn = loss_fn or (lambda m, px, lb: m(px, labels=lb)["loss"])
         self.grad_hook = grad_hook
+        self.capture_optimizer = capture_optimizer
+        if grad_hook is not None and capture_optimizer:
+            raise ValueError("GraphedTrainStep: a grad_hook needs capture_optimizer=False (collectives stay eager)")
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.static_in = [t.clone() for t in example_inputs]
         # warm-up on a side stream (lazy initialisations, workspace growth, optimizer state) as torch prescribes
@@ -48,22 +60,28 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
         with torch.cuda.graph(self.graph):
-            self.static_loss = self._eager_step(zero=False)
+            self.static_loss = self._eager_step(zero=False, tail=self.capture_optimizer)
 
-    def _eager_step(self, zero: bool = True) -> torch.Tensor:
-        if zero:
-            self.opt.zero_grad(set_to_none=True)
-        loss = self.loss_fn(self.model, *self.static_in)
-        loss.backward()
+    def _tail(self) -> None:
         if self.grad_hook is not None:
             self.grad_hook()
         if self.clip is not None:
             torch.nn.utils.clip_grad_norm_(self.params, self.clip, foreach=True)
         self.opt.step()
+
+    def _eager_step(self, zero: bool = True, tail: bool = True) -> torch.Tensor:
+        if zero:
+            self.opt.zero_grad(set_to_none=True)
+        loss = self.loss_fn(self.model, *self.static_in)
+        loss.backward()
+        if tail:
+            self._tail()
         return loss.detach()
 
     def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
         for dst, src in zip(self.static_in, inputs):
             dst.copy_(src, non_blocking=True)
-        self.graph.replay()
+        self.graph.replay()          # the captured backward (re)writes every .grad in place
+        if not self.capture_optimizer:
+            self._tail()
         return self.static_loss
