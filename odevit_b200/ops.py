@@ -235,6 +235,20 @@ def field_eval(x: torch.Tensor, spec: FieldSpec, weights: Dict[str, Optional[tor
 # ---------------------------------------------------------------------------------------------
 # the fixed-grid solve
 # ---------------------------------------------------------------------------------------------
+_ROW_INDEX_CACHE: Dict[Tuple[Tuple[int, ...], torch.device], torch.Tensor] = {}
+
+
+def _row_index_tensor(row_index: Tuple[int, ...], device: torch.device) -> torch.Tensor:
+    """Device copy of a control-point index list, made once: indexing with a Python list uploads it on every
+    call (a pageable host-to-device copy: a stall in eager mode, illegal inside a CUDA-graph capture)."""
+    key = (row_index, device)
+    t = _ROW_INDEX_CACHE.get(key)
+    if t is None:
+        t = torch.tensor(row_index, dtype=torch.long, device=device)
+        _ROW_INDEX_CACHE[key] = t
+    return t
+
+
 class _OdeSolve(torch.autograd.Function):
     """(states, final, rows, p_last, p_traj) = solve(x0).
 
@@ -279,7 +293,7 @@ class _OdeSolve(torch.autograd.Function):
                                              tape_p, tape_n, ws, ws_bytes, _stream())
         _lib.check(st, "odevit_solve_fwd")
         ctx.tape = tape
-        rows = states[list(row_index)] if len(row_index) else x0.new_empty(0)
+        rows = states.index_select(0, _row_index_tensor(tuple(row_index), states.device)) if len(row_index) else x0.new_empty(0)
         ctx.spec, ctx.method, ctx.names, ctx.row_index = spec, method, names, tuple(row_index)
         ctx.t_c, ctx.T = t_c, T
         ctx.has_p_last = p_last is not None

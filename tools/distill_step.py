@@ -61,6 +61,7 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--teacher", default="library", choices=["library", "hf"],
                     help="library: odevit_b200.ViTTeacher (encoder through libodevit.so, same precision mode); hf: the wrapped HF model in eager fp32 PyTorch, as the reference runs it")
+    ap.add_argument("--graph", action="store_true", help="replay student forward + teacher + losses + backward as one CUDA graph (odevit_b200.graphs)")
     a = ap.parse_args()
     from transformers import ViTConfig, ViTForImageClassification
     dev = torch.device("cuda", 0)
@@ -104,10 +105,23 @@ def main():
     for _ in range(a.warmup):
         step()
     torch.cuda.synchronize()
+    run = step
+    if a.graph:
+        from odevit_b200.graphs import GraphedTrainStep
+
+        def loss_fn(model, px_, lb_):
+            s_out = model(px_, labels=lb_, output_hidden_states=True, output_control_points=True, output_attentions=True, jasmin_k=2)
+            with torch.no_grad():
+                t_out = teacher(pixel_values=px_, output_hidden_states=True, output_attentions=True)
+            return distillation_loss(s_out, t_out)
+        stepper = GraphedTrainStep(student, opt, (px, lb), clip=1.0, loss_fn=loss_fn, warmup=1, capture_optimizer=False)
+        run = lambda: stepper(px, lb)   # noqa: E731
+        run()
+        torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
-        loss = step()
+        loss = run()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
@@ -115,7 +129,7 @@ def main():
         step(record=True)
     nfe = cfg["num_eval_steps"] - 1
     print(json.dumps({
-        "config": 3, "teacher": a.teacher, "workload": f"distillation step: ViT-B/16 teacher ({'odevit_b200.ViTTeacher' if a.teacher == 'library' else 'eager fp32 PyTorch'}, no grad) + ODE-ViT student r={a.ratio} "
+        "config": 3, "teacher": a.teacher, "launch_mode": "cuda_graph_replay" if a.graph else "eager", "workload": f"distillation step: ViT-B/16 teacher ({'odevit_b200.ViTTeacher' if a.teacher == 'library' else 'eager fp32 PyTorch'}, no grad) + ODE-ViT student r={a.ratio} "
         f"(N=207, Euler T=36), MSE full path + L1 attention mass + JaSMin k=2, batch {B}",
         "precision": a.precision, "ms_per_step": ms, "img_per_s": B / ms * 1e3, "student_field_evals_per_s": B * nfe / ms * 1e3,
         "loss": float(loss), "split_ms": {k: round(v / 3, 3) for k, v in split.items()},
