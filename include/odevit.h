@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define ODEVIT_ABI_VERSION 5
+#define ODEVIT_ABI_VERSION 6
 
 typedef struct CUstream_st* odevit_stream_t; /* == cudaStream_t */
 
@@ -166,6 +166,10 @@ int odevit_field_fwd(const odevit_desc* desc, const odevit_weights* w,
  *   p_last [B,H,N,N] or NULL: P of the LAST field evaluation (block.attentions after the solve);
  *   p_traj [(n_evals - p_traj_first_eval), B,H,N,N] or NULL: P of every evaluation e >=
  *          p_traj_first_eval, e = step*stages + stage (odefunc.attention_trajectory);
+ *   jas_traj [(n_evals - jas_first_eval), B,H] or NULL: the JaSMin statistic (see odevit_jasmin_rowmax) of
+ *          the map of every evaluation e >= jas_first_eval with parameter jas_k, WITHOUT exporting the maps:
+ *          what ViTNeuralODE.forward needs of attention_trajectory[-int(0.85 T):] (:614-618).  k <= 3 in the
+ *          fused bf16 attention kernel is formed on chip; every other case exports to scratch and reduces;
  *   tape (odevit_tape_bytes() bytes, 1024-aligned) or NULL: when given, the intermediates of every
  *          field evaluation (centred rows, q|k|v, [O|h], fc1 pre-activation, softmax row log-sums)
  *          are kept there for odevit_solve_bwd -- what autograd's saved tensors are in the reference
@@ -174,6 +178,7 @@ int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
                      const float* x0, const float* t_grid_host, int32_t n_grid,
                      float* states, float* final_state,
                      float* p_last, float* p_traj, int32_t p_traj_first_eval,
+                     float* jas_traj, int32_t jas_first_eval, int32_t jas_k,
                      void* tape, size_t tape_bytes,
                      void* workspace, size_t workspace_bytes, odevit_stream_t stream);
 

@@ -13,7 +13,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libodevit.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # enums of include/odevit.h
 FIELD_PARALLEL, FIELD_PARALLEL_L2, FIELD_MACARON = 0, 1, 2
@@ -84,7 +84,8 @@ def lib() -> ctypes.CDLL:
     L.odevit_solve_fwd.restype = ctypes.c_int
     L.odevit_solve_fwd.argtypes = [ctypes.POINTER(Desc), ctypes.POINTER(Weights), ctypes.c_int32, _vp,
                                    ctypes.POINTER(ctypes.c_float), ctypes.c_int32, _vp, _vp, _vp, _vp,
-                                   ctypes.c_int32, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _vp]
+                                   ctypes.c_int32, _vp, ctypes.c_int32, ctypes.c_int32, _vp, ctypes.c_size_t,
+                                   _vp, ctypes.c_size_t, _vp]
     L.odevit_tape_bytes.restype = ctypes.c_size_t
     L.odevit_tape_bytes.argtypes = [ctypes.POINTER(Desc), ctypes.c_int32, ctypes.c_int32]
     L.odevit_encoder_cache_bytes.restype = ctypes.c_size_t

@@ -346,11 +346,17 @@ int gemm(const Plan& p, const GemmArgs& g, cudaStream_t s) {
 // batched FFMA products + row kernels.  PARALLEL_L2 swaps the softmax for the L2 weights (:48-56).
 // ------------------------------------------------------------------------------------------------
 int attention_forward(const Plan& p, const void* qkv_v, void* oh, long long ld_oh, float* P, float* p_copy,
-                      float* lse, float* sq, Drop drop, cudaStream_t s) {
+                      float* lse, float* sq, Drop drop, cudaStream_t s, float* jas_out, int jas_k) {
   const int D = p.D;
   const bool l2 = (p.variant == ODEVIT_FIELD_PARALLEL_L2);
-  if (!l2 && p.precision == ODEVIT_BF16 && attn_fwd_tc_supports(p.N, D, p.H, p.act, ld_oh))
-    return attn_fwd_tc(qkv_v, oh, ld_oh, p_copy, lse, p.B, p.N, p.H, D, drop, s);
+  if (!l2 && p.precision == ODEVIT_BF16 && attn_fwd_tc_supports(p.N, D, p.H, p.act, ld_oh)) {
+    if (jas_out && !p_copy && !drop.thresh && attn_fwd_tc_jasmin_supports(p.N, jas_k))
+      return attn_fwd_tc(qkv_v, oh, ld_oh, nullptr, lse, p.B, p.N, p.H, D, drop, s, jas_out, jas_k);   // statistic in-kernel
+    float* pc = (jas_out && !p_copy) ? P : p_copy;     // JaSMin wanted but not built in-kernel for this case: export + row kernel
+    ODV_TRY(attn_fwd_tc(qkv_v, oh, ld_oh, pc, lse, p.B, p.N, p.H, D, drop, s));
+    if (jas_out) ODV_TRY(jasmin_rowmax(pc, (long long)p.B * p.H, p.N, jas_k, jas_out, s));
+    return 0;
+  }
   const HeadView hv = qkv_view(p);
   const char* qkv = reinterpret_cast<const char*>(qkv_v);
   const size_t e = dtype_size(p.act);
@@ -388,6 +394,7 @@ int attention_forward(const Plan& p, const void* qkv_v, void* oh, long long ld_o
     g.kclass = KC_ATTN_PV;
     ODV_TRY(gemm_simt(g, s));
   }
+  if (jas_out) ODV_TRY(jasmin_rowmax(P, (long long)p.B * p.H, p.N, jas_k, jas_out, s));   // P holds the (post-dropout) map
   return 0;
 }
 
@@ -489,7 +496,8 @@ namespace {
 
 // Forward evaluation at stage input `u`.  `rk` (nullable) is the epilogue of the last GEMM.
 int eval_forward(const Plan& p, const WeightBufs& wb, const StageCtx& c, const float* u, float* P,
-                 float* p_copy, float* sq, float* tmp, long long e, const Epi* rk, cudaStream_t s) {
+                 float* p_copy, float* sq, float* tmp, long long e, const Epi* rk, cudaStream_t s,
+                 float* jas_out = nullptr, int jas_k = 0) {
   if (p.variant == ODEVIT_FIELD_MACARON) return macaron_forward(p, wb, c, u, P, rk, s);
   const int D = p.D, hid = p.hid, R = 3 * D + hid, K2 = D + hid;
   ODV_TRY(center_rows(u, c.xc, p.act, nullptr, 0.f, p.M, D, s));
@@ -509,7 +517,7 @@ int eval_forward(const Plan& p, const WeightBufs& wb, const StageCtx& c, const f
     g.epi.drop = make_drop(p, DS_MLP_H, e);   // dropout after GELU (:196-197)
     ODV_TRY(gemm(p, g, s));
   }
-  ODV_TRY(attention_forward(p, c.qkv, c.oh, K2, P, p_copy, c.lse, sq, make_drop(p, DS_ATTN, e), s));
+  ODV_TRY(attention_forward(p, c.qkv, c.oh, K2, P, p_copy, c.lse, sq, make_drop(p, DS_ATTN, e), s, jas_out, jas_k));
   if (rk && p.split_out) {
     // out-proj and fc2 outputs take different dropout masks (:231 proj_drop, :199 mlp drop): two GEMMs,
     // the first parks scaler * drop(h W2^T) in `tmp`, the second adds it (Epi::resid) before the stage combine
@@ -897,11 +905,18 @@ int odevit_field_fwd(const odevit_desc* desc, const odevit_weights* w, const flo
 
 int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t method, const float* x0,
                      const float* t_grid_host, int32_t n_grid, float* states, float* final_state,
-                     float* p_last, float* p_traj, int32_t p_traj_first_eval, void* tape, size_t tape_bytes,
+                     float* p_last, float* p_traj, int32_t p_traj_first_eval, float* jas_traj,
+                     int32_t jas_first_eval, int32_t jas_k, void* tape, size_t tape_bytes,
                      void* workspace, size_t workspace_bytes, odevit_stream_t stream) {
   Plan p{};
   ODV_TRY(make_plan(desc, &p));
   ODV_TRY(check_weights(p, w));
+  if (jas_traj) {
+    ODV_TRY(check_device_ptr(jas_traj, "jas_traj"));
+    if (jas_k < 0 || jas_k > p.N || jas_first_eval < 0)
+      return set_error(ODEVIT_ERR_INVALID_ARG, "jas_k %d / jas_first_eval %d out of range", jas_k, jas_first_eval);
+    if (p.variant == ODEVIT_FIELD_MACARON) return set_error(ODEVIT_ERR_UNSUPPORTED, "MACARON has no attention-map output");
+  }
   const Tableau* tb = tableau_for(method);
   if (!tb) return set_error(ODEVIT_ERR_INVALID_ARG, "unknown method %d", method);
   if (!t_grid_host || n_grid < 1) return set_error(ODEVIT_ERR_INVALID_ARG, "t_grid must hold >= 1 point");
@@ -934,7 +949,7 @@ int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
     ODV_CUDA(cudaMemcpyAsync(states, x0, MD * 4, cudaMemcpyDeviceToDevice, s));
     y = states;
   }
-  if (solve_resident_supports(p, n_grid, p_traj != nullptr, tape != nullptr) && (tb->S == 1 || f.kbuf)) {
+  if (solve_resident_supports(p, n_grid, p_traj != nullptr || jas_traj != nullptr, tape != nullptr) && (tb->S == 1 || f.kbuf)) {
     // small-token shapes: the whole solve of an image in one persistent CTA, state resident on the chip
     return solve_resident(p, f.w, tb->S, tb->a, tb->b, x0, t_grid_host, n_grid, states, final_state, p_last, f.kbuf, s);
   }
@@ -953,7 +968,8 @@ int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
       if (p_traj && e >= p_traj_first_eval) p_copy = p_traj + (size_t)(e - p_traj_first_eval) * p.BHNN;
       else if (p_last && e == n_evals - 1) p_copy = p_last;
       const StageCtx ctx = tape ? tape_ctx(p, tape, e, nullptr, n_evals) : f.ctx;
-      ODV_TRY(eval_forward(p, f.w, ctx, u, f.P, p_copy, f.sq, f.tmp, e, &rk, s));
+      float* jas_out = (jas_traj && e >= jas_first_eval) ? jas_traj + (size_t)(e - jas_first_eval) * p.B * p.H : nullptr;
+      ODV_TRY(eval_forward(p, f.w, ctx, u, f.P, p_copy, f.sq, f.tmp, e, &rk, s, jas_out, jas_k));
       if (p_last && e == n_evals - 1 && p_copy != p_last)
         ODV_CUDA(cudaMemcpyAsync(p_last, p_copy, (size_t)p.BHNN * 4, cudaMemcpyDeviceToDevice, s));
     }

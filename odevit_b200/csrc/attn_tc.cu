@@ -53,12 +53,30 @@ struct AttnArgs {
   float* p_out;          // [B, H, N, N] fp32 or null
   float* lse_out;        // [B, H, N] fp32 or null: log2-domain log-sum-exp of each row (for the VJP)
   Drop drop;             // attention-map dropout (element (b*H+h)*N + i, j); thresh 0 = off
+  // JaSMin statistic of this evaluation's map without exporting it (ode_transformer_gpt.py:419-456): per (b, h)
+  // the max over query rows of log(g_1 / (g_k + 1e-12) + 1e-12), atomically maxed into jas_out[b*H + h]
+  float* jas_out;        // [B, H] fp32 (pre-set to -inf) or null
+  int jas_k;             // 0..3
 };
+
+// running 4 largest values (descending), branch-free insertion
+__device__ __forceinline__ void top4_insert(float (&t)[4], float v) {
+  float a;
+  a = fmaxf(t[0], v); v = fminf(t[0], v); t[0] = a;
+  a = fmaxf(t[1], v); v = fminf(t[1], v); t[1] = a;
+  a = fmaxf(t[2], v); v = fminf(t[2], v); t[2] = a;
+  t[3] = fmaxf(t[3], v);
+}
+// float atomic max through the ordered-integer views (the target starts at -inf)
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
 
 // Softmax of this thread's query row straight from tensor memory (S at t_row, n_chunks 16-column chunks; 0 for a
 // warp without valid rows), un-normalised exp packed to bf16 IN PLACE over the consumed S columns; EXPORT also
 // writes the normalised fp32 row.  Returns 1 / row sum (what the O epilogue needs; 1 in EXPORT mode's P).
-template <bool EXPORT, bool DROP>
+template <bool EXPORT, bool DROP, bool JAS = false>
 __device__ __forceinline__ float attn_softmax_row(const AttnArgs& a, uint32_t t_row, int n_chunks, int b, int h, int row,
                                                   float* stage = nullptr) {
   constexpr float LOG2E = 1.4426950408889634f;
@@ -66,6 +84,13 @@ __device__ __forceinline__ float attn_softmax_row(const AttnArgs& a, uint32_t t_
   // as four independent chains: with one row per thread and two warps per scheduler, a load / wait round trip
   // per 16 columns and one 208-long dependent FMNMX / FADD chain per pass left the passes latency-bound.
   float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  float tt[JAS ? 4 : 1][4];     // JAS: the 4 largest logits of each of the four chains
+  if constexpr (JAS) {
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tt[q4][i] = -INFINITY;
+  }
   for (int c0 = 0; c0 < n_chunks; c0 += 4) {
     float v[4][16];
 #pragma unroll
@@ -75,7 +100,11 @@ __device__ __forceinline__ float attn_softmax_row(const AttnArgs& a, uint32_t t_
 #pragma unroll
     for (int u = 0; u < 4; ++u)
       if (c0 + u < n_chunks) {
-        if ((c0 + u + 1) * 16 <= a.N) {   // every column of the chunk is a key: no per-element predicate
+        if constexpr (JAS) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            top4_insert(tt[j & 3], ((c0 + u) * 16 + j < a.N) ? v[u][j] : -INFINITY);
+        } else if ((c0 + u + 1) * 16 <= a.N) {   // every column of the chunk is a key: no per-element predicate
 #pragma unroll
           for (int j = 0; j < 16; ++j) m4[j & 3] = fmaxf(m4[j & 3], v[u][j]);
         } else {
@@ -84,6 +113,13 @@ __device__ __forceinline__ float attn_softmax_row(const AttnArgs& a, uint32_t t_
             if ((c0 + u) * 16 + j < a.N) m4[j & 3] = fmaxf(m4[j & 3], v[u][j]);
         }
       }
+  }
+  if constexpr (JAS) {
+#pragma unroll
+    for (int q4 = 1; q4 < 4; ++q4)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) top4_insert(tt[0], tt[q4][i]);
+    m4[0] = tt[0][0];
   }
   const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
   const float mxs = mx * LOG2E;
@@ -168,6 +204,26 @@ __device__ __forceinline__ float attn_softmax_row(const AttnArgs& a, uint32_t t_
   const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
   if constexpr (!EXPORT) inv = 1.f / sum;
   if (a.lse_out && row < a.N) a.lse_out[((long long)b * a.H + h) * a.N + row] = mxs + log2f(sum);
+  if constexpr (JAS) {
+    // x_(j): j-th largest probability, clamped like the reference's clamp(P, 1e-12, 1); its renormalisation by
+    // (sum of the clamped row + 1e-12) differs from 1 by < N * 1e-12 and is dropped
+    float x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = fmaxf(ex2_fast(fmaf(tt[0][i], LOG2E, -mxs)) * inv, 1e-12f);
+    const float g1 = x[0] * (1.f - x[0] + x[1]);
+    float val;
+    if (a.jas_k == 0) {
+      val = logf(g1 + 1e-12f);
+    } else {
+      const float xk = (a.jas_k == 1) ? x[0] : (a.jas_k == 2) ? x[1] : x[2];
+      const float xk1 = (a.jas_k == 1) ? x[1] : (a.jas_k == 2) ? x[2] : x[3];
+      val = logf(g1 / (xk * (1.f - xk + xk1) + 1e-12f) + 1e-12f);
+    }
+    if (!(row < a.N) || n_chunks == 0) val = -INFINITY;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) val = fmaxf(val, __shfl_xor_sync(0xffffffffu, val, o));
+    if ((threadIdx.x & 31) == 0 && val > -INFINITY) atomic_max_float(a.jas_out + (long long)b * a.H + h, val);
+  }
   return inv;
 }
 
@@ -196,7 +252,7 @@ __device__ __forceinline__ void attn_store_o_row(const AttnArgs& a, uint32_t t_o
   }
 }
 
-template <bool EXPORT, bool DROP>
+template <bool EXPORT, bool DROP, bool JAS = false>
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const __grid_constant__ AttnArgs a) {
@@ -263,7 +319,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int n_chunks = (mt * BMQ + warp * 32 < a.N) ? a.NP / 16 : 0;
   const int row = mt * BMQ + warp * 32 + lane;
   float* stage = EXPORT ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 64) + warp * (32 * 33) : nullptr;
-  const float inv = attn_softmax_row<EXPORT, DROP>(a, t_row, n_chunks, b, h, row, stage);
+  const float inv = attn_softmax_row<EXPORT, DROP, JAS>(a, t_row, n_chunks, b, h, row, stage);
   ptx::tmem_st_wait();
   ptx::tc_fence_before();
   __syncthreads();
@@ -308,7 +364,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 constexpr int PP_THREADS = 288;
 constexpr int PP_MAX_STAGES = 3;
 
-template <bool EXPORT, bool DROP>
+template <bool EXPORT, bool DROP, bool JAS = false>
 __global__ void __launch_bounds__(PP_THREADS, 1)
 attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const __grid_constant__ AttnArgs a, int n_stages) {
@@ -413,7 +469,7 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int n_chunks = (mt * BMQ + quarter * 32 < a.N) ? a.NP / 16 : 0;
       ptx::mbar_wait(bar_s + wg, ph);
       ptx::tc_fence_after();
-      const float inv = attn_softmax_row<EXPORT, DROP>(a, t_row, n_chunks, b, h, row);
+      const float inv = attn_softmax_row<EXPORT, DROP, JAS>(a, t_row, n_chunks, b, h, row);
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar_p + wg);
@@ -930,13 +986,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 
 }  // namespace
 
+namespace {
+__global__ void fill_f32_kernel(float* p, float v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+}  // namespace
+
+bool attn_fwd_tc_jasmin_supports(int N, int k) { return k >= 0 && k <= 3 && N >= 4; }
+
 bool attn_fwd_tc_supports(int N, int D, int H, int act_type, long long ld_oh) {
   return act_type == DT_BF16 && D % H == 0 && D / H == HD && N >= 1 && N <= 256 && D % 8 == 0 && ld_oh % 8 == 0;
 }
 
 // qkv: [B, N, 3D] bf16 (q | k | v per row); oh: [B*N, ld_oh] bf16; p_out: [B,H,N,N] fp32 or null.
 int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, float* lse_out, int B, int N, int H, int D,
-                Drop drop, cudaStream_t s) {
+                Drop drop, cudaStream_t s, float* jas_out, int jas_k) {
   if (!attn_fwd_tc_supports(N, D, H, DT_BF16, ld_oh))
     return set_error(ODEVIT_ERR_UNSUPPORTED, "attn_fwd_tc: unsupported shape N=%d D=%d H=%d", N, D, H);
   ProfScope prof(p_out ? KC_FUSED_ATTN_EXPORT : KC_FUSED_ATTN, s);
@@ -946,6 +1011,13 @@ int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, float*
   a.tiles_m = (N + BMQ - 1) / BMQ;
   a.oh = oh; a.ld_oh = ld_oh; a.p_out = p_out; a.lse_out = lse_out;
   a.drop = drop;
+  a.jas_out = jas_out; a.jas_k = jas_k;
+  if (jas_out) {
+    if (p_out || drop.thresh || !attn_fwd_tc_jasmin_supports(N, jas_k))
+      return set_error(ODEVIT_ERR_UNSUPPORTED, "attn_fwd_tc: in-kernel JaSMin needs k <= 3, N >= 4, no export, no dropout");
+    fill_f32_kernel<<<(B * H + 255) / 256, 256, 0, s>>>(jas_out, -INFINITY, B * H);
+    ODV_LAUNCH_CHECK();
+  }
   CUtensorMap tq, tkv;
   ODV_TRY(make_tmap_3d_bf16(&tq, qkv, 3 * D, N, B, 3 * D, (uint64_t)N * 3 * D, HD, BMQ, 1));
   ODV_TRY(make_tmap_3d_bf16(&tkv, qkv, 3 * D, N, B, 3 * D, (uint64_t)N * 3 * D, HD, a.NP, 1));
@@ -968,10 +1040,12 @@ int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, float*
       const int max_smem = 227 * 1024;
       ODV_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
       ODV_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      ODV_CUDA(cudaFuncSetAttribute(attn_fwd_pp_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
       configured_pp = true;
     }
     const int grid_pp = n_units < sms ? n_units : sms;
-    if (drop.thresh) attn_fwd_pp_kernel<false, true><<<grid_pp, PP_THREADS, smem_pp, s>>>(tq, tkv, a, n_stages);
+    if (jas_out) attn_fwd_pp_kernel<false, false, true><<<grid_pp, PP_THREADS, smem_pp, s>>>(tq, tkv, a, n_stages);
+    else if (drop.thresh) attn_fwd_pp_kernel<false, true><<<grid_pp, PP_THREADS, smem_pp, s>>>(tq, tkv, a, n_stages);
     else attn_fwd_pp_kernel<false, false><<<grid_pp, PP_THREADS, smem_pp, s>>>(tq, tkv, a, n_stages);
     ODV_LAUNCH_CHECK();
     return 0;
@@ -985,10 +1059,13 @@ int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, float*
     ODV_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     ODV_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     ODV_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    ODV_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;
   }
   const int smem_x = smem + 4 * 32 * 33 * 4;   // + the export staging tiles
-  if (drop.thresh) {
+  if (jas_out) {
+    attn_fwd_tc_kernel<false, false, true><<<grid, 128, smem, s>>>(tq, tkv, a);
+  } else if (drop.thresh) {
     if (p_out) attn_fwd_tc_kernel<true, true><<<grid, 128, smem_x, s>>>(tq, tkv, a);
     else attn_fwd_tc_kernel<false, true><<<grid, 128, smem, s>>>(tq, tkv, a);
   } else {

@@ -79,7 +79,8 @@ int gemm(const Plan& p, const GemmArgs& g, cudaStream_t s);
 // softmax(q k^T) v per (image, head) from the packed qkv buffer into oh[:, h*d ...] (leading dim ld_oh).
 // P: [B,H,N,N] fp32 scratch (unfused path); p_copy: optional export; lse: optional row log-sum-exp.
 int attention_forward(const Plan& p, const void* qkv, void* oh, long long ld_oh, float* P, float* p_copy,
-                      float* lse, float* sq, Drop drop, cudaStream_t s);
+                      float* lse, float* sq, Drop drop, cudaStream_t s,
+                      float* jas_out = nullptr, int jas_k = 0);
 // Its VJP: dO [M,D] (act) -> dq|dk|dv into dz (leading dim R, act).  g_p: optional cotangent of P.
 int attention_vjp(const Plan& p, const void* qkv, const void* oh, long long ld_oh, const float* lse, BwdBufs& b,
                   const float* g_p, void* dz, int R, Drop drop, cudaStream_t s);

@@ -169,7 +169,8 @@ bool gemm_tc_supports(const GemmArgs& g);
 // optional fp32 P export.  Covers head dim 64, N <= 256.
 bool attn_fwd_tc_supports(int N, int D, int H, int act_type, long long ld_oh);
 int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, float* lse_out, int B, int N, int H, int D,
-                Drop drop, cudaStream_t s);
+                Drop drop, cudaStream_t s, float* jas_out = nullptr, int jas_k = 0);
+bool attn_fwd_tc_jasmin_supports(int N, int k);
 // Fused attention VJP; needs the forward's lse2 [B,H,N]; writes delta [B,H,N] and dq|dk|dv into dz.
 size_t attn_bwd_tc_scratch_floats(int B, int N, int H);
 int attn_bwd_tc(const void* qkv, const void* dO, const void* oh, long long ld_oh, const float* lse2, float* delta,

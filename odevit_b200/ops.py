@@ -262,7 +262,8 @@ class _OdeSolve(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x0, spec: FieldSpec, method: str, t_host: torch.Tensor, row_index: Tuple[int, ...],
-                want_p_last: bool, p_traj_first: Optional[int], names: Tuple[str, ...], track: bool, *weights):
+                want_p_last: bool, p_traj_first: Optional[int], jas: Optional[Tuple[int, int]],
+                names: Tuple[str, ...], track: bool, *weights):
         x0 = _require_cuda(x0, "x0")
         B, N, D = x0.shape
         T = int(t_host.numel())
@@ -282,6 +283,11 @@ class _OdeSolve(torch.autograd.Function):
             first = max(0, min(int(p_traj_first), n_evals))
             if n_evals - first > 0:
                 p_traj = torch.empty(n_evals - first, B, spec.heads, N, N, device=x0.device, dtype=torch.float32)
+        jas_traj, jas_first, jas_k = None, 0, 0
+        if jas is not None and n_evals > 0:
+            jas_first, jas_k = max(0, min(int(jas[0]), n_evals)), int(jas[1])
+            if n_evals - jas_first > 0:
+                jas_traj = torch.empty(n_evals - jas_first, B, spec.heads, device=x0.device, dtype=torch.float32)
         buf, ws, ws_bytes = _workspace(desc, _lib.WS_SOLVE_FWD, _lib.METHODS[method], x0.device)
         # `track`: a backward pass can follow (grad mode on and something requires grad); decided by the
         # caller, because inside forward() grad mode is always off and needs_input_grad ignores no_grad()
@@ -290,7 +296,7 @@ class _OdeSolve(torch.autograd.Function):
         with torch.cuda.device(x0.device):
             st = _lib.lib().odevit_solve_fwd(ctypes.byref(desc), ctypes.byref(w), _lib.METHODS[method], _ptr(x0),
                                              t_c, T, _ptr(states), _ptr(final), _ptr(p_last), _ptr(p_traj), first,
-                                             tape_p, tape_n, ws, ws_bytes, _stream())
+                                             _ptr(jas_traj), jas_first, jas_k, tape_p, tape_n, ws, ws_bytes, _stream())
         _lib.check(st, "odevit_solve_fwd")
         ctx.tape = tape
         rows = states.index_select(0, _row_index_tensor(tuple(row_index), states.device)) if len(row_index) else x0.new_empty(0)
@@ -301,17 +307,18 @@ class _OdeSolve(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         empty = x0.new_empty(0)
         out_p_traj = p_traj if p_traj is not None else empty
-        ctx.mark_non_differentiable(out_p_traj)
-        return states, final, rows, (p_last if p_last is not None else empty), out_p_traj
+        out_jas = jas_traj if jas_traj is not None else x0.new_empty(0)
+        ctx.mark_non_differentiable(out_p_traj, out_jas)
+        return states, final, rows, (p_last if p_last is not None else empty), out_p_traj, out_jas
 
     @staticmethod
-    def backward(ctx, g_states, g_final, g_rows, g_p_last, _g_p_traj):
+    def backward(ctx, g_states, g_final, g_rows, g_p_last, _g_p_traj, _g_jas):
         states, *weights = ctx.saved_tensors
         spec, method, names = ctx.spec, ctx.method, ctx.names
         T, B, N, D = states.shape
         desc = spec.desc(B, N)
         w, keep = _pack_weights(names, weights)
-        needs = ctx.needs_input_grad[9:]
+        needs = ctx.needs_input_grad[10:]
         gw, gts = _alloc_grads(names, weights, needs)
         parts, index = [], []
         if g_final is not None:
@@ -338,26 +345,30 @@ class _OdeSolve(torch.autograd.Function):
                                              ws, ws_bytes, _stream())
         _lib.check(st, "odevit_solve_bwd")
         ctx.tape = None
-        return (g_x0 if ctx.needs_input_grad[0] else None, None, None, None, None, None, None, None, None, *gts)
+        return (g_x0 if ctx.needs_input_grad[0] else None, None, None, None, None, None, None, None, None, None, *gts)
 
 
 def ode_solve(x0: torch.Tensor, t: torch.Tensor, spec: FieldSpec, method: str,
               weights: Dict[str, Optional[torch.Tensor]], row_index: Sequence[int] = (),
-              want_p_last: bool = False, p_traj_first: Optional[int] = None):
+              want_p_last: bool = False, p_traj_first: Optional[int] = None,
+              jasmin: Optional[Tuple[int, int]] = None):
     """Fixed-grid solve of dx/dt = f(x) over the grid `t` (euler | midpoint | rk4 = 3/8 rule).
+    `jasmin=(first_eval, k)`: the JaSMin statistic [E,B,H] of the maps of evaluations >= first_eval, without
+    exporting them (`jas_traj`).
 
-    Returns dict(states, final, rows, p_last, p_traj); see `_OdeSolve`."""
+    Returns dict(states, final, rows, p_last, p_traj, jas_traj); see `_OdeSolve`."""
     if method not in _lib.METHODS:
         raise ValueError(f"unsupported solver {method!r}; fixed-grid euler | midpoint | rk4 are built")
     if t.ndim != 1 or t.numel() < 1:
         raise ValueError("t must be one dimensional")
     names = tuple(k for k, v in weights.items() if v is not None)
     track = torch.is_grad_enabled() and (x0.requires_grad or any(weights[k].requires_grad for k in names))
-    states, final, rows, p_last, p_traj = _OdeSolve.apply(
-        x0, spec, method, t, tuple(int(i) for i in row_index), want_p_last, p_traj_first, names, track,
+    states, final, rows, p_last, p_traj, jas_traj = _OdeSolve.apply(
+        x0, spec, method, t, tuple(int(i) for i in row_index), want_p_last, p_traj_first, jasmin, names, track,
         *[weights[k] for k in names])
     return {"states": states, "final": final, "rows": rows if len(row_index) else None,
-            "p_last": p_last if p_last.numel() else None, "p_traj": p_traj if p_traj.numel() else None}
+            "p_last": p_last if p_last.numel() else None, "p_traj": p_traj if p_traj.numel() else None,
+            "jas_traj": jas_traj if jas_traj.numel() else None}
 
 
 def fd_curvature(states: torch.Tensor, delta_t: float) -> torch.Tensor:

@@ -429,14 +429,17 @@ class ViTNeuralODE(nn.Module):
         if output_control_points:
             idx = self.get_proportional_control_points_with_temperature(temperature=temperature,
                                                                         num_eval_steps=num_eval_steps)
-        p_first = None
+        p_first, jas = None, None
+        window = int(self.num_eval_steps * 0.85)                            # :614-618
         if output_attention_trajectory:
             p_first = 0
-        elif output_attentions:
-            p_first = max(0, n_evals - int(self.num_eval_steps * 0.85))     # :614-618 window
+        elif output_attentions and window > 0:
+            # only the JaSMin statistic of the window's maps is consumed: formed inside the attention kernel, the
+            # maps themselves (0.85 T x B x H x N x N fp32) are never written
+            jas = (max(0, n_evals - window), int(jasmin_k))
         res = ops.ode_solve(tokens, t, block.field_spec(self.odefunc.scaler), self.solver, block.field_weights(),
                             row_index=idx.tolist() if idx is not None else (),
-                            want_p_last=True, p_traj_first=p_first)
+                            want_p_last=True, p_traj_first=p_first, jasmin=jas)
         states, final = res["states"], res["final"]
         block.attentions = res["p_last"]
 
@@ -456,13 +459,16 @@ class ViTNeuralODE(nn.Module):
             p_last = res["p_last"]
             out["attentions"] = p_last[:, :, :-R, :-R]
             out["attentions_register_tokens"] = p_last[:, :, -R:, :]
-            window = int(self.num_eval_steps * 0.85)
-            # :614-618 -- the reference sorts every row of every map of the window; same statistic from one
-            # pass over the exported maps (odevit_jasmin_rowmax), means over heads / images / maps here
-            if p_traj is None or p_traj.shape[0] == 0:
+            # :614-618 -- the reference sorts every row of every map of the window; here the per-(evaluation, image,
+            # head) row maxima come out of the solve (in-kernel, or odevit_jasmin_rowmax on exported maps), and the
+            # means over heads / images / maps are taken here
+            jt = res["jas_traj"]
+            if jt is None and p_traj is not None and p_traj.shape[0] and window > 0:
+                jt = ops.jasmin_rowmax(p_traj[-window:], jasmin_k)
+            if jt is None:
                 out["jasmin_loss"] = self.jasmin_loss([], k=jasmin_k, reduction="mean")
             else:
-                out["jasmin_loss"] = ops.jasmin_rowmax(p_traj[-window:], jasmin_k).mean(dim=2).mean(dim=1).mean()
+                out["jasmin_loss"] = jt.mean(dim=2).mean(dim=1).mean()
         if self.add_distillation_token:
             out["logits_dist"] = self.dist_head(final[:, 1])
         if labels is not None:
