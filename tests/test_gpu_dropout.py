@@ -240,3 +240,32 @@ def test_l2_field_dropout_fp32(monkeypatch):
     assert max_rel(x.grad, xr.grad) < 1e-4
     for kk, p in f.named_parameters():
         assert max_rel(p.grad, sd[kk].grad) < 1e-4, kk
+
+
+def test_persistent_attention_forward_with_dropout_equals_per_unit_kernel(monkeypatch):
+    """attn_fwd_pp_kernel<DROP=true> (taken when a launch has >= 2 units per SM) against the CTA-per-unit kernel:
+    same mask generator, same arithmetic -> bitwise equal trajectories, in training mode with attention dropout."""
+    import os
+    import odevit_b200 as ob
+    from odevit_b200 import ops
+    monkeypatch.setattr(ops, "draw_seed", lambda: SEED)
+    cfg = dict(img_size=32, patch_size=4, num_classes=10, embed_dim=192, num_heads=3, mlp_ratio=2.0, emulate_depth=12,
+               time_interval=1.0, num_eval_steps=3, solver="euler", register_tokens=4, attn_drop=0.25)
+    torch.manual_seed(2)
+    model = ob.ViTNeuralODE(**cfg).cuda().train()
+    model.precision = "bf16"
+    px = torch.randn(128, 3, 32, 32, generator=torch.Generator().manual_seed(3)).cuda()
+
+    def run(persist):
+        os.environ["ODEVIT_ATTN_PERSIST"] = "1" if persist else "0"
+        try:
+            with torch.no_grad():
+                return model(px, output_hidden_states=True)["states"].clone()
+        finally:
+            os.environ.pop("ODEVIT_ATTN_PERSIST", None)
+    a, b = run(True), run(False)
+    assert torch.equal(a, b)
+    model.eval()
+    with torch.no_grad():
+        c = model(px, output_hidden_states=True)["states"]
+    assert not torch.equal(a[-1], c[-1])          # the masks did something
