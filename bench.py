@@ -191,8 +191,14 @@ def run_ours(args, wl):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: one JSON line only
+        # stdout carries ONE JSON line: whatever NCCL logs (its version banner at WARN, the NVLS lines at INFO) goes
+        # to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # ... and so does anything a native library prints to file descriptor 1 (the bundled NCCL writes its
+        # "NCCL version" banner there even with NCCL_DEBUG unset): fd 1 points at stderr until the JSON line
+        sys.stdout.flush()
+        _saved_stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     cfg, B = wl["cfg"], args.batch or wl["batch"]
@@ -428,6 +434,9 @@ def run_ours(args, wl):
             "cpu_baseline": cpu_baseline,
             "grad_allreduce_bytes": reducer.bucket_bytes if world > 1 else 0,
         }
+        if world > 1:
+            sys.stdout.flush()
+            os.dup2(_saved_stdout_fd, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
