@@ -8,10 +8,12 @@ from .vit_ode import (CenterNorm, L2SelfAttention, MLP, MultiheadSelfAttention, 
 from .macaron import ViTMacaron  # noqa: F401
 from . import macaron, time_emb  # noqa: F401
 from .teacher import ViTTeacher  # noqa: F401
+from . import loss_trainer  # noqa: F401
+from .loss_trainer import ImageDistilTrainer  # noqa: F401
 from .time_emb import (LearnedSinusoidalPosEmb, ScaleShift, SinusoidalPosEmb, TimeEmbedding,  # noqa: F401
                        attach_time_modulation)
 
 __all__ = ["OdevitError", "LIB_PATH", "FieldSpec", "field_eval", "ode_solve", "CenterNorm", "MLP",
            "MultiheadSelfAttention", "ParallelAttentionMLP", "PatchEmbed", "ViT_ODEFunc", "ViTNeuralODE",
            "odeint", "launch_count", "reset_launch_count", "L2SelfAttention", "ViTMacaron", "macaron", "time_emb",
-           "ViTTeacher", "SinusoidalPosEmb", "LearnedSinusoidalPosEmb", "TimeEmbedding", "ScaleShift", "attach_time_modulation"]
+           "ViTTeacher", "ImageDistilTrainer", "loss_trainer", "SinusoidalPosEmb", "LearnedSinusoidalPosEmb", "TimeEmbedding", "ScaleShift", "attach_time_modulation"]

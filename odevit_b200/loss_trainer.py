@@ -1,0 +1,243 @@
+"""Teacher-student trajectory losses: the consumers of the hot path's outputs.
+
+Drop-in for the reference's `loss_trainer.ImageDistilTrainer` (loss_trainer.py:31-372): same constructor
+keywords, same `forward(inputs, labels, epoch)` (forward + losses + backward + clip 1.0 + optimizer/scheduler
+step), same keys in the returned dict.  The student is `odevit_b200.ViTNeuralODE`; its `control_points`,
+`attentions` and `jasmin_loss` outputs are consumed here exactly as the reference consumes them:
+
+    MSE on the CLS rows of the 12 control points vs the teacher's hidden states      loss_trainer.py:119-160
+    L1 on the thresholded, blurred CLS attention mass (last evaluation / last layer)  :80-117, :162-183
+    JaSMin added on top (no gradient: the maps are detached)                           :345-346
+    CE only after epoch 200 ("curriculum ad hoc")                                     :348-349
+
+What is NOT here: the reference's `compute_loss` (an older objective no script calls) is kept for API
+completeness only.  The arithmetic is plain PyTorch on the device the student lives on; the heavy parts
+(student solve, teacher encoder) are libodevit launches behind the two models.  Pinned against the
+UNMODIFIED reference trainer by `tests/golden/distill_trainer_*.npz` (`oracle/make_golden_distill.py`).
+"""
+from __future__ import annotations
+
+import math
+from typing import Mapping, Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+class TemperatureScheduler:
+    """loss_trainer.py:16-28 -- cosine decay from `initial_temp` to `final_temp` over `total_epochs`."""
+
+    def __init__(self, initial_temp=6.0, final_temp=1.5, total_epochs=100):
+        self.init_t, self.final_t, self.total_epochs = initial_temp, final_temp, total_epochs
+
+    def get_temp(self, epoch):
+        return self.final_t + 0.5 * (self.init_t - self.final_t) * (1 + math.cos(math.pi * epoch / self.total_epochs))
+
+
+def _blur3x3(x: torch.Tensor, sigma: float = 0.5) -> torch.Tensor:
+    """torchvision's `gaussian_blur(x, (3, 3), sigma)` on [B, C, h, w]: separable 3-tap kernel, reflect padding
+    (written out so the loss has no torchvision dependency on the device path)."""
+    taps = torch.exp(-0.5 * (torch.tensor([-1.0, 0.0, 1.0], device=x.device, dtype=x.dtype) / sigma) ** 2)
+    taps = taps / taps.sum()
+    k2 = (taps[:, None] * taps[None, :]).expand(x.shape[1], 1, 3, 3)
+    return F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), k2, groups=x.shape[1])
+
+
+def extract_mass(attn_rows: torch.Tensor, threshold: float = 0.8, smooth: bool = True, scale_factor: float = 40.0,
+                 return_mask: bool = False):
+    """loss_trainer.py:80-117.  attn_rows [B, heads, n] (the CLS query's weights over the n = side^2 patches):
+    per row, sort ascending, normalise, cumulative mass; a patch is kept (softly, sigmoid with slope
+    `scale_factor`) once the cumulative mass passes 1 - threshold; the kept weights go on the side x side
+    grid, are blurred 3x3 (sigma 0.5) and averaged over heads.
+    Returns (mean over heads [B, side, side], per head [B, heads, side, side], mask mean or None)."""
+    B, nh, n = attn_rows.shape
+    side = int(n ** 0.5 + 0.5)
+    val, order = torch.sort(attn_rows, dim=-1)
+    cum = torch.cumsum(val / (val.sum(dim=-1, keepdim=True) + 1e-8), dim=-1)
+    keep_sorted = torch.sigmoid((cum - (1 - threshold)) * scale_factor) if smooth else (cum > (1 - threshold)).float()
+    keep = torch.gather(keep_sorted, -1, torch.argsort(order, dim=-1)).view(B, nh, side, side).float()
+    kept = attn_rows.view(B, nh, side, side) * keep
+    if smooth:
+        kept = _blur3x3(kept, 0.5)
+    return kept.mean(dim=1), kept, (keep.mean(dim=1) if return_mask else None)
+
+
+class ImageDistilTrainer(nn.Module):
+    def __init__(self, teacher_model=None, student_model=None, optimizer=None, scheduler=None,
+                 mse_full_path: bool = False, use_distillation: bool = True, use_supervision: bool = True,
+                 use_mse_loss: bool = True, temperature=None, jasmin_k: int = 10, lambda_param=None,
+                 curriculum: bool = False, patience_factor: int = 0.1):
+        super().__init__()
+        self.teacher, self.student = teacher_model, student_model
+        self.loss_function = nn.KLDivLoss(reduction="batchmean")
+        self.mse_loss = nn.MSELoss(reduction="none")
+        self.L1_loss = nn.L1Loss(reduction="none")
+        self.conjugate_l1 = False
+        self.teacher.eval()
+        self.student.train()
+        self.temperature, self.lambda_param = temperature, lambda_param
+        self.mse_loss_full_path, self.use_mse_loss = mse_full_path, use_mse_loss
+        self.use_distillation, self.use_supervision = use_distillation, use_supervision
+        self.jasmin_k, self.patience_factor = jasmin_k, patience_factor
+        self.optimizer, self.scheduler = optimizer, scheduler
+        self.temperature_scheduler = TemperatureScheduler(initial_temp=temperature, final_temp=1.0, total_epochs=300)
+        self.alpha_param = 0.01
+        self.representation_checkpoint = None
+        self.train_class = False
+        self.curriculum = curriculum
+        self.epoch = 0
+
+    # the reference exposes extract_mass as a method (loss_trainer.py:80)
+    def extract_mass(self, attentions_last_head, threshold=0.8, patch_size: int = 16, smooth=True, scale_factor=40,
+                     return_mask: bool = False):
+        return extract_mass(attentions_last_head, threshold, smooth, scale_factor, return_mask)
+
+    # -- loss_trainer.py:119-160 ------------------------------------------------------------------------------
+    def compute_mse_loss(self, student_intermediate_representations, teacher_intermediate_representations,
+                         normalize: bool = False):
+        s, t = student_intermediate_representations, teacher_intermediate_representations
+        if normalize:
+            s, t = F.normalize(s, p=2, dim=-1), F.normalize(t, p=2, dim=-1)
+        if self.mse_loss_full_path:
+            # one scalar per control point: mean squared distance of the CLS rows (zip stops at the shorter one)
+            terms = [self.mse_loss(ti[:, 0], si[:, 0]).mean() for ti, si in zip(t, s)]
+            names = [f"mse_loss_t@{i}" for i in range(len(terms))]
+        else:
+            terms = [self.mse_loss(t[-1, :, 0], s[-1, :, 0]).mean()]
+            names = [f"mse_loss_t@{t.size(0) - 1}"]
+        return sum(terms), dict(zip(names, terms))
+
+    # -- loss_trainer.py:162-183 ------------------------------------------------------------------------------
+    def compute_l1_attention_loss(self, student_output_attentions, teacher_output_attentions, compute_per_head=False):
+        row_t = teacher_output_attentions[-1][:, :, 0, 1:]        # last layer, CLS query, without CLS->CLS
+        row_s = student_output_attentions[:, :, 0, 1:]
+        mass_s, _, _ = extract_mass(row_s, threshold=0.5)
+        mass_t, _, _ = extract_mass(row_t, threshold=0.7)
+        if self.conjugate_l1:
+            mass_t = mass_t.flatten(1, 2).max(dim=-1).values[:, None, None] - mass_t
+        return self.L1_loss(mass_s, mass_t).sum() * self.lambda_param
+
+    # -- loss_trainer.py:185-254 (symmetrised KL on the attention mass; not called by forward) ----------------
+    def compute_distillation_loss(self, student_output_attentions, teacher_output_attentions, eps=1e-8,
+                                  compute_per_head: bool = True):
+        row_t = teacher_output_attentions[-1][:, :, 0, 1:]
+        row_s = student_output_attentions[:, :, 0, 1:]
+        mean_s, heads_s, _ = extract_mass(row_s, threshold=0.5)
+        mean_t, heads_t, _ = extract_mass(row_t, threshold=0.7)
+        heads_t = 1 - heads_t
+        mean_t = mean_t.flatten(1, 2).max(dim=-1).values[:, None, None] - mean_t
+        temp = getattr(self, "temperature", 1.0)
+        if compute_per_head:
+            ls = F.log_softmax(torch.log(heads_s + eps).sum(dim=3) / temp, dim=2)
+            pt = F.softmax(torch.log(heads_t + eps).sum(dim=3) / temp, dim=2)
+            kl_st = F.kl_div(ls, pt, reduction="none").sum(dim=2).mean(dim=0)
+            kl_ts = F.kl_div(pt.log(), ls.exp(), reduction="none").sum(dim=2).mean(dim=0)
+            total = (0.5 * (kl_st + kl_ts) * temp ** 2).mean()
+        else:
+            ls = F.log_softmax(torch.log(mean_s.clamp(min=eps) + eps).sum(dim=1) / temp, dim=-1)
+            pt = F.softmax(torch.log(mean_t.clamp(min=eps) + eps).sum(dim=1) / temp, dim=-1)
+            total = 0.5 * (F.kl_div(ls, pt, reduction="batchmean") +
+                           F.kl_div(pt.log(), ls.exp(), reduction="batchmean")) * temp ** 2
+        return total * self.lambda_param
+
+    # -- loss_trainer.py:256-303 ------------------------------------------------------------------------------
+    def train_batch_representation(self, student_output, teacher_output):
+        teacher_states = torch.stack(tuple(teacher_output["hidden_states"]), dim=0)[1:]
+        cps = student_output.get("control_points", None)
+        if cps is None:
+            # evenly spaced rows of the full trajectory (the fallback when control points were not requested)
+            states = student_output["states"]
+            n_t = teacher_states.shape[0]
+            idx = torch.cumsum(torch.full((n_t,), states.shape[0] / n_t), dim=0).long()
+            idx[-1] -= 1
+            cps = states[idx]
+        mse, parts = self.compute_mse_loss(cps, teacher_states)
+        loss = 0.0 + mse
+        out = {"mse_loss": mse}
+        if self.use_distillation:
+            self.temperature_scheduler.get_temp(epoch=self.epoch)
+            l1 = self.compute_l1_attention_loss(student_output["attentions"], teacher_output["attentions"])
+            if l1.isnan().any():
+                print("KL loss is NaN")
+            else:
+                loss = loss + l1
+            out["kl_loss"] = l1
+        loss = loss * self.lambda_param
+        out["loss"] = loss
+        out.update(parts)
+        return out
+
+    def _models(self, inputs, labels):
+        kw = dict(inputs) if isinstance(inputs, Mapping) else {"pixel_values": inputs}
+        s_out = self.student(**kw, labels=labels, output_hidden_states=True, output_control_points=True,
+                             output_attentions=True, jasmin_k=self.jasmin_k)
+        with torch.no_grad():
+            t_out = self.teacher(**kw, output_hidden_states=True, output_attentions=True)
+        return s_out, t_out
+
+    def loss_only(self, inputs, labels, epoch: Optional[int] = 0):
+        """Forward + every loss term, no backward / optimizer (what a CUDA-graph capture of the step wraps)."""
+        self.epoch = epoch
+        s_out, t_out = self._models(inputs, labels)
+        rep = self.train_batch_representation(s_out, t_out)
+        loss = 0.0 + rep["loss"] + s_out["jasmin_loss"]
+        if self.use_supervision and epoch > 200:
+            loss = loss + s_out["loss"]
+        out = {"student_output": s_out, "teacher_output": t_out,
+               "second_derivative_upper_bound": s_out.get("second_derivative_upper_bound"),
+               "finite_difference_upper_bound": s_out.get("finite_difference_upper_bound")}
+        out.update(rep)
+        out.update({"jasmin_loss": s_out["jasmin_loss"], "supervision_loss": s_out["loss"], "loss": loss})
+        return out
+
+    # -- loss_trainer.py:305-372 ------------------------------------------------------------------------------
+    def forward(self, inputs, labels, epoch: Optional[int] = 0):
+        self.optimizer.zero_grad(set_to_none=True)
+        out = self.loss_only(inputs, labels, epoch)
+        loss = out["loss"]
+        if not torch.isfinite(loss):
+            print(out)
+            raise ValueError("Loss is NaN or Inf!")
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.student.parameters(), 1.0)
+        self.optimizer.step()
+        if self.scheduler is not None:
+            self.scheduler.step()
+        return out
+
+    # -- loss_trainer.py:374-457 (older objective; no script of the reference calls it) -----------------------
+    def compute_loss(self, inputs, labels, return_outputs=True):
+        kw = dict(inputs) if isinstance(inputs, Mapping) else {"pixel_values": inputs}
+        s_out = self.student(**kw, labels=labels, output_hidden_states=True, output_control_points=True,
+                             jasmin_k=self.jasmin_k)
+        with torch.no_grad():
+            t_out = self.teacher(**kw, output_hidden_states=True, output_attentions=True)
+        out = {"student_output": s_out}
+        total = 0.0
+        if self.use_mse_loss:
+            if self.mse_loss_full_path:
+                cps = s_out["control_points"][:, :, 0, :]
+                t_cls = torch.stack(tuple(t_out["hidden_states"]))[1:, :, 0, :]
+                n = len(cps)
+                parts = {f"mse_loss_t@{i}": self.mse_loss(t_cls[i], cps[i]) for i in range(n)}
+                mse = sum((n - i) * parts[f"mse_loss_t@{i}"] for i in range(n)) / n
+                out["mse_losses"] = parts
+            else:
+                last_t, last_s = t_out["hidden_states"][-1], s_out["states"][-1]
+                first_patch = 2 if self.use_distillation else 1
+                mse = self.mse_loss(last_t[:, 0], last_s[:, 0]) + 0.1 * self.mse_loss(last_t[:, 1:], last_s[:, first_patch:])
+            total = total + mse * self.alpha_param
+            out["mse_loss"] = mse
+        if self.use_distillation:
+            kd = self.loss_function(F.log_softmax(s_out["logits_dist"] / self.temperature, dim=-1),
+                                    F.softmax(t_out["logits"] / self.temperature, dim=-1)) * self.temperature ** 2
+            kd = self.lambda_param * kd
+            total = total + kd
+            out["kd loss"] = kd
+        if self.use_supervision:
+            ce = s_out["loss"] * (1 - self.lambda_param)
+            total = total + ce
+            out["student_target_loss"] = ce
+        out["loss"] = total
+        return out
