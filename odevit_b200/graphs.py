@@ -61,6 +61,13 @@ class GraphedTrainStep:
         self.opt.zero_grad(set_to_none=True)
         with torch.cuda.graph(self.graph):
             self.static_loss = self._eager_step(zero=False, tail=self.capture_optimizer)
+        # The captured backward writes these very tensors at every replay.  Anything that re-binds `p.grad`
+        # between replays (`zero_grad(set_to_none=True)`, an eager step on the same model) would leave the eager
+        # tail reading stale or missing gradients: __call__ binds them back before the tail runs.
+        self.static_grads = [p.grad for p in self.params]
+        # device scratch whose addresses are baked into the graph: keep it alive as long as the graph is
+        from . import ops
+        self._pinned_workspaces = ops.live_workspaces()
 
     def _tail(self) -> None:
         if self.grad_hook is not None:
@@ -81,7 +88,10 @@ class GraphedTrainStep:
     def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
         for dst, src in zip(self.static_in, inputs):
             dst.copy_(src, non_blocking=True)
-        self.graph.replay()          # the captured backward (re)writes every .grad in place
+        self.graph.replay()          # the captured backward (re)writes every static gradient tensor in place
+        for p, g in zip(self.params, self.static_grads):
+            if p.grad is not g:
+                p.grad = g
         if not self.capture_optimizer:
             self._tail()
         return self.static_loss

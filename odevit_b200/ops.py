@@ -76,24 +76,34 @@ def _ptr(t: Optional[torch.Tensor]):
     return _vp(t.data_ptr()) if t is not None else None
 
 
-_WS_CACHE: Dict[Tuple[int, int], torch.Tensor] = {}
+_WS_CACHE: Dict[Tuple[int, int, int], torch.Tensor] = {}
 
 
 def _workspace(desc: _lib.Desc, kind: int, method: int, device: torch.device):
-    """A cached, 1024-byte aligned device workspace (stream-ordered reuse through torch's allocator)."""
+    """A cached, 1024-byte aligned device workspace per (device, kind, STREAM).
+
+    Keyed by the current stream so that (a) two streams never share scratch memory and (b) a CUDA-graph capture
+    -- which runs on its own capture stream -- allocates its workspace from the graph's private pool: the graph
+    then owns the buffer its kernels have baked in, and nothing an eager call does later (a larger batch, another
+    method) can free or reuse it under a replay.  A buffer that must grow is replaced, never resized in place;
+    `GraphedTrainStep` additionally pins the buffers that were live when it captured."""
     n = _lib.lib().odevit_workspace_bytes(ctypes.byref(desc), kind, method)
     if n == 0:
         _lib.check(-1, "odevit_workspace_bytes")
-    key = (device.index if device.index is not None else torch.cuda.current_device(), kind)
+    dev = device.index if device.index is not None else torch.cuda.current_device()
+    key = (dev, kind, int(torch.cuda.current_stream(device).cuda_stream))
     buf = _WS_CACHE.get(key)
     if buf is None or buf.numel() < n + 1024:
-        _WS_CACHE.pop(key, None)
-        buf = None
         buf = torch.empty(int(n * 1.05) + 2048, dtype=torch.uint8, device=device)
         _WS_CACHE[key] = buf
     base = buf.data_ptr()
     aligned = (base + 1023) & ~1023
     return buf, _vp(aligned), buf.numel() - (aligned - base)
+
+
+def live_workspaces() -> List[torch.Tensor]:
+    """The workspace buffers currently cached (a captured graph keeps these alive: see graphs.py)."""
+    return list(_WS_CACHE.values())
 
 
 def free_workspaces() -> None:

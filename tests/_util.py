@@ -50,6 +50,12 @@ def max_rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
+def cosine(a, b):
+    a = torch.as_tensor(a).detach().double().cpu().flatten()
+    b = torch.as_tensor(b).detach().double().cpu().flatten()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-300))
+
+
 VIT_CASES = ["c10_rk4_T5_B2", "c10_euler_T13_B2", "tiny_euler_T6_B3", "tiny_rk4_T4_B3",
              "tiny_midpoint_T5_B2", "tiny_rk4_tgrid_B2", "tiny_dist_token_B2"]
 MACARON_CASES = ["macaron_rk4_T4_B2", "macaron_euler_T13_B2"]

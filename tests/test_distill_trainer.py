@@ -14,7 +14,7 @@ import torch
 from torch import nn
 
 import odevit_oracle as orc
-from _util import Golden, max_rel
+from _util import Golden, cosine, max_rel
 
 SCALARS = ("loss", "mse_loss", "kl_loss", "jasmin_loss", "supervision_loss") + tuple(f"mse_loss_t@{i}" for i in range(12))
 
@@ -40,22 +40,31 @@ class OracleStudent(nn.Module):
         return orc.vit_ode_forward(sd, self.cfg, pixel_values, labels=labels, **kw)
 
 
-def _check(out, student_named_grads, g: Golden, tag, tol_loss, tol_grad, cos_min=None):
+def _check(out, student_named_grads, g: Golden, tag, tol_loss, tol_grad, cos_min=None, tol_term=None):
+    """Every scalar loss term and every (post-clip) parameter gradient against the golden; returns a report.
+    `tol_term`: per-term overrides -- JaSMin is ill-conditioned on near-one-hot rows (g_1 = x_1 (1 - x_1 + x_2)
+    cancels: a 1e-7 change of x_1 = 1 - 1e-4 is a 1e-3 change of g_1), and the L1 attention-mass term sits behind a
+    slope-40 sigmoid on the cumulative mass of the exported map (bf16 mode: the map itself is held to 5e-2)."""
+    tol_term = tol_term or {}
+    report = {"terms": {}, "grads": {}}
+    bad = []
     for k in SCALARS:
-        want = float(g.get(f"{tag}/{k}"))
-        assert float(out[k]) == pytest.approx(want, rel=tol_loss, abs=tol_loss * 1e-2), (tag, k)
-    worst = 0.0
+        want, got = float(g.get(f"{tag}/{k}")), float(out[k].detach())
+        tol = tol_term.get(k, tol_loss)
+        report["terms"][k] = abs(got - want) / max(abs(want), 1e-30)
+        if not got == pytest.approx(want, rel=tol, abs=tol * 1e-2):
+            bad.append((tag, k, got, want))
     for k, grad in student_named_grads:
         want = g.get(f"{tag}/grad/{k}")
         if float(want.abs().max()) == 0.0:
             continue
         assert grad is not None, k
-        worst = max(worst, max_rel(grad, want))
-        assert max_rel(grad, want) < tol_grad, (tag, k)
-        if cos_min is not None and want.numel() > 1:
-            cos = torch.nn.functional.cosine_similarity(grad.detach().double().cpu().flatten(), want.double().flatten(), dim=0)
-            assert float(cos) > cos_min, (tag, k, float(cos))
-    return worst
+        rel, cos = max_rel(grad, want), (cosine(grad, want) if want.numel() > 1 else 1.0)
+        report["grads"][k] = [round(rel, 6), round(cos, 7)]
+        if rel >= tol_grad or (cos_min is not None and cos <= cos_min):
+            bad.append((tag, k, rel, cos))
+    report["bad"] = bad
+    return report
 
 
 def test_blur_matches_torchvision():
@@ -73,7 +82,8 @@ def test_trainer_restatement_cpu_vs_reference_trainer(tag, epoch):
     opt = torch.optim.SGD(student.parameters(), lr=0.0)
     tr = ImageDistilTrainer(teacher_model=_teacher(g), student_model=student, optimizer=opt, **g.meta["trainer"])
     out = tr({"pixel_values": g.get("in/pixel_values")}, g.get("in/labels"), epoch=epoch)
-    _check(out, [(n, p.grad) for n, p in zip(student.names, student.ps)], g, tag, 2e-5, 2e-4)
+    rep = _check(out, [(n, p.grad) for n, p in zip(student.names, student.ps)], g, tag, 2e-5, 2e-4)
+    assert not rep["bad"], rep["bad"]
     assert max_rel(out["student_output"]["control_points"], g.get(f"{tag}/control_points")) < 1e-5
 
 
@@ -94,10 +104,16 @@ def test_trainer_gpu_vs_reference_trainer(precision, tol_loss, tol_grad, teacher
     opt = torch.optim.SGD(student.parameters(), lr=0.0)
     tr = ImageDistilTrainer(teacher_model=teacher, student_model=student, optimizer=opt, **g.meta["trainer"])
     px, lb = g.get("in/pixel_values").cuda(), g.get("in/labels").cuda()
+    fp32 = precision == "fp32"
+    tol_term = {"jasmin_loss": 2e-3} if fp32 else {"jasmin_loss": 2e-2, "kl_loss": 8e-2}
+    bad = []
     for tag, epoch in (("e0", 0), ("e201", 201)):
         out = tr({"pixel_values": px}, lb, epoch=epoch)
-        worst = _check(out, [(n, p.grad) for n, p in student.named_parameters()], g, tag, tol_loss, tol_grad,
-                       cos_min=0.999 if precision == "bf16" else 0.999999)
-        print(json.dumps({"case": tag, "precision": precision, "teacher": teacher_kind, "loss": float(out["loss"]),
-                          "worst_grad_max_rel": worst}))
+        rep = _check(out, [(n, p.grad) for n, p in student.named_parameters()], g, tag, tol_loss, tol_grad,
+                     cos_min=0.999999 if fp32 else 0.999, tol_term=tol_term)
+        print(json.dumps({"case": tag, "precision": precision, "teacher": teacher_kind, "loss": float(out["loss"].detach()),
+                          "terms": {k: round(v, 6) for k, v in rep["terms"].items() if not k.startswith("mse_loss_t@")},
+                          "worst_grad": max(rep["grads"].values()), "min_cos": min(v[1] for v in rep["grads"].values())}))
+        bad += rep["bad"]
+    assert not bad, bad
     assert out["student_output"]["logits"].argmax(-1).cpu().tolist() == g.get("e201/logits").argmax(-1).tolist()

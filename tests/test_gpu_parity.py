@@ -10,13 +10,14 @@ import pytest
 import torch
 
 import odevit_oracle as orc
-from _util import Golden, VIT_CASES, max_rel
+from _util import Golden, VIT_CASES, cosine, max_rel
 
 pytestmark = pytest.mark.gpu
 
 FP32_TOL = 1e-4
 BF16_TOL = 2e-2
 GRAD_TOL = 2e-3
+BF16_GRAD_REL, BF16_GRAD_COS = 3e-2, 0.999   # bf16 mode: per-parameter max-rel and cosine vs the fp32 reference
 
 
 def _objective(out, attn_w, ctrl_w):
@@ -82,10 +83,7 @@ def test_vit_golden_bf16(name):
     want = g.group("out")
     assert max_rel(out["states"][-1], want["states"][-1]) < BF16_TOL
     assert max_rel(out["logits"], want["logits"]) < BF16_TOL
-    top2 = want["logits"].topk(2, -1).values
-    decided = (top2[:, 0] - top2[:, 1]) > 4 * BF16_TOL * want["logits"].abs().max()
-    same = out["logits"].argmax(-1).cpu() == want["logits"].argmax(-1)
-    assert bool(same[decided].all())
+    assert out["logits"].argmax(-1).cpu().tolist() == want["logits"].argmax(-1).tolist()   # north_star: identical top-1
 
 
 def test_bf16_gradients_close():
@@ -95,10 +93,11 @@ def test_bf16_gradients_close():
     out = model(px, labels=g.get("in/labels").cuda(), **g.call)
     _objective(out, g.get("in/attn_w").cuda(), g.meta["ctrl_w"]).backward()
     grads = g.group("grad")
-    assert max_rel(px.grad, grads["pixel_values"]) < 0.1
+    assert max_rel(px.grad, grads["pixel_values"]) < BF16_GRAD_REL and cosine(px.grad, grads["pixel_values"]) > BF16_GRAD_COS
     for k, p in model.named_parameters():
         if grads[k].abs().max() > 0:
-            assert max_rel(p.grad, grads[k]) < 0.1, k
+            assert max_rel(p.grad, grads[k]) < BF16_GRAD_REL and cosine(p.grad, grads[k]) > BF16_GRAD_COS, \
+                (k, max_rel(p.grad, grads[k]), cosine(p.grad, grads[k]))
 
 
 def test_field_golden_fp32():
@@ -219,7 +218,8 @@ def test_c100_shape_training_gradients_bf16():
     assert max_rel(out["logits"], want["logits"]) < BF16_TOL
     for k, p in model.named_parameters():
         if sdr[k].grad is not None and float(sdr[k].grad.abs().max()) > 0:
-            assert max_rel(p.grad, sdr[k].grad) < 0.1, k
+            assert max_rel(p.grad, sdr[k].grad) < BF16_GRAD_REL and cosine(p.grad, sdr[k].grad) > BF16_GRAD_COS, \
+                (k, max_rel(p.grad, sdr[k].grad), cosine(p.grad, sdr[k].grad))
 
 
 # ---- size-independent properties at BASELINE sizes -------------------------------------------
@@ -535,28 +535,3 @@ def test_jasmin_in_kernel_equals_exported_maps(N_img, R, B, k):
     # the in-kernel form skips that renormalisation
     assert torch.allclose(a["jas_traj"][0], want[0], rtol=5e-3, atol=2e-5)
     assert torch.equal(a["states"][:2], b["states"][:2])
-
-
-@pytest.mark.parametrize("train_mode", [False, True])
-def test_top1_identical_on_fixed_batch_bf16(train_mode):
-    """North-star check: top-1 predictions on a fixed synthetic batch are identical to the oracle's in the bf16 mode
-    too (C10 model, 64 images, RK4 T=5) -- through the on-chip-state solver in eval mode and through the
-    multi-kernel path with the tape in train mode."""
-    model = _c10_model(T=5, solver="rk4", prec="bf16")
-    model = model.train() if train_mode else model.eval()
-    px = torch.randn(64, 3, 32, 32, generator=torch.Generator().manual_seed(1234))
-    cfg = dict(img_size=32, patch_size=4, num_classes=10, embed_dim=192, num_heads=3, mlp_ratio=4.0,
-               emulate_depth=12, time_interval=1.0, num_eval_steps=5, solver="rk4", register_tokens=4)
-    sd = orc.reference_like_init(cfg, 10, seed=1)
-    with torch.set_grad_enabled(train_mode):
-        out = model(px.cuda())
-    with torch.no_grad():
-        want = orc.vit_ode_forward(sd, cfg, px)
-    assert max_rel(out["logits"], want["logits"]) < BF16_TOL
-    top2 = want["logits"].topk(2, dim=-1).values
-    margin = (top2[:, 0] - top2[:, 1]) / want["logits"].abs().max()
-    agree = out["logits"].argmax(-1).cpu() == want["logits"].argmax(-1)
-    # identical wherever the oracle's own decision is not a tie at the bf16 tolerance
-    assert bool(agree[margin > 2 * BF16_TOL].all())
-    assert float(agree.float().mean()) >= 0.95
-    print("top-1 agreement", float(agree.float().mean()), "smallest margin", float(margin.min()))
