@@ -495,25 +495,27 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 //     dq = dS k,  dk = dS^T q,  dv = P^T dO
 // PERSISTENT kernel: one CTA per SM walks the (b, h) items c, c+G, c+2G, ...; everything is in the
 // TRANSPOSED orientation (thread = key row), so that P^T and dS^T are A operands that never leave
-// tensor memory, and the operand tiles of the NEXT item stream in while this one is computed:
-//   warp 8 (one lane)  TMA + all MMAs.  Operand tiles live in three rotating 64 KB sets
-//        {K, Q, V, dO} x 128 rows: item i keeps rows [0,128) in set s0 and rows [128,256) in s1; the
-//        third set receives rows [0,128) of item i+1 at the start of item i, and s0 is refilled with
-//        rows [128,256) of item i+1 as soon as its last reader has retired.
-//        per (key chunk kc, query tile qt):
-//          S^T  = K_kc Q_qt^T,  dP^T = V_kc dO_qt^T                 (SS)  -> TMEM [0,128), [128,256)
-//          dV_kc += P^T dO_qt,  dK_kc += dS^T Q_qt                  (TS: A = bf16 P^T / dS^T in TMEM)
-//          dQ_qt += dS K_kc     (A = dS^T tile in shared memory read MN-major, B = K chunk MN-major)
+// tensor memory.  An iteration is one (128-key chunk kc, 128-query tile qt) pair:
+//   warp 16 (one lane)  TMA + all MMAs.  Operand tiles live in three rotating 64 KB sets
+//        {K, Q, V, dO} x 128 rows (item i: rows [0,128) in s0, rows [128,256) in s1; the third set receives
+//        rows [0,128) of item i+1 at the start of item i, s0 its rows [128,256) once its last reader retired).
+//        per iteration:
+//          A:  S^T = K_kc Q_qt^T,  dP^T = V_kc dO_qt^T                 (SS, N = the tile's query count: 128-wide
+//              MMAs run at the tensor rate, 64-wide SS MMAs are bound by the shared-memory operand reads)
+//          C:  dV_kc += P^T dO_qt,  dK_kc += dS^T Q_qt                  (TS: A = bf16 P^T / dS^T in TMEM)
+//          Q:  dQ_qt += dS K_kc     (A = the dS^T tile in shared memory read MN-major, B = K chunk MN-major)
+//        Issue order  C(i) A(i+1) Q(i):  S^T / dP^T of the next iteration are ready while dQ still runs.
 //        dK, dV, dQ_0, dQ_1 accumulate in TMEM [256,512): no partial sum ever goes through memory.
-//   warps 0-7          two warpgroups split the query columns of a tile; thread = key row:
-//          P^T, dS^T from S^T, dP^T (per-query lse / delta broadcast from shared memory), packed to
-//          bf16 in registers; dS^T also goes to a 128-byte-swizzled shared-memory tile; after a
-//          barrier among the 256 threads the packed values overwrite S^T / dP^T in place
-//          (tcgen05.st).  Epilogues: dK | dV per key chunk (one warpgroup each), dQ at the item's end.
-//   warps 9-12         lse and delta = <dO_i, O_i> of the NEXT item into shared memory (double
-//          buffered): the only global loads that are not TMA, kept off the compute warps.
-// The cotangent of an exported P (`attentions`, last evaluation only) is not handled here; that
-// single evaluation takes the CUDA-core path (api.cu::attention_vjp).
+//   warps 0-15          four warpgroups split the query columns of a tile (32 each); thread = key row:
+//          P^T, dS^T of its 128 x 32 block from S^T, dP^T (per-query lse / delta broadcast from shared memory),
+//          packed to bf16 and written back IN PLACE over columns the same thread has already read (warpgroup w
+//          parks its packed columns at [32 w, 32 w + 16) of the tile: no cross-thread hazard, no barrier); dS^T
+//          also goes to the 128-byte-swizzled shared-memory tile.  Key rows past N need no predicate: their K / V
+//          rows are TMA zero fill, so whatever they produce multiplies zeros or lands in accumulator rows that are
+//          never stored.  Read-outs: dK | dV per key chunk and dQ at the item's end, 32 x 32 per warp, signalled to
+//          the producer as soon as the values are in registers, staged through the warp's own slots of the dS^T tile.
+//   warps 17-19         lse and delta = <dO_i, O_i> of the NEXT item into shared memory: the only global
+//          loads that are not TMA, kept off the compute warps.
 struct AttnBwdArgs {
   int B, N, H, D, R;
   int n_t;                      // 128-row tiles per item: 1 or 2 (keys and queries alike)
@@ -531,8 +533,13 @@ struct AttnBwdArgs {
 };
 
 constexpr int BWD_TMEM_COLS = 512;
-constexpr int T_ST = 0, T_DPT = 128, T_DK = 256, T_DV = 320, T_DQ = 384;  // T_DQ + 64*qt
-constexpr int BWD_THREADS = 13 * 32;
+constexpr int T_S0 = 0, T_DP0 = 128, T_DK = 256, T_DV = 320, T_DQ = 384;  // dQ_qt at T_DQ + 64 qt
+constexpr int BWD_COMPUTE_WARPS = 16;
+constexpr int BWD_MMA_WARP = 16;
+constexpr int BWD_TMA_WARP = 17;
+constexpr int BWD_LOADER_WARP = 18;
+constexpr int BWD_LOADER_THREADS = 64;   // 2 warps: 20 warps in all leave 96 registers per thread
+constexpr int BWD_THREADS = (BWD_LOADER_WARP * 32) + BWD_LOADER_THREADS;
 constexpr int SLOT = 16384;               // one [128 x 64] bf16 tile
 constexpr int SET = 4 * SLOT;             // {K, Q, V, dO}
 enum { SL_K = 0, SL_Q = 1, SL_V = 2, SL_DO = 3 };
@@ -548,86 +555,91 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
-__device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// This warp's 32 accumulator rows x 64 fp32 columns -> bf16 -> global rows of `stride` elements.
-// Thread = row out of TMEM; a 4 KB staging tile (16-byte chunks XOR-swizzled by row) turns the
-// row-per-thread layout into 128 contiguous bytes per 8 lanes, so every store instruction covers
-// 4 full lines instead of 32 partial ones.
-__device__ __forceinline__ void store_rows_bf16(__nv_bfloat16* g_row0, long long stride, uint32_t t_addr,
-                                                uint8_t* stage, int lane, int rows_valid) {
-  float v[64];
-#pragma unroll
-  for (int c = 0; c < HD / 16; ++c) ptx::tmem_ld16(t_addr + c * 16, v + c * 16);
+// Accumulator read-out: this warp's 32 rows x 32 fp32 columns -> 16 packed bf16 pairs per thread (thread = row).
+__device__ __forceinline__ void acc_load_pack32(uint32_t t_addr, uint32_t (&w)[16]) {
+  float v[32];
+  ptx::tmem_ld32(t_addr, v);
   ptx::tmem_ld_wait();
 #pragma unroll
-  for (int c = 0; c < HD / 8; ++c) {
-    uint32_t w[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      __nv_bfloat162 hh = __floats2bfloat162_rn(v[c * 8 + 2 * j], v[c * 8 + 2 * j + 1]);
-      w[j] = *reinterpret_cast<uint32_t*>(&hh);
-    }
-    *reinterpret_cast<uint4*>(stage + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+  for (int j = 0; j < 16; ++j) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    w[j] = *reinterpret_cast<uint32_t*>(&hh);
   }
-  __syncwarp();
-  const int c = lane & 7;
+}
+// ... -> the 16-byte slots of the dS^T tile that THIS thread writes in the main loop (row `trow`, atom `hf`, chunks
+// sh*4 .. sh*4+3 under the 128-byte swizzle).  With warpgroups (0, 1) holding the column halves of one accumulator and
+// (2, 3) of the other, atom 0 and atom 1 become two [128 rows x 64 columns] tiles in exactly the layout a
+// SWIZZLE_128B tensor map describes: one TMA store per tile takes them to global memory (rows past N are clipped by
+// the map), asynchronously -- the threads do not wait for the store traffic, which arrives in bursts because the
+// persistent CTAs run in phase.
+__device__ __forceinline__ void acc_stage32(const uint32_t (&w)[16], uint8_t* atom, int trow, int sh) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = i * 4 + (lane >> 3);
-    const uint4 val = *reinterpret_cast<const uint4*>(stage + row * 128 + ((c ^ (row & 7)) << 4));
-    if (row < rows_valid) *reinterpret_cast<uint4*>(g_row0 + row * stride + c * 8) = val;
-  }
-  __syncwarp();
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(atom + trow * 128 + (((sh * 4 + c) ^ (trow & 7)) << 4)) =
+        make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
 }
 
 #ifdef ATTN_TRACE
-__device__ uint32_t tr[3][100];
-__device__ uint8_t tr_id[3][100];
+__device__ uint32_t tr[3][256];
+__device__ uint8_t tr_id[3][256];
 __device__ int tr_n[3];
-#define TRC(slot) ((slot) >= 100 ? 2 : ((slot) & 1))
-#define TR(slot) do { if (blockIdx.x == 0 && tr_on && tr_n[TRC(slot)] < 100) { const int _c = TRC(slot); const int _i = tr_n[_c]++; tr[_c][_i] = (uint32_t)clock(); tr_id[_c][_i] = (slot); } } while (0)
+// (the event counter lives in a register of the one tracing thread per role: a trace point is two plain stores)
+#define TR(role, id) do { if (tr_on && ((role) != 1 || warp == BWD_LOADER_WARP) && tr_i < 256) { tr[role][tr_i] = (uint32_t)clock(); tr_id[role][tr_i] = (id); ++tr_i; } } while (0)
 #else
-#define TR(slot) do { } while (0)
+#define TR(role, id) do { } while (0)
 #endif
 
 template <bool DROP, bool GP>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                   const __grid_constant__ AttnBwdArgs a) {
+                   const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ AttnBwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sSets = smem;                       // 3 sets x 4 slots x 16 KB
-  uint8_t* sDS = sSets + 3 * SET;              // 32 KB: dS^T tile
+  uint8_t* sDS = sSets + 3 * SET;              // 32 KB: dS^T tile [128 keys][128 queries] (two 64-query atoms)
   float* sLse = reinterpret_cast<float*>(sDS + 32768);   // [256]
   float* sDelta = sLse + 256;                             // [256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
   uint64_t* bar_full = bars;      // [3] operand set landed
   uint64_t* bar_sdp = bars + 3;   // S^T / dP^T of an iteration are in TMEM
-  uint64_t* bar_pds = bars + 4;   // P^T / dS^T written (TMEM + shared memory)
-  uint64_t* bar_c = bars + 5;     // the dV / dK / dQ MMAs of an iteration have retired
-  uint64_t* bar_epi = bars + 6;   // accumulators of a key chunk (and dQ at the item's end) read out
-  uint64_t* bar_aux = bars + 7;   // lse / delta of an item are in shared memory
-  uint64_t* bar_item = bars + 8;  // an item is finished by the compute warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-#ifdef ATTN_TRACE
-  if (threadIdx.x == 0 && blockIdx.x == 0) { tr_n[0] = 0; tr_n[1] = 0; tr_n[2] = 0; }
-#endif
+  uint64_t* bar_pds = bars + 5;   // P^T / dS^T written (TMEM + shared memory), 512 arrivals
+  uint64_t* bar_c = bars + 7;     // every MMA of an iteration (dV, dK, dQ) has retired
+  uint64_t* bar_epi = bars + 8;   // accumulators of a key chunk (and dQ at the item's end) read out
+  uint64_t* bar_aux = bars + 9;   // lse / delta of an item are in shared memory
+  uint64_t* bar_item = bars + 10; // the compute warps no longer read the item's lse / delta
+  uint64_t* bar_kv = bars + 11;   // dV / dK of a key chunk are complete (its last query tile's C MMAs have retired)
+  uint64_t* bar_free = bars + 12; // [3] every MMA that reads an operand set has retired
+  uint64_t* bar_staged = bars + 15;      // accumulator tiles are staged in the dS^T tile (512 arrivals)
+  uint64_t* bar_stage_free = bars + 16;  // their TMA stores have read the tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef ATTN_TRACE
-  const bool tr_on = (threadIdx.x == 0) || (warp == 8 && lane == 0) || (warp == 9 && lane == 0);
+  const bool tr_on = (blockIdx.x == 0) && (lane == 0) && (warp == 0 || warp == BWD_LOADER_WARP || warp == BWD_MMA_WARP);
+  int tr_i = 0;
 #endif
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 3; ++i) ptx::mbar_init(bar_full + i, 1);
+    for (int i = 0; i < 3; ++i) { ptx::mbar_init(bar_full + i, 1); ptx::mbar_init(bar_free + i, 1); }
     ptx::mbar_init(bar_sdp, 1);
-    ptx::mbar_init(bar_pds, 256);
+    ptx::mbar_init(bar_pds, BWD_COMPUTE_WARPS * 32);
     ptx::mbar_init(bar_c, 1);
-    ptx::mbar_init(bar_epi, 256);
-    ptx::mbar_init(bar_aux, 128);
-    ptx::mbar_init(bar_item, 256);
+    ptx::mbar_init(bar_kv, 1);
+    ptx::mbar_init(bar_staged, BWD_COMPUTE_WARPS * 32);
+    ptx::mbar_init(bar_stage_free, 1);
+    ptx::mbar_init(bar_epi, BWD_COMPUTE_WARPS * 32);
+    ptx::mbar_init(bar_aux, BWD_LOADER_THREADS);
+    ptx::mbar_init(bar_item, BWD_COMPUTE_WARPS * 32);
     ptx::fence_barrier_init();
   }
-  if (warp == 8) ptx::tmem_alloc(tmem_slot, BWD_TMEM_COLS);
+  if (warp == BWD_MMA_WARP) ptx::tmem_alloc(tmem_slot, BWD_TMEM_COLS);
+  if (warp < BWD_COMPUTE_WARPS) {
+    // the dS^T tile feeds dQ with rows / columns the compute warps never write (keys, queries past N): those meet
+    // zero operand rows, but must be finite
+    uint4* z = reinterpret_cast<uint4*>(sDS) + threadIdx.x * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    ptx::fence_async_shared();
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -637,58 +649,75 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   const int n_iter = nt * nt;
   const int n_mine = (a.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (warp == 8) {
-    // =========================== producer: TMA + every MMA ===========================
-    // The whole warp walks the schedule (uniform control flow keeps descriptors in uniform registers);
-    // only the elected lane issues TMA / MMA / commit.  The schedule is flattened over (item, kc, qt):
-    // the descriptors of iteration gi+1 are formed BEFORE waiting for the compute warps of iteration
-    // gi, so that S^T / dP^T of gi+1 are issued back to back with the accumulating MMAs of gi.
-    const bool leader = ptx::elect_one();
-    if (leader) {
+  if (warp == BWD_TMA_WARP) {
+    // =========================== operand loader: TMA only ===========================
+    // The operand sets form a ring of three over the sequence of half-item loads j = nt * item index + t (rows
+    // [128 t, 128 t + 128) of the item): load j goes to set j % 3 once the MMAs that read load j - 3 have retired
+    // (bar_free, committed by the MMA warp).  (Issuing a 64 KB set costs the issuing thread ~1-2 k cycles: kept off the
+    // warp that feeds the tensor core.)
+    if (lane == 0) {
       ptx::prefetch_tensormap(&tmQKV);
       ptx::prefetch_tensormap(&tmDO);
-    }
-    uint32_t ph_full[3] = {0, 0, 0};
-    uint32_t n_epi = 0;      // accumulator read-outs the producer has waited for
-    uint32_t n_epi_due = 0;  // read-outs the compute warps will have signalled before the next first-of-chunk C
-    // rows [128*t, 128*t+128) of item `item` -> set `set`
-    auto load_set = [&](int item, int t, int set) {
-      const int hh = item % a.H, bb = item / a.H;
-      uint8_t* base = sSets + set * SET;
-      if (leader) {
+      const int n_loads = n_mine * nt;
+      for (int j = 0; j < n_loads; ++j) {
+        const int set = j % 3, idx = j / nt, t = j - idx * nt;
+        const int item = (int)blockIdx.x + idx * (int)gridDim.x;
+        const int hh = item % a.H, bb = item / a.H;
+        if (j >= 3) ptx::mbar_wait(bar_free + set, (uint32_t)((j / 3 - 1) & 1));
+        uint8_t* base = sSets + set * SET;
         ptx::mbar_expect_tx(bar_full + set, SET);
         ptx::tma_load_3d(base + SL_K * SLOT, &tmQKV, bar_full + set, a.D + hh * HD, t * 128, bb);
         ptx::tma_load_3d(base + SL_Q * SLOT, &tmQKV, bar_full + set, hh * HD, t * 128, bb);
         ptx::tma_load_3d(base + SL_V * SLOT, &tmQKV, bar_full + set, 2 * a.D + hh * HD, t * 128, bb);
         ptx::tma_load_3d(base + SL_DO * SLOT, &tmDO, bar_full + set, hh * HD, t * 128, bb);
       }
-      __syncwarp();
-    };
+    } else if (lane == 1) {
+      // ---- accumulator tiles out: per item, one group per key chunk ([dK | dV] staged in the two atoms of the dS^T
+      //      tile) and a last one with [dQ_0 | dQ_1].  (A second thread of this warp: issuing a TMA store costs its
+      //      thread several hundred cycles per 16 KB tile, which none of the compute warps can spare.) ----
+      ptx::prefetch_tensormap(&tmDZ);
+      uint32_t n_grp = 0;
+      for (int idx = 0; idx < n_mine; ++idx) {
+        const int item = (int)blockIdx.x + idx * (int)gridDim.x;
+        const int hh = item % a.H, bb = item / a.H;
+        for (int grp = 0; grp <= nt; ++grp, ++n_grp) {
+          ptx::mbar_wait(bar_staged, n_grp & 1);
+          if (grp < nt) {
+            ptx::tma_store_3d(&tmDZ, sDS, a.D + hh * HD, grp * 128, bb);               // dK tile = atom 0
+            ptx::tma_store_3d(&tmDZ, sDS + 16384, 2 * a.D + hh * HD, grp * 128, bb);   // dV tile = atom 1
+          } else {
+            ptx::tma_store_3d(&tmDZ, sDS, hh * HD, 0, bb);
+            if (nt > 1) ptx::tma_store_3d(&tmDZ, sDS + 16384, hh * HD, 128, bb);
+          }
+          ptx::bulk_commit_group();
+          ptx::bulk_wait_group_read0();
+          ptx::mbar_arrive(bar_stage_free);
+        }
+      }
+      ptx::bulk_wait_group0();   // the last tiles have reached global memory
+    }
+  } else if (warp == BWD_MMA_WARP) {
+    // =========================== producer: every MMA ===========================
+    // The whole warp walks the schedule (uniform control flow keeps descriptors in uniform registers);
+    // only the elected lane issues MMA / commit.  The schedule is flattened over (item, kc, qt).
+    const bool leader = ptx::elect_one();
+    uint32_t n_epi = 0;      // accumulator read-outs the producer has waited for
+    uint32_t n_epi_due = 0;  // read-outs the compute warps will have signalled before the next first-of-chunk C
     struct Iter {
       uint64_t dk_k, dq_k, dv_k, ddo_k;   // K-major descriptors (S^T, dP^T)
       uint64_t ddo_mn, dq_mn, dk_mn;      // MN-major descriptors (dV, dK, dQ)
       uint32_t id_s, acc_q, acc_k;
-      int nq, nk, qt, it;
+      int nq, nk, qt, it;                 // 16-query / 16-key steps of the tile / chunk
     };
-    // nt == 2: an item holds two sets (rows [0,128) in s0, rows [128,256) in s1), the third one (sf)
-    //          receives rows [0,128) of the next item during iteration 0 and s0 is refilled with its rows
-    //          [128,256) during iteration 3;  (s0, s1, sf) <- (sf, s0, s1) at every item boundary.
-    // nt == 1: an item holds one set; item i lives in set i % 3 and is loaded two items ahead.
-    int s0 = 0, s1 = 1, sf = 2;
-    bool t1_ready = (nt == 1);
-    // describes iteration `it` of the item whose sets are (s0, s1); waits for the operand sets it touches first
-    auto make_iter = [&](int it) {
+    // describes iteration `it` of item index `idx` (rows [0,128) in set (nt idx) % 3, rows [128,256) in the next one of
+    // the ring); waits for the operand sets the iteration touches first
+    auto make_iter = [&](int idx, int it) {
       Iter r;
       const int kc = (nt == 2) ? (it >> 1) : 0, qt = (nt == 2) ? (it & 1) : 0;
-      if (it == 0) {
-        ptx::mbar_wait(bar_full + s0, ph_full[s0]);
-        ph_full[s0] ^= 1;
-        t1_ready = (nt == 1);
-      } else if (!t1_ready) {
-        ptx::mbar_wait(bar_full + s1, ph_full[s1]);
-        ph_full[s1] ^= 1;
-        t1_ready = true;
-      }
+      const int j0 = nt * idx, j1 = j0 + 1;
+      const int s0 = j0 % 3, s1 = j1 % 3;
+      if (it == 0) ptx::mbar_wait(bar_full + s0, (uint32_t)((j0 / 3) & 1));
+      else if (it == 1) ptx::mbar_wait(bar_full + s1, (uint32_t)((j1 / 3) & 1));
       const int qw = min(128, NP - qt * 128), cw = min(128, NP - kc * 128);  // multiples of 16
       const uint32_t kset = ptx::smem_u32(sSets + (kc ? s1 : s0) * SET), qset = ptx::smem_u32(sSets + (qt ? s1 : s0) * SET);
       const uint32_t k_addr = kset + SL_K * SLOT, v_addr = kset + SL_V * SLOT;
@@ -706,99 +735,98 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       r.qt = qt; r.it = it;
       return r;
     };
-    auto issue_a = [&](const Iter& r) {  // S^T = K Q^T, dP^T = V dO^T
-      if (leader) {
+    // Every tcgen05 instruction below is PREDICATED on the elected lane instead of sitting in an `if (leader)` branch:
+    // inside a divergent region the compiler has to form each descriptor in vector registers and move it to uniform
+    // ones (R2UR) right in front of every MMA -- ~13 dependent instructions per MMA pair, more than the MMA itself
+    // takes -- while a converged warp keeps the whole schedule in the uniform datapath.
+    const uint32_t lead = leader ? 1u : 0u;
+    const uint32_t a_sdp = ptx::smem_u32(bar_sdp), a_c = ptx::smem_u32(bar_c), a_kv = ptx::smem_u32(bar_kv);
+    auto issue_a = [&](const Iter& r) {   // S^T = K Q^T, dP^T = V dO^T
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) ptx::mma_bf16_ss(tmem + T_ST, r.dk_k + 2 * k, r.dq_k + 2 * k, r.id_s, k > 0 ? 1u : 0u);
+      for (int k = 0; k < HD / 16; ++k) ptx::mma_ss_pred(tmem + T_S0, r.dk_k + 2 * k, r.dq_k + 2 * k, r.id_s, k > 0 ? 1u : 0u, lead);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) ptx::mma_bf16_ss(tmem + T_DPT, r.dv_k + 2 * k, r.ddo_k + 2 * k, r.id_s, k > 0 ? 1u : 0u);
-        ptx::mma_commit(bar_sdp);
-      }
-      __syncwarp();
+      for (int k = 0; k < HD / 16; ++k) ptx::mma_ss_pred(tmem + T_DP0, r.dv_k + 2 * k, r.ddo_k + 2 * k, r.id_s, k > 0 ? 1u : 0u, lead);
+      ptx::commit_pred(a_sdp, lead);
     };
     const uint32_t id_ts = ptx::idesc_bf16(128, HD, 0, 1);   // A from TMEM, B MN-major
     const uint32_t id_dq = ptx::idesc_bf16(128, HD, 1, 1);   // A, B MN-major
     const uint64_t dds_mn = ptx::smem_desc_sw128(ptx::smem_u32(sDS), 16384, 1024);
+    // dV += P^T dO, dK += dS^T Q: contraction over the tile's queries, 16 per MMA; warpgroup w = ks >> 1 keeps its
+    // packed columns at [32 w, 32 w + 16) of the tile
+    auto issue_c = [&](const Iter& r) {
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        if (ks < r.nq) {
+          const uint32_t acc = ks > 0 ? 1u : r.acc_q;
+          const uint32_t a_col = (ks >> 1) * 32 + (ks & 1) * 8;
+          ptx::mma_ts_pred(tmem + T_DV, tmem + T_S0 + a_col, r.ddo_mn + 128 * ks, id_ts, acc, lead);
+          ptx::mma_ts_pred(tmem + T_DK, tmem + T_DP0 + a_col, r.dq_mn + 128 * ks, id_ts, acc, lead);
+        }
+      }
+    };
+    auto issue_dq = [&](const Iter& r) {   // contraction over the chunk's keys
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+        if (ks < r.nk)
+          ptx::mma_ss_pred(tmem + T_DQ + r.qt * 64, dds_mn + 128 * ks, r.dk_mn + 128 * ks, id_dq, ks > 0 ? 1u : r.acc_k, lead);
+      ptx::commit_pred(a_c, lead);
+    };
     const int total = n_mine * n_iter;
     if (n_mine > 0) {
-      load_set(blockIdx.x, 0, s0);
-      if (nt > 1) load_set(blockIdx.x, 1, s1);
-      else if (n_mine > 1) load_set((int)blockIdx.x + (int)gridDim.x, 0, 1);
-      TR(1);
-      Iter cur = make_iter(0);
+      Iter cur = make_iter(0, 0);
       issue_a(cur);
       int idx = 0;
       for (int gi = 0; gi < total; ++gi) {
-        // ---- operand prefetch, into sets whose last reader has retired ----
-        if (nt == 1) {
-          if (idx + 2 < n_mine) {
-            if (gi > 0) ptx::mbar_wait(bar_c, (gi - 1) & 1);
-            load_set((int)blockIdx.x + (idx + 2) * (int)gridDim.x, 0, (idx + 2) % 3);   // the set of item idx-1
-          }
-        } else if (idx + 1 < n_mine && (cur.it == 0 || cur.it == 3)) {
-          const int next_item = (int)blockIdx.x + (idx + 1) * (int)gridDim.x;
-          if (gi > 0) ptx::mbar_wait(bar_c, (gi - 1) & 1);   // every accumulating MMA issued so far has retired
-          if (cur.it == 0) load_set(next_item, 0, sf);        // sf: rows [128,256) of the previous item
-          else load_set(next_item, 1, s0);                    // s0: last read by iteration 2
-        }
         // ---- the next iteration's descriptors, before the wait ----
         const bool has_next = gi + 1 < total;
+        const bool chunk_end = (cur.qt == nt - 1);
+        const int cur_it = cur.it, cur_idx = idx;
         Iter nxt = cur;
         if (has_next) {
-          if (cur.it == n_iter - 1) {
-            ++idx;
-            if (nt == 1) { s0 = idx % 3; }
-            else { const int t = s0; s0 = sf; sf = s1; s1 = t; }   // (s0, s1, sf) <- (sf, s0, s1)
-            nxt = make_iter(0);
-          } else {
-            nxt = make_iter(cur.it + 1);
-          }
+          if (cur.it == n_iter - 1) { ++idx; nxt = make_iter(idx, 0); }
+          else nxt = make_iter(idx, cur.it + 1);
         }
-        TR(3);
-        // ---- wait for P^T / dS^T (TMEM) and dS^T (shared memory) of iteration gi ----
+        // ---- P^T / dS^T ready -> dV, dK partial sums, then S^T / dP^T of the next iteration, then dQ ----
+        TR(2, 1);
         ptx::mbar_wait(bar_pds, gi & 1);
         ptx::tc_fence_after();
+        TR(2, 3);
         if (cur.qt == 0 && n_epi < n_epi_due) {  // the accumulators of the previous chunk have been read out
           ptx::mbar_wait(bar_epi, n_epi & 1);
           ++n_epi;
           ptx::tc_fence_after();
         }
-        TR(5);
-        if (leader) {
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {  // contraction over the tile's queries (16 rows = 2048 B = 128 units)
-            if (ks < cur.nq) {
-              ptx::mma_bf16_ts(tmem + T_DV, tmem + T_ST + ks * 8, cur.ddo_mn + 128 * ks, id_ts, ks > 0 ? 1u : cur.acc_q);
-              ptx::mma_bf16_ts(tmem + T_DK, tmem + T_DPT + ks * 8, cur.dq_mn + 128 * ks, id_ts, ks > 0 ? 1u : cur.acc_q);
-            }
-          }
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks)    // contraction over the chunk's keys
-            if (ks < cur.nk)
-              ptx::mma_bf16_ss(tmem + T_DQ + cur.qt * 64, dds_mn + 128 * ks, cur.dk_mn + 128 * ks, id_dq,
-                               ks > 0 ? 1u : cur.acc_k);
-          ptx::mma_commit(bar_c);
+        issue_c(cur);
+        if (chunk_end) {
+          ptx::commit_pred(a_kv, lead);
+          ++n_epi_due;  // the compute warps read this chunk's accumulators out next
         }
-        __syncwarp();
-        if (cur.qt == nt - 1) ++n_epi_due;  // the compute warps read this chunk's accumulators out next
+        TR(2, 4);
         if (has_next) issue_a(nxt);
-        TR(7);
+        TR(2, 6);
+        issue_dq(cur);
+        // ---- operand sets this iteration was the last to read go back to the TMA warp ----
+        if (nt == 1) {
+          ptx::commit_pred(ptx::smem_u32(bar_free + cur_idx % 3), lead);
+        } else if (cur_it >= 2) {
+          ptx::commit_pred(ptx::smem_u32(bar_free + (2 * cur_idx + cur_it - 2) % 3), lead);   // it 2: rows [0,128); it 3: rows [128,256)
+        }
+        TR(2, 5);
         cur = nxt;
       }
     }
-  } else if (warp >= 9) {
-    // =========================== lse / delta loader (128 threads) ===========================
+  } else if (warp >= BWD_LOADER_WARP) {
+    // =========================== lse / delta loader (64 threads) ===========================
     // The values of item idx are formed in registers while item idx-1 is being computed and dropped
     // into the (single) shared-memory buffer the moment that item is finished.
-    const int tl = threadIdx.x - 9 * 32;
+    const int tl = threadIdx.x - BWD_LOADER_WARP * 32;
     for (int idx = 0; idx < n_mine; ++idx) {
       const int item = (int)blockIdx.x + idx * (int)gridDim.x;
       const int hh = item % a.H, bb = item / a.H;
-      TR(100);
-      float lse[2], dl[2];
+      float lse[4], dl[4];
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int q = tl + r * 128;
+      for (int r = 0; r < 4; ++r) {
+        const int q = tl + r * BWD_LOADER_THREADS;
         lse[r] = INFINITY;
         dl[r] = 0.f;
         if (q < a.N) {
@@ -824,161 +852,187 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           if constexpr (GP) dl[r] += a.dext[(long long)item * a.N + q];
         }
       }
-      TR(102);
+      TR(1, 20);
       if (idx >= 1) ptx::mbar_wait(bar_item, (idx - 1) & 1);  // the previous item no longer reads the buffer
-      TR(104);
+      TR(1, 21);
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        sLse[tl + r * 128] = lse[r];
-        sDelta[tl + r * 128] = dl[r];
+      for (int r = 0; r < 4; ++r) {
+        if (tl + r * BWD_LOADER_THREADS < 256) {
+          sLse[tl + r * BWD_LOADER_THREADS] = lse[r];
+          sDelta[tl + r * BWD_LOADER_THREADS] = dl[r];
+        }
       }
       ptx::mbar_arrive(bar_aux);
+      TR(1, 22);
     }
   } else {
     // =========================== compute warps (thread = key row) ===========================
     const int wg = warp >> 2, quarter = warp & 3;
+    const int hf = wg >> 1, sh = wg & 1;   // 64-column atom of the dS^T tile and 32-column half of it: columns [32 wg, 32 wg + 32)
     const int trow = quarter * 32 + lane;  // row inside a 128-row tile / chunk
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-    __nv_bfloat16* dz = reinterpret_cast<__nv_bfloat16*>(a.dz);
+    const uint32_t t_s = t_lane + T_S0 + hf * 64 + sh * 32, t_dp = t_lane + T_DP0 + hf * 64 + sh * 32;
+    const int col0 = hf * 64 + sh * 32;    // first query column (inside the tile) of this warpgroup
     constexpr float LOG2E = 1.4426950408889634f;
-    uint32_t g = 0;  // global iteration counter (phases of bar_sdp / bar_c)
+    uint32_t g = 0;  // global iteration counter (phases of bar_sdp / bar_pds / bar_c)
+    uint32_t n_chunk = 0;   // key chunks finished (phase of bar_kv)
+    bool store_pending = false;
+    uint32_t n_grp = 0;     // store groups whose completion has been waited for (phase of bar_stage_free)
     for (int idx = 0; idx < n_mine; ++idx) {
       const int item = (int)blockIdx.x + idx * (int)gridDim.x;
-      const int h = item % a.H, b = item / a.H;
-      const float* lse_s = sLse;
-      const float* dl_s = sDelta;
       const uint32_t drow0 = (uint32_t)((long long)item * a.N);   // dropout row coordinate of query 0
-      TR(22);
+      TR(hf, 14);
       ptx::mbar_wait(bar_aux, idx & 1);
-      TR(24);
+      TR(hf, 15);
       for (int it = 0; it < n_iter; ++it, ++g) {
         const int kc = it / nt, qt = it - kc * nt;
         const int qw = min(128, NP - qt * 128);
-        const int nch = qw / 16;
-        const int c_lo = wg ? (nch + 1) / 2 : 0, c_hi = wg ? nch : (nch + 1) / 2;   // this warpgroup's chunks
-        const bool key_ok = (kc * 128 + trow) < a.N;
-        TR(0);
+        // chunks of 16 query columns this warpgroup owns in this tile (0, 1 or 2); a warp whose 32 key rows all lie
+        // past N has nothing to do either: its S^T / dP^T rows are exact zeros (= zero bf16 pairs for the MMAs)
+        int n_c = min(2, max(0, (qw - col0) / 16));
+        if (kc * 128 + quarter * 32 >= a.N) n_c = 0;
+        TR(hf, 0);
         ptx::mbar_wait(bar_sdp, g & 1);
         ptx::tc_fence_after();
-        TR(2);
-        uint32_t pP[4][8], pDS[4][8];
+        TR(hf, 2);
+        // chunk by chunk (32 live accumulator registers, not 64): load, form P^T / dS^T, pack, park both in tensor memory
+        // over columns this very thread has consumed (chunk 0 of its own block); dS^T is kept for the shared tile
+        uint32_t pDS[2][8];
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-          const int c = c_lo + ci;
-          if (c < c_hi) {
+        for (int c = 0; c < 2; ++c) {
+          if (c < n_c) {
             float sv[16], dp[16];
-            ptx::tmem_ld16(t_lane + T_ST + c * 16, sv);
-            ptx::tmem_ld16(t_lane + T_DPT + c * 16, dp);
-            // per-query lse / delta of the chunk: 16-byte broadcast loads (the row offset is a multiple of 16 floats)
-            float lsq[16], dlq[16];
-            float gq[GP ? 16 : 1];
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 l4 = reinterpret_cast<const float4*>(lse_s + qt * 128 + c * 16)[j4];
-              const float4 d4 = reinterpret_cast<const float4*>(dl_s + qt * 128 + c * 16)[j4];
-              lsq[4 * j4] = l4.x; lsq[4 * j4 + 1] = l4.y; lsq[4 * j4 + 2] = l4.z; lsq[4 * j4 + 3] = l4.w;
-              dlq[4 * j4] = d4.x; dlq[4 * j4 + 1] = d4.y; dlq[4 * j4 + 2] = d4.z; dlq[4 * j4 + 3] = d4.w;
-            }
+            ptx::tmem_ld16(t_s + c * 16, sv);
+            ptx::tmem_ld16(t_dp + c * 16, dp);
             if constexpr (GP) {
               // + the cotangent of the exported map, read transposed: lanes = consecutive keys of query row q
               const int key = kc * 128 + trow;
+              float gq[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                const int q = qt * 128 + c * 16 + j;
-                gq[j] = (key_ok && q < a.N) ? __ldg(a.gp + ((long long)item * a.N + q) * a.N + key) : 0.f;
+                const int q = qt * 128 + col0 + c * 16 + j;
+                gq[j] = (key < a.N && q < a.N) ? __ldg(a.gp + ((long long)item * a.N + q) * a.N + key) : 0.f;
               }
-            }
-            ptx::tmem_ld_wait();
+              ptx::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int q = qt * 128 + c * 16 + j;
-              if constexpr (GP) dp[j] += gq[j];
-              const float p = key_ok ? ex2_fast(fmaf(sv[j], LOG2E, -lsq[j])) : 0.f;
-              if constexpr (DROP) {
-                // O = drop(P) V:  dV needs drop(P)^T, dS = P o (drop'(dP) - delta)
-                const float f = drop_factor(a.drop, drow0 + q, kc * 128 + trow);
-                sv[j] = p * f;
-                dp[j] = p * (dp[j] * f - dlq[j]);
-              } else {
-                sv[j] = p;
-                dp[j] = p * (dp[j] - dlq[j]);
+              for (int j = 0; j < 16; ++j) dp[j] += gq[j];
+            } else {
+              ptx::tmem_ld_wait();
+            }
+            const float4* l4p = reinterpret_cast<const float4*>(sLse + qt * 128 + col0 + c * 16);
+            const float4* d4p = reinterpret_cast<const float4*>(sDelta + qt * 128 + col0 + c * 16);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 l4 = l4p[j4], d4 = d4p[j4];
+              const float lsq[4] = {l4.x, l4.y, l4.z, l4.w}, dlq[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = j4 * 4 + jj;
+                const float p = ex2_fast(fmaf(sv[j], LOG2E, -lsq[jj]));
+                if constexpr (DROP) {
+                  // O = drop(P) V:  dV needs drop(P)^T, dS = P o (drop'(dP) - delta)
+                  const float f = drop_factor(a.drop, drow0 + qt * 128 + col0 + c * 16 + j, kc * 128 + trow);
+                  sv[j] = p * f;
+                  dp[j] = p * (dp[j] * f - dlq[jj]);
+                } else {
+                  sv[j] = p;
+                  dp[j] = p * (dp[j] - dlq[jj]);
+                }
               }
             }
+            uint32_t pP[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               __nv_bfloat162 hp = __floats2bfloat162_rn(sv[2 * j], sv[2 * j + 1]);
               __nv_bfloat162 hd = __floats2bfloat162_rn(dp[2 * j], dp[2 * j + 1]);
-              pP[ci][j] = *reinterpret_cast<uint32_t*>(&hp);
-              pDS[ci][j] = *reinterpret_cast<uint32_t*>(&hd);
+              pP[j] = *reinterpret_cast<uint32_t*>(&hp);
+              pDS[c][j] = *reinterpret_cast<uint32_t*>(&hd);
             }
+            tmem_st8(t_s + c * 8, pP);
+            tmem_st8(t_dp + c * 8, pDS[c]);
           }
         }
         // the dS^T tile is single-buffered: the dQ MMA of the previous iteration must have retired
-        TR(4);
+        TR(hf, 4);
         if (g > 0) ptx::mbar_wait(bar_c, (g - 1) & 1);
-        TR(6);
-#pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-          const int c = c_lo + ci;
-          if (c < c_hi) {
-            store_bf16x8_sw128(sDS, trow, c * 16, pDS[ci]);
-            store_bf16x8_sw128(sDS, trow, c * 16 + 8, pDS[ci] + 4);
-          }
+        if (store_pending) {   // the accumulator tiles staged in the dS^T tile have been read by their TMA stores
+          ptx::mbar_wait(bar_stage_free, n_grp & 1);
+          ++n_grp;
+          store_pending = false;
         }
-        ptx::tc_fence_before();
-        TR(8);
-        compute_bar_sync();  // every thread has read its S^T / dP^T columns: they may be overwritten
-        ptx::tc_fence_after();
-        TR(10);
+        TR(hf, 6);
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-          const int c = c_lo + ci;
-          if (c < c_hi) {
-            tmem_st8(t_lane + T_ST + c * 8, pP[ci]);
-            tmem_st8(t_lane + T_DPT + c * 8, pDS[ci]);
+        for (int c = 0; c < 2; ++c) {
+          if (c < n_c) {
+            store_bf16x8_sw128(sDS, trow, col0 + c * 16, pDS[c]);
+            store_bf16x8_sw128(sDS, trow, col0 + c * 16 + 8, pDS[c] + 4);
           }
         }
         ptx::tmem_st_wait();
-        TR(12);
         ptx::fence_async_shared();
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar_pds);
-        TR(14);
+        TR(hf, 8);
+        if (it == n_iter - 1) ptx::mbar_arrive(bar_item);   // lse / delta of this item have been read for the last time
         if (qt == nt - 1) {
-          // ---- dK | dV of this key chunk: warpgroup 0 -> dK, warpgroup 1 -> dV (thread = key row) ----
-          ptx::mbar_wait(bar_c, g & 1);
+          // ---- accumulators of this key chunk, 32 rows x 32 columns per warp (thread = key row): warpgroups 0, 1 ->
+          //      the two column halves of dK, warpgroups 2, 3 -> of dV.  The producer may overwrite them as soon as
+          //      they are in registers (bar_epi); packing, staging and the global stores follow. ----
+          ptx::mbar_wait(bar_kv, n_chunk & 1);
+          ++n_chunk;
           ptx::tc_fence_after();
-          TR(16);
-          // (the dS^T tile is idle here -- every MMA that reads it has retired -- and serves as staging)
-          uint8_t* stage = sDS + warp * 4096;
+          TR(hf, 10);
+          const bool item_end = (kc == nt - 1);
           const int key0 = kc * 128 + quarter * 32;  // first of this warp's 32 key rows
-          store_rows_bf16(dz + ((long long)b * a.N + key0) * a.R + (wg + 1) * a.D + h * HD, a.R,
-                          t_lane + (wg ? T_DV : T_DK), stage, lane, a.N - key0);
-          if (kc == nt - 1 && wg < nt) {
-            // ---- dQ: warpgroup qt reads tile qt (thread = query row); every MMA of the item has retired
-            const int q0 = wg * 128 + quarter * 32;
-            store_rows_bf16(dz + ((long long)b * a.N + q0) * a.R + h * HD, a.R, t_lane + T_DQ + wg * 64, stage, lane,
-                            a.N - q0);
+          uint32_t wkv[16];
+          if (key0 < a.N) acc_load_pack32(t_lane + (wg < 2 ? T_DK : T_DV) + (wg & 1) * 32, wkv);
+          if (!item_end) {
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(bar_epi);
           }
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(bar_epi);
-          compute_bar_sync();  // staging regions are dS^T rows of other warps in the next iteration
-          TR(18);
+          TR(hf, 11);
+          // the staging slots belong to the dS^T tile the dQ product of this iteration reads
+          ptx::mbar_wait(bar_c, g & 1);
+          TR(hf, 13);
+          uint8_t* atom = sDS + hf * 16384;
+          if (key0 < a.N) acc_stage32(wkv, atom, trow, sh);
+          ptx::fence_async_shared();
+          ptx::mbar_arrive(bar_staged);      // -> the store thread (TMA warp) takes [dK | dV] out
+          store_pending = true;
+          if (item_end) {
+            // ---- dQ of query tile wg >> 1, column half wg & 1 (thread = query row): every MMA of the item has retired;
+            //      the tiles go through the same two atoms once the dK / dV stores have read them
+            const int tq = wg >> 1;
+            const bool have = (tq < nt) && (tq * 128 + quarter * 32 < a.N);
+            ptx::tc_fence_after();
+            if (have) acc_load_pack32(t_lane + T_DQ + tq * 64 + (wg & 1) * 32, wkv);
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(bar_epi);
+            TR(hf, 16);
+            ptx::mbar_wait(bar_stage_free, n_grp & 1);
+            TR(hf, 17);
+            ++n_grp;
+            if (have) acc_stage32(wkv, atom, trow, sh);
+            ptx::fence_async_shared();
+            ptx::mbar_arrive(bar_staged);
+          }
+          TR(hf, 12);
         }
       }
-      TR(20);
-      ptx::mbar_arrive(bar_item);
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
 #ifdef ATTN_TRACE
+  if (tr_on) tr_n[warp == 0 ? 0 : warp == BWD_LOADER_WARP ? 1 : 2] = tr_i;
+  __threadfence();
+  __syncthreads();
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     for (int w = 0; w < 3; ++w)
       for (int i = 0; i < tr_n[w]; ++i) printf("TR %d %d %u\n", w, (int)tr_id[w][i], tr[w][i]);
   }
 #endif
-  if (warp == 8) {
+  if (warp == BWD_MMA_WARP) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem, BWD_TMEM_COLS);
   }
@@ -1105,7 +1159,9 @@ int attn_bwd_tc(const void* qkv, const void* dO, const void* oh, long long ld_oh
   CUtensorMap tqkv, tdo;
   ODV_TRY(make_tmap_3d_bf16(&tqkv, qkv, 3 * D, N, B, 3 * D, (uint64_t)N * 3 * D, HD, 128, 1));
   ODV_TRY(make_tmap_3d_bf16(&tdo, dO, D, N, B, D, (uint64_t)N * D, HD, 128, 1));
-  const int smem = 3 * SET + 32768 + 2048 + 128;
+  CUtensorMap tdz;   // dq | dk | dv tiles leave through TMA stores: [B][N][R], boxes of 128 rows x 64 columns
+  ODV_TRY(make_tmap_3d_bf16(&tdz, dz, R, N, B, R, (uint64_t)N * R, HD, 128, 1));
+  const int smem = 3 * SET + 32768 + 2048 + 256;   // operand sets, dS^T tile, lse | delta, 17 mbarriers + the TMEM slot
   static bool configured = false;
   static int sms = 148;
   if (!configured) {
@@ -1118,9 +1174,9 @@ int attn_bwd_tc(const void* qkv, const void* dO, const void* oh, long long ld_oh
     configured = true;
   }
   const int grid = a.items < sms ? a.items : sms;
-  if (gp) attn_bwd_tc_kernel<false, true><<<grid, BWD_THREADS, smem, s>>>(tqkv, tdo, a);
-  else if (drop.thresh) attn_bwd_tc_kernel<true, false><<<grid, BWD_THREADS, smem, s>>>(tqkv, tdo, a);
-  else attn_bwd_tc_kernel<false, false><<<grid, BWD_THREADS, smem, s>>>(tqkv, tdo, a);
+  if (gp) attn_bwd_tc_kernel<false, true><<<grid, BWD_THREADS, smem, s>>>(tqkv, tdo, tdz, a);
+  else if (drop.thresh) attn_bwd_tc_kernel<true, false><<<grid, BWD_THREADS, smem, s>>>(tqkv, tdo, tdz, a);
+  else attn_bwd_tc_kernel<false, false><<<grid, BWD_THREADS, smem, s>>>(tqkv, tdo, tdz, a);
   ODV_LAUNCH_CHECK();
   return 0;
 }
