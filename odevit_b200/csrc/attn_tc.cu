@@ -495,27 +495,34 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 //     dq = dS k,  dk = dS^T q,  dv = P^T dO
 // PERSISTENT kernel: one CTA per SM walks the (b, h) items c, c+G, c+2G, ...; everything is in the
 // TRANSPOSED orientation (thread = key row), so that P^T and dS^T are A operands that never leave
-// tensor memory.  An iteration is one (128-key chunk kc, 128-query tile qt) pair:
-//   warp 16 (one lane)  TMA + all MMAs.  Operand tiles live in three rotating 64 KB sets
-//        {K, Q, V, dO} x 128 rows (item i: rows [0,128) in s0, rows [128,256) in s1; the third set receives
-//        rows [0,128) of item i+1 at the start of item i, s0 its rows [128,256) once its last reader retired).
-//        per iteration:
-//          A:  S^T = K_kc Q_qt^T,  dP^T = V_kc dO_qt^T                 (SS, N = the tile's query count: 128-wide
-//              MMAs run at the tensor rate, 64-wide SS MMAs are bound by the shared-memory operand reads)
-//          C:  dV_kc += P^T dO_qt,  dK_kc += dS^T Q_qt                  (TS: A = bf16 P^T / dS^T in TMEM)
-//          Q:  dQ_qt += dS K_kc     (A = the dS^T tile in shared memory read MN-major, B = K chunk MN-major)
-//        Issue order  C(i) A(i+1) Q(i):  S^T / dP^T of the next iteration are ready while dQ still runs.
-//        dK, dV, dQ_0, dQ_1 accumulate in TMEM [256,512): no partial sum ever goes through memory.
-//   warps 0-15          four warpgroups split the query columns of a tile (32 each); thread = key row:
-//          P^T, dS^T of its 128 x 32 block from S^T, dP^T (per-query lse / delta broadcast from shared memory),
-//          packed to bf16 and written back IN PLACE over columns the same thread has already read (warpgroup w
-//          parks its packed columns at [32 w, 32 w + 16) of the tile: no cross-thread hazard, no barrier); dS^T
-//          also goes to the 128-byte-swizzled shared-memory tile.  Key rows past N need no predicate: their K / V
-//          rows are TMA zero fill, so whatever they produce multiplies zeros or lands in accumulator rows that are
-//          never stored.  Read-outs: dK | dV per key chunk and dQ at the item's end, 32 x 32 per warp, signalled to
-//          the producer as soon as the values are in registers, staged through the warp's own slots of the dS^T tile.
-//   warps 17-19         lse and delta = <dO_i, O_i> of the NEXT item into shared memory: the only global
+// tensor memory.  An iteration is one (128-key chunk kc, 128-query tile qt) pair, its S^T / dP^T tiles split into
+// two HALVES of 64 query columns with their own "ready" / "done" barriers:
+//   warp 16             every MMA (all lanes walk the schedule; tcgen05 instructions predicated on the elected lane).
+//        per iteration, for half hf = 0, 1:
+//          A(hf):  S^T[hf] = K_kc Q_(qt,hf)^T,  dP^T[hf] = V_kc dO_(qt,hf)^T       (SS)   128 x 64 fp32 each
+//          C(hf):  dV_kc += P^T[hf] dO_(qt,hf),  dK_kc += dS^T[hf] Q_(qt,hf)        (TS: A = bf16 in TMEM)
+//        and once both halves are done   dQ_qt += dS K_kc   (A = the dS^T tile in shared memory, MN-major).
+//        Issue order  C(i,0) A(i+1,0) | C(i,1) A(i+1,1) dQ(i)  (at a key chunk's last query tile: C, C, dQ, A, A -- the
+//        compute warps go to the accumulator read-out first).  dK, dV, dQ_0, dQ_1 accumulate in TMEM [256,512).
+//   warp 17, lane 0     TMA loads: the operand tiles {K, Q, V, dO} x 128 rows live in a ring of three 64 KB sets over the
+//        sequence of half-item loads (full / free barriers; "free" is a tcgen05.commit of the MMA warp).
+//   warp 17, lane 1     TMA stores: dq | dk | dv leave as [128 x 64] tiles staged in the dS^T tile (see acc_stage32).
+//        (Issuing a 16 KB TMA box costs its thread several hundred cycles: neither the MMA warp nor a compute warp.)
+//   warps 0-15          four warpgroups split the query columns of a tile (32 each: warpgroups 0, 1 = half 0); thread =
+//          key row: P^T, dS^T of its 128 x 32 block from S^T, dP^T (per-query lse / delta broadcast from shared memory),
+//          packed to bf16 and written back IN PLACE over columns the same thread has already read (warpgroup w parks its
+//          packed columns at [32 w, 32 w + 16) of the tile: no cross-thread hazard, no barrier); dS^T also goes to the
+//          128-byte-swizzled shared-memory tile.  Key rows past N need no predicate: their K / V rows are TMA zero
+//          fill, so whatever they produce multiplies zeros or lands in accumulator rows the stores clip.  Read-outs:
+//          dK | dV per key chunk and dQ at the item's end, 32 x 32 per warp, signalled to the MMA warp as soon as the
+//          values are in registers.
+//   warps 18-19         lse and delta = <dO_i, O_i> of the NEXT item into shared memory: the only global
 //          loads that are not TMA, kept off the compute warps.
+// Measured (B200, 64 x 12 items of 207 tokens): 95 us (round 1: 8 compute warps, one barrier per phase, TMA and MMA
+// issued by one thread, register -> global epilogue) -> 72 us.  What bounds it now (clock trace, -DATTN_TRACE): per
+// iteration ~1.2 k cycles of P^T / dS^T formation (issue- and MUFU-bound with all 16 warps busy), ~1.3-1.9 k cycles of
+// MMAs (64-column MMAs cost ~48 cycles, 128-column ones ~68: tools/ubench/mma_rate.cu) and ~1 k cycles of
+// hand-offs, only partly overlapped because tensor memory holds a single S^T / dP^T tile next to the accumulators.
 struct AttnBwdArgs {
   int B, N, H, D, R;
   int n_t;                      // 128-row tiles per item: 1 or 2 (keys and queries alike)
@@ -585,7 +592,7 @@ __device__ uint32_t tr[3][256];
 __device__ uint8_t tr_id[3][256];
 __device__ int tr_n[3];
 // (the event counter lives in a register of the one tracing thread per role: a trace point is two plain stores)
-#define TR(role, id) do { if (tr_on && ((role) != 1 || warp == BWD_LOADER_WARP) && tr_i < 256) { tr[role][tr_i] = (uint32_t)clock(); tr_id[role][tr_i] = (id); ++tr_i; } } while (0)
+#define TR(role, id) do { if (tr_on && ((role) < 20) && tr_i < 256) { tr[role][tr_i] = (uint32_t)clock(); tr_id[role][tr_i] = (id); ++tr_i; } } while (0)
 #else
 #define TR(role, id) do { } while (0)
 #endif
@@ -601,8 +608,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   float* sDelta = sLse + 256;                             // [256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
   uint64_t* bar_full = bars;      // [3] operand set landed
-  uint64_t* bar_sdp = bars + 3;   // S^T / dP^T of an iteration are in TMEM
-  uint64_t* bar_pds = bars + 5;   // P^T / dS^T written (TMEM + shared memory), 512 arrivals
+  uint64_t* bar_sdp = bars + 3;   // [2] S^T / dP^T of a half (64 query columns) are in TMEM
+  uint64_t* bar_pds = bars + 5;   // [2] P^T / dS^T of a half written (TMEM + shared memory), 256 arrivals
   uint64_t* bar_c = bars + 7;     // every MMA of an iteration (dV, dK, dQ) has retired
   uint64_t* bar_epi = bars + 8;   // accumulators of a key chunk (and dQ at the item's end) read out
   uint64_t* bar_aux = bars + 9;   // lse / delta of an item are in shared memory
@@ -615,13 +622,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef ATTN_TRACE
-  const bool tr_on = (blockIdx.x == 0) && (lane == 0) && (warp == 0 || warp == BWD_LOADER_WARP || warp == BWD_MMA_WARP);
+  const bool tr_on = (blockIdx.x == 0) && (lane == 0) && (warp == 0 || warp == 8 || warp == BWD_MMA_WARP);
   int tr_i = 0;
 #endif
   if (threadIdx.x == 0) {
     for (int i = 0; i < 3; ++i) { ptx::mbar_init(bar_full + i, 1); ptx::mbar_init(bar_free + i, 1); }
-    ptx::mbar_init(bar_sdp, 1);
-    ptx::mbar_init(bar_pds, BWD_COMPUTE_WARPS * 32);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_sdp + i, 1); ptx::mbar_init(bar_pds + i, BWD_COMPUTE_WARPS * 16); }
     ptx::mbar_init(bar_c, 1);
     ptx::mbar_init(bar_kv, 1);
     ptx::mbar_init(bar_staged, BWD_COMPUTE_WARPS * 32);
@@ -706,7 +712,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     struct Iter {
       uint64_t dk_k, dq_k, dv_k, ddo_k;   // K-major descriptors (S^T, dP^T)
       uint64_t ddo_mn, dq_mn, dk_mn;      // MN-major descriptors (dV, dK, dQ)
-      uint32_t id_s, acc_q, acc_k;
+      uint32_t id_s[2], acc_q, acc_k;
+      int w[2];                           // query columns of each half (multiples of 16, 0 = empty half)
       int nq, nk, qt, it;                 // 16-query / 16-key steps of the tile / chunk
     };
     // describes iteration `it` of item index `idx` (rows [0,128) in set (nt idx) % 3, rows [128,256) in the next one of
@@ -729,7 +736,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       r.ddo_mn = ptx::smem_desc_sw128(do_addr, 8192, 1024);
       r.dq_mn = ptx::smem_desc_sw128(q_addr, 8192, 1024);
       r.dk_mn = ptx::smem_desc_sw128(k_addr, 8192, 1024);
-      r.id_s = ptx::idesc_bf16(128, qw, 0, 0);
+      r.w[0] = min(64, qw); r.w[1] = max(0, qw - 64);
+      r.id_s[0] = ptx::idesc_bf16(128, r.w[0], 0, 0);
+      r.id_s[1] = ptx::idesc_bf16(128, max(16, r.w[1]), 0, 0);
       r.nq = qw / 16; r.nk = cw / 16;
       r.acc_q = qt > 0 ? 1u : 0u; r.acc_k = kc > 0 ? 1u : 0u;
       r.qt = qt; r.it = it;
@@ -741,21 +750,29 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     // takes -- while a converged warp keeps the whole schedule in the uniform datapath.
     const uint32_t lead = leader ? 1u : 0u;
     const uint32_t a_sdp = ptx::smem_u32(bar_sdp), a_c = ptx::smem_u32(bar_c), a_kv = ptx::smem_u32(bar_kv);
-    auto issue_a = [&](const Iter& r) {   // S^T = K Q^T, dP^T = V dO^T
+    // S^T[hf] = K Q_hf^T, dP^T[hf] = V dO_hf^T for the 64 query columns of half hf (query rows hf*64.. of the Q / dO
+    // tiles: +8192 bytes = 512 descriptor units).  A 64-wide MMA costs ~48 cycles against ~68 for 128 columns
+    // (tools/ubench/mma_rate.cu), but the halves give the compute warps two independent buffers to alternate on.
+    auto issue_a = [&](const Iter& r, int hf) {
+      if (r.w[hf] > 0) {
 #pragma unroll
-      for (int k = 0; k < HD / 16; ++k) ptx::mma_ss_pred(tmem + T_S0, r.dk_k + 2 * k, r.dq_k + 2 * k, r.id_s, k > 0 ? 1u : 0u, lead);
+        for (int k = 0; k < HD / 16; ++k)
+          ptx::mma_ss_pred(tmem + T_S0 + hf * 64, r.dk_k + 2 * k, r.dq_k + 512 * hf + 2 * k, r.id_s[hf], k > 0 ? 1u : 0u, lead);
 #pragma unroll
-      for (int k = 0; k < HD / 16; ++k) ptx::mma_ss_pred(tmem + T_DP0, r.dv_k + 2 * k, r.ddo_k + 2 * k, r.id_s, k > 0 ? 1u : 0u, lead);
-      ptx::commit_pred(a_sdp, lead);
+        for (int k = 0; k < HD / 16; ++k)
+          ptx::mma_ss_pred(tmem + T_DP0 + hf * 64, r.dv_k + 2 * k, r.ddo_k + 512 * hf + 2 * k, r.id_s[hf], k > 0 ? 1u : 0u, lead);
+      }
+      ptx::commit_pred(a_sdp + 8 * hf, lead);
     };
     const uint32_t id_ts = ptx::idesc_bf16(128, HD, 0, 1);   // A from TMEM, B MN-major
     const uint32_t id_dq = ptx::idesc_bf16(128, HD, 1, 1);   // A, B MN-major
     const uint64_t dds_mn = ptx::smem_desc_sw128(ptx::smem_u32(sDS), 16384, 1024);
-    // dV += P^T dO, dK += dS^T Q: contraction over the tile's queries, 16 per MMA; warpgroup w = ks >> 1 keeps its
-    // packed columns at [32 w, 32 w + 16) of the tile
-    auto issue_c = [&](const Iter& r) {
+    // dV += P^T dO, dK += dS^T Q over the half's queries, 16 per MMA; warpgroup w = ks >> 1 keeps its packed columns
+    // at [32 w, 32 w + 16) of the tile
+    auto issue_c = [&](const Iter& r, int hf) {
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const int ks = hf * 4 + k4;
         if (ks < r.nq) {
           const uint32_t acc = ks > 0 ? 1u : r.acc_q;
           const uint32_t a_col = (ks >> 1) * 32 + (ks & 1) * 8;
@@ -774,10 +791,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     const int total = n_mine * n_iter;
     if (n_mine > 0) {
       Iter cur = make_iter(0, 0);
-      issue_a(cur);
+      issue_a(cur, 0);
+      issue_a(cur, 1);
       int idx = 0;
       for (int gi = 0; gi < total; ++gi) {
-        // ---- the next iteration's descriptors, before the wait ----
+        // ---- the next iteration's descriptors, before the waits ----
         const bool has_next = gi + 1 < total;
         const bool chunk_end = (cur.qt == nt - 1);
         const int cur_it = cur.it, cur_idx = idx;
@@ -786,9 +804,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           if (cur.it == n_iter - 1) { ++idx; nxt = make_iter(idx, 0); }
           else nxt = make_iter(idx, cur.it + 1);
         }
-        // ---- P^T / dS^T ready -> dV, dK partial sums, then S^T / dP^T of the next iteration, then dQ ----
+        // ---- half 0: P^T / dS^T ready -> dV, dK partial sums; S^T / dP^T of the next iteration's half 0 ----
         TR(2, 1);
-        ptx::mbar_wait(bar_pds, gi & 1);
+        ptx::mbar_wait(bar_pds + 0, gi & 1);
         ptx::tc_fence_after();
         TR(2, 3);
         if (cur.qt == 0 && n_epi < n_epi_due) {  // the accumulators of the previous chunk have been read out
@@ -796,15 +814,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           ++n_epi;
           ptx::tc_fence_after();
         }
-        issue_c(cur);
+        issue_c(cur, 0);
+        // (at a key chunk's last query tile every compute warp goes to the read-out first: dK / dV and dQ are finished
+        //  before the next S^T / dP^T are queued)
+        if (has_next && !chunk_end) issue_a(nxt, 0);
+        TR(2, 4);
+        // ---- half 1 ----
+        ptx::mbar_wait(bar_pds + 1, gi & 1);
+        ptx::tc_fence_after();
+        issue_c(cur, 1);
         if (chunk_end) {
           ptx::commit_pred(a_kv, lead);
           ++n_epi_due;  // the compute warps read this chunk's accumulators out next
+          issue_dq(cur);
+          if (has_next) { issue_a(nxt, 0); issue_a(nxt, 1); }
+        } else {
+          if (has_next) issue_a(nxt, 1);
+          issue_dq(cur);
         }
-        TR(2, 4);
-        if (has_next) issue_a(nxt);
         TR(2, 6);
-        issue_dq(cur);
         // ---- operand sets this iteration was the last to read go back to the TMA warp ----
         if (nt == 1) {
           ptx::commit_pred(ptx::smem_u32(bar_free + cur_idx % 3), lead);
@@ -852,9 +880,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           if constexpr (GP) dl[r] += a.dext[(long long)item * a.N + q];
         }
       }
-      TR(1, 20);
+      TR(20, 20);
       if (idx >= 1) ptx::mbar_wait(bar_item, (idx - 1) & 1);  // the previous item no longer reads the buffer
-      TR(1, 21);
+      TR(20, 21);
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         if (tl + r * BWD_LOADER_THREADS < 256) {
@@ -863,7 +891,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         }
       }
       ptx::mbar_arrive(bar_aux);
-      TR(1, 22);
+      TR(20, 22);
     }
   } else {
     // =========================== compute warps (thread = key row) ===========================
@@ -892,7 +920,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         int n_c = min(2, max(0, (qw - col0) / 16));
         if (kc * 128 + quarter * 32 >= a.N) n_c = 0;
         TR(hf, 0);
-        ptx::mbar_wait(bar_sdp, g & 1);
+        ptx::mbar_wait(bar_sdp + hf, g & 1);
         ptx::tc_fence_after();
         TR(hf, 2);
         // chunk by chunk (32 live accumulator registers, not 64): load, form P^T / dS^T, pack, park both in tensor memory
@@ -971,7 +999,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         ptx::tmem_st_wait();
         ptx::fence_async_shared();
         ptx::tc_fence_before();
-        ptx::mbar_arrive(bar_pds);
+        ptx::mbar_arrive(bar_pds + hf);
         TR(hf, 8);
         if (it == n_iter - 1) ptx::mbar_arrive(bar_item);   // lse / delta of this item have been read for the last time
         if (qt == nt - 1) {
@@ -1024,7 +1052,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   ptx::tc_fence_before();
   __syncthreads();
 #ifdef ATTN_TRACE
-  if (tr_on) tr_n[warp == 0 ? 0 : warp == BWD_LOADER_WARP ? 1 : 2] = tr_i;
+  if (tr_on) tr_n[warp == 0 ? 0 : warp == 8 ? 1 : 2] = tr_i;
   __threadfence();
   __syncthreads();
   if (blockIdx.x == 0 && threadIdx.x == 0) {

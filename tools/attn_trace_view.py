@@ -19,7 +19,7 @@ names = {0: {0: "h0 wait sdp", 2: "h0 got sdp", 4: "h0 computed", 6: "h0 got bar
          2: {1: "P wait pds0", 3: "P got pds0", 4: "P issued C", 6: "P issued A(next)", 5: "P issued dQ"}}
 ev = sorted(((c - t0) & 0xFFFFFFFF, w, i) for w in L for i, c in L[w])
 for t, w, i in ev[:n_show]:
-    print(f"{t:8d}  {'            ' * w}{names[w][i]}")
+    print(f"{t:8d}  {'            ' * w}{names[w].get(i, names[0].get(i, str(i)).replace('h0', 'h1'))}")
 print("span", ev[-1][0])
 for w in L:
     seq = [(i, (c - t0) & 0xFFFFFFFF) for i, c in L[w]]
