@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define ODEVIT_ABI_VERSION 6
+#define ODEVIT_ABI_VERSION 7
 
 typedef struct CUstream_st* odevit_stream_t; /* == cudaStream_t */
 
@@ -84,17 +84,22 @@ typedef struct {
   int32_t variant;     /* odevit_variant                                                      */
   int32_t precision;   /* odevit_precision                                                    */
   float scaler;        /* ViT_ODEFunc.scaler (emulate_depth if time_interval == 1 else 1)     */
-  /* Training-mode dropout (0 = off; PARALLEL / PARALLEL_L2): on the attention map (the returned P is
-   * post-dropout), after out_proj, and after GELU + after fc2 (ode_transformer_gpt.py:56, :61, :196-199,
-   * :217-231).  Masks are re-drawn at every field evaluation from a counter-based generator keyed
-   * by (seed, evaluation index, site, element): the reverse sweep regenerates them, nothing is stored.
-   * Not bit-compatible with PyTorch's Philox stream. */
+  /* Training-mode dropout (0 = off): on the attention map (the returned P is post-dropout), after out_proj, and
+   * after GELU + after fc2 (ode_transformer_gpt.py:56, :61, :196-199, :217-231; MACARON: after GELU and after
+   * ffn.3 of BOTH half steps with separate masks, on the attention map, after out_proj -- macaron.py:58-61, :88-94).
+   * Masks are re-drawn at every field evaluation from a counter-based generator keyed by (seed, evaluation
+   * index, site, element): the reverse sweep regenerates them, nothing is stored.  Not bit-compatible with
+   * PyTorch's Philox stream.
+   * The 64-bit seed is either given here (drop_seed_lo/hi) or READ FROM DEVICE MEMORY at kernel time
+   * (drop_seed_dev != NULL: two uint32, lo then hi): a step captured in a CUDA graph then draws new masks at every
+   * replay when something on the device advances the seed (odevit_drop_state_advance).  The forward and the
+   * backward call of one step must see the same value. */
   float attn_drop;
   float proj_drop;
   float mlp_drop;
   uint32_t drop_seed_lo;
   uint32_t drop_seed_hi;
-  int32_t reserved[2];
+  const uint32_t* drop_seed_dev; /* device pointer or NULL */
 } odevit_desc;
 
 /* Weights of the vector field, fp32 device pointers in state_dict layout; unused = NULL.
@@ -247,6 +252,11 @@ int odevit_encoder_fwd(const odevit_desc* desc, const odevit_weights* layers, in
  * evaluations (tiny).  1 <= tokens <= 1024, 0 <= k <= tokens. */
 int odevit_jasmin_rowmax(const float* p_maps, int64_t n_slices, int32_t tokens, int32_t k, float* out,
                          odevit_stream_t stream);
+
+/* Advances a device-resident dropout state by one step (a 1-thread kernel, capturable in a CUDA graph):
+ *   state[0] base seed (set once by the caller), state[1] step counter += 1, state[2] = the seed of this step
+ *   (a 64-bit mix of base and counter; pass &state[2] as odevit_desc.drop_seed_dev, or a copy of it). */
+int odevit_drop_state_advance(uint64_t* state, odevit_stream_t stream);
 
 /* Number of kernels the library launched (process-wide, all threads) since the last reset (bench.py's
  * gpu_launches claim is counted, not estimated). */

@@ -134,11 +134,19 @@ int make_plan(const odevit_desc* desc, Plan* p) {
   p->seed_lo = desc->drop_seed_lo; p->seed_hi = desc->drop_seed_hi;
   for (float q : {p->p_attn, p->p_proj, p->p_mlp})
     if (!(q >= 0.f && q < 1.f)) return set_error(ODEVIT_ERR_INVALID_ARG, "dropout probability %g outside [0, 1)", q);
-  p->split_out = (p->p_proj > 0.f || p->p_mlp > 0.f);
-  if (p->variant == ODEVIT_FIELD_MACARON && (p->split_out || p->p_attn > 0.f))
-    return set_error(ODEVIT_ERR_UNSUPPORTED, "dropout > 0 is not built for the MACARON field");
+  p->any_drop = (p->p_attn > 0.f || p->p_proj > 0.f || p->p_mlp > 0.f);
+  p->seed_dev = p->any_drop ? desc->drop_seed_dev : nullptr;
+  p->drop_keys = nullptr;
+  // PARALLEL: out-proj and fc2 share one GEMM unless their outputs take different masks.  MACARON runs them as
+  // separate GEMMs anyway.
+  p->split_out = (p->variant != ODEVIT_FIELD_MACARON) && (p->p_proj > 0.f || p->p_mlp > 0.f);
   p->BHNN = (long long)p->B * p->H * p->N * p->N;
   return 0;
+}
+
+// Device-seeded dropout: the key table sits at the head of every workspace layout.
+uint32_t* take_drop_keys(const Plan& p, Arena& a) {
+  return p.seed_dev ? reinterpret_cast<uint32_t*>(a.take((size_t)kDropKeyEvals * DS_SITES * 4)) : nullptr;
 }
 
 WeightBufs take_weights(const Plan& p, Arena& a) {
@@ -178,6 +186,7 @@ StageCtx take_ctx(const Plan& p, Arena& a, bool with_hpre) {
 }
 
 struct FwdBufs {
+  uint32_t* drop_keys;
   WeightBufs w;
   StageCtx ctx;
   float* P;
@@ -190,6 +199,7 @@ struct FwdBufs {
 };
 FwdBufs layout_fwd(const Plan& p, Arena& a, int S) {
   FwdBufs f;
+  f.drop_keys = take_drop_keys(p, a);
   f.w = take_weights(p, a);
   f.ctx = take_ctx(p, a, false);
   f.P = a.f32(p.BHNN);
@@ -208,6 +218,7 @@ BwdBufs layout_bwd(const Plan& p, Arena& a, int S) {
   const size_t MD = (size_t)p.M * p.D;
   const size_t R = 3 * (size_t)p.D + p.hid, K2 = (size_t)p.D + p.hid;
   BwdBufs b;
+  b.drop_keys = take_drop_keys(p, a);
   b.w = take_weights(p, a);
   for (int i = 0; i < 4; ++i) b.ctx[i] = (i < S) ? take_ctx(p, a, true) : StageCtx{};
   b.P = a.f32(p.BHNN);
@@ -332,8 +343,19 @@ Drop make_drop(const Plan& p, int site, long long e) {
   d.thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
   if (d.thresh == 0) d.thresh = 1;
   d.scale = 1.f / (1.f - q);
-  d.key = drop_mix(p.seed_lo ^ drop_mix(p.seed_hi ^ 0x632BE5ABu) ^ ((uint32_t)(e * 4 + site + 1) * 0x27D4EB2Fu));
+  if (p.drop_keys) d.key_ptr = p.drop_keys + e * DS_SITES + site;   // resolved on the device from the resident seed
+  else d.key = drop_site_key(p.seed_lo, p.seed_hi, e, site);
   return d;
+}
+
+// Device-seeded dropout: the key table (head of every workspace layout) is filled at the start of the call.
+static int prepare_drop_keys(Plan& p, uint32_t* table, long long n_evals, cudaStream_t s) {
+  if (!p.seed_dev) return 0;
+  if (n_evals > kDropKeyEvals)
+    return set_error(ODEVIT_ERR_UNSUPPORTED, "device-seeded dropout addresses %d field evaluations per call, %lld asked", kDropKeyEvals, n_evals);
+  ODV_TRY(check_device_ptr(p.seed_dev, "drop_seed_dev"));
+  p.drop_keys = table;
+  return resolve_drop_keys(p.seed_dev, table, (int)(n_evals > 0 ? n_evals : 1) * DS_SITES, s);
 }
 
 int gemm(const Plan& p, const GemmArgs& g, cudaStream_t s) {
@@ -498,7 +520,7 @@ namespace {
 int eval_forward(const Plan& p, const WeightBufs& wb, const StageCtx& c, const float* u, float* P,
                  float* p_copy, float* sq, float* tmp, long long e, const Epi* rk, cudaStream_t s,
                  float* jas_out = nullptr, int jas_k = 0) {
-  if (p.variant == ODEVIT_FIELD_MACARON) return macaron_forward(p, wb, c, u, P, rk, s);
+  if (p.variant == ODEVIT_FIELD_MACARON) return macaron_forward(p, wb, c, u, P, rk, e, s);
   const int D = p.D, hid = p.hid, R = 3 * D + hid, K2 = D + hid;
   ODV_TRY(center_rows(u, c.xc, p.act, nullptr, 0.f, p.M, D, s));
   {
@@ -594,7 +616,7 @@ int eval_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b,
              bool need_c2, const odevit_weight_grads* gw, long long ev, const Epi& mu_epi, cudaStream_t s) {
   if (p.variant == ODEVIT_FIELD_MACARON) {
     if (g_p) return set_error(ODEVIT_ERR_UNSUPPORTED, "MACARON has no attention-map output (macaron.py:60-65)");
-    return macaron_vjp(p, wb, c, b, gw, mu_epi, s);
+    return macaron_vjp(p, wb, c, b, gw, mu_epi, ev, s);
   }
   const int D = p.D, hid = p.hid, R = 3 * D + hid, K2 = D + hid;
   const size_t e = dtype_size(p.act);
@@ -738,6 +760,11 @@ const char* odevit_build_info(void) {
 
 const char* odevit_last_error_string(void) { return g_err; }
 
+int odevit_drop_state_advance(uint64_t* state, odevit_stream_t stream) {
+  ODV_TRY(check_device_ptr(state, "state"));
+  return drop_state_advance(reinterpret_cast<unsigned long long*>(state), reinterpret_cast<cudaStream_t>(stream));
+}
+
 int64_t odevit_launch_count(void) { return g_launches.load(); }
 void odevit_reset_launch_count(void) { g_launches.store(0); }
 
@@ -846,7 +873,8 @@ int encoder_plan(const odevit_desc* desc, Plan* p) {
   ODV_TRY(make_plan(desc, p));
   p->variant = ODEVIT_FIELD_MACARON;   // the four weight blocks unfolded, biases on
   p->dd_type = DT_F32;
-  if (p->split_out || p->p_attn > 0.f) return set_error(ODEVIT_ERR_UNSUPPORTED, "the encoder stack is inference-only: dropout must be 0");
+  if (p->any_drop) return set_error(ODEVIT_ERR_UNSUPPORTED, "the encoder stack is inference-only: dropout must be 0");
+  p->split_out = false;
   return 0;
 }
 }  // namespace
@@ -895,6 +923,7 @@ int odevit_field_fwd(const odevit_desc* desc, const odevit_weights* w, const flo
   FwdBufs f = layout_fwd(p, a, 1);
   ODV_TRY(check_ws(workspace, workspace_bytes, a.off));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  ODV_TRY(prepare_drop_keys(p, f.drop_keys, 1, s));
   ODV_TRY(prepare_weights(p, w, f.w, s));
   Epi rk;
   rk.out = dx;
@@ -942,6 +971,7 @@ int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
   ODV_TRY(check_ws(workspace, workspace_bytes, a.off));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const size_t MD = (size_t)p.M * p.D;
+  ODV_TRY(prepare_drop_keys(p, f.drop_keys, (long long)(n_grid - 1) * tb->S, s));
   ODV_TRY(prepare_weights(p, w, f.w, s));
 
   const float* y = x0;
@@ -1013,6 +1043,7 @@ int odevit_solve_bwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
   const size_t MD = (size_t)p.M * p.D;
   const int S = tb->S;
   const bool need_c2 = wants_c2(gw);
+  ODV_TRY(prepare_drop_keys(p, b.drop_keys, (long long)(n_grid - 1) * S, s));
   ODV_TRY(prepare_weights(p, w, b.w, s));
   ODV_CUDA(cudaMemsetAsync(b.G1, 0, b.acc_bytes, s));
 
@@ -1183,6 +1214,7 @@ int odevit_field_bwd(const odevit_desc* desc, const odevit_weights* w, const flo
   BwdBufs b = layout_bwd(p, a, 1);
   ODV_TRY(check_ws(workspace, workspace_bytes, a.off));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  ODV_TRY(prepare_drop_keys(p, b.drop_keys, 1, s));
   ODV_TRY(prepare_weights(p, w, b.w, s));
   ODV_CUDA(cudaMemsetAsync(b.G1, 0, b.acc_bytes, s));
   ODV_TRY(eval_forward(p, b.w, b.ctx[0], x, b.P, nullptr, b.sq, b.tmp, 0, nullptr, s));

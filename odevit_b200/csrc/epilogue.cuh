@@ -32,9 +32,15 @@ __host__ __device__ __forceinline__ uint32_t drop_mix(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
   return x;
 }
+// key of dropout site `site` of field evaluation `e` under the 64-bit seed (lo, hi) -- one formula for the host path
+// (api.cu::make_drop) and the device-seeded path (rows.cu::resolve_drop_keys)
+__host__ __device__ __forceinline__ uint32_t drop_site_key(uint32_t lo, uint32_t hi, long long e, int site) {
+  return drop_mix(lo ^ drop_mix(hi ^ 0x632BE5ABu) ^ ((uint32_t)(e * DS_SITES + site + 1) * 0x27D4EB2Fu));
+}
 // multiplier of element (r, c): 0 (dropped) or 1/(1-p)
 __device__ __forceinline__ float drop_factor(const Drop& d, uint32_t r, uint32_t c) {
-  return drop_mix((r * 0x9E3779B1U) ^ (c * 0x85EBCA77U) ^ d.key) >= d.thresh ? d.scale : 0.f;
+  const uint32_t key = d.key_ptr ? __ldg(d.key_ptr) : d.key;
+  return drop_mix((r * 0x9E3779B1U) ^ (c * 0x85EBCA77U) ^ key) >= d.thresh ? d.scale : 0.f;
 }
 
 template <int EPI, bool ATOMIC>

@@ -24,8 +24,8 @@ constexpr float kLnEps = 1e-5f;  // nn.LayerNorm default (macaron.py:80-82)
 
 inline void* off(void* p, size_t elems, int type) { return reinterpret_cast<char*>(p) + elems * dtype_size(type); }
 
-// h = GELU(n @ W1^T + b1)  (hpre kept for the VJP)
-int ffn_up(const Plan& p, const WeightBufs& wb, const void* n, void* h, long long ld_h, void* hpre, cudaStream_t s) {
+// h = drop(GELU(n @ W1^T + b1))  (hpre kept for the VJP)
+int ffn_up(const Plan& p, const WeightBufs& wb, const void* n, void* h, long long ld_h, void* hpre, Drop drop, cudaStream_t s) {
   const int D = p.D, hid = p.hid;
   GemmArgs g;
   g.M = p.M; g.N = hid; g.K = D;
@@ -38,6 +38,7 @@ int ffn_up(const Plan& p, const WeightBufs& wb, const void* n, void* h, long lon
   g.epi.out2 = h; g.epi.ld_out2 = ld_h;
   g.epi.out3 = hpre; g.epi.ld_out3 = hid;
   g.epi.aux_type = p.act;
+  g.epi.drop = drop;   // macaron.py:88-94: Dropout(mlp_drop) after GELU
   return gemm(p, g, s);
 }
 
@@ -58,7 +59,7 @@ int proj_down(const Plan& p, const void* A, long long lda, int K, const void* W,
 }  // namespace
 
 int macaron_forward(const Plan& p, const WeightBufs& wb, const StageCtx& c, const float* u, float* P,
-                    const Epi* rk, cudaStream_t s) {
+                    const Epi* rk, long long ev, cudaStream_t s) {
   const int D = p.D, hid = p.hid, K2 = D + hid;
   const odevit_weights* w = wb.user;
   const size_t MD = (size_t)p.M * D;
@@ -68,10 +69,11 @@ int macaron_forward(const Plan& p, const WeightBufs& wb, const StageCtx& c, cons
     return set_error(ODEVIT_ERR_CUDA, "macaron_forward: stage-input copy failed");
   // ---- first half-FFN ----
   ODV_TRY(ln_rows(u, w->norm_a_w, w->norm_a_b, c.xc, p.act, kLnEps, p.M, D, s));
-  ODV_TRY(ffn_up(p, wb, c.xc, h1, K2, c.hpre, s));
+  ODV_TRY(ffn_up(p, wb, c.xc, h1, K2, c.hpre, make_drop(p, DS_MLP_H, ev), s));
   {
     Epi e;
     e.bias = w->fc2_b; e.alpha = 1.f; e.dev_scale = w->res_scale;
+    e.drop = make_drop(p, DS_MLP_OUT, ev);   // Dropout(mlp_drop) after ffn.3, before the residual
     e.c_new = 0.5f; e.y = u; e.y_coef = 1.f; e.out = c.x1;
     ODV_TRY(proj_down(p, h1, K2, hid, off(wb.w2cat, D, p.act), K2, e, s));
   }
@@ -88,20 +90,22 @@ int macaron_forward(const Plan& p, const WeightBufs& wb, const StageCtx& c, cons
     g.epi.out = c.qkv; g.epi.out_type = p.act; g.epi.ld_out = 3 * D;
     ODV_TRY(gemm(p, g, s));
   }
-  ODV_TRY(attention_forward(p, c.qkv, c.oh, K2, P, nullptr, c.lse, nullptr, Drop{}, s));
+  ODV_TRY(attention_forward(p, c.qkv, c.oh, K2, P, nullptr, c.lse, nullptr, make_drop(p, DS_ATTN, ev), s));
   {
     Epi e;
     e.bias = w->out_proj_b; e.alpha = 1.f; e.dev_scale = w->res_scale;
+    e.drop = make_drop(p, DS_PROJ, ev);      // macaron.py:58-61: proj_drop after the out-projection
     e.c_new = 1.f; e.y = c.x1; e.y_coef = 1.f; e.out = c.x2;
     ODV_TRY(proj_down(p, c.oh, K2, D, wb.w2cat, K2, e, s));
   }
   // ---- second half-FFN ----
   ODV_TRY(ln_rows(c.x2, w->norm_c_w, w->norm_c_b, c.n3, p.act, kLnEps, p.M, D, s));
-  ODV_TRY(ffn_up(p, wb, c.n3, c.h3, hid, c.hpre3, s));
+  ODV_TRY(ffn_up(p, wb, c.n3, c.h3, hid, c.hpre3, make_drop(p, DS_MLP_H2, ev), s));
   if (rk) {
-    // k = scaler * (x2 + 1/2 rs (h3 W2^T + b2)), then the caller's stage combine on k
+    // k = scaler * (x2 + 1/2 rs drop(h3 W2^T + b2)), then the caller's stage combine on k
     Epi e = *rk;
     e.bias = w->fc2_b; e.alpha = 0.5f * p.scaler; e.dev_scale = w->res_scale;
+    e.drop = make_drop(p, DS_MLP_OUT2, ev);
     e.resid = c.x2; e.resid_coef = p.scaler;
     ODV_TRY(proj_down(p, c.h3, hid, hid, off(wb.w2cat, D, p.act), K2, e, s));
   }
@@ -153,7 +157,7 @@ int encoder_forward(const Plan& p, const WeightBufs* layers, int n_layers, float
     }
     // ---- MLP block ----
     ODV_TRY(ln_rows(c.x1, w->norm_b_w, w->norm_b_b, c.xc, p.act, ln_eps, p.M, D, s));
-    ODV_TRY(ffn_up(p, wb, c.xc, h1, K2, nullptr, s));
+    ODV_TRY(ffn_up(p, wb, c.xc, h1, K2, nullptr, Drop{}, s));
     {
       Epi e;
       e.bias = w->fc2_b; e.alpha = 1.f;
@@ -170,10 +174,12 @@ namespace {
 // One half-FFN branch of the VJP.  In: b.ddc = cast(1/2 g) [M,D] (act).  Out: b.dn = cotangent of
 // the LayerNorm output feeding this branch (fp32 [M,D]); G1 / c1 (fc1 rows) and G2 / c3 accumulate.
 int ffn_vjp(const Plan& p, const WeightBufs& wb, BwdBufs& b, const void* n, const void* h, long long ld_h,
-            const void* hpre, cudaStream_t s) {
+            const void* hpre, Drop drop_h, Drop drop_out, cudaStream_t s) {
   const int D = p.D, hid = p.hid, R = 3 * D + hid, K2 = D + hid;
   void* dh = off(b.dz, 0, p.act);  // [M, hid] scratch inside dz ([M, R])
-  {  // dh = rs * (ddc @ W2) o GELU'(hpre)
+  // the branch output went through drop_out before the residual: its cotangent is ddc o mask
+  if (drop_out.thresh) ODV_TRY(drop_rows_inplace(b.ddc, p.act, drop_out, p.M, D, s));
+  {  // dh = rs * (ddc @ W2) o mask_h o GELU'(hpre)
     GemmArgs g;
     g.M = p.M; g.N = hid; g.K = D;
     g.A = b.ddc; g.a_type = p.act; g.a_rs = D; g.a_cs = 1;
@@ -184,9 +190,10 @@ int ffn_vjp(const Plan& p, const WeightBufs& wb, BwdBufs& b, const void* n, cons
     g.epi.out2 = dh; g.epi.ld_out2 = hid;
     g.epi.aux = hpre; g.epi.ld_aux = hid; g.epi.aux_type = p.act;
     g.epi.dev_scale = wb.user->res_scale;
+    g.epi.drop = drop_h;
     ODV_TRY(gemm(p, g, s));
   }
-  {  // G2[:, D:] += ddc^T @ h      (the rs = 1 sum)
+  {  // G2[:, D:] += ddc^T @ h      (the rs = 1 sum; h as the forward left it: after its dropout)
     GemmArgs g;
     g.M = D; g.N = hid; g.K = p.M;
     g.A = b.ddc; g.a_type = p.act; g.a_rs = 1; g.a_cs = D;
@@ -224,7 +231,7 @@ int ffn_vjp(const Plan& p, const WeightBufs& wb, BwdBufs& b, const void* n, cons
 
 // In: b.dd = g3 = scaler * lambda (fp32 [M,D], cotangent of x3).  Out: mu = J(u)^T lambda through mu_epi.
 int macaron_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b, const odevit_weight_grads* gw,
-                const Epi& mu_epi, cudaStream_t s) {
+                const Epi& mu_epi, long long ev, cudaStream_t s) {
   const int D = p.D, hid = p.hid, R = 3 * D + hid, K2 = D + hid;
   const odevit_weights* w = wb.user;
   float* g = reinterpret_cast<float*>(b.dd);
@@ -236,7 +243,7 @@ int macaron_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs&
     ODV_TRY(vjp_combine(c0, p.M, D, s));
   }
   // ---- second half-FFN:  g2 = g3 + LN3'(x2)^T dn3 ----
-  ODV_TRY(ffn_vjp(p, wb, b, c.n3, c.h3, hid, c.hpre3, s));
+  ODV_TRY(ffn_vjp(p, wb, b, c.n3, c.h3, hid, c.hpre3, make_drop(p, DS_MLP_H2, ev), make_drop(p, DS_MLP_OUT2, ev), s));
   {
     LnBwdArgs a;
     a.x = c.x2; a.dn = b.dn; a.w = w->norm_c_w; a.g_in = g; a.g_out = g;
@@ -245,6 +252,10 @@ int macaron_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs&
     ODV_TRY(ln_bwd_rows(a, p.M, D, s));
   }
   // ---- attention:  g1 = g2 + LN2'(x1)^T dn2 ----
+  {
+    const Drop dp = make_drop(p, DS_PROJ, ev);   // the out-projection's output went through proj_drop
+    if (dp.thresh) ODV_TRY(drop_rows_inplace(b.ddc, p.act, dp, p.M, D, s));
+  }
   {  // dO = rs * (ddc @ Wo)
     GemmArgs gm;
     gm.M = p.M; gm.N = D; gm.K = D;
@@ -267,7 +278,7 @@ int macaron_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs&
     ODV_TRY(gemm(p, gm, s));
   }
   ODV_TRY(colsum_accum(b.ddc, p.act, D, p.M, D, b.c2, s));
-  ODV_TRY(attention_vjp(p, c.qkv, c.oh, K2, c.lse, b, nullptr, b.dz, R, Drop{}, s));  // dq|dk|dv -> dz[:, :3D] (ld R)
+  ODV_TRY(attention_vjp(p, c.qkv, c.oh, K2, c.lse, b, nullptr, b.dz, R, make_drop(p, DS_ATTN, ev), s));  // dq|dk|dv -> dz[:, :3D] (ld R)
   {  // dn2 = dz[:, :3D] @ W_in (q rows scaled)
     GemmArgs gm;
     gm.M = p.M; gm.N = D; gm.K = 3 * D;
@@ -297,7 +308,7 @@ int macaron_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs&
     ODV_TRY(ln_bwd_rows(a, p.M, D, s));
   }
   // ---- first half-FFN:  g0 = g1 + LN1'(x0)^T dn1 ----
-  ODV_TRY(ffn_vjp(p, wb, b, c.xc, h1, K2, c.hpre, s));
+  ODV_TRY(ffn_vjp(p, wb, b, c.xc, h1, K2, c.hpre, make_drop(p, DS_MLP_H, ev), make_drop(p, DS_MLP_OUT, ev), s));
   {
     LnBwdArgs a;
     a.x = c.x0; a.dn = b.dn; a.w = w->norm_a_w; a.g_in = g; a.g_out = g;

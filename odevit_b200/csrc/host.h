@@ -14,6 +14,9 @@ struct Plan {
   // training-mode dropout (0 = off) and the per-call seed of the mask generator
   float p_attn, p_proj, p_mlp;
   uint32_t seed_lo, seed_hi;
+  const uint32_t* seed_dev;   // device-resident seed (or null): keys come from `drop_keys`
+  uint32_t* drop_keys;        // [kDropKeyEvals * DS_SITES] key table in the workspace (device seed only)
+  bool any_drop;
   bool split_out;   // proj / mlp dropout on: out-proj and fc2 run as two GEMMs (their outputs take different masks)
 };
 // mask of dropout site `site` in field evaluation `e` (e = step * stages + stage)
@@ -54,6 +57,7 @@ struct StageCtx {
 };
 
 struct BwdBufs {
+  uint32_t* drop_keys;   // device-seeded dropout: key table (head of the workspace) or null
   WeightBufs w;
   StageCtx ctx[4];
   float *P, *dP;
@@ -96,9 +100,9 @@ int solve_resident(const Plan& p, const WeightBufs& wb, int S, const float (*ta)
 
 // MACARON field (field_macaron.cu)
 int macaron_forward(const Plan& p, const WeightBufs& wb, const StageCtx& c, const float* u, float* P,
-                    const Epi* rk, cudaStream_t s);
+                    const Epi* rk, long long e, cudaStream_t s);
 int macaron_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b,
-                const odevit_weight_grads* gw, const Epi& mu_epi, cudaStream_t s);
+                const odevit_weight_grads* gw, const Epi& mu_epi, long long e, cudaStream_t s);
 
 // Pre-LN encoder stack, forward only (field_macaron.cu): the distillation teacher
 int encoder_forward(const Plan& p, const WeightBufs* layers, int n_layers, float ln_eps, const float* x0, float* hidden,

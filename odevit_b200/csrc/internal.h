@@ -104,12 +104,17 @@ enum EpiMode : int {
 
 // One dropout site of one field evaluation: element (r, c) is kept iff hash(key, r, c) >= thresh and then
 // multiplied by scale = 1/(1-p).  thresh == 0: no dropout.
+// key_ptr != null: the key is read from device memory (a table the library fills from a device-resident seed at the
+// start of the call, rows.cu::resolve_drop_keys) instead of being formed on the host.
 struct Drop {
   uint32_t key = 0;
   uint32_t thresh = 0;
   float scale = 1.f;
+  const uint32_t* key_ptr = nullptr;
 };
-enum DropSite : int { DS_ATTN = 0, DS_PROJ = 1, DS_MLP_H = 2, DS_MLP_OUT = 3 };
+// sites of one field evaluation (MACARON: the second half-FFN has its own two)
+enum DropSite : int { DS_ATTN = 0, DS_PROJ = 1, DS_MLP_H = 2, DS_MLP_OUT = 3, DS_MLP_H2 = 4, DS_MLP_OUT2 = 5, DS_SITES = 8 };
+constexpr int kDropKeyEvals = 1024;   // evaluations a device-seeded call can address (key table: 32 KB of workspace)
 
 struct Epi {
   float alpha = 1.f;
@@ -220,6 +225,11 @@ int jasmin_rowmax(const float* P, long long n_slices, int N, int k, float* out, 
 int drop_pair_rows(const void* x, void* out1, void* out2, int type, Drop d1, Drop d2, int rows, int D, cudaStream_t s);
 // p[r, c] = keep(r, c) ? p[r, c] * scale : 0   (fp32 [rows, n]; the attention map of the CUDA-core path)
 int drop_inplace_f32(float* p, float* copy_to, Drop d, long long rows, int n, cudaStream_t s);
+// x <- x o mask(d) in place on an [rows, D] activation-typed buffer
+int drop_rows_inplace(void* x, int type, Drop d, int rows, int D, cudaStream_t s);
+// table[i] = key of (evaluation i / DS_SITES, site i % DS_SITES) from the 64-bit seed at seed_dev
+int resolve_drop_keys(const uint32_t* seed_dev, uint32_t* table, int n, cudaStream_t s);
+int drop_state_advance(unsigned long long* state, cudaStream_t s);
 
 // y[i] += a * x[i]
 int axpy_f32(float* y, const float* x, float a, long long n, cudaStream_t s);

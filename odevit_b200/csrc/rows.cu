@@ -248,6 +248,28 @@ __global__ void __launch_bounds__(256) drop_pair_kernel(const void* x, void* out
   }
 }
 
+__global__ void __launch_bounds__(256) drop_rows_inplace_kernel(void* x, int type, Drop d, long long n, int D) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride)
+    store_elem(x, i, type, load_elem_rw(x, i, type) * drop_factor(d, (uint32_t)(i / D), (uint32_t)(i % D)));
+}
+
+__global__ void resolve_drop_keys_kernel(const uint32_t* __restrict__ seed, uint32_t* __restrict__ table, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) table[i] = drop_site_key(seed[0], seed[1], i / DS_SITES, i % DS_SITES);
+}
+
+// state[0] base seed, state[1] step counter, state[2] the seed of the current step (splitmix64 of base + counter)
+__global__ void drop_state_advance_kernel(unsigned long long* state) {
+  const unsigned long long c = state[1] + 1ull;
+  unsigned long long z = state[0] + c * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  state[1] = c;
+  state[2] = z ^ (z >> 31);
+}
+
 __global__ void __launch_bounds__(256) drop_inplace_kernel(float* p, float* copy_to, Drop d, long long total, int n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -844,6 +866,27 @@ int drop_pair_rows(const void* x, void* out1, void* out2, int type, Drop d1, Dro
   const long long n = (long long)rows * D;
   const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
   drop_pair_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(x, out1, out2, type, d1, d2, n, D);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int drop_rows_inplace(void* x, int type, Drop d, int rows, int D, cudaStream_t s) {
+  ProfScope prof(KC_COMBINE, s);
+  const long long n = (long long)rows * D;
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  drop_rows_inplace_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(x, type, d, n, D);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int resolve_drop_keys(const uint32_t* seed_dev, uint32_t* table, int n, cudaStream_t s) {
+  resolve_drop_keys_kernel<<<(n + 255) / 256, 256, 0, s>>>(seed_dev, table, n);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
+int drop_state_advance(unsigned long long* state, cudaStream_t s) {
+  drop_state_advance_kernel<<<1, 1, 0, s>>>(state);
   ODV_LAUNCH_CHECK();
   return 0;
 }

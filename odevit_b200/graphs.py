@@ -12,9 +12,9 @@ the fp32 atomics of the weight-gradient accumulation.
         loss = stepper(px, labels)          # device tensor; .item() it when you need the number
 
 Restrictions: fixed input shapes; no data-dependent Python control flow in the step (the reference's step has
-none: train.py:40-67); dropout masks are keyed by a per-call seed drawn on the host, so a captured step would
-replay the SAME masks -- models with dropout > 0 are refused; the optimizer must be capturable
-(`torch.optim.AdamW(..., fused=True, capturable=True)`)."""
+none: train.py:40-67); the optimizer must be capturable (`torch.optim.AdamW(..., fused=True, capturable=True)`) when
+it is part of the graph.  Dropout (the shipped YAMLs use 0.1-0.3) works under replay: the mask seed lives in device
+memory and a 1-thread kernel inside the captured step advances it (ops.DropState), so every replay draws new masks."""
 from __future__ import annotations
 
 from typing import Callable, Optional, Sequence
@@ -32,10 +32,11 @@ class GraphedTrainStep:
         forward + backward only and runs grad_hook / clipping / optimizer.step() eagerly after each replay (a
         few dozen launches): required with a grad_hook that issues NCCL collectives -- capturing them hung a
         2-GPU run here -- and it lifts the `capturable=True` requirement on the optimizer."""
+        # dropout under replay: the mask seed must live in device memory BEFORE the capture starts (ops.DropState is
+        # created by the warm-up steps below; vit_ode._next_drop_seed reads this flag)
         for m in model.modules():
-            drops = getattr(m, "_drops", None)       # (attn_drop, proj_drop, mlp_drop) of the ODE blocks
-            if drops is not None and any(float(d) > 0.0 for d in drops) and model.training:
-                raise ValueError("GraphedTrainStep: dropout > 0 would replay one mask set every step")
+            if getattr(m, "_drops", None) is not None:
+                m.device_seed = True
         # `block.attentions` (ode_transformer_gpt.py:276) keeps the last forward's map WITH its autograd graph, hence
         # the AccumulateGrad nodes of earlier eager steps on the legacy stream: a capture must not depend on that stream
         for m in model.modules():

@@ -19,7 +19,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib, ops
-from .vit_ode import DEFAULT_PRECISION, _check_no_dropout
+from .vit_ode import DEFAULT_PRECISION, _next_drop_seed
 
 
 class PatchEmbed(nn.Module):
@@ -91,9 +91,15 @@ class ParallelAttentionMLP(nn.Module):
         self.precision = DEFAULT_PRECISION
 
     def field_spec(self, scaler: float) -> ops.FieldSpec:
+        # training-mode dropout (macaron.py:58-61, :88-94): attention map, after out_proj, after GELU and after ffn.3 of
+        # both half steps (each with its own mask), re-drawn at every field evaluation
+        attn_drop, proj_drop, mlp_drop = self._drops if self.training else (0.0, 0.0, 0.0)
+        seed_kw = _next_drop_seed(self) if (attn_drop > 0 or proj_drop > 0 or mlp_drop > 0) else {}
         return ops.FieldSpec(dim=self.dim, heads=self.num_heads, hidden=self.ffn[0].weight.shape[0],
                              scaler=float(scaler), variant=_lib.FIELD_MACARON, precision=self.precision,
-                             backward=getattr(self, "backward_mode", "auto"))
+                             backward=getattr(self, "backward_mode", "auto"),
+                             attn_drop=float(attn_drop), proj_drop=float(proj_drop), mlp_drop=float(mlp_drop),
+                             **seed_kw)
 
     def field_weights(self) -> Dict[str, Optional[torch.Tensor]]:
         mha = self.attn.mha
@@ -109,7 +115,6 @@ class ParallelAttentionMLP(nn.Module):
         }
 
     def forward(self, x: torch.Tensor, t: Optional[torch.Tensor] = None) -> torch.Tensor:
-        _check_no_dropout(self, *self._drops)
         x3, _ = ops.field_eval(x, self.field_spec(1.0), self.field_weights(), want_p=False)
         return x3
 
@@ -125,7 +130,6 @@ class ViT_ODEFunc(nn.Module):
         self.scaler = float(emulate_depth) if time_interval == 1.0 else 1.0
 
     def forward(self, t: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-        _check_no_dropout(self.block, *self.block._drops)
         dx, _ = ops.field_eval(x, self.block.field_spec(self.scaler), self.block.field_weights(), want_p=False)
         return dx
 
@@ -234,7 +238,6 @@ class ViTMacaron(nn.Module):
                 t_grid: Optional[torch.Tensor] = None, temperature: Optional[float] = 100.0):
         """:302-352."""
         block = self.odefunc.block
-        _check_no_dropout(block, *block._drops)
         tokens = self.embed(pixel_values)
         if t_grid is None:
             num_eval_steps, t = self.num_eval_steps, self.t_grid

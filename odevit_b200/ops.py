@@ -37,6 +37,9 @@ class FieldSpec:
     proj_drop: float = 0.0
     mlp_drop: float = 0.0
     seed: int = 0
+    # a device-resident seed (int64[1] CUDA tensor, see `DropState`) read at kernel time instead of `seed`: what makes
+    # dropout work under CUDA-graph replay (the captured launches hold the address, not the value)
+    seed_dev: Optional[torch.Tensor] = None
 
     def desc(self, batch: int, tokens: int) -> _lib.Desc:
         d = _lib.Desc()
@@ -47,6 +50,7 @@ class FieldSpec:
         d.scaler = float(self.scaler)
         d.attn_drop, d.proj_drop, d.mlp_drop = float(self.attn_drop), float(self.proj_drop), float(self.mlp_drop)
         d.drop_seed_lo, d.drop_seed_hi = self.seed & 0xFFFFFFFF, (self.seed >> 32) & 0xFFFFFFFF
+        d.drop_seed_dev = self.seed_dev.data_ptr() if (self.seed_dev is not None and self.has_dropout) else None
         return d
 
     @property
@@ -54,11 +58,38 @@ class FieldSpec:
         return self.attn_drop > 0 or self.proj_drop > 0 or self.mlp_drop > 0
 
 
+def _dp_rank() -> int:
+    try:
+        import torch.distributed as dist
+        return dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+    except Exception:  # noqa: BLE001
+        return 0
+
+
 def draw_seed() -> int:
     """A fresh 64-bit mask seed from PyTorch's default CPU generator (so `torch.manual_seed` makes
-    dropout reproducible, as it does in the reference)."""
+    dropout reproducible, as it does in the reference), mixed with the data-parallel rank: replicas that
+    seeded identically still draw different masks (rank 0 is unchanged)."""
     hi, lo = torch.randint(0, 2 ** 31 - 1, (2,)).tolist()
-    return (int(hi) << 32) | int(lo)
+    return ((int(hi) << 32) | int(lo)) ^ ((_dp_rank() * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF)
+
+
+class DropState:
+    """Device-resident dropout seed of one vector-field module: int64[3] = (base seed, step counter, seed of the
+    current step).  `next_seed()` advances it with a 1-thread kernel (`odevit_drop_state_advance`) and returns a
+    device copy of the new step seed: the forward AND the backward launches of that step read the copy, later steps
+    get their own.  Everything is a device operation on fixed addresses, so a step captured in a CUDA graph draws
+    fresh masks at every replay (PyTorch's own Philox capture works the same way).  The base seed comes from
+    `draw_seed()` (hence `torch.manual_seed`) mixed with the data-parallel rank: replicas draw different masks."""
+
+    def __init__(self, device: torch.device):
+        self.state = torch.tensor([draw_seed() & 0x7FFFFFFFFFFFFFFF, 0, 0], dtype=torch.int64, device=device)
+
+    def next_seed(self) -> torch.Tensor:
+        with torch.cuda.device(self.state.device):
+            st = _lib.lib().odevit_drop_state_advance(_vp(self.state.data_ptr()), _stream())
+        _lib.check(st, "odevit_drop_state_advance")
+        return self.state[2:3].clone()
 
 
 # ---------------------------------------------------------------------------------------------

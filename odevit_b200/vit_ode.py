@@ -97,12 +97,22 @@ class L2SelfAttention(nn.Module):
         self.proj_drop = nn.Dropout(proj_drop)
 
 
-def _check_no_dropout(mod: nn.Module, *ps: float) -> None:
-    """Variants whose kernels have no dropout (Macaron)."""
-    if mod.training and any(p > 0 for p in ps):
-        raise NotImplementedError(
-            "odevit_b200: dropout > 0 in training mode is not built for this field (the reference "
-            "re-samples dropout at every field evaluation; SURVEY 2.3 quirk 16). Use p=0 or .eval().")
+def _next_drop_seed(block: nn.Module) -> dict:
+    """FieldSpec seed arguments of this call.  Eager calls draw a 64-bit host seed from PyTorch's CPU generator
+    (`torch.manual_seed` reproduces a step, as in the reference).  While a CUDA graph is being captured -- or when
+    `block.device_seed` is set, which GraphedTrainStep does before its warm-up -- the seed lives in device memory
+    (ops.DropState) and a 1-thread kernel advances it, so every replay of the captured step draws new masks.
+    `block.last_drop_seed` keeps what was used (int or int64[1] CUDA tensor): tests restate the masks from it."""
+    if getattr(block, "device_seed", False) or torch.cuda.is_current_stream_capturing():
+        dev = next(block.parameters()).device
+        st = getattr(block, "_drop_state", None)
+        if st is None or st.state.device != dev:
+            st = ops.DropState(dev)
+            block._drop_state = st
+        block.last_drop_seed = st.next_seed()
+        return dict(seed_dev=block.last_drop_seed)
+    block.last_drop_seed = ops.draw_seed()
+    return dict(seed=block.last_drop_seed)
 
 
 class ParallelAttentionMLP(nn.Module):
@@ -132,13 +142,13 @@ class ParallelAttentionMLP(nn.Module):
         # dropout is live in training mode only; every call draws a fresh seed, and inside a solve the
         # masks are re-drawn at every field evaluation from (seed, evaluation index) -- SURVEY 2.3 quirk 16
         attn_drop, proj_drop, mlp_drop = self._drops if self.training else (0.0, 0.0, 0.0)
-        seed = ops.draw_seed() if (attn_drop > 0 or proj_drop > 0 or mlp_drop > 0) else 0
+        seed_kw = _next_drop_seed(self) if (attn_drop > 0 or proj_drop > 0 or mlp_drop > 0) else {}
         return ops.FieldSpec(dim=self.dim, heads=self.num_heads, hidden=hidden, scaler=float(scaler),
                              variant=_lib.FIELD_PARALLEL_L2 if self.use_l2 else _lib.FIELD_PARALLEL,
                              precision=self.precision,
                              backward=getattr(self, "backward_mode", "auto"),
                              attn_drop=float(attn_drop), proj_drop=float(proj_drop), mlp_drop=float(mlp_drop),
-                             seed=seed)
+                             **seed_kw)
 
     def field_weights(self) -> Dict[str, Optional[torch.Tensor]]:
         """odevit_weights field name -> parameter, read at call time."""
@@ -206,8 +216,6 @@ def odeint(func: ViT_ODEFunc, y0: torch.Tensor, t: torch.Tensor, *, method: str 
         record_attention = False   # macaron.py:60-65: need_weights=False, the block exposes no map
     if options:
         raise NotImplementedError("odeint options (step_size, ...) are not used by the reference and not built")
-    if hasattr(func.block, "res_scale"):
-        _check_no_dropout(func.block, *func.block._drops)
     res = ops.ode_solve(y0, t, func.block.field_spec(func.scaler), method, func.block.field_weights(),
                         want_p_last=record_attention, p_traj_first=0 if record_attention else None)
     if record_attention:
