@@ -306,15 +306,130 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
   return fmaf(x * (phi * (1.f - phi)), d, phi);
 }
 
-// The tcgen05 GEMM's epilogue on one lane's share of a 32 x 32 accumulator chunk: 8 float4s, w[i] holding
-// columns [n, n+4) of row m0 + 4*i (rows >= M masked).  All global loads of the chunk are issued
-// before any dependent arithmetic and before every store (8 independent 16-byte loads in flight per
-// lane and operand): the epilogue is latency-bound otherwise.
-template <int EPI, bool ATOMIC>
-__device__ __forceinline__ void epi_rows8(const Epi& e, int m0, int M, int n, float4 (&w)[8]) {
-  bool ok[8];
+// ------------------------------------------------------------------------------------------------
+// The tcgen05 GEMM's epilogue on one lane's share of a 32 x 32 accumulator chunk: 8 float4s, w[i] holding columns
+// [n, n+4) of row m0 + 4*i.  Written for instruction count and latency -- with eight to twelve epilogue warps per SM
+// every instruction of this code is paid ~24 times per 128 x 32 accumulator slab, and the first version (per-row
+// bounds branches, run-time type switches per store, 64-bit index arithmetic per access: ~520 instructions per
+// chunk, measured) made the epilogue, not the main loop, the bound of every fused GEMM:
+//   * two phases.  `epi8_issue` starts the chunk's global LOADS (state y / GELU input / accumulator) before the
+//     accumulator is even waited for; `epi8_finish` consumes them.  The loads are asm volatile: they stay where they
+//     are put.
+//   * FULL: the 32-row slab lies inside M (every tile but the last row of tiles) -> no row predicates at all.
+//   * element types are tested once per chunk (warp-uniform branch), rows are `base + i * step` off one 64-bit base.
+// ------------------------------------------------------------------------------------------------
+struct EpiPre {
+  Raw4 a[8];
+};
+
+template <bool FULL>
+__device__ __forceinline__ bool row_in(int m0, int i, int M) {
+  if constexpr (FULL) return true;
+  else return (m0 + 4 * i) < M;
+}
+
+__device__ __forceinline__ Raw4 ldg_f32x4(const float* p) {
+  Raw4 r;
+  asm volatile("ld.global.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ Raw4 ldg_bf16x4(const __nv_bfloat16* p) {
+  Raw4 r;
+  asm volatile("ld.global.v2.b32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  r.z = 0; r.w = 0;
+  return r;
+}
+__device__ __forceinline__ float4 raw_f32(const Raw4& r) {
+  return make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
+}
+__device__ __forceinline__ float4 raw_bf16(const Raw4& r) {
+  return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                     __uint_as_float(r.y & 0xffff0000u));
+}
+__device__ __forceinline__ void stg_f32x4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void stg_bf16x4(__nv_bfloat16* p, float4 v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 t;
+  t.x = *reinterpret_cast<const uint32_t*>(&a);
+  t.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+// 8 rows of one output: row i at element offset i * step from `base` (type tested once)
+template <bool FULL>
+__device__ __forceinline__ void store_rows8(void* base, int type, long long idx0, int step, int m0, int M,
+                                            const float4 (&v)[8]) {
+  if (type == DT_F32) {
+    float* p = reinterpret_cast<float*>(base) + idx0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) ok[i] = (m0 + 4 * i) < M;
+    for (int i = 0; i < 8; ++i)
+      if (row_in<FULL>(m0, i, M)) stg_f32x4(p + i * step, v[i]);
+  } else {
+    __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(base) + idx0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (row_in<FULL>(m0, i, M)) stg_bf16x4(p + i * step, v[i]);
+  }
+}
+template <bool FULL>
+__device__ __forceinline__ void load_rows8_f32(const float* base, long long idx0, int step, int m0, int M, Raw4 (&t)[8]) {
+  const float* p = base + idx0;
+  const Raw4 zero = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[i] = row_in<FULL>(m0, i, M) ? ldg_f32x4(p + i * step) : zero;
+}
+
+// ---- phase 1: the chunk's first global operand, issued ahead of the accumulator read-out ----
+template <int EPI, bool ATOMIC, bool FULL>
+__device__ __forceinline__ void epi8_issue(const Epi& e, int m0, int M, int n, EpiPre& pre) {
+  if constexpr ((EPI & 7) == EPI_RK) {
+    if (e.y) load_rows8_f32<FULL>(e.y, (long long)m0 * e.ld_out + n, 4 * (int)e.ld_out, m0, M, pre.a);
+  } else if constexpr ((EPI & 7) == EPI_BWD3) {
+    if (n >= e.split) {
+      const long long idx0 = (long long)m0 * e.ld_aux + (n - e.split);
+      const int step = 4 * (int)e.ld_aux;
+      const Raw4 zero = {0u, 0u, 0u, 0u};
+      if (e.aux_type == DT_F32) {
+        load_rows8_f32<FULL>(reinterpret_cast<const float*>(e.aux), idx0, step, m0, M, pre.a);
+      } else {
+        const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(e.aux) + idx0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pre.a[i] = row_in<FULL>(m0, i, M) ? ldg_bf16x4(p + i * step) : zero;
+      }
+    }
+  } else if constexpr ((EPI & 7) == EPI_ACCUM && !ATOMIC) {
+    load_rows8_f32<FULL>(reinterpret_cast<const float*>(e.out), (long long)m0 * e.ld_out + n, 4 * (int)e.ld_out, m0, M, pre.a);
+  }
+}
+
+// ---- L2 prefetch of the operand rows phase 1 will load for a LATER tile: lane = one row of the 32-row slab,
+//      `cols` consecutive columns from n0 (a 128-byte line per row and 32-column fp32 chunk) ----
+// (plain prefetch instructions, one per 32-byte sector: `cp.async.bulk.prefetch.L2` per lane queued ~800 tiny
+// operations per tile in front of the producer's operand loads in the TMA unit and made every GEMM slower)
+__device__ __forceinline__ void prefetch_l2_row(const char* p, int bytes) {
+#pragma unroll
+  for (int o = 0; o < 128; o += 32)
+    if (o < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+}
+template <int EPI, bool ATOMIC>
+__device__ __forceinline__ void epi_prefetch_rows(const Epi& e, int m, int M, int n0, int N) {
+  if (m >= M || n0 >= N) return;
+  const int cols = min(32, N - n0);
+  if constexpr ((EPI & 7) == EPI_RK) {
+    if (e.y) prefetch_l2_row(reinterpret_cast<const char*>(e.y + (long long)m * e.ld_out + n0), cols * 4);
+  } else if constexpr ((EPI & 7) == EPI_BWD3) {
+    if (n0 >= e.split) {
+      const long long idx = (long long)m * e.ld_aux + (n0 - e.split);
+      if (e.aux_type == DT_F32) prefetch_l2_row(reinterpret_cast<const char*>(reinterpret_cast<const float*>(e.aux) + idx), cols * 4);
+      else prefetch_l2_row(reinterpret_cast<const char*>(reinterpret_cast<const __nv_bfloat16*>(e.aux) + idx), cols * 2);
+    }
+  } else if constexpr ((EPI & 7) == EPI_ACCUM && !ATOMIC) {
+    prefetch_l2_row(reinterpret_cast<const char*>(reinterpret_cast<const float*>(e.out) + (long long)m * e.ld_out + n0), cols * 4);
+  }
+}
+
+// ---- phase 2 ----
+template <int EPI, bool ATOMIC, bool FULL>
+__device__ __forceinline__ void epi8_finish(const Epi& e, int m0, int M, int n, float4 (&w)[8], const EpiPre& pre) {
   float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
   if constexpr ((EPI & 7) == EPI_STORE || (EPI & 7) == EPI_FWD1 || (EPI & 7) == EPI_RK) {
     if (e.bias) bias = *reinterpret_cast<const float4*>(e.bias + n);
@@ -324,127 +439,130 @@ __device__ __forceinline__ void epi_rows8(const Epi& e, int m0, int M, int n, fl
     if (e.dev_scale) ds = *e.dev_scale;
   }
   if constexpr ((EPI & 7) == EPI_STORE) {
+    const float a = e.alpha * ds;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (ok[i]) store4(e.out, (long long)(m0 + 4 * i) * e.ld_out + n, e.out_type, fma4(e.alpha * ds, w[i], bias));
+    for (int i = 0; i < 8; ++i) w[i] = fma4(a, w[i], bias);
+    store_rows8<FULL>(e.out, e.out_type, (long long)m0 * e.ld_out + n, 4 * (int)e.ld_out, m0, M, w);
   } else if constexpr ((EPI & 7) == EPI_FWD1) {
-    if (n < e.split) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (ok[i]) store4(e.out, (long long)(m0 + 4 * i) * e.ld_out + n, e.out_type, add4(w[i], bias));
+    for (int i = 0; i < 8; ++i) w[i] = add4(w[i], bias);
+    if (n < e.split) {
+      store_rows8<FULL>(e.out, e.out_type, (long long)m0 * e.ld_out + n, 4 * (int)e.ld_out, m0, M, w);
     } else {
       const int c = n - e.split;
+      if (e.out3) store_rows8<FULL>(e.out3, e.aux_type, (long long)m0 * e.ld_out3 + c, 4 * (int)e.ld_out3, m0, M, w);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        if (!ok[i]) continue;
-        const float4 v = add4(w[i], bias);
-        if (e.out3) store4(e.out3, (long long)(m0 + 4 * i) * e.ld_out3 + c, e.aux_type, v);
-        float4 gv = make_float4(gelu_fast(v.x), gelu_fast(v.y), gelu_fast(v.z), gelu_fast(v.w));
+        w[i] = make_float4(gelu_fast(w[i].x), gelu_fast(w[i].y), gelu_fast(w[i].z), gelu_fast(w[i].w));
         if constexpr ((EPI & EPI_DROP) != 0) {
           const uint32_t r = m0 + 4 * i;
-          gv.x *= drop_factor(e.drop, r, c); gv.y *= drop_factor(e.drop, r, c + 1);
-          gv.z *= drop_factor(e.drop, r, c + 2); gv.w *= drop_factor(e.drop, r, c + 3);
+          w[i].x *= drop_factor(e.drop, r, c); w[i].y *= drop_factor(e.drop, r, c + 1);
+          w[i].z *= drop_factor(e.drop, r, c + 2); w[i].w *= drop_factor(e.drop, r, c + 3);
         }
-        store4(e.out2, (long long)(m0 + 4 * i) * e.ld_out2 + c, e.aux_type, gv);
       }
+      store_rows8<FULL>(e.out2, e.aux_type, (long long)m0 * e.ld_out2 + c, 4 * (int)e.ld_out2, m0, M, w);
     }
   } else if constexpr ((EPI & 7) == EPI_RK) {
-    float4 r[8];
-    Raw4 t[8];
+    // Two half-batches of 4 rows: with 14 warps per CTA a thread has 128 registers, and the prefetched state rows
+    // (pre, 32) + the accumulator (w, 32) leave room for 16 + 16 more, not 32 + 32.
+    const long long idx0 = (long long)m0 * e.ld_out + n;
+    const int step = 4 * (int)e.ld_out;
+    const float a = e.alpha * ds;
     const Raw4 zero = {0u, 0u, 0u, 0u};
-    if (e.y) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) t[i] = ok[i] ? ldg_raw4(e.y, (long long)(m0 + 4 * i) * e.ld_out + n, DT_F32) : zero;
-    }
-    auto mask_rows = [&]() {
+    for (int h = 0; h < 2; ++h) {
+      Raw4 t[4];
+      float4 v[4], r[4];
+      if (e.resid) {   // (Macaron) batched ahead of the arithmetic
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] = row_in<FULL>(m0, 4 * h + i, M) ? ldg_f32x4(e.resid + idx0 + (4 * h + i) * step) : zero;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = scale4(a, add4(w[4 * h + i], bias));
       if constexpr ((EPI & EPI_DROP) != 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t rr = m0 + 4 * i;
-          w[i].x *= drop_factor(e.drop, rr, n); w[i].y *= drop_factor(e.drop, rr, n + 1);
-          w[i].z *= drop_factor(e.drop, rr, n + 2); w[i].w *= drop_factor(e.drop, rr, n + 3);
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t rr = m0 + 4 * (4 * h + i);
+          v[i].x *= drop_factor(e.drop, rr, n); v[i].y *= drop_factor(e.drop, rr, n + 1);
+          v[i].z *= drop_factor(e.drop, rr, n + 2); v[i].w *= drop_factor(e.drop, rr, n + 3);
         }
       }
-    };
-    if (e.resid) {   // v = drop(alpha*ds*(acc+bias)) + resid_coef*resid (loads batched like the others)
-      Raw4 q[8];
+      if (e.resid) {   // v = drop(alpha*ds*(acc+bias)) + resid_coef*resid
 #pragma unroll
-      for (int i = 0; i < 8; ++i) q[i] = ok[i] ? ldg_raw4(e.resid, (long long)(m0 + 4 * i) * e.ld_out + n, DT_F32) : zero;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) w[i] = scale4(e.alpha * ds, add4(w[i], bias));
-      mask_rows();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) w[i] = fma4(e.resid_coef, raw_to_float4(q[i], DT_F32), w[i]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) w[i] = scale4(e.alpha * ds, add4(w[i], bias));
-      mask_rows();
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) r[i] = scale4(e.c_new, w[i]);
-    if (e.y) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) r[i] = fma4(e.y_coef, raw_to_float4(t[i], DT_F32), r[i]);
-    }
-#pragma unroll
-    for (int k = 0; k < Epi::kMaxTerms; ++k) {
-      if (e.kin[k]) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          t[i] = ok[i] ? ldg_raw4(e.kin[k], (long long)(m0 + 4 * i) * e.ld_out + n, DT_F32) : zero;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) r[i] = fma4(e.c_k[k], raw_to_float4(t[i], DT_F32), r[i]);
+        for (int i = 0; i < 4; ++i) v[i] = fma4(e.resid_coef, raw_f32(t[i]), v[i]);
       }
-    }
+      if (e.k_store) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (!ok[i]) continue;
-      const long long idx = (long long)(m0 + 4 * i) * e.ld_out + n;
-      if (e.k_store) store4(e.k_store, idx, DT_F32, w[i]);
-      if (e.out) store4(e.out, idx, DT_F32, r[i]);
-      if (e.out2) store4(e.out2, idx, e.aux_type, scale4(e.out2_scale, r[i]));
+        for (int i = 0; i < 4; ++i)
+          if (row_in<FULL>(m0, 4 * h + i, M)) stg_f32x4(e.k_store + idx0 + (4 * h + i) * step, v[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = scale4(e.c_new, v[i]);
+      if (e.y) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[i] = fma4(e.y_coef, raw_f32(pre.a[4 * h + i]), r[i]);
+      }
+#pragma unroll 1   // (rolled: ONE operand batch live at a time)
+      for (int k = 0; k < Epi::kMaxTerms; ++k) {
+        const float* kp = e.kin[k];
+        if (kp) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) t[i] = row_in<FULL>(m0, 4 * h + i, M) ? ldg_f32x4(kp + idx0 + (4 * h + i) * step) : zero;
+          const float ck = e.c_k[k];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) r[i] = fma4(ck, raw_f32(t[i]), r[i]);
+        }
+      }
+      if (e.out) {
+        float* po = reinterpret_cast<float*>(e.out) + idx0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (row_in<FULL>(m0, 4 * h + i, M)) stg_f32x4(po + (4 * h + i) * step, r[i]);
+      }
+      if (e.out2) {
+        if (e.aux_type == DT_F32) {
+          float* po = reinterpret_cast<float*>(e.out2) + idx0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (row_in<FULL>(m0, 4 * h + i, M)) stg_f32x4(po + (4 * h + i) * step, scale4(e.out2_scale, r[i]));
+        } else {
+          __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(e.out2) + idx0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (row_in<FULL>(m0, 4 * h + i, M)) stg_bf16x4(po + (4 * h + i) * step, scale4(e.out2_scale, r[i]));
+        }
+      }
     }
   } else if constexpr ((EPI & 7) == EPI_BWD3) {
     if (n < e.split) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (ok[i]) store4(e.out, (long long)(m0 + 4 * i) * e.ld_out + n, e.out_type, w[i]);
+      store_rows8<FULL>(e.out, e.out_type, (long long)m0 * e.ld_out + n, 4 * (int)e.ld_out, m0, M, w);
     } else {
       const int c = n - e.split;
-      Raw4 hr[8];
-      const Raw4 zero = {0u, 0u, 0u, 0u};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) hr[i] = ok[i] ? ldg_raw4(e.aux, (long long)(m0 + 4 * i) * e.ld_aux + c, e.aux_type) : zero;
+      const bool f32 = (e.aux_type == DT_F32);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        if (!ok[i]) continue;
-        const float4 hp = raw_to_float4(hr[i], e.aux_type);
-        float4 v = scale4(ds, w[i]);
-        v.x *= gelu_grad_fast(hp.x); v.y *= gelu_grad_fast(hp.y);
-        v.z *= gelu_grad_fast(hp.z); v.w *= gelu_grad_fast(hp.w);
+        const float4 hp = f32 ? raw_f32(pre.a[i]) : raw_bf16(pre.a[i]);
+        w[i].x *= ds * gelu_grad_fast(hp.x); w[i].y *= ds * gelu_grad_fast(hp.y);
+        w[i].z *= ds * gelu_grad_fast(hp.z); w[i].w *= ds * gelu_grad_fast(hp.w);
         if constexpr ((EPI & EPI_DROP) != 0) {
           const uint32_t r = m0 + 4 * i;
-          v.x *= drop_factor(e.drop, r, c); v.y *= drop_factor(e.drop, r, c + 1);
-          v.z *= drop_factor(e.drop, r, c + 2); v.w *= drop_factor(e.drop, r, c + 3);
+          w[i].x *= drop_factor(e.drop, r, c); w[i].y *= drop_factor(e.drop, r, c + 1);
+          w[i].z *= drop_factor(e.drop, r, c + 2); w[i].w *= drop_factor(e.drop, r, c + 3);
         }
-        store4(e.out2, (long long)(m0 + 4 * i) * e.ld_out2 + c, e.aux_type, v);
       }
+      store_rows8<FULL>(e.out2, e.aux_type, (long long)m0 * e.ld_out2 + c, 4 * (int)e.ld_out2, m0, M, w);
     }
   } else if constexpr ((EPI & 7) == EPI_ACCUM) {
+    float* p = reinterpret_cast<float*>(e.out) + (long long)m0 * e.ld_out + n;
+    const int step = 4 * (int)e.ld_out;
     if constexpr (ATOMIC) {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        if (ok[i])
-          atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (long long)(m0 + 4 * i) * e.ld_out + n),
-                    scale4(e.alpha, w[i]));
+        if (row_in<FULL>(m0, i, M)) atomicAdd(reinterpret_cast<float4*>(p + i * step), scale4(e.alpha, w[i]));
     } else {
-      Raw4 t[8];
-      const Raw4 zero = {0u, 0u, 0u, 0u};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) t[i] = ok[i] ? ldg_raw4(e.out, (long long)(m0 + 4 * i) * e.ld_out + n, DT_F32) : zero;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        if (ok[i]) store4(e.out, (long long)(m0 + 4 * i) * e.ld_out + n, DT_F32, fma4(e.alpha, w[i], raw_to_float4(t[i], DT_F32)));
+        if (row_in<FULL>(m0, i, M)) stg_f32x4(p + i * step, fma4(e.alpha, w[i], raw_f32(pre.a[i])));
     }
   }
 }

@@ -16,18 +16,20 @@
 //            (UMMA 128*CG x BN x 16, operands straight from both CTAs' shared memory through
 //            matrix descriptors), releases ring slots and publishes accumulators with
 //            tcgen05.commit multicast to both CTAs
-//   warps 2-9 epilogue: tcgen05.ld 32 columns of this CTA's 128 accumulator rows (thread = row),
-//            transpose through a swizzled shared-memory scratch so that 8 consecutive lanes hold
-//            128 contiguous bytes of one output row, apply the fused epilogue on float4s with
-//            coalesced global loads / stores.  Two accumulator buffers in TMEM let the epilogue of
-//            tile i overlap the main loop of tile i+1; the peer CTA's epilogue warps release the
-//            buffer with a remote arrive on the leader's `acc_empty` barrier.
+//   warps 2-9 epilogue (TMEM lane quarter x 2 column groups): tcgen05.ld 32 columns of 32 accumulator rows
+//            (thread = row), transpose through a swizzled shared-memory scratch so that 8 consecutive lanes
+//            hold 128 contiguous bytes of one output row, apply the fused epilogue on float4s with coalesced
+//            global loads / stores (epilogue.cuh: loads issued before the accumulator wait, operand rows of the
+//            next tile prefetched to L2).  Two accumulator buffers in TMEM let the epilogue of tile i overlap
+//            the main loop of tile i+1; the peer CTA's epilogue warps release the buffer with a remote arrive
+//            on the leader's `acc_empty` barrier.
 // Operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows], i.e. the
 // transposed products of the weight-gradient GEMMs); out-of-range rows / K are zero-filled by TMA.
 #include <cuda.h>
 
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 
 #include "epilogue.cuh"
 #include "internal.h"
@@ -37,8 +39,29 @@ namespace odevit {
 
 namespace {
 
+// -DGEMM_TRACE: CTA 0 prints where its MMA thread and its first epilogue warp spent their cycles (diagnostic build only)
+#ifdef GEMM_TRACE
+#define GT_DECL() long long gt_acc[3] = {0, 0, 0}, gt_t0 = 0, gt_begin = clock64(); (void)gt_t0
+#define GT_T0() gt_t0 = clock64()
+#define GT_ADD(i) gt_acc[i] += clock64() - gt_t0
+#define GT_REPORT(role, a, b, c, tiles)                                                                              \
+  do {                                                                                                               \
+    if (blockIdx.x == 0)                                                                                             \
+      printf("GT %s EPI %d BN %d tiles %d total %lld | %s %lld | %s %lld | %s %lld\n", role, EPI, BN, (int)(tiles), \
+             clock64() - gt_begin, a, gt_acc[0], b, gt_acc[1], c, gt_acc[2]);                                        \
+  } while (0)
+#else
+#define GT_DECL() do { } while (0)
+#define GT_T0() do { } while (0)
+#define GT_ADD(i) do { } while (0)
+#define GT_REPORT(role, a, b, c, tiles) do { } while (0)
+#endif
+
 constexpr int BM = 128, BK = 64;
-constexpr int NUM_EPI_WARPS = 8;
+// column groups of epilogue warps (x 4 TMEM lane quarters).  3 groups (14 warps -> 128 registers per thread) were
+// measured: no faster for the GELU epilogues and slower for EPI_RK (its operand batches spill).
+constexpr int EPI_GROUPS = 2;
+constexpr int NUM_EPI_WARPS = 4 * EPI_GROUPS;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int ACC_STRIDE = 256;  // TMEM columns between the two accumulator buffers
 
@@ -48,7 +71,9 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = STAGE_BYTES > 40000 ? 4 : (STAGE_BYTES > 30000 ? 5 : 6);
+  // as many stages as fit next to the epilogue scratch: the ring must cover the operand round trip (L2 -> shared memory
+  // ~1.6 k cycles under load, tools/ubench/tma_feed.cu) at 64-73 bytes per clock, i.e. well over 100 KB IN FLIGHT
+  static constexpr int STAGES = (232448 - 1024 - 256 - NUM_EPI_WARPS * 4096) / STAGE_BYTES;
   static constexpr int TMEM_COLS = (BN <= 128) ? 256 : 512;  // two accumulator buffers, power of two
   static constexpr int ACC2 = (BN <= 128) ? 128 : ACC_STRIDE;
   static constexpr int SCRATCH_BYTES = NUM_EPI_WARPS * 4096;
@@ -60,8 +85,126 @@ struct Cfg {
 struct DevArgs {
   int M, N, K;
   int tiles_m, tiles_n, split_k, kb_per_split, num_kb;
+  int l2_prefetch;   // epilogue operand rows of the next tile -> L2 (experiment switch ODEVIT_GEMM_PREFETCH)
+  int dbg;           // diagnostic builds only (ODEVIT_GEMM_DBG): 1 = skip the shared-memory transposition (wrong results)
   Epi epi;
 };
+
+// The epilogue warps' role.  (Inlined: as a real call its `g` would be a generic pointer to the kernel parameters and
+// every epilogue field a global-path load instead of a constant-bank operand -- measured 20-30 % slower.)
+template <int CG, int BN, int EPI>
+__device__ __forceinline__ void epilogue_role(const DevArgs& g, float* scratch, uint64_t* acc_full, uint64_t* acc_empty,
+                                           uint32_t tmem_base, uint32_t rank, int unit, int num_units, int total_tiles) {
+  using C = Cfg<CG, BN>;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    // TMEM lane quarter q = warp % 4 (hardware rule) x column group grp; a warp owns the 32-column chunks grp,
+    // grp + EPI_GROUPS, ... of its quarter's 32 accumulator rows.
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int grp = ew >> 2;
+    constexpr int NCHT = BN / 32;                                   // chunks per quarter
+    const int my_chunks = (NCHT - grp + EPI_GROUPS - 1) / EPI_GROUPS;
+    const uint32_t scr = ptx::smem_u32(scratch + ew * 1024);        // this warp's 32 x 32 fp32 transposition tile
+    const uint32_t acc_empty_addr0 = ptx::mapa(&acc_empty[0], 0), acc_empty_addr1 = ptx::mapa(&acc_empty[1], 0);
+    const int ch = lane & 7, rsub = lane >> 3;
+    // transposition addresses (16-byte chunks XOR-swizzled by row % 8: both phases are bank-conflict free), kept as
+    // three registers: store j of lane (= row) at st_base ^ (j << 4); load i (row 4 i + rsub) at ld_base[i & 1] + 512 i
+    const uint32_t st_base = (scr + (uint32_t)lane * 128u) | ((uint32_t)(lane & 7) << 4);
+    const uint32_t ld_base0 = scr + (uint32_t)rsub * 128u + ((uint32_t)(ch ^ rsub) << 4);
+    const uint32_t ld_base1 = scr + (uint32_t)rsub * 128u + ((uint32_t)(ch ^ (rsub + 4)) << 4);
+    auto tile_coords = [&](int tile, int& m_base, int& n_tile) {
+      const int nt = tile % g.tiles_n;
+      const int mt = (tile / g.tiles_n) % g.tiles_m;
+      m_base = (mt * CG + (int)rank) * BM + q * 32;
+      n_tile = nt * BN;
+    };
+    constexpr bool IS_ACCUM = (EPI & 7) == EPI_ACCUM;
+    const bool atomic = IS_ACCUM && g.split_k > 1;
+    GT_DECL();
+    int it = 0;
+    for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
+      int m_base, n_tile;
+      tile_coords(tile, m_base, n_tile);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const uint32_t taddr = tmem_base + acc * C::ACC2 + (static_cast<uint32_t>(q * 32) << 16);
+      const int m0 = m_base + rsub;
+      // the operand rows the NEXT tile's epilogue will load (state / GELU input / accumulator) -> L2, one tile ahead
+      if (g.l2_prefetch && tile + num_units < total_tiles) {
+        int mb2, nt2;
+        tile_coords(tile + num_units, mb2, nt2);
+        for (int k = 0; k < my_chunks; ++k) {
+          if (atomic) epi_prefetch_rows<EPI, true>(g.epi, mb2 + lane, g.M, nt2 + (grp + k * EPI_GROUPS) * 32, g.N);
+          else epi_prefetch_rows<EPI, false>(g.epi, mb2 + lane, g.M, nt2 + (grp + k * EPI_GROUPS) * 32, g.N);
+        }
+      }
+      // FULL: the 32-row slab lies inside M (no row predicates); ATOMIC: split-K accumulation
+      auto chunks = [&](auto full_c, auto atomic_c) {
+        constexpr bool FULL = decltype(full_c)::value, ATOMIC = decltype(atomic_c)::value;
+#pragma unroll 1
+        for (int k = 0; k < my_chunks; ++k) {
+          const int c = grp + k * EPI_GROUPS;
+          const int n = n_tile + c * 32 + ch * 4;
+          const bool live = n < g.N;
+          if (k == 0) {
+            GT_T0();
+            ptx::mbar_wait(&acc_full[acc], acc_phase);
+            GT_ADD(0);
+            ptx::tc_fence_after();
+          }
+          GT_T0();
+          // the chunk's global operand loads are issued behind the (asynchronous) accumulator load and overlap it and
+          // the transposition; their rows were prefetched to L2 one tile ago.  (Issued in FRONT of the accumulator wait
+          // they would be spilled at once: tcgen05.ld wants 32 consecutive registers and ptxas evicts whatever sits
+          // there to local memory.)
+          float v[32];
+          ptx::tmem_ld32(taddr + c * 32, v);
+          EpiPre pre;
+          if (live) epi8_issue<EPI, ATOMIC, FULL>(g.epi, m0, g.M, n, pre);
+          ptx::tmem_ld_wait();
+          GT_ADD(1);
+          GT_T0();
+          if (k == my_chunks - 1) {
+            // every column of this warp's slice is in registers: hand the accumulator back
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (CG == 2) ptx::mbar_arrive_cluster(acc ? acc_empty_addr1 : acc_empty_addr0);
+              else ptx::mbar_arrive(&acc_empty[acc]);
+            }
+          }
+          // transpose: lane = row  ->  (row = i*4 + lane/8, 4 columns at (lane%8)*4)
+          float4 w[8];
+#ifdef GEMM_TRACE
+          if (g.dbg & 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else
+#endif
+          {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ptx::sts_f32x4(st_base ^ (uint32_t)(j << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = ptx::lds_f32x4(((i & 1) ? ld_base1 : ld_base0) + (uint32_t)(512 * i));
+            __syncwarp();
+          }
+          if (live) epi8_finish<EPI, ATOMIC, FULL>(g.epi, m0, g.M, n, w, pre);
+          GT_ADD(2);
+        }
+      };
+      const bool full = (m_base + 32 <= g.M);
+      if constexpr (IS_ACCUM) {
+        if (atomic) { if (full) chunks(std::true_type{}, std::true_type{}); else chunks(std::false_type{}, std::true_type{}); }
+        else { if (full) chunks(std::true_type{}, std::false_type{}); else chunks(std::false_type{}, std::false_type{}); }
+      } else {
+        if (full) chunks(std::true_type{}, std::false_type{}); else chunks(std::false_type{}, std::false_type{});
+      }
+    }
+    if (warp == 2 && lane == 0 && rank == 0) { GT_REPORT("epi", "wait acc_full", "tmem ld + operand issue", "transpose + finish", it); }
+  }
+}
 
 template <int CG, int BN, int EPI, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -166,6 +309,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
     if (lane == 0 && rank == 0) {
+      GT_DECL();
       constexpr uint32_t idesc = ptx::idesc_bf16(BM * CG, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       // K-major: 8-row groups 1024 B apart, one UMMA_K (16 elements) = 32 B along the row.
       // MN-major: 64-wide MN blocks (BK*128 B apart), 8-k-row groups 1024 B apart, UMMA_K = 2 groups.
@@ -180,11 +324,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        GT_T0();
         ptx::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        GT_ADD(0);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * C::ACC2;
         for (int kb = kb0; kb < kb1; ++kb) {
+          GT_T0();
           ptx::mbar_wait(&full[stage], phase);
+          GT_ADD(1);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
@@ -204,62 +352,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if constexpr (CG == 2) ptx::mma_commit_pair(&acc_full[acc], 3);  // accumulator complete
         else ptx::mma_commit(&acc_full[acc]);
       }
+      GT_REPORT("mma", "wait acc_empty", "wait full", "-", it);
     }
   } else {
-    // ======================================= epilogue =======================================
-    const int ew = warp - 2;
-    const int q = warp & 3;     // TMEM lane quarter this warp may access
-    const int half = ew >> 2;   // which half of the tile's columns
-    constexpr int NCH = BN / 64;  // 32-column chunks per warp
-    float* scr = scratch + ew * 1024;
-    const uint32_t acc_empty_addr0 = ptx::mapa(&acc_empty[0], 0), acc_empty_addr1 = ptx::mapa(&acc_empty[1], 0);
-    int it = 0;
-    for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
-      const int nt = tile % g.tiles_n;
-      const int mt = (tile / g.tiles_n) % g.tiles_m;
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      ptx::mbar_wait(&acc_full[acc], acc_phase);
-      ptx::tc_fence_after();
-      const int m_base = (mt * CG + (int)rank) * BM + q * 32;
-      const int n_base = nt * BN + half * (BN / 2);
-      const uint32_t taddr = tmem_base + acc * C::ACC2 + half * (BN / 2) + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < NCH; ++c) {
-        float v[32];
-        ptx::tmem_ld32(taddr + c * 32, v);
-        ptx::tmem_ld_wait();
-        if (c == NCH - 1) {
-          // every column of this warp's slice is in registers: hand the accumulator back
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if constexpr (CG == 2) ptx::mbar_arrive_cluster(acc ? acc_empty_addr1 : acc_empty_addr0);
-            else ptx::mbar_arrive(&acc_empty[acc]);
-          }
-        }
-        // transpose: lane = row  ->  (row = i*4 + lane/8, 4 columns at (lane%8)*4); 16-byte chunks are
-        // XOR-swizzled by row%8 so both phases are bank-conflict free
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(scr + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        __syncwarp();
-        const int ch = lane & 7;
-        const int n = n_base + c * 32 + ch * 4;
-        float4 w[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + (lane >> 3);
-          w[i] = *reinterpret_cast<const float4*>(scr + r * 32 + ((ch ^ (r & 7)) << 2));
-        }
-        __syncwarp();
-        if (n < g.N) {
-          if (g.split_k > 1) epi_rows8<EPI, true>(g.epi, m_base + (lane >> 3), g.M, n, w);
-          else epi_rows8<EPI, false>(g.epi, m_base + (lane >> 3), g.M, n, w);
-        }
-      }
-    }
+    epilogue_role<CG, BN, EPI>(g, scratch, acc_full, acc_empty, tmem_base, rank, unit, num_units, total_tiles);
   }
 
   ptx::tc_fence_before();
@@ -474,6 +570,12 @@ int gemm_tc(const GemmArgs& g, cudaStream_t s) {
   d.kb_per_split = (d.num_kb + d.split_k - 1) / d.split_k;
   d.split_k = (d.num_kb + d.kb_per_split - 1) / d.kb_per_split;
   d.epi = g.epi;
+  {
+    static const int pf = [] { const char* e = getenv("ODEVIT_GEMM_PREFETCH"); return e ? atoi(e) : 0; }();
+    d.l2_prefetch = pf;   // off: measured neutral to slightly negative (the operand loads are not what the epilogues wait for)
+    static const int dbg = [] { const char* e = getenv("ODEVIT_GEMM_DBG"); return e ? atoi(e) : 0; }();
+    d.dbg = dbg;
+  }
   CUtensorMap ta, tb;
   const int brows = bn / cg;
   if (!mn) {

@@ -56,6 +56,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ---- shared-memory vector accesses by 32-bit shared address (the compiler cannot prove the address space of
+//      pointers derived from an aligned-up dynamic shared base and would emit generic LD/ST) ----
+__device__ __forceinline__ void sts_f32x4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // ---- fences -----------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_async_shared() {  // generic-proxy smem writes -> async proxy (UMMA/TMA)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
