@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define ODEVIT_ABI_VERSION 7
+#define ODEVIT_ABI_VERSION 8
 
 typedef struct CUstream_st* odevit_stream_t; /* == cudaStream_t */
 
@@ -252,6 +252,24 @@ int odevit_encoder_fwd(const odevit_desc* desc, const odevit_weights* layers, in
  * evaluations (tiny).  1 <= tokens <= 1024, 0 <= k <= tokens. */
 int odevit_jasmin_rowmax(const float* p_maps, int64_t n_slices, int32_t tokens, int32_t k, float* out,
                          odevit_stream_t stream);
+
+/* The fixed-grid solve WITHOUT a materialised trajectory (inference: the reference returns `states` only on
+ * request, ode_transformer_gpt.py:628-630, but always needs the finite-difference bound :529-543 and may need the
+ * control-point rows :632-639).  The states live in a ring of three inside the workspace.
+ *   final_state [B,N,D]: the last state (required);
+ *   rows_out [n_rows,B,N,D] or NULL: trajectory rows row_index_host[0..n_rows) (host array, repeats allowed);
+ *   fd_max [B*N] or NULL: max over steps j and features d of |s[j+2] - 2 s[j+1] + s[j]| (NOT divided by dt^2),
+ *          folded into the epilogue of the step's last GEMM; zero when the grid has fewer than 3 points;
+ *   p_last, jas_traj, jas_first_eval, jas_k: as in odevit_solve_fwd.  Workspace: ODEVIT_WS_SOLVE_FWD. */
+int odevit_solve_fwd_lean(const odevit_desc* desc, const odevit_weights* w, int32_t method, const float* x0,
+                          const float* t_grid_host, int32_t n_grid, float* final_state, float* rows_out,
+                          const int32_t* row_index_host, int32_t n_rows, float* fd_max, float* p_last,
+                          float* jas_traj, int32_t jas_first_eval, int32_t jas_k, void* workspace,
+                          size_t workspace_bytes, odevit_stream_t stream);
+
+/* 1 when odevit_solve_fwd runs this inference solve in the on-chip-state kernel (one persistent CTA per image,
+ * trajectory rows written from shared memory): the caller then has no reason to prefer the trajectory-free form. */
+int odevit_solve_uses_resident(const odevit_desc* desc, int32_t method, int32_t n_grid);
 
 /* Advances a device-resident dropout state by one step (a 1-thread kernel, capturable in a CUDA graph):
  *   state[0] base seed (set once by the caller), state[1] step counter += 1, state[2] = the seed of this step

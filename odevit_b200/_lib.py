@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # ODEVIT_LIB: a diagnostic build of the same library (e.g. the -DATTN_TRACE clock-trace build), never a fallback
 LIB_PATH = os.environ.get("ODEVIT_LIB") or os.path.join(_HERE, "csrc", "libodevit.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # enums of include/odevit.h
 FIELD_PARALLEL, FIELD_PARALLEL_L2, FIELD_MACARON = 0, 1, 2
@@ -104,6 +104,13 @@ def lib() -> ctypes.CDLL:
                                    ctypes.POINTER(ctypes.c_float), ctypes.c_int32, _vp, _vp, _vp,
                                    ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, _vp, _vp,
                                    ctypes.POINTER(WeightGrads), _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _vp]
+    L.odevit_solve_fwd_lean.restype = ctypes.c_int
+    L.odevit_solve_fwd_lean.argtypes = [ctypes.POINTER(Desc), ctypes.POINTER(Weights), ctypes.c_int32, _vp,
+                                        ctypes.POINTER(ctypes.c_float), ctypes.c_int32, _vp, _vp,
+                                        ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, _vp, _vp, _vp, ctypes.c_int32,
+                                        ctypes.c_int32, _vp, ctypes.c_size_t, _vp]
+    L.odevit_solve_uses_resident.restype = ctypes.c_int
+    L.odevit_solve_uses_resident.argtypes = [ctypes.POINTER(Desc), ctypes.c_int32, ctypes.c_int32]
     L.odevit_drop_state_advance.restype = ctypes.c_int
     L.odevit_drop_state_advance.argtypes = [_vp, _vp]
     L.odevit_gemm_bf16.restype = ctypes.c_int
@@ -160,6 +167,6 @@ def profile_read() -> dict:
 
 DECLARED_SYMBOLS = ("odevit_abi_version", "odevit_build_info", "odevit_last_error_string",
                     "odevit_workspace_bytes", "odevit_field_fwd", "odevit_solve_fwd", "odevit_solve_bwd",
-                    "odevit_field_bwd", "odevit_tape_bytes", "odevit_fd_curvature", "odevit_jasmin_rowmax", "odevit_encoder_cache_bytes", "odevit_encoder_fwd", "odevit_launch_count", "odevit_reset_launch_count", "odevit_drop_state_advance",
+                    "odevit_field_bwd", "odevit_tape_bytes", "odevit_fd_curvature", "odevit_jasmin_rowmax", "odevit_encoder_cache_bytes", "odevit_encoder_fwd", "odevit_launch_count", "odevit_reset_launch_count", "odevit_drop_state_advance", "odevit_solve_fwd_lean", "odevit_solve_uses_resident",
                     "odevit_gemm_bf16", "odevit_profile_enable", "odevit_profile_reserve", "odevit_profile_num_classes", "odevit_profile_class_name",
                     "odevit_profile_read")

@@ -192,7 +192,7 @@ struct FwdBufs {
   float* P;
   float* u;
   float* k[3];
-  float* ytmp[2];
+  float* ytmp[3];   // trajectory-free solves: a ring of three states (the finite-difference window)
   float* sq;
   float* tmp;
   float* kbuf;
@@ -205,8 +205,7 @@ FwdBufs layout_fwd(const Plan& p, Arena& a, int S) {
   f.P = a.f32(p.BHNN);
   f.u = a.f32((size_t)p.M * p.D);
   for (int i = 0; i < 3; ++i) f.k[i] = (i < S - 1) ? a.f32((size_t)p.M * p.D) : nullptr;
-  f.ytmp[0] = a.f32((size_t)p.M * p.D);
-  f.ytmp[1] = a.f32((size_t)p.M * p.D);
+  for (int i = 0; i < 3; ++i) f.ytmp[i] = a.f32((size_t)p.M * p.D);
   f.sq = (p.variant == ODEVIT_FIELD_PARALLEL_L2) ? a.f32((size_t)2 * p.B * p.H * p.N) : nullptr;
   f.tmp = p.split_out ? a.f32((size_t)p.M * p.D) : nullptr;
   f.kbuf = (S > 1 && solve_resident_shape_ok(p)) ? a.f32(solve_resident_scratch_floats(p)) : nullptr;
@@ -932,11 +931,20 @@ int odevit_field_fwd(const odevit_desc* desc, const odevit_weights* w, const flo
   return eval_forward(p, f.w, f.ctx, x, f.P, p_out, f.sq, f.tmp, 0, &rk, s);
 }
 
-int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t method, const float* x0,
-                     const float* t_grid_host, int32_t n_grid, float* states, float* final_state,
-                     float* p_last, float* p_traj, int32_t p_traj_first_eval, float* jas_traj,
-                     int32_t jas_first_eval, int32_t jas_k, void* tape, size_t tape_bytes,
-                     void* workspace, size_t workspace_bytes, odevit_stream_t stream) {
+namespace {
+// Trajectory-free outputs (odevit_solve_fwd_lean): selected trajectory rows and the finite-difference maxima.
+struct LeanOut {
+  float* rows_out;
+  const int32_t* row_index;
+  int n_rows;
+  float* fd_max;
+};
+
+int solve_fwd_impl(const odevit_desc* desc, const odevit_weights* w, int32_t method, const float* x0,
+                   const float* t_grid_host, int32_t n_grid, float* states, float* final_state,
+                   float* p_last, float* p_traj, int32_t p_traj_first_eval, float* jas_traj,
+                   int32_t jas_first_eval, int32_t jas_k, void* tape, size_t tape_bytes,
+                   void* workspace, size_t workspace_bytes, odevit_stream_t stream, const LeanOut* lean) {
   Plan p{};
   ODV_TRY(make_plan(desc, &p));
   ODV_TRY(check_weights(p, w));
@@ -979,6 +987,56 @@ int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
     ODV_CUDA(cudaMemcpyAsync(states, x0, MD * 4, cudaMemcpyDeviceToDevice, s));
     y = states;
   }
+  if (lean) {
+    // ---- trajectory-free: rows live in a ring of three (the finite-difference window), in the caller's slots of
+    //      `rows_out` when they are control points, in `final_state` when last ----
+    if (states || tape) return set_error(ODEVIT_ERR_INVALID_ARG, "the trajectory-free solve keeps neither states nor a tape");
+    for (int i = 0; i < lean->n_rows; ++i)
+      if (lean->row_index[i] < 0 || lean->row_index[i] >= n_grid)
+        return set_error(ODEVIT_ERR_INVALID_ARG, "row_index[%d]=%d outside [0,%d)", i, lean->row_index[i], n_grid);
+    if (lean->fd_max) ODV_CUDA(cudaMemsetAsync(lean->fd_max, 0, (size_t)p.M * 4, s));
+    auto slot_of = [&](int j) -> float* {   // first caller slot that wants row j
+      for (int i = 0; i < lean->n_rows; ++i)
+        if (lean->row_index[i] == j) return lean->rows_out + (size_t)i * MD;
+      return nullptr;
+    };
+    auto fan_out = [&](int j, const float* src) -> int {   // row j into every further slot that names it
+      bool first = true;
+      for (int i = 0; i < lean->n_rows; ++i) {
+        if (lean->row_index[i] != j) continue;
+        float* dst = lean->rows_out + (size_t)i * MD;
+        if (first && dst == src) { first = false; continue; }
+        first = false;
+        ODV_CUDA(cudaMemcpyAsync(dst, src, MD * 4, cudaMemcpyDeviceToDevice, s));
+      }
+      return 0;
+    };
+    ODV_TRY(fan_out(0, x0));
+    const int S = tb->S;
+    const long long n_evals = (long long)(n_grid - 1) * S;
+    const float* row_prev = nullptr;   // row j - 1
+    const float* row_cur = x0;         // row j
+    for (int j = 0; j + 1 < n_grid; ++j) {
+      const float dt = t_grid_host[j + 1] - t_grid_host[j];
+      float* y_next = slot_of(j + 1);
+      if (!y_next) y_next = (j + 2 == n_grid && final_state) ? final_state : f.ytmp[(j + 1) % 3];
+      for (int st = 0; st < S; ++st) {
+        const long long e = (long long)j * S + st;
+        const float* u = (st == 0) ? row_cur : f.u;
+        float* out = (st == S - 1) ? y_next : f.u;
+        Epi rk = rk_epilogue(*tb, st, dt, row_cur, f.k, out);
+        if (st == S - 1 && row_prev && lean->fd_max) { rk.fd_prev = row_prev; rk.fd_out = lean->fd_max; }
+        float* p_copy = (p_last && e == n_evals - 1) ? p_last : nullptr;
+        float* jas_out = (jas_traj && e >= jas_first_eval) ? jas_traj + (size_t)(e - jas_first_eval) * p.B * p.H : nullptr;
+        ODV_TRY(eval_forward(p, f.w, f.ctx, u, f.P, p_copy, f.sq, f.tmp, e, &rk, s, jas_out, jas_k));
+      }
+      ODV_TRY(fan_out(j + 1, y_next));
+      row_prev = row_cur;
+      row_cur = y_next;
+    }
+    if (final_state && row_cur != final_state) ODV_CUDA(cudaMemcpyAsync(final_state, row_cur, MD * 4, cudaMemcpyDeviceToDevice, s));
+    return 0;
+  }
   if (solve_resident_supports(p, n_grid, p_traj != nullptr || jas_traj != nullptr, tape != nullptr) && (tb->S == 1 || f.kbuf)) {
     // small-token shapes: the whole solve of an image in one persistent CTA, state resident on the chip
     return solve_resident(p, f.w, tb->S, tb->a, tb->b, x0, t_grid_host, n_grid, states, final_state, p_last, f.kbuf, s);
@@ -1009,6 +1067,39 @@ int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
     ODV_CUDA(cudaMemcpyAsync(final_state, y, MD * 4, cudaMemcpyDeviceToDevice, s));
   }
   return 0;
+}
+}  // namespace
+
+int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t method, const float* x0,
+                     const float* t_grid_host, int32_t n_grid, float* states, float* final_state,
+                     float* p_last, float* p_traj, int32_t p_traj_first_eval, float* jas_traj,
+                     int32_t jas_first_eval, int32_t jas_k, void* tape, size_t tape_bytes,
+                     void* workspace, size_t workspace_bytes, odevit_stream_t stream) {
+  return solve_fwd_impl(desc, w, method, x0, t_grid_host, n_grid, states, final_state, p_last, p_traj, p_traj_first_eval,
+                        jas_traj, jas_first_eval, jas_k, tape, tape_bytes, workspace, workspace_bytes, stream, nullptr);
+}
+
+int odevit_solve_fwd_lean(const odevit_desc* desc, const odevit_weights* w, int32_t method, const float* x0,
+                          const float* t_grid_host, int32_t n_grid, float* final_state, float* rows_out,
+                          const int32_t* row_index_host, int32_t n_rows, float* fd_max, float* p_last,
+                          float* jas_traj, int32_t jas_first_eval, int32_t jas_k, void* workspace,
+                          size_t workspace_bytes, odevit_stream_t stream) {
+  if (!final_state) return set_error(ODEVIT_ERR_INVALID_ARG, "final_state is NULL");
+  if (n_rows < 0 || (n_rows > 0 && (!rows_out || !row_index_host)))
+    return set_error(ODEVIT_ERR_INVALID_ARG, "rows_out / row_index_host missing");
+  if (rows_out) ODV_TRY(check_device_ptr(rows_out, "rows_out"));
+  if (fd_max) ODV_TRY(check_device_ptr(fd_max, "fd_max"));
+  const LeanOut lean{rows_out, row_index_host, n_rows, fd_max};
+  return solve_fwd_impl(desc, w, method, x0, t_grid_host, n_grid, nullptr, final_state, p_last, nullptr, 0, jas_traj,
+                        jas_first_eval, jas_k, nullptr, 0, workspace, workspace_bytes, stream, &lean);
+}
+
+int odevit_solve_uses_resident(const odevit_desc* desc, int32_t method, int32_t n_grid) {
+  Plan p{};
+  if (make_plan(desc, &p) != 0) return 0;
+  const Tableau* tb = tableau_for(method);
+  if (!tb) return 0;
+  return solve_resident_supports(p, n_grid, false, false) ? 1 : 0;
 }
 
 int odevit_solve_bwd(const odevit_desc* desc, const odevit_weights* w, int32_t method,

@@ -79,6 +79,8 @@ __device__ __forceinline__ void epi_apply(const Epi& e, int m, int n, float acc,
       if (e.kin[i]) r = fmaf(e.c_k[i], e.kin[i][idx], r);
     if (e.out) reinterpret_cast<float*>(e.out)[idx] = r;
     if (e.out2) store_elem(e.out2, idx, e.aux_type, e.out2_scale * r);
+    if (e.fd_out)   // (CUDA-core path: one atomic per element; the tcgen05 epilogue reduces over the row first)
+      atomicMax(reinterpret_cast<int*>(e.fd_out) + m, __float_as_int(fabsf(r - 2.f * e.y[idx] + e.fd_prev[idx])));
   } else if constexpr ((EPI & 7) == EPI_BWD3) {
     if (n < e.split) {
       store_elem(e.out, (long long)m * e.ld_out + n, e.out_type, acc);
@@ -511,6 +513,23 @@ __device__ __forceinline__ void epi8_finish(const Epi& e, int m0, int M, int n, 
           const float ck = e.c_k[k];
 #pragma unroll
           for (int i = 0; i < 4; ++i) r[i] = fma4(ck, raw_f32(t[i]), r[i]);
+        }
+      }
+      if constexpr ((EPI & EPI_FD) != 0) {
+        // second finite difference of the trajectory at the row y: |r - 2 y + prev|, max over this lane's 4 columns,
+        // then over the 8 lanes that share a row, then into fd_out[row]
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] = row_in<FULL>(m0, 4 * h + i, M) ? ldg_f32x4(e.fd_prev + idx0 + (4 * h + i) * step) : zero;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 yy = raw_f32(pre.a[4 * h + i]), pp = raw_f32(t[i]);
+          float mx = fmaxf(fmaxf(fabsf(r[i].x - 2.f * yy.x + pp.x), fabsf(r[i].y - 2.f * yy.y + pp.y)),
+                           fmaxf(fabsf(r[i].z - 2.f * yy.z + pp.z), fabsf(r[i].w - 2.f * yy.w + pp.w)));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+          if ((threadIdx.x & 7) == 0 && row_in<FULL>(m0, 4 * h + i, M))
+            atomicMax(reinterpret_cast<int*>(e.fd_out) + m0 + 4 * (4 * h + i), __float_as_int(mx));
         }
       }
       if (e.out) {

@@ -443,6 +443,11 @@ int launch_epi(int epi_mode, bool mn, const CUtensorMap& ta, const CUtensorMap& 
       if (d.epi.drop.thresh) return launch_major<CG, BN, EPI_FWD1 | EPI_DROP>(mn, ta, tb, d, units, s);
       return launch_major<CG, BN, EPI_FWD1>(mn, ta, tb, d, units, s);
     case EPI_RK:
+      if (d.epi.fd_out) {
+        if (d.epi.drop.thresh || !d.epi.y || !d.epi.fd_prev || d.N % 32)   // (whole warps reduce over rows: no dead lanes)
+          return set_error(ODEVIT_ERR_INVALID_ARG, "gemm_tc: the finite-difference epilogue needs y, fd_prev, N %% 32 == 0 and no dropout");
+        return launch_major<CG, BN, EPI_RK | EPI_FD>(mn, ta, tb, d, units, s);
+      }
       if (d.epi.drop.thresh) return launch_major<CG, BN, EPI_RK | EPI_DROP>(mn, ta, tb, d, units, s);
       return launch_major<CG, BN, EPI_RK>(mn, ta, tb, d, units, s);
     case EPI_BWD3:
@@ -532,6 +537,7 @@ bool gemm_tc_supports(const GemmArgs& g) {
   if (g.batch_outer * g.batch_inner != 1) return false;
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return false;
   if (g.N % 16) return false;
+  if (g.epi.fd_out && (g.N % 32 || g.epi.drop.thresh)) return false;   // whole warps reduce over rows: no dead lanes
   const bool a_k = (g.a_cs == 1), a_mn = (g.a_rs == 1 && g.a_cs != 1);
   const bool b_k = (g.b_cs == 1), b_mn = (g.b_rs == 1 && g.b_cs != 1);
   if (!(a_k || a_mn) || !(b_k || b_mn)) return false;

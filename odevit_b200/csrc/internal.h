@@ -99,7 +99,10 @@ enum EpiMode : int {
                   // n >= split: out2[m,n-split] = acc * gelu'(aux[m,n-split])   (d h_pre)
   EPI_ACCUM = 4,  // out[m,n] += alpha*acc   (fp32; atomic when split-K)
   // template-only flag: the epilogue applies Epi::drop (kernels without it carry no mask code at all)
-  EPI_DROP = 8
+  EPI_DROP = 8,
+  // template-only flag (EPI_RK): the epilogue also folds the second finite difference of the trajectory into
+  // Epi::fd_out (trajectory-free inference: ode_transformer_gpt.py:529-543 without the [T,B,N,D] tensor)
+  EPI_FD = 16
 };
 
 // One dropout site of one field evaluation: element (r, c) is kept iff hash(key, r, c) >= thresh and then
@@ -145,6 +148,10 @@ struct Epi {
   float resid_coef = 0.f;
   // dropout on the epilogue's value: EPI_FWD1 after GELU, EPI_RK on v (before resid), EPI_BWD3 on d h
   Drop drop;
+  // EPI_RK, when r is the NEXT trajectory row and y the current one: fd_out[m] = max(fd_out[m], max_n |r - 2 y + fd_prev|)
+  // with fd_prev the row before y ([M] fp32 maxima, atomicMax on the bit pattern of non-negative floats)
+  const float* fd_prev = nullptr;
+  float* fd_out = nullptr;
 };
 
 struct GemmArgs {

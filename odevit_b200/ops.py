@@ -412,6 +412,57 @@ def ode_solve(x0: torch.Tensor, t: torch.Tensor, spec: FieldSpec, method: str,
             "jas_traj": jas_traj if jas_traj.numel() else None}
 
 
+def solve_uses_resident(spec: FieldSpec, batch: int, tokens: int, method: str, n_grid: int) -> bool:
+    """True when the inference solve of this shape runs in the on-chip-state kernel (odevit_solve_uses_resident)."""
+    desc = spec.desc(batch, tokens)
+    return bool(_lib.lib().odevit_solve_uses_resident(ctypes.byref(desc), _lib.METHODS[method], int(n_grid)))
+
+
+@torch.no_grad()
+def ode_solve_lean(x0: torch.Tensor, t: torch.Tensor, spec: FieldSpec, method: str,
+                   weights: Dict[str, Optional[torch.Tensor]], row_index: Sequence[int] = (),
+                   want_p_last: bool = False, jasmin: Optional[Tuple[int, int]] = None):
+    """Inference solve WITHOUT the [T,B,N,D] trajectory (odevit_solve_fwd_lean): the reference materialises `states`
+    for every call but returns them only on request (ode_transformer_gpt.py:628-630); what it always needs from them
+    is the finite-difference bound (:529-543), formed here inside the solve, and the control-point rows (:632-639),
+    written straight into `rows`.  No autograd (the reverse sweep needs the trajectory).
+
+    Returns dict(final [B,N,D], rows [Q,B,N,D] | None, fd_max [B,N] = max_j,d |s[j+2] - 2 s[j+1] + s[j]|,
+    p_last, jas_traj)."""
+    if method not in _lib.METHODS:
+        raise ValueError(f"unsupported solver {method!r}; fixed-grid euler | midpoint | rk4 are built")
+    names = tuple(k for k, v in weights.items() if v is not None)
+    x0 = _require_cuda(x0.detach(), "x0")
+    B, N, D = x0.shape
+    T = int(t.numel())
+    S = _lib.STAGES[method]
+    desc = spec.desc(B, N)
+    w, keep = _pack_weights(names, [weights[k].detach() for k in names])
+    t_host = t.detach().to("cpu", torch.float32).contiguous()
+    t_c = (ctypes.c_float * T)(*t_host.tolist())
+    n_evals = (T - 1) * S
+    final = torch.empty(B, N, D, device=x0.device, dtype=torch.float32)
+    row_index = [int(i) for i in row_index]
+    rows = torch.empty(len(row_index), B, N, D, device=x0.device, dtype=torch.float32) if row_index else None
+    idx_c = (ctypes.c_int32 * max(1, len(row_index)))(*row_index)
+    fd_max = torch.empty(B, N, device=x0.device, dtype=torch.float32)
+    p_last = (torch.empty(B, spec.heads, N, N, device=x0.device, dtype=torch.float32)
+              if (want_p_last and n_evals > 0) else None)
+    jas_traj, jas_first, jas_k = None, 0, 0
+    if jasmin is not None and n_evals > 0:
+        jas_first, jas_k = max(0, min(int(jasmin[0]), n_evals)), int(jasmin[1])
+        if n_evals - jas_first > 0:
+            jas_traj = torch.empty(n_evals - jas_first, B, spec.heads, device=x0.device, dtype=torch.float32)
+    buf, ws, ws_bytes = _workspace(desc, _lib.WS_SOLVE_FWD, _lib.METHODS[method], x0.device)
+    with torch.cuda.device(x0.device):
+        st = _lib.lib().odevit_solve_fwd_lean(ctypes.byref(desc), ctypes.byref(w), _lib.METHODS[method], _ptr(x0), t_c, T,
+                                              _ptr(final), _ptr(rows), idx_c, len(row_index), _ptr(fd_max), _ptr(p_last),
+                                              _ptr(jas_traj), jas_first, jas_k, ws, ws_bytes, _stream())
+    _lib.check(st, "odevit_solve_fwd_lean")
+    return {"states": None, "final": final, "rows": rows, "fd_max": fd_max, "p_last": p_last, "p_traj": None,
+            "jas_traj": jas_traj}
+
+
 def fd_curvature(states: torch.Tensor, delta_t: float) -> torch.Tensor:
     """per_seq [B,N] = max over time and features of |s[j+2] - 2 s[j+1] + s[j]| / delta_t^2, one pass
     over the trajectory (ode_transformer_gpt.py:458-468 + the norms/maxima of :529-543)."""

@@ -396,13 +396,18 @@ class ViTNeuralODE(nn.Module):
         return (math.e ** L - 1) / (2 * L * self.num_eval_steps) * (factor1 * factor2) / factor3
 
     @torch.no_grad()
-    def compute_upper_bound_by_fininte_difference(self, x, L, N):
-        """:529-543"""
+    def compute_upper_bound_by_fininte_difference(self, x, L, N, fd_max=None):
+        """:529-543.  `fd_max` [B,N]: the maxima of |s[j+2] - 2 s[j+1] + s[j]| when the solve formed them itself
+        (trajectory-free inference, x is None then)."""
         first = (math.e ** L - 1) / (2 * L * N)
-        if x.shape[0] < 3:
-            raise RuntimeError("finite-difference bound needs a trajectory of at least 3 states "
-                               "(the reference's max() over an empty tensor fails the same way)")
-        per_seq = ops.fd_curvature(x, 1 / N)           # one pass over [T,B,N,D] (odevit_fd_curvature)
+        if x is None:
+            delta_t = 1 / N
+            per_seq = fd_max / (delta_t * delta_t)
+        else:
+            if x.shape[0] < 3:
+                raise RuntimeError("finite-difference bound needs a trajectory of at least 3 states "
+                                   "(the reference's max() over an empty tensor fails the same way)")
+            per_seq = ops.fd_curvature(x, 1 / N)           # one pass over [T,B,N,D] (odevit_fd_curvature)
         per_batch = per_seq.max(-1)[0]
         g = first * per_batch.max()
         # the reference returns a Python float here (:541), i.e. one host sync per forward; inside a CUDA-graph
@@ -445,9 +450,23 @@ class ViTNeuralODE(nn.Module):
             # only the JaSMin statistic of the window's maps is consumed: formed inside the attention kernel, the
             # maps themselves (0.85 T x B x H x N x N fp32) are never written
             jas = (max(0, n_evals - window), int(jasmin_k))
-        res = ops.ode_solve(tokens, t, block.field_spec(self.odefunc.scaler), self.solver, block.field_weights(),
-                            row_index=idx.tolist() if idx is not None else (),
-                            want_p_last=True, p_traj_first=p_first, jasmin=jas)
+        spec, weights = block.field_spec(self.odefunc.scaler), block.field_weights()
+        # Inference that does not ask for `states`: no [T,B,N,D] tensor at all (36 x 8192 x 207 x 768 fp32 would be
+        # 188 GB) -- the finite-difference bound is formed inside the solve, the control-point rows are written
+        # directly.  Not for shapes the on-chip-state kernel takes (its trajectory rows cost one bulk copy each) and
+        # not when a backward pass can follow (the reverse sweep reads the trajectory).
+        track = torch.is_grad_enabled() and (tokens.requires_grad or any(
+            v is not None and v.requires_grad for v in weights.values()))
+        lean = (not output_hidden_states and not output_attention_trajectory and not track and num_eval_steps >= 3
+                and getattr(self, "trajectory_free_inference", True)
+                and not ops.solve_uses_resident(spec, tokens.shape[0], tokens.shape[1], self.solver, num_eval_steps))
+        if lean:
+            res = ops.ode_solve_lean(tokens, t, spec, self.solver, weights,
+                                     row_index=idx.tolist() if idx is not None else (), want_p_last=True, jasmin=jas)
+        else:
+            res = ops.ode_solve(tokens, t, spec, self.solver, weights,
+                                row_index=idx.tolist() if idx is not None else (),
+                                want_p_last=True, p_traj_first=p_first, jasmin=jas)
         states, final = res["states"], res["final"]
         block.attentions = res["p_last"]
 
@@ -455,7 +474,8 @@ class ViTNeuralODE(nn.Module):
             "logits": self.head(final[:, 0]),
             "second_derivative_upper_bound": self.compute_upper_bound_by_second_derivative(R=jasmin_k, L=1 / 2),
             "finite_difference_upper_bound": self.compute_upper_bound_by_fininte_difference(
-                states.detach(), 0.5, 1 / self.num_eval_steps),
+                states.detach() if states is not None else None, 0.5, 1 / self.num_eval_steps,
+                fd_max=res.get("fd_max")),
         }
         p_traj = res["p_traj"]
         if output_attention_trajectory:

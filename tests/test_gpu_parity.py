@@ -564,3 +564,35 @@ def test_jasmin_in_kernel_equals_exported_maps(N_img, R, B, k):
     # the in-kernel form skips that renormalisation
     assert torch.allclose(a["jas_traj"][0], want[0], rtol=5e-3, atol=2e-5)
     assert torch.equal(a["states"][:2], b["states"][:2])
+
+
+@pytest.mark.parametrize("solver,prec", [("euler", "bf16"), ("rk4", "bf16"), ("euler", "fp32")])
+def test_trajectory_free_inference_equals_materialised(solver, prec):
+    """Inference without `output_hidden_states` keeps no [T,B,N,D] tensor (odevit_solve_fwd_lean: ring of three states,
+    finite-difference bound folded into the epilogue of each step's last GEMM, control-point rows written directly):
+    every output equals the materialised path's -- logits / control points / attentions bit for bit (same kernels,
+    same order), the bound to rounding (|r - 2y + p| is formed from the same three fp32 values)."""
+    import odevit_b200 as ob
+    cfg = dict(img_size=224, patch_size=16, num_classes=100, embed_dim=768, num_heads=12, mlp_ratio=1.0, emulate_depth=12,
+               time_interval=1.0, num_eval_steps=13, solver=solver, register_tokens=10)
+    torch.manual_seed(0)
+    model = ob.ViTNeuralODE(**cfg).cuda().eval()
+    model.precision = prec
+    px = torch.randn(3, 3, 224, 224, generator=torch.Generator().manual_seed(5)).cuda()
+    kw = dict(output_control_points=True, output_attentions=True, jasmin_k=2, temperature=100.0)
+    with torch.no_grad():
+        ob.reset_launch_count()
+        lean = model(px, **kw)
+        n_lean = ob.launch_count()
+        model.trajectory_free_inference = False
+        full = model(px, **kw)
+        ref = model(px, output_hidden_states=True, **kw)
+    assert "states" not in lean and "states" in ref
+    for k in ("logits", "control_points", "attentions", "attentions_register_tokens", "jasmin_loss"):
+        assert torch.equal(lean[k], full[k]), k
+        assert torch.equal(lean[k], ref[k]), k
+    a, b = lean["finite_difference_upper_bound"], full["finite_difference_upper_bound"]
+    assert a["global_upper_bound"] == pytest.approx(b["global_upper_bound"], rel=1e-5)
+    assert max_rel(a["batched_upper_bound_per_seq"], b["batched_upper_bound_per_seq"]) < 1e-5
+    assert max_rel(a["batched_upper_bound"], b["batched_upper_bound"]) < 1e-5
+    assert n_lean > 0

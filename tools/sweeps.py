@@ -76,17 +76,19 @@ def main():
     if "4" in which:
         m = build(S38, a.precision)
         nfe = (S38["num_eval_steps"] - 1)
-        for B in (64, 256, 1024, 2048):
+        for B in (64, 256, 1024, 2048, 4096, 8192):
             px = torch.randn(B, 3, 224, 224, device="cuda")
             with torch.no_grad():
                 ms = timed(lambda: m(px), max(2, a.reps if B <= 256 else 2))
             tf = B * nfe * flops_fwd(S38) / (ms * 1e-3) / 1e12
-            out.append({"config": 4, "workload": "S3.8M-shape inference, Euler T=36 (trajectory + FD bound kept, as the "
-                        "reference's forward does)", "precision": a.precision, "batch": B, "ms_per_call": ms,
+            out.append({"config": 4, "workload": "S3.8M-shape inference, Euler T=36 (no materialised trajectory: FD bound "
+                        "formed inside the solve, odevit_solve_fwd_lean)", "precision": a.precision, "batch": B, "ms_per_call": ms,
+                        "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
                         "img_per_s": B / ms * 1e3, "nfe_per_s": B * nfe / ms * 1e3, "algorithmic_tflops": tf})
             del px
             ob.ops.free_workspaces()
             torch.cuda.empty_cache()
+            torch.cuda.reset_peak_memory_stats()
     if "5" in which:
         B = 512
         px = torch.randn(B, 3, 32, 32, device="cuda")
