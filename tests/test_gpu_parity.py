@@ -582,6 +582,7 @@ def test_trajectory_free_inference_equals_materialised(solver, prec):
     kw = dict(output_control_points=True, output_attentions=True, jasmin_k=2, temperature=100.0)
     with torch.no_grad():
         ob.reset_launch_count()
+        model.trajectory_free_inference = True       # (default "auto": only when the trajectory would crowd the memory)
         lean = model(px, **kw)
         n_lean = ob.launch_count()
         model.trajectory_free_inference = False
