@@ -271,6 +271,21 @@ int odevit_solve_fwd_lean(const odevit_desc* desc, const odevit_weights* w, int3
  * trajectory rows written from shared memory): the caller then has no reason to prefer the trajectory-free form. */
 int odevit_solve_uses_resident(const odevit_desc* desc, int32_t method, int32_t n_grid);
 
+/* GPU-side image preprocessing: what the reference's collator asks of HF `ViTImageProcessor`
+ * (datasets/collator.py:11-22): resize to out_h x out_w with Pillow's BILINEAR resampling (bit-exact: fixed point,
+ * horizontal then vertical pass, uint8 rounding after each), multiply by `rescale` (1/255), subtract mean, divide by std.
+ *   images [B,H,W,3] uint8 (RGB, the layout of np.asarray(PIL image)), device;
+ *   bounds_h [out_w,2], kk_h [out_w, ksize(W,out_w)], bounds_v [out_h,2], kk_v [out_h, ksize(H,out_h)]: Pillow's
+ *          coefficient tables, built on the HOST by odevit_pil_bilinear_tables and copied to the device by the caller;
+ *   tmp [B,H,out_w,3] uint8 device scratch;  out [B,3,out_h,out_w] fp32;  out_u8 [B,out_h,out_w,3] or NULL: the
+ *          resized uint8 image itself (what PIL.Image.resize returns). */
+int odevit_pil_bilinear_ksize(int32_t in_size, int32_t out_size);
+int odevit_pil_bilinear_tables(int32_t in_size, int32_t out_size, int32_t* bounds_host, int32_t* kk_host);
+int odevit_preprocess_u8(const uint8_t* images, int32_t batch, int32_t height, int32_t width, int32_t out_h, int32_t out_w,
+                         const int32_t* bounds_h, const int32_t* kk_h, const int32_t* bounds_v, const int32_t* kk_v,
+                         float rescale, const float* mean3_host, const float* std3_host, uint8_t* tmp, float* out,
+                         uint8_t* out_u8, odevit_stream_t stream);
+
 /* Advances a device-resident dropout state by one step (a 1-thread kernel, capturable in a CUDA graph):
  *   state[0] base seed (set once by the caller), state[1] step counter += 1, state[2] = the seed of this step
  *   (a 64-bit mix of base and counter; pass &state[2] as odevit_desc.drop_seed_dev, or a copy of it). */

@@ -1291,6 +1291,39 @@ int odevit_jasmin_rowmax(const float* p_maps, int64_t n_slices, int32_t tokens, 
   return jasmin_rowmax(p_maps, n_slices, tokens, k, out, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int odevit_pil_bilinear_ksize(int32_t in_size, int32_t out_size) {
+  if (in_size <= 0 || out_size <= 0) return 0;
+  return pil_bilinear_ksize(in_size, out_size);
+}
+
+int odevit_pil_bilinear_tables(int32_t in_size, int32_t out_size, int32_t* bounds_host, int32_t* kk_host) {
+  if (in_size <= 0 || out_size <= 0 || !bounds_host || !kk_host)
+    return set_error(ODEVIT_ERR_INVALID_ARG, "pil_bilinear_tables: bad arguments");
+  if (pil_bilinear_ksize(in_size, out_size) > 64)
+    return set_error(ODEVIT_ERR_UNSUPPORTED, "pil_bilinear_tables: down-scaling by more than 31x is not built");
+  pil_bilinear_tables(in_size, out_size, bounds_host, kk_host);
+  return 0;
+}
+
+int odevit_preprocess_u8(const uint8_t* images, int32_t batch, int32_t height, int32_t width, int32_t out_h, int32_t out_w,
+                         const int32_t* bounds_h, const int32_t* kk_h, const int32_t* bounds_v, const int32_t* kk_v,
+                         float rescale, const float* mean3_host, const float* std3_host, uint8_t* tmp, float* out,
+                         uint8_t* out_u8, odevit_stream_t stream) {
+  if (batch <= 0 || height <= 0 || width <= 0 || out_h <= 0 || out_w <= 0 || !mean3_host || !std3_host)
+    return set_error(ODEVIT_ERR_INVALID_ARG, "preprocess_u8: bad arguments");
+  ODV_TRY(check_device_ptr(images, "images"));
+  ODV_TRY(check_device_ptr(bounds_h, "bounds_h"));
+  ODV_TRY(check_device_ptr(kk_h, "kk_h"));
+  ODV_TRY(check_device_ptr(bounds_v, "bounds_v"));
+  ODV_TRY(check_device_ptr(kk_v, "kk_v"));
+  ODV_TRY(check_device_ptr(tmp, "tmp"));
+  ODV_TRY(check_device_ptr(out, "out"));
+  if (out_u8) ODV_TRY(check_device_ptr(out_u8, "out_u8"));
+  return preprocess_u8(images, batch, height, width, out_h, out_w, bounds_h, kk_h, pil_bilinear_ksize(width, out_w), bounds_v,
+                       kk_v, pil_bilinear_ksize(height, out_h), rescale, mean3_host, std3_host, tmp, out, out_u8,
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+
 int odevit_field_bwd(const odevit_desc* desc, const odevit_weights* w, const float* x, const float* g_dx,
                      const float* g_p, float* g_x, const odevit_weight_grads* gw, void* workspace,
                      size_t workspace_bytes, odevit_stream_t stream) {

@@ -238,6 +238,14 @@ int drop_rows_inplace(void* x, int type, Drop d, int rows, int D, cudaStream_t s
 int resolve_drop_keys(const uint32_t* seed_dev, uint32_t* table, int n, cudaStream_t s);
 int drop_state_advance(unsigned long long* state, cudaStream_t s);
 
+// preprocess.cu: PIL-exact bilinear resize of uint8 HWC images + rescale + normalise -> fp32 NCHW
+int preprocess_u8(const uint8_t* images, int B, int H, int W, int So_h, int So_w, const int32_t* bounds_h,
+                  const int32_t* kk_h, int ksize_h, const int32_t* bounds_v, const int32_t* kk_v, int ksize_v,
+                  float rescale, const float* mean, const float* stdv, uint8_t* tmp, float* out, uint8_t* out_u8,
+                  cudaStream_t s);
+int pil_bilinear_ksize(int in_size, int out_size);
+void pil_bilinear_tables(int in_size, int out_size, int32_t* bounds, int32_t* kk);
+
 // y[i] += a * x[i]
 int axpy_f32(float* y, const float* x, float a, long long n, cudaStream_t s);
 

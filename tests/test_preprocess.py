@@ -1,0 +1,103 @@
+"""GPU-side image preprocessing (datasets/collator.py:11-22) against Pillow and the HF
+`ViTImageProcessor` the reference's collator calls.
+
+  * CPU: the coefficient tables the library builds on the host (`odevit_pil_bilinear_tables`), applied with integer
+    numpy arithmetic in Pillow's order (horizontal pass, uint8, vertical pass, uint8), reproduce `PIL.Image.resize(...,
+    BILINEAR)` bit for bit -- up- and down-scaling, odd sizes;
+  * GPU: `GpuImageProcessor` returns the same uint8 image and `pixel_values` within fp32 rounding of the processor's."""
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from odevit_b200.data import Collator, GpuImageProcessor
+
+PRECISION_BITS = 22
+
+
+def _apply(img, bounds, kk, axis):
+    """One Pillow resampling pass with the integer tables along `axis` (0 = vertical, 1 = horizontal)."""
+    img = np.moveaxis(img.astype(np.int64), axis, 0)
+    out = np.empty((bounds.shape[0],) + img.shape[1:], dtype=np.uint8)
+    for o in range(bounds.shape[0]):
+        lo, n = int(bounds[o, 0]), int(bounds[o, 1])
+        acc = (1 << (PRECISION_BITS - 1)) + np.tensordot(kk[o, :n].astype(np.int64), img[lo:lo + n], axes=(0, 0))
+        out[o] = np.clip(acc >> PRECISION_BITS, 0, 255).astype(np.uint8)
+    return np.moveaxis(out, 0, axis)
+
+
+@pytest.mark.parametrize("H,W,S", [(32, 32, 224), (37, 53, 224), (500, 375, 224), (224, 224, 224), (300, 640, 96)])
+def test_host_tables_reproduce_pillow_bilinear(H, W, S):
+    rng = np.random.default_rng(H * 1000 + W)
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    want = np.asarray(Image.fromarray(img).resize((S, S), resample=Image.BILINEAR))
+    bh, kh = GpuImageProcessor.host_tables(W, S)
+    bv, kv = GpuImageProcessor.host_tables(H, S)
+    got = _apply(_apply(img, bh, kh, axis=1), bv, kv, axis=0)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,W,B", [(32, 32, 16), (37, 53, 3), (400, 300, 2)])
+def test_gpu_processor_matches_hf_processor(H, W, B):
+    from transformers import ViTImageProcessor
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    hf = ViTImageProcessor(size={"height": 224, "width": 224}, resample=2, image_mean=mean, image_std=std)
+    rng = np.random.default_rng(B)
+    imgs = [Image.fromarray(rng.integers(0, 256, (H, W, 3), dtype=np.uint8)) for _ in range(B)]
+    want = hf(imgs, return_tensors="pt")["pixel_values"]
+    proc = GpuImageProcessor(size=224, image_mean=mean, image_std=std)
+    got = proc(imgs, return_uint8=True)
+    want_u8 = np.stack([np.asarray(im.resize((224, 224), resample=Image.BILINEAR)) for im in imgs])
+    assert np.array_equal(got["resized_uint8"].cpu().numpy(), want_u8)          # bit-exact resize
+    assert got["pixel_values"].shape == want.shape and got["pixel_values"].is_cuda
+    assert float((got["pixel_values"].cpu() - want).abs().max()) < 1e-6
+
+
+@pytest.mark.gpu
+def test_collator_output_feeds_the_model_like_the_reference():
+    """train.py:40-53: `model(**data["pixel_values"], labels=...)` with the collator's dict."""
+    import odevit_b200 as ob
+    rng = np.random.default_rng(0)
+    batch = [(Image.fromarray(rng.integers(0, 256, (32, 32, 3), dtype=np.uint8)), int(i % 10)) for i in range(4)]
+    proc = GpuImageProcessor(size=32)
+    for defer in (False, True):
+        col = Collator(proc, defer=defer)
+        data = col.finish(col.classification_collate_fn(batch))
+        assert set(data) >= {"pixel_values", "labels", "raw_images"}
+        model = ob.ViTNeuralODE(img_size=32, patch_size=4, num_classes=10, embed_dim=192, num_heads=3, mlp_ratio=2.0,
+                                num_eval_steps=3, solver="euler", register_tokens=4).cuda()
+        out = model(**data["pixel_values"], labels=data["labels"].cuda())
+        assert torch.isfinite(out["loss"])
+
+
+@pytest.mark.gpu
+def test_launcher_runs_the_shipped_yaml_shape_on_synthetic_images(tmp_path):
+    """`python -m odevit_b200.train --config <yaml> --synthetic N`: YAML keys of configs/classification/experiment_vit_edo.yaml
+    (written here: the reference tree is not on the GPU box), uint8 images through the deferred GPU collator, the
+    reference's step semantics, one epoch; the loss comes back finite."""
+    import json
+    import subprocess
+    import sys
+    import os
+    cfg = tmp_path / "exp.yaml"
+    cfg.write_text("""
+setup:
+    dict: {jasmin: 10, epochs: 300, accumulation_steps: 2, log_every: 10}
+data:
+    dataset: {name: cifar10, dataset_path: /nonexistent}
+    collator:
+        train: {shuffle: True, batch_size: 16, pin_memory: True, num_workers: 0, drop_last: True}
+modeling:
+    type: vit
+    inputs: {img_size: 32, patch_size: 4, in_chans: 3, num_classes: 10, embed_dim: 192, num_heads: 3, mlp_ratio: 2.0,
+             emulate_depth: 12.0, time_interval: 1.0, num_eval_steps: 4, attn_drop: 0.1, proj_drop: 0.1, mlp_drop: 0.1,
+             l2_attention: False, add_distillation_token: False, register_tokens: 4, pos_embed_register_tokens: False,
+             solver: euler}
+""")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "odevit_b200.train", "--config", str(cfg), "--synthetic", "64", "--epochs", "1",
+                        "modeling.inputs.num_eval_steps=3"], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["epoch"] == 1 and line["loss"] == line["loss"] and line["world"] == 1
