@@ -51,7 +51,14 @@ def test_gpu_processor_matches_hf_processor(H, W, B):
     want_u8 = np.stack([np.asarray(im.resize((224, 224), resample=Image.BILINEAR)) for im in imgs])
     assert np.array_equal(got["resized_uint8"].cpu().numpy(), want_u8)          # bit-exact resize
     assert got["pixel_values"].shape == want.shape and got["pixel_values"].is_cuda
-    assert float((got["pixel_values"].cpu() - want).abs().max()) < 1e-6
+    # the processor's own arithmetic on Pillow's resize: (u8 / 255 - mean) / std in float32
+    want_pil = (want_u8.astype(np.float32) / 255.0 - np.array(mean, dtype=np.float32)) / np.array(std, dtype=np.float32)
+    assert float(np.abs(got["pixel_values"].cpu().numpy() - want_pil.transpose(0, 3, 1, 2)).max()) < 1e-6
+    # the installed transformers (5.x) resizes through torch for general sizes and lands within ONE uint8 level of
+    # Pillow there; for the CIFAR case (32 -> 224) it is Pillow's result exactly
+    diff = (got["pixel_values"].cpu() - want).abs()
+    assert float(diff.max()) < (1e-6 if (H, W) == (32, 32) else 1.01 / 255 / min(std))
+    assert float(diff.mean()) < 2e-3
 
 
 @pytest.mark.gpu
