@@ -271,6 +271,20 @@ int odevit_solve_fwd_lean(const odevit_desc* desc, const odevit_weights* w, int3
  * trajectory rows written from shared memory): the caller then has no reason to prefer the trajectory-free form. */
 int odevit_solve_uses_resident(const odevit_desc* desc, int32_t method, int32_t n_grid);
 
+/* The L1-attention-loss front-end, loss_trainer.py:80-117 (`ImageDistilTrainer.extract_mass`), one launch:
+ *   attn_rows [B,H,n] fp32: the CLS query's attention over the n = side^2 patches (contiguous);
+ *   per row: ascending sort, normalise by (sum + 1e-8), cumulative sum c, mask = sigmoid((c - (1 - threshold)) *
+ *   scale_factor) (smooth != 0) or [c > 1 - threshold]; the mask goes back to the original positions, multiplies the
+ *   row, the [side, side] tile is blurred (3 x 3 gaussian, sigma 0.5, reflect padding; smooth only);
+ *   out_mean [B,n]: mean over heads; out_heads [B,H,n] or NULL: per head; out_mask [B,n] or NULL: mean mask.
+ * odevit_extract_mass_bwd: g_rows [B,H,n] = VJP for the cotangents g_mean [B,n] and/or g_heads [B,H,n] (smooth: through
+ * the blur, the mask and the normalised cumulative sum; hard mask: through the product only, as autograd does). */
+int odevit_extract_mass_fwd(const float* attn_rows, int32_t batch, int32_t heads, int32_t n, float threshold, int32_t smooth,
+                            float scale_factor, float* out_mean, float* out_heads, float* out_mask, odevit_stream_t stream);
+int odevit_extract_mass_bwd(const float* attn_rows, int32_t batch, int32_t heads, int32_t n, float threshold, int32_t smooth,
+                            float scale_factor, const float* g_mean, const float* g_heads, float* g_rows,
+                            odevit_stream_t stream);
+
 /* GPU-side image preprocessing: what the reference's collator asks of HF `ViTImageProcessor`
  * (datasets/collator.py:11-22): resize to out_h x out_w with Pillow's BILINEAR resampling (bit-exact: fixed point,
  * horizontal then vertical pass, uint8 rounding after each), multiply by `rescale` (1/255), subtract mean, divide by std.

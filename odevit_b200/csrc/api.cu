@@ -1291,6 +1291,30 @@ int odevit_jasmin_rowmax(const float* p_maps, int64_t n_slices, int32_t tokens, 
   return jasmin_rowmax(p_maps, n_slices, tokens, k, out, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int odevit_extract_mass_fwd(const float* attn_rows, int32_t batch, int32_t heads, int32_t n, float threshold, int32_t smooth,
+                            float scale_factor, float* out_mean, float* out_heads, float* out_mask, odevit_stream_t stream) {
+  if (batch <= 0 || heads <= 0 || n <= 0) return set_error(ODEVIT_ERR_INVALID_ARG, "extract_mass: non-positive dimension");
+  ODV_TRY(check_device_ptr(attn_rows, "attn_rows"));
+  ODV_TRY(check_device_ptr(out_mean, "out_mean"));
+  if (out_heads) ODV_TRY(check_device_ptr(out_heads, "out_heads"));
+  if (out_mask) ODV_TRY(check_device_ptr(out_mask, "out_mask"));
+  return extract_mass_fwd(attn_rows, batch, heads, n, threshold, smooth, scale_factor, out_mean, out_heads, out_mask,
+                          reinterpret_cast<cudaStream_t>(stream));
+}
+
+int odevit_extract_mass_bwd(const float* attn_rows, int32_t batch, int32_t heads, int32_t n, float threshold, int32_t smooth,
+                            float scale_factor, const float* g_mean, const float* g_heads, float* g_rows,
+                            odevit_stream_t stream) {
+  if (batch <= 0 || heads <= 0 || n <= 0) return set_error(ODEVIT_ERR_INVALID_ARG, "extract_mass: non-positive dimension");
+  if (!g_mean && !g_heads) return set_error(ODEVIT_ERR_INVALID_ARG, "extract_mass: no cotangent given");
+  ODV_TRY(check_device_ptr(attn_rows, "attn_rows"));
+  ODV_TRY(check_device_ptr(g_rows, "g_rows"));
+  if (g_mean) ODV_TRY(check_device_ptr(g_mean, "g_mean"));
+  if (g_heads) ODV_TRY(check_device_ptr(g_heads, "g_heads"));
+  return extract_mass_bwd(attn_rows, batch, heads, n, threshold, smooth, scale_factor, g_mean, g_heads, g_rows,
+                          reinterpret_cast<cudaStream_t>(stream));
+}
+
 int odevit_pil_bilinear_ksize(int32_t in_size, int32_t out_size) {
   if (in_size <= 0 || out_size <= 0) return 0;
   return pil_bilinear_ksize(in_size, out_size);

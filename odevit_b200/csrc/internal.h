@@ -238,6 +238,12 @@ int drop_rows_inplace(void* x, int type, Drop d, int rows, int D, cudaStream_t s
 int resolve_drop_keys(const uint32_t* seed_dev, uint32_t* table, int n, cudaStream_t s);
 int drop_state_advance(unsigned long long* state, cudaStream_t s);
 
+// mass.cu: the L1-attention front-end (loss_trainer.py:80-117), forward and exact VJP
+int extract_mass_fwd(const float* a, int B, int H, int n, float threshold, int smooth, float scale, float* out_mean,
+                     float* out_heads, float* out_mask, cudaStream_t s);
+int extract_mass_bwd(const float* a, int B, int H, int n, float threshold, int smooth, float scale, const float* g_mean,
+                     const float* g_heads, float* g_a, cudaStream_t s);
+
 // preprocess.cu: PIL-exact bilinear resize of uint8 HWC images + rescale + normalise -> fp32 NCHW
 int preprocess_u8(const uint8_t* images, int B, int H, int W, int So_h, int So_w, const int32_t* bounds_h,
                   const int32_t* kk_h, int ksize_h, const int32_t* bounds_v, const int32_t* kk_v, int ksize_v,

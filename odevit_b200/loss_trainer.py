@@ -51,6 +51,11 @@ def extract_mass(attn_rows: torch.Tensor, threshold: float = 0.8, smooth: bool =
     `scale_factor`) once the cumulative mass passes 1 - threshold; the kept weights go on the side x side
     grid, are blurred 3x3 (sigma 0.5) and averaged over heads.
     Returns (mean over heads [B, side, side], per head [B, heads, side, side], mask mean or None)."""
+    if attn_rows.is_cuda:
+        from . import ops                  # one launch forward, one backward (csrc/mass.cu); no CPU fallback for CUDA tensors
+        return ops.extract_mass(attn_rows, threshold, smooth, scale_factor, return_mask)
+    # CPU tensors: the plain composition (what tests/test_distill_trainer.py pins against the reference's trainer on the
+    # oracle student; the device path above is pinned against this one and against the reference's golden)
     B, nh, n = attn_rows.shape
     side = int(n ** 0.5 + 0.5)
     val, order = torch.sort(attn_rows, dim=-1)

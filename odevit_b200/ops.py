@@ -412,6 +412,55 @@ def ode_solve(x0: torch.Tensor, t: torch.Tensor, spec: FieldSpec, method: str,
             "jas_traj": jas_traj if jas_traj.numel() else None}
 
 
+class _ExtractMass(torch.autograd.Function):
+    """odevit_extract_mass_fwd / _bwd: the L1-attention-loss front-end (loss_trainer.py:80-117) as one launch each way."""
+
+    @staticmethod
+    def forward(ctx, rows, threshold: float, smooth: bool, scale_factor: float, want_mask: bool):
+        rows = _require_cuda(rows, "attn_rows")
+        B, H, n = rows.shape
+        mean = torch.empty(B, n, device=rows.device, dtype=torch.float32)
+        heads = torch.empty(B, H, n, device=rows.device, dtype=torch.float32)
+        mask = torch.empty(B, n, device=rows.device, dtype=torch.float32) if want_mask else None
+        with torch.cuda.device(rows.device):
+            st = _lib.lib().odevit_extract_mass_fwd(_ptr(rows), B, H, n, float(threshold), int(bool(smooth)), float(scale_factor),
+                                                    _ptr(mean), _ptr(heads), _ptr(mask), _stream())
+        _lib.check(st, "odevit_extract_mass_fwd")
+        ctx.save_for_backward(rows)
+        ctx.cfg = (float(threshold), int(bool(smooth)), float(scale_factor))
+        ctx.set_materialize_grads(False)
+        if mask is None:
+            mask = rows.new_empty(0)
+        ctx.mark_non_differentiable(mask)
+        return mean, heads, mask
+
+    @staticmethod
+    def backward(ctx, g_mean, g_heads, _g_mask):
+        (rows,) = ctx.saved_tensors
+        if g_mean is None and g_heads is None:
+            return None, None, None, None, None
+        B, H, n = rows.shape
+        g_mean = _require_cuda(g_mean, "g_mean") if g_mean is not None else None
+        g_heads = _require_cuda(g_heads, "g_heads") if g_heads is not None else None
+        g_rows = torch.empty_like(rows)
+        thr, smooth, scale = ctx.cfg
+        with torch.cuda.device(rows.device):
+            st = _lib.lib().odevit_extract_mass_bwd(_ptr(rows), B, H, n, thr, smooth, scale, _ptr(g_mean), _ptr(g_heads),
+                                                    _ptr(g_rows), _stream())
+        _lib.check(st, "odevit_extract_mass_bwd")
+        return g_rows, None, None, None, None
+
+
+def extract_mass(attn_rows: torch.Tensor, threshold: float = 0.8, smooth: bool = True, scale_factor: float = 40.0,
+                 return_mask: bool = False):
+    """loss_trainer.py:80-117 on a CUDA tensor [B, heads, n = side^2]: (mean over heads [B,side,side], per head
+    [B,heads,side,side], mean mask [B,side,side] | None), differentiable (csrc/mass.cu)."""
+    B, H, n = attn_rows.shape
+    side = int(n ** 0.5 + 0.5)
+    mean, heads, mask = _ExtractMass.apply(attn_rows.contiguous().float(), threshold, smooth, scale_factor, return_mask)
+    return mean.view(B, side, side), heads.view(B, H, side, side), (mask.view(B, side, side) if return_mask else None)
+
+
 def solve_uses_resident(spec: FieldSpec, batch: int, tokens: int, method: str, n_grid: int) -> bool:
     """True when the inference solve of this shape runs in the on-chip-state kernel (odevit_solve_uses_resident)."""
     desc = spec.desc(batch, tokens)
