@@ -271,6 +271,31 @@ int odevit_solve_fwd_lean(const odevit_desc* desc, const odevit_weights* w, int3
  * trajectory rows written from shared memory): the caller then has no reason to prefer the trajectory-free form. */
 int odevit_solve_uses_resident(const odevit_desc* desc, int32_t method, int32_t n_grid);
 
+/* Token assembly, ode_transformer_gpt.py:148-182 (PatchEmbed.forward): the patch projection written straight into
+ * the token tensor.
+ *   cols_bf16 [B*P, k] bf16: im2col rows of the images (k = C * patch^2, order (c, i, j) as Conv2d's weight);
+ *   w_bf16 [dim, k] bf16: proj.weight reshaped;  patch_add [P, dim] fp32: proj.bias + the positional rows of the patch
+ *   tokens;  x0 [B, tokens, dim] fp32 out: rows [first_patch_row, first_patch_row + P) of every image come from the
+ *   GEMM's epilogue; special_rows [n_special, dim] fp32 (cls / distillation / register rows, positional rows already
+ *   added where the reference adds them) go to token positions special_index [n_special] (device int32) of every image. */
+int odevit_tokens_fwd(const void* cols_bf16, const void* w_bf16, int32_t batch, int32_t patches, int32_t k, int32_t dim,
+                      int32_t tokens, int32_t first_patch_row, const float* patch_add, const float* special_rows,
+                      const int32_t* special_index, int32_t n_special, float* x0, odevit_stream_t stream);
+
+/* Head + loss, ode_transformer_gpt.py:588-589, :626: logits = head(final[:, 0]), F.cross_entropy(label_smoothing).
+ *   x: first CLS row, x_stride = elements between the CLS rows of consecutive images (tokens * dim for final[:, 0]);
+ *   w [classes, dim], bias [classes] or NULL;  logits [B, classes] out;
+ *   loss_rows [B] or NULL: the per-image smoothed loss (the module's `loss` is its mean), lse [B] kept for the backward.
+ * odevit_head_ce_bwd: dz [B, classes] scratch/out = g_logits (or 0) + g_loss[0] / B * d loss_rows / d logits;
+ *   g_x (stride gx_stride) or NULL = dz @ w;  g_w, g_bias (or NULL): += dz^T @ x, += column sums (caller zero-fills). */
+int odevit_head_ce_fwd(const float* x, int64_t x_stride, const float* w, const float* bias, const int64_t* labels,
+                       int32_t batch, int32_t classes, int32_t dim, float label_smoothing, float* logits, float* loss_rows,
+                       float* lse, odevit_stream_t stream);
+int odevit_head_ce_bwd(const float* x, int64_t x_stride, const float* w, const int64_t* labels, const float* logits,
+                       const float* lse, const float* g_logits, const float* g_loss, int32_t batch, int32_t classes,
+                       int32_t dim, float label_smoothing, float* dz, float* g_x, int64_t gx_stride, float* g_w, float* g_bias,
+                       odevit_stream_t stream);
+
 /* The L1-attention-loss front-end, loss_trainer.py:80-117 (`ImageDistilTrainer.extract_mass`), one launch:
  *   attn_rows [B,H,n] fp32: the CLS query's attention over the n = side^2 patches (contiguous);
  *   per row: ascending sort, normalise by (sum + 1e-8), cumulative sum c, mask = sigmoid((c - (1 - threshold)) *

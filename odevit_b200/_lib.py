@@ -111,6 +111,14 @@ def lib() -> ctypes.CDLL:
                                         ctypes.c_int32, _vp, ctypes.c_size_t, _vp]
     L.odevit_solve_uses_resident.restype = ctypes.c_int
     L.odevit_solve_uses_resident.argtypes = [ctypes.POINTER(Desc), ctypes.c_int32, ctypes.c_int32]
+    L.odevit_tokens_fwd.restype = ctypes.c_int
+    L.odevit_tokens_fwd.argtypes = [_vp, _vp] + [ctypes.c_int32] * 6 + [_vp, _vp, _vp, ctypes.c_int32, _vp, _vp]
+    L.odevit_head_ce_fwd.restype = ctypes.c_int
+    L.odevit_head_ce_fwd.argtypes = [_vp, ctypes.c_int64, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                     ctypes.c_float, _vp, _vp, _vp, _vp]
+    L.odevit_head_ce_bwd.restype = ctypes.c_int
+    L.odevit_head_ce_bwd.argtypes = [_vp, ctypes.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32,
+                                     ctypes.c_int32, ctypes.c_float, _vp, _vp, ctypes.c_int64, _vp, _vp, _vp]
     L.odevit_extract_mass_fwd.restype = ctypes.c_int
     L.odevit_extract_mass_fwd.argtypes = [_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_float, ctypes.c_int32,
                                           ctypes.c_float, _vp, _vp, _vp, _vp]
@@ -181,6 +189,6 @@ def profile_read() -> dict:
 
 DECLARED_SYMBOLS = ("odevit_abi_version", "odevit_build_info", "odevit_last_error_string",
                     "odevit_workspace_bytes", "odevit_field_fwd", "odevit_solve_fwd", "odevit_solve_bwd",
-                    "odevit_field_bwd", "odevit_tape_bytes", "odevit_fd_curvature", "odevit_jasmin_rowmax", "odevit_encoder_cache_bytes", "odevit_encoder_fwd", "odevit_launch_count", "odevit_reset_launch_count", "odevit_drop_state_advance", "odevit_solve_fwd_lean", "odevit_solve_uses_resident", "odevit_extract_mass_fwd", "odevit_extract_mass_bwd", "odevit_pil_bilinear_ksize", "odevit_pil_bilinear_tables", "odevit_preprocess_u8",
+                    "odevit_field_bwd", "odevit_tape_bytes", "odevit_fd_curvature", "odevit_jasmin_rowmax", "odevit_encoder_cache_bytes", "odevit_encoder_fwd", "odevit_launch_count", "odevit_reset_launch_count", "odevit_drop_state_advance", "odevit_solve_fwd_lean", "odevit_solve_uses_resident", "odevit_tokens_fwd", "odevit_head_ce_fwd", "odevit_head_ce_bwd", "odevit_extract_mass_fwd", "odevit_extract_mass_bwd", "odevit_pil_bilinear_ksize", "odevit_pil_bilinear_tables", "odevit_preprocess_u8",
                     "odevit_gemm_bf16", "odevit_profile_enable", "odevit_profile_reserve", "odevit_profile_num_classes", "odevit_profile_class_name",
                     "odevit_profile_read")

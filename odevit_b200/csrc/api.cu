@@ -1291,6 +1291,72 @@ int odevit_jasmin_rowmax(const float* p_maps, int64_t n_slices, int32_t tokens, 
   return jasmin_rowmax(p_maps, n_slices, tokens, k, out, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int odevit_tokens_fwd(const void* cols_bf16, const void* w_bf16, int32_t batch, int32_t patches, int32_t k, int32_t dim,
+                      int32_t tokens, int32_t first_patch_row, const float* patch_add, const float* special_rows,
+                      const int32_t* special_index, int32_t n_special, float* x0, odevit_stream_t stream) {
+  if (batch <= 0 || patches <= 0 || k <= 0 || dim <= 0 || tokens < patches + n_special || first_patch_row < 0 ||
+      first_patch_row + patches > tokens || n_special < 0)
+    return set_error(ODEVIT_ERR_INVALID_ARG, "tokens_fwd: inconsistent sizes");
+  ODV_TRY(check_device_ptr(cols_bf16, "cols"));
+  ODV_TRY(check_device_ptr(w_bf16, "w"));
+  ODV_TRY(check_device_ptr(patch_add, "patch_add"));
+  ODV_TRY(check_device_ptr(x0, "x0"));
+  if (n_special) {
+    ODV_TRY(check_device_ptr(special_rows, "special_rows"));
+    ODV_TRY(check_device_ptr(special_index, "special_index"));
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  GemmArgs g;
+  g.M = batch * patches; g.N = dim; g.K = k;
+  g.A = cols_bf16; g.a_type = DT_BF16; g.a_rs = k; g.a_cs = 1;
+  g.B = w_bf16; g.b_type = DT_BF16; g.b_rs = k; g.b_cs = 1;
+  g.epi_mode = EPI_TOKENS;
+  g.kclass = KC_OTHER;
+  g.epi.out = x0; g.epi.out_type = DT_F32; g.epi.ld_out = dim;
+  g.epi.split = patches; g.epi.out_bo = (long long)tokens * dim; g.epi.out_bi = first_patch_row;
+  g.epi.y = patch_add;
+  if (gemm_tc_supports(g)) ODV_TRY(gemm_tc(g, s));
+  else ODV_TRY(gemm_simt(g, s));
+  return tokens_special_rows(special_rows, special_index, n_special, batch, tokens, dim, x0, s);
+}
+
+int odevit_head_ce_fwd(const float* x, int64_t x_stride, const float* w, const float* bias, const int64_t* labels,
+                       int32_t batch, int32_t classes, int32_t dim, float label_smoothing, float* logits, float* loss_rows,
+                       float* lse, odevit_stream_t stream) {
+  if (batch <= 0 || classes <= 0 || dim <= 0) return set_error(ODEVIT_ERR_INVALID_ARG, "head_ce: non-positive dimension");
+  if ((size_t)(dim + classes) * 4 > 48 * 1024) return set_error(ODEVIT_ERR_UNSUPPORTED, "head_ce: dim + classes > 12288 is not built");
+  ODV_TRY(check_device_ptr(x, "x"));
+  ODV_TRY(check_device_ptr(w, "w"));
+  ODV_TRY(check_device_ptr(logits, "logits"));
+  if (loss_rows) {
+    ODV_TRY(check_device_ptr(labels, "labels"));
+    ODV_TRY(check_device_ptr(loss_rows, "loss_rows"));
+    ODV_TRY(check_device_ptr(lse, "lse"));
+  }
+  return head_ce_fwd(x, x_stride, w, bias, reinterpret_cast<const long long*>(labels), batch, classes, dim, label_smoothing,
+                     logits, loss_rows, lse, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int odevit_head_ce_bwd(const float* x, int64_t x_stride, const float* w, const int64_t* labels, const float* logits,
+                       const float* lse, const float* g_logits, const float* g_loss, int32_t batch, int32_t classes,
+                       int32_t dim, float label_smoothing, float* dz, float* g_x, int64_t gx_stride, float* g_w, float* g_bias,
+                       odevit_stream_t stream) {
+  if (batch <= 0 || classes <= 0 || dim <= 0) return set_error(ODEVIT_ERR_INVALID_ARG, "head_ce: non-positive dimension");
+  if ((size_t)classes * 4 > 48 * 1024) return set_error(ODEVIT_ERR_UNSUPPORTED, "head_ce: more than 12288 classes are not built");
+  if (!g_logits && !g_loss) return set_error(ODEVIT_ERR_INVALID_ARG, "head_ce_bwd: no cotangent given");
+  ODV_TRY(check_device_ptr(x, "x"));
+  ODV_TRY(check_device_ptr(w, "w"));
+  ODV_TRY(check_device_ptr(dz, "dz"));
+  if (g_loss) {
+    ODV_TRY(check_device_ptr(g_loss, "g_loss"));
+    ODV_TRY(check_device_ptr(labels, "labels"));
+    ODV_TRY(check_device_ptr(logits, "logits"));
+    ODV_TRY(check_device_ptr(lse, "lse"));
+  }
+  return head_ce_bwd(x, x_stride, w, reinterpret_cast<const long long*>(labels), logits, lse, g_logits, g_loss, batch, classes, dim,
+                     label_smoothing, dz, g_x, gx_stride, g_w, g_bias, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int odevit_extract_mass_fwd(const float* attn_rows, int32_t batch, int32_t heads, int32_t n, float threshold, int32_t smooth,
                             float scale_factor, float* out_mean, float* out_heads, float* out_mask, odevit_stream_t stream) {
   if (batch <= 0 || heads <= 0 || n <= 0) return set_error(ODEVIT_ERR_INVALID_ARG, "extract_mass: non-positive dimension");

@@ -91,6 +91,10 @@ __device__ __forceinline__ void epi_apply(const Epi& e, int m, int n, float acc,
       if constexpr ((EPI & EPI_DROP) != 0) acc *= drop_factor(e.drop, m, c);
       store_elem(e.out2, (long long)m * e.ld_out2 + c, e.aux_type, acc * gelu_erf_grad(hp));
     }
+  } else if constexpr ((EPI & 7) == EPI_TOKENS) {
+    const int b = m / e.split, r = m - b * e.split;
+    reinterpret_cast<float*>(e.out)[(long long)b * e.out_bo + (long long)(r + e.out_bi) * e.ld_out + n] =
+        acc + e.y[(long long)r * e.ld_out + n];
   } else if constexpr ((EPI & 7) == EPI_ACCUM) {
     float* o = reinterpret_cast<float*>(e.out) + (long long)m * e.ld_out + n;
     if constexpr (ATOMIC) atomicAdd(o, e.alpha * acc);
@@ -570,6 +574,15 @@ __device__ __forceinline__ void epi8_finish(const Epi& e, int m0, int M, int n, 
         }
       }
       store_rows8<FULL>(e.out2, e.aux_type, (long long)m0 * e.ld_out2 + c, 4 * (int)e.ld_out2, m0, M, w);
+    }
+  } else if constexpr ((EPI & 7) == EPI_TOKENS) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (!row_in<FULL>(m0, i, M)) continue;
+      const int m = m0 + 4 * i;
+      const int b = m / e.split, r = m - b * e.split;
+      const float4 add = *reinterpret_cast<const float4*>(e.y + (long long)r * e.ld_out + n);
+      stg_f32x4(reinterpret_cast<float*>(e.out) + (long long)b * e.out_bo + (long long)(r + e.out_bi) * e.ld_out + n, add4(w[i], add));
     }
   } else if constexpr ((EPI & 7) == EPI_ACCUM) {
     float* p = reinterpret_cast<float*>(e.out) + (long long)m0 * e.ld_out + n;

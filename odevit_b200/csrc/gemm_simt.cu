@@ -116,6 +116,7 @@ int gemm_simt(const GemmArgs& g, cudaStream_t s) {
       else gemm_simt_kernel<EPI_BWD3><<<grid, 256, 0, s>>>(g);
       break;
     case EPI_ACCUM: gemm_simt_kernel<EPI_ACCUM><<<grid, 256, 0, s>>>(g); break;
+    case EPI_TOKENS: gemm_simt_kernel<EPI_TOKENS><<<grid, 256, 0, s>>>(g); break;
     default: return set_error(ODEVIT_ERR_INVALID_ARG, "gemm_simt: bad epilogue %d", g.epi_mode);
   }
   ODV_LAUNCH_CHECK();

@@ -454,6 +454,7 @@ int launch_epi(int epi_mode, bool mn, const CUtensorMap& ta, const CUtensorMap& 
       if (d.epi.drop.thresh) return launch_major<CG, BN, EPI_BWD3 | EPI_DROP>(mn, ta, tb, d, units, s);
       return launch_major<CG, BN, EPI_BWD3>(mn, ta, tb, d, units, s);
     case EPI_ACCUM: return launch_major<CG, BN, EPI_ACCUM>(mn, ta, tb, d, units, s);
+    case EPI_TOKENS: return launch_major<CG, BN, EPI_TOKENS>(mn, ta, tb, d, units, s);
     default: return set_error(ODEVIT_ERR_INVALID_ARG, "gemm_tc: bad epilogue %d", epi_mode);
   }
 }
@@ -550,13 +551,14 @@ bool gemm_tc_supports(const GemmArgs& g) {
   if (a_mn ? (g.M % 8) : (g.K % 8)) return false;
   if (b_mn ? (g.N % 8) : (g.K % 8)) return false;
   switch (g.epi_mode) {
-    case EPI_STORE: case EPI_FWD1: case EPI_RK: case EPI_BWD3: case EPI_ACCUM: break;
+    case EPI_STORE: case EPI_FWD1: case EPI_RK: case EPI_BWD3: case EPI_ACCUM: case EPI_TOKENS: break;
     default: return false;
   }
   if (g.epi_mode == EPI_FWD1 || g.epi_mode == EPI_BWD3) {
     if (g.epi.split % 16 || g.epi.ld_out2 % 8 || (g.epi.out3 && g.epi.ld_out3 % 8)) return false;
   }
-  if (g.epi.ld_out % (g.epi.out_type == DT_F32 || g.epi_mode == EPI_RK || g.epi_mode == EPI_ACCUM ? 4 : 8)) return false;
+  if (g.epi.ld_out % (g.epi.out_type == DT_F32 || g.epi_mode == EPI_RK || g.epi_mode == EPI_ACCUM || g.epi_mode == EPI_TOKENS ? 4 : 8)) return false;
+  if (g.epi_mode == EPI_TOKENS && (mn || g.epi.split <= 0 || !g.epi.y || g.epi.out_bo % 4)) return false;
   return true;
 }
 

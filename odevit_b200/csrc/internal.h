@@ -98,6 +98,9 @@ enum EpiMode : int {
   EPI_BWD3 = 3,   // n <  split: out[m,n] = acc                    (dO)
                   // n >= split: out2[m,n-split] = acc * gelu'(aux[m,n-split])   (d h_pre)
   EPI_ACCUM = 4,  // out[m,n] += alpha*acc   (fp32; atomic when split-K)
+  EPI_TOKENS = 5, // patch projection straight into the token tensor (ode_transformer_gpt.py:148-182): with P = split
+                  // rows per image, out[(m / P) * out_bo + (m % P + out_bi) * ld_out + n] = acc + y[(m % P) * ld_out + n]
+                  // (y = bias + positional rows of the patch tokens, [P, D] fp32)
   // template-only flag: the epilogue applies Epi::drop (kernels without it carry no mask code at all)
   EPI_DROP = 8,
   // template-only flag (EPI_RK): the epilogue also folds the second finite difference of the trajectory into
@@ -237,6 +240,14 @@ int drop_rows_inplace(void* x, int type, Drop d, int rows, int D, cudaStream_t s
 // table[i] = key of (evaluation i / DS_SITES, site i % DS_SITES) from the 64-bit seed at seed_dev
 int resolve_drop_keys(const uint32_t* seed_dev, uint32_t* table, int n, cudaStream_t s);
 int drop_state_advance(unsigned long long* state, cudaStream_t s);
+
+// tokens.cu: token assembly around the patch GEMM, head + cross-entropy
+int tokens_special_rows(const float* rows, const int* index, int n_special, int B, int N, int D, float* x0, cudaStream_t s);
+int head_ce_fwd(const float* x, long long x_stride, const float* W, const float* bias, const long long* labels, int B, int C, int D,
+                float eps, float* logits, float* loss, float* lse, cudaStream_t s);
+int head_ce_bwd(const float* x, long long x_stride, const float* W, const long long* labels, const float* logits, const float* lse,
+                const float* g_logits, const float* g_loss, int B, int C, int D, float eps, float* dz, float* g_x,
+                long long gx_stride, float* g_W, float* g_bias, cudaStream_t s);
 
 // mass.cu: the L1-attention front-end (loss_trainer.py:80-117), forward and exact VJP
 int extract_mass_fwd(const float* a, int B, int H, int n, float threshold, int smooth, float scale, float* out_mean,

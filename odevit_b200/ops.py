@@ -654,3 +654,158 @@ class _PatchProj(torch.autograd.Function):
 def patch_project(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], patch: int) -> torch.Tensor:
     """[B, C, H, W] -> [B, (H/p)(W/p), D] patch tokens (before cls / register / positional assembly)."""
     return _PatchProj.apply(x, weight, bias, patch)
+
+
+class _TokenAssembly(torch.autograd.Function):
+    """PatchEmbed.forward (ode_transformer_gpt.py:148-182) in two launches after the im2col cast: the patch GEMM writes
+    its rows of x0 [B,N,D] with bias + positional rows added in the epilogue (odevit_tokens_fwd, EPI_TOKENS); the cls /
+    distillation / register rows are broadcast by one small kernel.  Token order: cls, [dist], patches, registers; the
+    positional rows go to the first `n_pos` tokens (the reference's slicing, including its offset with a dist token)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, cls, dist, reg, pos, patch: int, n_pos: int):
+        x = _require_cuda(x, "pixel_values")
+        Bn, C, H, W = x.shape
+        g_h, g_w = H // patch, W // patch
+        P, K, D = g_h * g_w, C * patch * patch, weight.shape[0]
+        off = 1 + (1 if dist is not None else 0)
+        R = reg.shape[0] if reg is not None else 0
+        N = off + P + R
+        dev = x.device
+        a = torch.empty(Bn, g_h, g_w, C, patch, patch, dtype=torch.bfloat16, device=dev)
+        a.copy_(x.view(Bn, C, g_h, patch, g_w, patch).permute(0, 2, 4, 1, 3, 5))
+        w = weight.detach().reshape(D, K).to(torch.bfloat16)
+        pe = pos.detach().reshape(-1, D)
+        n_pos = min(int(n_pos), N, pe.shape[0])
+        patch_add = torch.zeros(P, D, device=dev, dtype=torch.float32)
+        if bias is not None:
+            patch_add += bias.detach()
+        hi = max(off, min(n_pos, off + P))
+        patch_add[:hi - off] += pe[off:hi]
+        rows = [cls.detach().reshape(1, D) + pe[0:1]]
+        index = [0]
+        if dist is not None:
+            rows.append(dist.detach().reshape(1, D) + (pe[1:2] if n_pos > 1 else 0))
+            index.append(1)
+        if R:
+            r = reg.detach().clone()
+            lo = off + P
+            if n_pos > lo:
+                r[:n_pos - lo] += pe[lo:n_pos]
+            rows.append(r)
+            index.extend(range(lo, lo + R))
+        special = torch.cat(rows, 0).contiguous().float()
+        idx_t = _row_index_tensor(tuple(index), dev).to(torch.int32)
+        x0 = torch.empty(Bn, N, D, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            st = _lib.lib().odevit_tokens_fwd(_ptr(a), _ptr(w), Bn, P, K, D, N, off, _ptr(patch_add), _ptr(special), _ptr(idx_t),
+                                              len(index), _ptr(x0), _stream())
+        _lib.check(st, "odevit_tokens_fwd")
+        ctx.save_for_backward(a, w)
+        ctx.meta = (Bn, C, H, W, patch, tuple(weight.shape), bias is not None, dist is not None, R, off, P, n_pos,
+                    tuple(pos.shape), tuple(cls.shape))
+        return x0
+
+    @staticmethod
+    def backward(ctx, g):
+        a, w = ctx.saved_tensors
+        Bn, C, H, W, patch, w_shape, has_bias, has_dist, R, off, P, n_pos, pos_shape, cls_shape = ctx.meta
+        g = g.contiguous()
+        D = w_shape[0]
+        K = C * patch * patch
+        M = Bn * P
+        need = ctx.needs_input_grad
+        g_x = g_w = g_b = g_cls = g_dist = g_reg = g_pos = None
+        gp = g[:, off:off + P]
+        if need[0] or need[1]:
+            gy = gp.to(torch.bfloat16).reshape(M, D).contiguous()
+            if need[1]:
+                g_w = torch.empty(D, K, dtype=torch.float32, device=g.device)
+                _gemm_bf16(D, K, M, 1, gy, a.view(M, K), g_w)
+                g_w = g_w.view(w_shape)
+            if need[0]:
+                cols = torch.empty(M, K, dtype=torch.float32, device=g.device)
+                _gemm_bf16(M, K, D, 0, gy, w.t().contiguous(), cols)
+                g_h, g_w_ = H // patch, W // patch
+                g_x = cols.view(Bn, g_h, g_w_, C, patch, patch).permute(0, 3, 1, 4, 2, 5).reshape(Bn, C, H, W)
+        col = g.sum(0) if (need[3] or need[4] or need[5] or need[6] or (has_bias and need[2])) else None     # [N, D]
+        if has_bias and need[2]:
+            g_b = col[off:off + P].sum(0)
+        if need[3]:
+            g_cls = col[0].reshape(cls_shape)
+        if has_dist and need[4]:
+            g_dist = col[1].reshape(cls_shape)
+        if R and need[5]:
+            g_reg = col[off + P:].clone()
+        if need[6]:
+            g_pos = torch.zeros(pos_shape, device=g.device, dtype=torch.float32)
+            g_pos.view(-1, D)[:n_pos] = col[:n_pos]
+        return g_x, g_w, g_b, g_cls, g_dist, g_reg, g_pos, None, None
+
+
+def token_assembly(x, weight, bias, cls, dist, reg, pos, patch: int, n_pos: int) -> torch.Tensor:
+    """[B,C,H,W] pixels -> x0 [B,N,D] tokens (cls, [dist], patches, registers) with positional rows, bf16 GEMM."""
+    return _TokenAssembly.apply(x, weight, bias, cls, dist, reg, pos, patch, n_pos)
+
+
+class _HeadCE(torch.autograd.Function):
+    """logits = head(final[:, 0]) and F.cross_entropy(logits, labels, label_smoothing) (ode_transformer_gpt.py:588-589,
+    :626) as one launch (odevit_head_ce_fwd); backward: d logits from the loss and / or a cotangent on the logits, d
+    cls row, d head.weight / bias (odevit_head_ce_bwd)."""
+
+    @staticmethod
+    def forward(ctx, final, weight, bias, labels, eps: float):
+        final = _require_cuda(final, "final")
+        B, N, D = final.shape
+        C = weight.shape[0]
+        dev = final.device
+        w = _require_cuda(weight.detach(), "head.weight")
+        b = _require_cuda(bias.detach(), "head.bias") if bias is not None else None
+        logits = torch.empty(B, C, device=dev, dtype=torch.float32)
+        has_loss = labels is not None
+        rows = torch.empty(B, device=dev, dtype=torch.float32) if has_loss else None
+        lse = torch.empty(B, device=dev, dtype=torch.float32) if has_loss else None
+        lab = labels.to(dev, torch.int64).contiguous() if has_loss else None
+        with torch.cuda.device(dev):
+            st = _lib.lib().odevit_head_ce_fwd(_ptr(final), N * D, _ptr(w), _ptr(b), _ptr(lab), B, C, D, float(eps), _ptr(logits),
+                                               _ptr(rows), _ptr(lse), _stream())
+        _lib.check(st, "odevit_head_ce_fwd")
+        ctx.save_for_backward(final, w, lab if has_loss else final.new_empty(0), logits, lse if has_loss else final.new_empty(0))
+        ctx.cfg = (float(eps), has_loss, bias is not None)
+        ctx.set_materialize_grads(False)
+        loss = rows.mean() if has_loss else final.new_zeros(())
+        return logits, loss
+
+    @staticmethod
+    def backward(ctx, g_logits, g_loss):
+        final, w, lab, logits, lse = ctx.saved_tensors
+        eps, has_loss, has_bias = ctx.cfg
+        B, N, D = final.shape
+        C = w.shape[0]
+        dev = final.device
+        if not has_loss:
+            g_loss = None
+        if g_logits is None and g_loss is None:
+            return None, None, None, None, None
+        g_logits = _require_cuda(g_logits, "g_logits") if g_logits is not None else None
+        g_loss = g_loss.reshape(1).float().contiguous() if g_loss is not None else None
+        dz = torch.empty(B, C, device=dev, dtype=torch.float32)
+        need = ctx.needs_input_grad
+        g_final = torch.zeros_like(final) if need[0] else None
+        g_w = torch.zeros_like(w) if need[1] else None
+        g_b = torch.zeros(C, device=dev, dtype=torch.float32) if (has_bias and need[2]) else None
+        if g_b is not None and g_w is None:
+            g_w = torch.zeros_like(w)
+        with torch.cuda.device(dev):
+            st = _lib.lib().odevit_head_ce_bwd(_ptr(final), N * D, _ptr(w), _ptr(lab if has_loss else None), _ptr(logits),
+                                               _ptr(lse if has_loss else None), _ptr(g_logits), _ptr(g_loss), B, C, D, eps,
+                                               _ptr(dz), _ptr(g_final), N * D, _ptr(g_w), _ptr(g_b), _stream())
+        _lib.check(st, "odevit_head_ce_bwd")
+        return g_final, (g_w if need[1] else None), g_b, None, None
+
+
+def head_ce(final: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], labels: Optional[torch.Tensor],
+            label_smoothing: float = 0.05):
+    """(logits [B,C], loss 0-d | None) from the final state [B,N,D] (CLS row 0) and the head's parameters."""
+    logits, loss = _HeadCE.apply(final, weight, bias, labels, label_smoothing)
+    return logits, (loss if labels is not None else None)

@@ -258,6 +258,15 @@ class PatchEmbed(nn.Module):
     def forward(self, x: torch.Tensor, learn_ivp: bool = False) -> torch.Tensor:
         p = self.proj.kernel_size[0]
         if (getattr(self, "precision", "fp32") == "bf16" and x.is_cuda and x.dtype == torch.float32
+                and x.shape[-1] % p == 0 and x.shape[-2] % p == 0 and not learn_ivp and self.pos_drop.p == 0.0
+                and self.proj.out_channels % 4 == 0 and getattr(self, "fused_assembly", True)):
+            # bf16 mode: im2col + ONE tcgen05 GEMM whose epilogue writes the patch rows of the token tensor with bias and
+            # positional rows added; cls / dist / register rows by one small kernel (ops.token_assembly, row (f)1)
+            n_pos = self.num_patches + 1 + (self.num_register_tokens if self.pos_embed_register_tokens else 0)
+            return ops.token_assembly(x, self.proj.weight, self.proj.bias, self.cls_token,
+                                      self.dist_token if self.add_distillation_token else None,
+                                      self.register_tokens if self.num_register_tokens else None, self.pos_embed, p, n_pos)
+        if (getattr(self, "precision", "fp32") == "bf16" and x.is_cuda and x.dtype == torch.float32
                 and x.shape[-1] % p == 0 and x.shape[-2] % p == 0):
             # bf16 mode: im2col + tcgen05 GEMM (ops.patch_project) instead of cuDNN's TF32 convolution
             x = ops.patch_project(x, self.proj.weight, self.proj.bias, p)
@@ -478,8 +487,15 @@ class ViTNeuralODE(nn.Module):
         states, final = res["states"], res["final"]
         block.attentions = res["p_last"]
 
+        fused_head = (final.is_cuda and type(self.head) is nn.Linear and final.dtype == torch.float32
+                      and getattr(self, "fused_head", True))
+        if fused_head:
+            # head + smoothed cross-entropy in one launch each way (ops.head_ce, row (f)1)
+            logits, loss = ops.head_ce(final, self.head.weight, self.head.bias, labels, 0.05)
+        else:
+            logits, loss = self.head(final[:, 0]), None
         out = {
-            "logits": self.head(final[:, 0]),
+            "logits": logits,
             "second_derivative_upper_bound": self.compute_upper_bound_by_second_derivative(R=jasmin_k, L=1 / 2),
             "finite_difference_upper_bound": self.compute_upper_bound_by_fininte_difference(
                 states.detach() if states is not None else None, 0.5, 1 / self.num_eval_steps,
@@ -508,7 +524,7 @@ class ViTNeuralODE(nn.Module):
         if self.add_distillation_token:
             out["logits_dist"] = self.dist_head(final[:, 1])
         if labels is not None:
-            out["loss"] = F.cross_entropy(out["logits"], labels, label_smoothing=0.05)
+            out["loss"] = loss if fused_head else F.cross_entropy(out["logits"], labels, label_smoothing=0.05)
         if output_hidden_states:
             out["states"] = states
         if output_control_points:
