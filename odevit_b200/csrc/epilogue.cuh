@@ -459,7 +459,8 @@ __device__ __forceinline__ void epi8_finish(const Epi& e, int m0, int M, int n, 
       if (e.out3) store_rows8<FULL>(e.out3, e.aux_type, (long long)m0 * e.ld_out3 + c, 4 * (int)e.ld_out3, m0, M, w);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        w[i] = make_float4(gelu_fast(w[i].x), gelu_fast(w[i].y), gelu_fast(w[i].z), gelu_fast(w[i].w));
+        if constexpr ((EPI & EPI_EXACT) != 0) w[i] = make_float4(gelu_erf(w[i].x), gelu_erf(w[i].y), gelu_erf(w[i].z), gelu_erf(w[i].w));
+        else w[i] = make_float4(gelu_fast(w[i].x), gelu_fast(w[i].y), gelu_fast(w[i].z), gelu_fast(w[i].w));
         if constexpr ((EPI & EPI_DROP) != 0) {
           const uint32_t r = m0 + 4 * i;
           w[i].x *= drop_factor(e.drop, r, c); w[i].y *= drop_factor(e.drop, r, c + 1);
@@ -565,8 +566,13 @@ __device__ __forceinline__ void epi8_finish(const Epi& e, int m0, int M, int n, 
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 hp = f32 ? raw_f32(pre.a[i]) : raw_bf16(pre.a[i]);
-        w[i].x *= ds * gelu_grad_fast(hp.x); w[i].y *= ds * gelu_grad_fast(hp.y);
-        w[i].z *= ds * gelu_grad_fast(hp.z); w[i].w *= ds * gelu_grad_fast(hp.w);
+        if constexpr ((EPI & EPI_EXACT) != 0) {
+          w[i].x *= ds * gelu_erf_grad(hp.x); w[i].y *= ds * gelu_erf_grad(hp.y);
+          w[i].z *= ds * gelu_erf_grad(hp.z); w[i].w *= ds * gelu_erf_grad(hp.w);
+        } else {
+          w[i].x *= ds * gelu_grad_fast(hp.x); w[i].y *= ds * gelu_grad_fast(hp.y);
+          w[i].z *= ds * gelu_grad_fast(hp.z); w[i].w *= ds * gelu_grad_fast(hp.w);
+        }
         if constexpr ((EPI & EPI_DROP) != 0) {
           const uint32_t r = m0 + 4 * i;
           w[i].x *= drop_factor(e.drop, r, c); w[i].y *= drop_factor(e.drop, r, c + 1);

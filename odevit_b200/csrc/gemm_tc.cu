@@ -440,6 +440,7 @@ int launch_epi(int epi_mode, bool mn, const CUtensorMap& ta, const CUtensorMap& 
   switch (epi_mode) {
     case EPI_STORE: return launch_major<CG, BN, EPI_STORE>(mn, ta, tb, d, units, s);
     case EPI_FWD1:
+      if (d.epi.exact_gelu) return launch_major<CG, BN, EPI_FWD1 | EPI_EXACT>(mn, ta, tb, d, units, s);
       if (d.epi.drop.thresh) return launch_major<CG, BN, EPI_FWD1 | EPI_DROP>(mn, ta, tb, d, units, s);
       return launch_major<CG, BN, EPI_FWD1>(mn, ta, tb, d, units, s);
     case EPI_RK:
@@ -451,6 +452,7 @@ int launch_epi(int epi_mode, bool mn, const CUtensorMap& ta, const CUtensorMap& 
       if (d.epi.drop.thresh) return launch_major<CG, BN, EPI_RK | EPI_DROP>(mn, ta, tb, d, units, s);
       return launch_major<CG, BN, EPI_RK>(mn, ta, tb, d, units, s);
     case EPI_BWD3:
+      if (d.epi.exact_gelu) return launch_major<CG, BN, EPI_BWD3 | EPI_EXACT>(mn, ta, tb, d, units, s);
       if (d.epi.drop.thresh) return launch_major<CG, BN, EPI_BWD3 | EPI_DROP>(mn, ta, tb, d, units, s);
       return launch_major<CG, BN, EPI_BWD3>(mn, ta, tb, d, units, s);
     case EPI_ACCUM: return launch_major<CG, BN, EPI_ACCUM>(mn, ta, tb, d, units, s);
@@ -538,7 +540,8 @@ bool gemm_tc_supports(const GemmArgs& g) {
   if (g.batch_outer * g.batch_inner != 1) return false;
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return false;
   if (g.N % 16) return false;
-  if (g.epi.fd_out && (g.N % 32 || g.epi.drop.thresh)) return false;   // whole warps reduce over rows: no dead lanes
+  if (g.epi.fd_out && (g.N % 32 || g.epi.drop.thresh)) return false;
+  if (g.epi.exact_gelu && g.epi.drop.thresh) return false;   // (that combination is not instantiated)   // whole warps reduce over rows: no dead lanes
   const bool a_k = (g.a_cs == 1), a_mn = (g.a_rs == 1 && g.a_cs != 1);
   const bool b_k = (g.b_cs == 1), b_mn = (g.b_rs == 1 && g.b_cs != 1);
   if (!(a_k || a_mn) || !(b_k || b_mn)) return false;

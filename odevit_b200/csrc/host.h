@@ -18,6 +18,11 @@ struct Plan {
   uint32_t* drop_keys;        // [kDropKeyEvals * DS_SITES] key table in the workspace (device seed only)
   bool any_drop;
   bool split_out;   // proj / mlp dropout on: out-proj and fc2 run as two GEMMs (their outputs take different masks)
+  // fp32 mode on the tensor core: scratch for the bf16 hi / lo split of a GEMM's operands (api.cu::gemm_split3); set by
+  // the workspace layouts (null: the FFMA kernel runs)
+  mutable void* split_a = nullptr;
+  mutable void* split_b = nullptr;
+  mutable size_t split_a_bytes = 0, split_b_bytes = 0;
 };
 // mask of dropout site `site` in field evaluation `e` (e = step * stages + stage)
 Drop make_drop(const Plan& p, int site, long long e);

@@ -105,7 +105,9 @@ enum EpiMode : int {
   EPI_DROP = 8,
   // template-only flag (EPI_RK): the epilogue also folds the second finite difference of the trajectory into
   // Epi::fd_out (trajectory-free inference: ode_transformer_gpt.py:529-543 without the [T,B,N,D] tensor)
-  EPI_FD = 16
+  EPI_FD = 16,
+  // template-only flag (EPI_FWD1 / EPI_BWD3): erf-form GELU instead of the fitted logistic form (the fp32 mode)
+  EPI_EXACT = 32
 };
 
 // One dropout site of one field evaluation: element (r, c) is kept iff hash(key, r, c) >= thresh and then
@@ -155,6 +157,9 @@ struct Epi {
   // with fd_prev the row before y ([M] fp32 maxima, atomicMax on the bit pattern of non-negative floats)
   const float* fd_prev = nullptr;
   float* fd_out = nullptr;
+  // the tcgen05 epilogues use GELU's erf form (set by the fp32 mode's split-bf16 GEMMs; the bf16 mode's fitted form is
+  // 2.6e-5 off, inside bf16 rounding but not inside the fp32 mode's 1e-4)
+  bool exact_gelu = false;
 };
 
 struct GemmArgs {
@@ -262,6 +267,12 @@ int preprocess_u8(const uint8_t* images, int B, int H, int W, int So_h, int So_w
                   cudaStream_t s);
 int pil_bilinear_ksize(int in_size, int out_size);
 void pil_bilinear_tables(int in_size, int out_size, int32_t* bounds, int32_t* kk);
+
+// dst (bf16) = bf16 pieces of the fp32 matrix src [rows, cols] (row stride ld): x = hi + mid + lo with hi = bf16(x),
+// mid = bf16(x - hi), lo = bf16(x - hi - mid); segment i of the output holds piece[i] (0 hi, 1 mid, 2 lo), the segments
+// concatenated along the columns (concat_rows = 0: dst [rows, nseg cols]) or along the rows (dst [nseg rows, cols])
+int split_bf16(const float* src, long long ld, int rows, int cols, int concat_rows, int nseg, const int* piece, void* dst,
+               cudaStream_t s);
 
 // y[i] += a * x[i]
 int axpy_f32(float* y, const float* x, float a, long long n, cudaStream_t s);

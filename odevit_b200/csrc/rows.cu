@@ -870,6 +870,53 @@ int drop_pair_rows(const void* x, void* out1, void* out2, int type, Drop d1, Dro
   return 0;
 }
 
+namespace {
+struct SplitPlan {
+  int nseg;
+  int piece[6];   // which of (hi, mid, lo) goes into segment i
+};
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ src, long long ld, int rows, int cols, int concat_rows,
+                                                         SplitPlan sp, __nv_bfloat16* __restrict__ dst) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const long long total = (long long)rows * cols;
+  if (i >= total) return;
+  const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);   // cols % 4 == 0: the 4 elements share a row
+  const float4 v = *reinterpret_cast<const float4*>(src + (long long)r * ld + c);
+  const float x[4] = {v.x, v.y, v.z, v.w};
+  __nv_bfloat16 pc[3][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float rem = x[j];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      pc[q][j] = __float2bfloat16_rn(rem);
+      rem -= __bfloat162float(pc[q][j]);
+    }
+  }
+  uint2 P[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) P[q] = make_uint2(*reinterpret_cast<uint32_t*>(&pc[q][0]), *reinterpret_cast<uint32_t*>(&pc[q][2]));
+  for (int sg = 0; sg < sp.nseg; ++sg) {
+    const uint2 val = sp.piece[sg] == 0 ? P[0] : (sp.piece[sg] == 1 ? P[1] : P[2]);
+    if (concat_rows) *reinterpret_cast<uint2*>(dst + (long long)sg * total + (long long)r * cols + c) = val;
+    else *reinterpret_cast<uint2*>(dst + (long long)r * sp.nseg * cols + (long long)sg * cols + c) = val;
+  }
+}
+}  // namespace
+
+int split_bf16(const float* src, long long ld, int rows, int cols, int concat_rows, int nseg, const int* piece, void* dst,
+               cudaStream_t s) {
+  if (cols % 4 || ld % 4 || nseg < 1 || nseg > 6) return set_error(ODEVIT_ERR_UNSUPPORTED, "split_bf16: bad shape");
+  ProfScope prof(KC_WEIGHTS, s);
+  SplitPlan sp;
+  sp.nseg = nseg;
+  for (int i = 0; i < 6; ++i) sp.piece[i] = i < nseg ? piece[i] : 0;
+  const long long n4 = (long long)rows * cols / 4;
+  split_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(src, ld, rows, cols, concat_rows, sp, reinterpret_cast<__nv_bfloat16*>(dst));
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
 int drop_rows_inplace(void* x, int type, Drop d, int rows, int D, cudaStream_t s) {
   ProfScope prof(KC_COMBINE, s);
   const long long n = (long long)rows * D;
