@@ -460,6 +460,25 @@ def run_ours(args, wl):
                 model(px_d)
             ms_inf = timed(lambda: model(px_d), max(2, args.steps), "inference")
     model.train()
+    # ---- the same step with the shipped YAML's dropout (experiment_vit_edo.yaml:53-55: 0.3 on the attention map, after
+    # out_proj, after GELU and after fc2), replayed as a CUDA graph: the mask seed lives in device memory and a 1-thread
+    # kernel inside the captured step advances it (every replay draws new masks).  An extra key, not the headline.
+    ms_drop = None
+    if not args.quick and not wl.get("distill") and stepper is not None and world == 1:
+        try:
+            from odevit_b200.graphs import GraphedTrainStep
+            torch.manual_seed(0)
+            model_d = ob.ViTNeuralODE(**dict(cfg, attn_drop=0.3, proj_drop=0.3, mlp_drop=0.3)).to(dev).train()
+            model_d.precision = args.precision
+            opt_d = torch.optim.AdamW([p for p in model_d.parameters() if p.requires_grad], lr=1e-4, weight_decay=5e-2,
+                                      fused=True, capturable=True)
+            step_d = GraphedTrainStep(model_d, opt_d, (px_d, lb_d), clip=1.0, warmup=2, capture_optimizer=False)
+            for _ in range(2):
+                step_d(px_d, lb_d)
+            ms_drop = timed(lambda: step_d(px_d, lb_d), args.steps, "value_dropout_0.3")
+            del step_d, opt_d, model_d
+        except Exception as e:  # noqa: BLE001
+            ms_drop = f"failed: {type(e).__name__}: {str(e)[:100]}"
     gc.enable()
 
     nfe = (cfg["num_eval_steps"] - 1) * STAGES[cfg["solver"]]
@@ -535,6 +554,7 @@ def run_ours(args, wl):
             "config": workload_config(wl, B, world, args.precision),
             "field_evals_per_sec": ips * nfe,
             "train_tflops_algorithmic": step_flops * world / (ms_step * 1e-3) / 1e12,
+            "ms_per_step_dropout_0.3": ms_drop,
             "inference_images_per_sec": world * B / (ms_inf * 1e-3),
             "inference_field_evals_per_sec": world * B * nfe / (ms_inf * 1e-3),
             "e2e": {"value": ips_e2e, "unit": "img/s", "ms_per_step": ms_e2e,
