@@ -388,6 +388,8 @@ def run_ours(args, wl):
             graph_launches = ob.launch_count() // 2       # one warm-up step + the captured one
             launch_mode = "cuda_graph_replay (forward+backward; all-reduce/clip/AdamW eager)"
         except Exception as e:  # noqa: BLE001
+            import traceback
+            traceback.print_exc(file=sys.stderr)
             stepper, launch_mode = None, f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
             torch.cuda.synchronize()
 

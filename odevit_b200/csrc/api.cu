@@ -159,6 +159,7 @@ WeightBufs take_weights(const Plan& p, Arena& a) {
   w.w2catT = a.take(K2 * p.D * e);
   w.b1cat = a.f32(R);
   w.b2 = a.f32(p.D);
+  w.fmean = a.f32(R);
   w.user = nullptr;
   return w;
 }
@@ -334,6 +335,7 @@ int prepare_weights(const Plan& p, const odevit_weights* w, WeightBufs& wb, cuda
   f.fold_norm = (p.variant != ODEVIT_FIELD_MACARON);
   f.w1cat = wb.w1cat; f.w1catT = wb.w1catT; f.w_type = p.act;
   f.b1cat = wb.b1cat; f.w2cat = wb.w2cat; f.w2catT = wb.w2catT; f.b2 = wb.b2;
+  f.fmean = wb.fmean;
   wb.user = w;
   return fold_weights_parallel(f, s);
 }

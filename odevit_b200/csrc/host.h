@@ -48,6 +48,7 @@ struct Arena {
 struct WeightBufs {
   void *w1cat, *w1catT, *w2cat, *w2catT;
   float *b1cat, *b2;
+  float* fmean;   // [3D+hid] row means of W1cat (what the transposed copy subtracts)
   const odevit_weights* user;  // the caller's fp32 parameters (biases, LayerNorm affines, res_scale)
 };
 

@@ -287,6 +287,7 @@ struct FoldArgs {
   void* w1catT;              // [D, 3D+hid] or null; each W1cat row is CENTRED over D here (so that
                              // dz @ W1cat directly yields the centring VJP mu = zsum - mean_D zsum)
   float* b1cat;              // [3D+hid]
+  float* fmean;              // [3D+hid] scratch: row means of W1cat (fold_w1_kernel -> fold_w1_transpose_kernel)
   void* w2cat;               // [D, D+hid]
   void* w2catT;              // [D+hid, D] or null
   float* b2;                 // [D] (out_proj_b + fc2_b) -- zero if absent

@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(128) unfold_w2_macaron_kernel(UnfoldArgs a, od
 // q*(1/sqrt(d)) of nn.MultiheadAttention).  out_proj and fc2 concatenate along K:
 //   [O | h] @ [Wo | W2]^T.
 __global__ void __launch_bounds__(128) fold_w1_kernel(FoldArgs a, odevit_weights w) {
-  const int D = a.D, hid = a.hid, R = 3 * D + hid;
+  const int D = a.D;
   const int j = blockIdx.x;
   const bool attn = j < 3 * D;
   const float* Wrow = attn ? w.in_proj_w + (long long)j * D : w.fc1_w + (long long)(j - 3 * D) * D;
@@ -686,17 +686,40 @@ __global__ void __launch_bounds__(128) fold_w1_kernel(FoldArgs a, odevit_weights
     float t = red[0] + red[1] + red[2] + red[3];
     if (lb) t += lb[j - (attn ? 0 : 3 * D)];
     a.b1cat[j] = qs * t;
+    // row mean for the transposed, row-centred copy (fold_w1_transpose_kernel: a thread-per-element store at stride R
+    // here scattered 2.4 M two-byte writes and made the fold a 58 us kernel)
+    if (a.fmean) a.fmean[j] = fn ? (red2[0] + red2[1] + red2[2] + red2[3]) / (float)D : 0.f;
   }
-  if (a.w1catT) {
-    // the transposed copy feeds dL/dxc = dz @ W1cat followed by the centring VJP (subtract the
-    // row mean over D): fold that subtraction into the weight, row j centred over i
-    const float fmean = fn ? (red2[0] + red2[1] + red2[2] + red2[3]) / (float)D : 0.f;
-    for (int i = threadIdx.x; i < D; i += 128) {
+}
+
+// w1catT[i, j] = f(j, i) - fmean[j] for one 32 x 32 tile of (j, i): rows of W read coalesced, the transposed tile written
+// coalesced (32 consecutive j per output row) through shared memory; f is recomputed with fold_w1_kernel's expression.
+__global__ void __launch_bounds__(256) fold_w1_transpose_kernel(FoldArgs a, odevit_weights w) {
+  const int D = a.D, hid = a.hid, R = 3 * D + hid;
+  const int j0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool fn = a.fold_norm;
+  const float s_cn = fn ? (float)D / ((float)D - 1.f) : 1.f;
+  __shared__ float tile[32][33];
+  for (int r = warp; r < 32; r += 8) {
+    const int j = j0 + r, i = i0 + lane;
+    float v = 0.f;
+    if (j < R && i < D) {
+      const bool attn = j < 3 * D;
+      const float* Wrow = attn ? w.in_proj_w + (long long)j * D : w.fc1_w + (long long)(j - 3 * D) * D;
+      const float* nw = attn ? w.norm_a_w : w.norm_b_w;
+      const float* msc = attn ? w.mod_attn_scale : w.mod_mlp_scale;
       float we = fn ? nw[i] : 1.f;
       if (fn && msc) we *= (1.f + msc[i]);
-      const float f = qs * s_cn * Wrow[i] * we;
-      store_elem(a.w1catT, (long long)i * R + j, a.w_type, f - fmean);
+      const float qs = (j < D) ? a.q_scale : 1.f;
+      v = qs * s_cn * Wrow[i] * we - a.fmean[j];
     }
+    tile[r][lane] = v;
+  }
+  __syncthreads();
+  for (int c = warp; c < 32; c += 8) {
+    const int i = i0 + c, j = j0 + lane;
+    if (i < D && j < R) store_elem(a.w1catT, (long long)i * R + j, a.w_type, tile[lane][c]);
   }
 }
 
@@ -706,13 +729,31 @@ __global__ void __launch_bounds__(128) fold_w2_kernel(FoldArgs a, odevit_weights
   for (int c = threadIdx.x; c < K2; c += 128) {
     const float v = (c < D) ? w.out_proj_w[(long long)i * D + c] : w.fc2_w[(long long)i * hid + (c - D)];
     store_elem(a.w2cat, (long long)i * K2 + c, a.w_type, v);
-    if (a.w2catT) store_elem(a.w2catT, (long long)c * D + i, a.w_type, v);
   }
   if (threadIdx.x == 0) {
     float b = 0.f;
     if (w.out_proj_b) b += w.out_proj_b[i];
     if (w.fc2_b) b += w.fc2_b[i];
     a.b2[i] = b;
+  }
+}
+
+// w2catT[c, i] = [Wo | W2][i, c] through a 32 x 32 shared-memory tile (coalesced reads and writes)
+__global__ void __launch_bounds__(256) fold_w2_transpose_kernel(FoldArgs a, odevit_weights w) {
+  const int D = a.D, hid = a.hid, K2 = D + hid;
+  const int i0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ float tile[32][33];
+  for (int r = warp; r < 32; r += 8) {
+    const int i = i0 + r, c = c0 + lane;
+    float v = 0.f;
+    if (i < D && c < K2) v = (c < D) ? w.out_proj_w[(long long)i * D + c] : w.fc2_w[(long long)i * hid + (c - D)];
+    tile[r][lane] = v;
+  }
+  __syncthreads();
+  for (int r = warp; r < 32; r += 8) {
+    const int c = c0 + r, i = i0 + lane;
+    if (c < K2 && i < D) store_elem(a.w2catT, (long long)c * D + i, a.w_type, tile[lane][r]);
   }
 }
 
@@ -1050,10 +1091,19 @@ int unfold_grads_macaron(const UnfoldArgs& a, cudaStream_t s) {
 
 int fold_weights_parallel(const FoldArgs& a, cudaStream_t s) {
   ProfScope prof(KC_WEIGHTS, s);
-  fold_w1_kernel<<<3 * a.D + a.hid, 128, 0, s>>>(a, *a.w);
+  const int R = 3 * a.D + a.hid, K2 = a.D + a.hid;
+  fold_w1_kernel<<<R, 128, 0, s>>>(a, *a.w);
   ODV_LAUNCH_CHECK();
   fold_w2_kernel<<<a.D, 128, 0, s>>>(a, *a.w);
   ODV_LAUNCH_CHECK();
+  if (a.w1catT) {
+    fold_w1_transpose_kernel<<<dim3((R + 31) / 32, (a.D + 31) / 32), 256, 0, s>>>(a, *a.w);
+    ODV_LAUNCH_CHECK();
+  }
+  if (a.w2catT) {
+    fold_w2_transpose_kernel<<<dim3((a.D + 31) / 32, (K2 + 31) / 32), 256, 0, s>>>(a, *a.w);
+    ODV_LAUNCH_CHECK();
+  }
   return 0;
 }
 

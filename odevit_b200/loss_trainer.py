@@ -163,7 +163,10 @@ class ImageDistilTrainer(nn.Module):
         if self.use_distillation:
             self.temperature_scheduler.get_temp(epoch=self.epoch)
             l1 = self.compute_l1_attention_loss(student_output["attentions"], teacher_output["attentions"])
-            if l1.isnan().any():
+            if l1.is_cuda and torch.cuda.is_current_stream_capturing():
+                # the reference's host-side NaN test (a sync: illegal inside a CUDA-graph capture) as a device select
+                loss = loss + torch.where(l1.isnan(), torch.zeros_like(l1), l1)
+            elif l1.isnan().any():
                 print("KL loss is NaN")
             else:
                 loss = loss + l1

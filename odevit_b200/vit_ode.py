@@ -470,13 +470,14 @@ class ViTNeuralODE(nn.Module):
                 and not ops.solve_uses_resident(spec, tokens.shape[0], tokens.shape[1], self.solver, num_eval_steps))
         if lean:
             # "auto": only when the trajectory would take a large share of the free memory -- the in-epilogue bound
-            # costs ~3 % more time than one pass over a materialised trajectory (measured, S3.8M shape, batch 1024)
+            # costs ~3 % more time than one pass over a materialised trajectory (measured, S3.8M shape, batch 1024), while
+            # allocating and touching a multi-GB trajectory per call has its own cost: the switch sits at 5 % of free memory
             mode = getattr(self, "trajectory_free_inference", os.environ.get("ODEVIT_TRAJECTORY_FREE", "auto"))
             if mode in (False, "0", "off"):
                 lean = False
             elif mode == "auto":
                 need = 4 * num_eval_steps * tokens.numel()
-                lean = need > 0.2 * torch.cuda.mem_get_info(tokens.device)[0]
+                lean = need > 0.05 * torch.cuda.mem_get_info(tokens.device)[0]
         if lean:
             res = ops.ode_solve_lean(tokens, t, spec, self.solver, weights,
                                      row_index=idx.tolist() if idx is not None else (), want_p_last=True, jasmin=jas)

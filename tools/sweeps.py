@@ -81,7 +81,7 @@ def main():
             with torch.no_grad():
                 ms = timed(lambda: m(px), max(2, a.reps if B <= 256 else 2))
             tf = B * nfe * flops_fwd(S38) / (ms * 1e-3) / 1e12
-            lean = 4 * S38["num_eval_steps"] * B * 207 * 768 > 0.2 * torch.cuda.mem_get_info()[0]
+            lean = 4 * S38["num_eval_steps"] * B * 207 * 768 > 0.05 * torch.cuda.mem_get_info()[0]
             out.append({"config": 4, "workload": "S3.8M-shape inference, Euler T=36", "trajectory": "none (FD bound formed inside "
                         "the solve, odevit_solve_fwd_lean)" if lean else "materialised (one FD pass over it)",
                         "precision": a.precision, "batch": B, "ms_per_call": ms,
