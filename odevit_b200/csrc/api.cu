@@ -693,6 +693,9 @@ int eval_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b,
   const int D = p.D, hid = p.hid, R = 3 * D + hid, K2 = D + hid;
   const size_t e = dtype_size(p.act);
   char* dz = reinterpret_cast<char*>(b.dz);
+  static const bool colsum_fuse_off = [] { const char* v = getenv("ODEVIT_FUSED_COLSUM"); return v && v[0] == '0'; }();
+  // (softmax attention, no attention-map dropout, the single-GEMM form of d[O|h]: see below)
+  bool fused_colsum = !colsum_fuse_off && p.variant == ODEVIT_FIELD_PARALLEL && p.p_attn == 0.f && !p.split_out;
   if (p.split_out) {
     // the cotangent enters the out-proj branch under the proj mask and the fc2 branch under the mlp-output mask
     if (gw->fc2_b) return set_error(ODEVIT_ERR_UNSUPPORTED, "dropout with an fc2 bias is not built (the reference has none)");
@@ -754,6 +757,15 @@ int eval_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b,
     g.epi.split = D;
     g.epi.out2 = dz + (size_t)3 * D * e; g.epi.ld_out2 = R;
     g.epi.aux = c.hpre; g.epi.ld_aux = hid; g.epi.aux_type = p.act;
+    // Bias-gradient column sums without a pass over dz (81 MB at the bench shape).  Softmax attention without map
+    // dropout gives two of the four blocks for free:  sum_j dK_j = sum_i q_i (sum_j dS_ij) = 0  (rows of the softmax
+    // Jacobian sum to zero) and  sum_j dV_j = sum_i (sum_j P_ij) dO_i = sum_i dO_i;  dO and d h_pre are summed in the
+    // epilogue that produces them, and only the dq block is left for colsum_accum below.
+    if (fused_colsum) {
+      g.epi.colsum_a = b.c1 + 2 * D;   // the v rows of c1
+      g.epi.colsum_b = b.c1 + 3 * D;   // the fc1 rows of c1
+      if (!(p.precision == ODEVIT_BF16 && gemm_tc_supports(g))) { g.epi.colsum_a = g.epi.colsum_b = nullptr; fused_colsum = false; }
+    }
     ODV_TRY(gemm(p, g, s));
   }
   {  // G2 += dd^T @ [O|h]
@@ -795,7 +807,8 @@ int eval_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b,
     g.kclass = KC_BWD_GEMM_G1;
     ODV_TRY(gemm(p, g, s));
   }
-  ODV_TRY(colsum_accum(b.dz, p.act, R, p.M, R, b.c1, s));
+  if (fused_colsum) ODV_TRY(colsum_accum(b.dz, p.act, R, p.M, D, b.c1, s));     // the dq block only
+  else ODV_TRY(colsum_accum(b.dz, p.act, R, p.M, R, b.c1, s));
   return 0;
 }
 

@@ -433,6 +433,20 @@ __device__ __forceinline__ void epi_prefetch_rows(const Epi& e, int m, int M, in
   }
 }
 
+// column sums of the lane's 8 rows x 4 columns, reduced over the four lanes that hold the same columns (lane, lane ^ 8,
+// lane ^ 16, lane ^ 24), one float4 atomic per column group.  Every lane of the warp must call it.
+__device__ __forceinline__ void colsum_rows8(float* dst, const float4 (&w)[8]) {
+  float4 s = w[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) s = add4(s, w[i]);
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    s.x += __shfl_xor_sync(0xffffffffu, s.x, o); s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+    s.z += __shfl_xor_sync(0xffffffffu, s.z, o); s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
+  }
+  if ((threadIdx.x & 31) < 8) atomicAdd(reinterpret_cast<float4*>(dst), s);
+}
+
 // ---- phase 2 ----
 template <int EPI, bool ATOMIC, bool FULL>
 __device__ __forceinline__ void epi8_finish(const Epi& e, int m0, int M, int n, float4 (&w)[8], const EpiPre& pre) {
@@ -560,6 +574,7 @@ __device__ __forceinline__ void epi8_finish(const Epi& e, int m0, int M, int n, 
   } else if constexpr ((EPI & 7) == EPI_BWD3) {
     if (n < e.split) {
       store_rows8<FULL>(e.out, e.out_type, (long long)m0 * e.ld_out + n, 4 * (int)e.ld_out, m0, M, w);
+      if (e.colsum_a) colsum_rows8(e.colsum_a + n, w);     // (rows past M hold exact zeros: zero-filled operand rows)
     } else {
       const int c = n - e.split;
       const bool f32 = (e.aux_type == DT_F32);
@@ -580,6 +595,7 @@ __device__ __forceinline__ void epi8_finish(const Epi& e, int m0, int M, int n, 
         }
       }
       store_rows8<FULL>(e.out2, e.aux_type, (long long)m0 * e.ld_out2 + c, 4 * (int)e.ld_out2, m0, M, w);
+      if (e.colsum_b) colsum_rows8(e.colsum_b + c, w);
     }
   } else if constexpr ((EPI & 7) == EPI_TOKENS) {
 #pragma unroll

@@ -541,7 +541,8 @@ bool gemm_tc_supports(const GemmArgs& g) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return false;
   if (g.N % 16) return false;
   if (g.epi.fd_out && (g.N % 32 || g.epi.drop.thresh)) return false;
-  if (g.epi.exact_gelu && g.epi.drop.thresh) return false;   // (that combination is not instantiated)   // whole warps reduce over rows: no dead lanes
+  if (g.epi.exact_gelu && g.epi.drop.thresh) return false;   // (that combination is not instantiated)
+  if ((g.epi.colsum_a || g.epi.colsum_b) && (g.epi_mode != EPI_BWD3 || g.N % 32 || g.epi.split % 32)) return false;   // whole warps reduce over rows: no dead lanes
   const bool a_k = (g.a_cs == 1), a_mn = (g.a_rs == 1 && g.a_cs != 1);
   const bool b_k = (g.b_cs == 1), b_mn = (g.b_rs == 1 && g.b_cs != 1);
   if (!(a_k || a_mn) || !(b_k || b_mn)) return false;

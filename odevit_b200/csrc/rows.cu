@@ -168,35 +168,56 @@ __global__ void __launch_bounds__(128) colsum_kernel(const void* X, int x_type, 
   atomicAdd(acc + c, s);
 }
 
-// bf16 fast path: a warp covers 256 columns with one 16-byte load per lane; the 4 warps of a block
-// take interleaved rows of a 128-row panel and meet in shared memory (cols % 8 == 0, ld % 8 == 0).
-__global__ void __launch_bounds__(128) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long long ld,
-                                                          int rows, int cols, float* acc) {
-  __shared__ float part[4][256];
+// bf16 fast path: a warp covers 256 columns with one 16-byte load per lane; the 8 warps of a block take interleaved
+// rows of an `rpb`-row panel (8 independent loads in flight per lane) and meet in shared memory; one atomic per column
+// and block (cols % 8 == 0, ld % 8 == 0).  Same-address atomics serialise in L2 (~27 cycles each): panels are kept
+// tall (few blocks per column) and the memory-level parallelism comes from the unrolled loads instead.
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long long ld,
+                                                          int rows, int cols, int rpb, float* acc) {
+  __shared__ float part[8][256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = blockIdx.x * 256 + lane * 8;
-  const int r0 = blockIdx.y * 128;
-  const int r1 = min(rows, r0 + 128);
+  const int r0 = blockIdx.y * rpb;
+  const int r1 = min(rows, r0 + rpb);
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (c0 < cols) {
-#pragma unroll 4
-    for (int r = r0 + warp; r < r1; r += 4) {
+    int r = r0 + warp;
+    for (; r + 56 < r1; r += 64) {
+      uint4 t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = *reinterpret_cast<const uint4*>(X + (long long)(r + 8 * u) * ld + c0);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t w[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          s[2 * i] += __uint_as_float(w[i] << 16);
+          s[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+        }
+      }
+    }
+    for (; r < r1; r += 8) {
       const uint4 t = *reinterpret_cast<const uint4*>(X + (long long)r * ld + c0);
       const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-        s[2 * i] += __low2float(b);
-        s[2 * i + 1] += __high2float(b);
+        s[2 * i] += __uint_as_float(w[i] << 16);
+        s[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
       }
     }
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) part[warp][lane * 8 + i] = s[i];
   __syncthreads();
-  for (int c = threadIdx.x; c < 256; c += 128) {
+  {
+    const int c = threadIdx.x;
     const int col = blockIdx.x * 256 + c;
-    if (col < cols) atomicAdd(acc + col, part[0][c] + part[1][c] + part[2][c] + part[3][c]);
+    if (col < cols) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += part[w][c];
+      atomicAdd(acc + col, t);
+    }
   }
 }
 
@@ -882,8 +903,12 @@ int softmax_bwd_rows(const float* p, float* dp, const float* dpx, long long rows
 int colsum_accum(const void* X, int x_type, long long ld, int rows, int cols, float* acc, cudaStream_t s) {
   ProfScope prof(KC_BWD_COLSUM, s);
   if (x_type == DT_BF16 && cols % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
-    dim3 grid((cols + 255) / 256, (rows + 127) / 128);
-    colsum_bf16_kernel<<<grid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(X), ld, rows, cols, acc);
+    // rows per block: 256 for wide matrices, fewer for narrow ones so that there are at least two blocks per SM
+    const int col_blocks = (cols + 255) / 256;
+    int rpb = 256;
+    while (rpb > 64 && (long long)col_blocks * ((rows + rpb - 1) / rpb) < 296) rpb >>= 1;
+    dim3 grid(col_blocks, (rows + rpb - 1) / rpb);
+    colsum_bf16_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(X), ld, rows, cols, rpb, acc);
     ODV_LAUNCH_CHECK();
     return 0;
   }
