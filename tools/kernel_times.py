@@ -21,10 +21,11 @@ ap.add_argument("--ratio", type=float, default=1.0)
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--steps", type=int, default=3, help="Euler steps per solve")
 ap.add_argument("--precision", default="bf16")
+ap.add_argument("--drop", type=float, default=0.0, help="attention / projection / MLP dropout (training mode)")
 a = ap.parse_args()
 torch.manual_seed(0)
 f = ob.ViT_ODEFunc(dim=a.dim, num_heads=a.heads, mlp_ratio=a.ratio, emulate_depth=12, time_interval=1.0,
-                   l2_attention=False).cuda()
+                   l2_attention=False, attn_drop=a.drop, proj_drop=a.drop, mlp_drop=a.drop).cuda().train()
 f.block.precision = a.precision
 x = torch.randn(a.batch, a.tokens, a.dim, device="cuda", requires_grad=True)
 t = torch.linspace(0, 1, a.steps + 1)
