@@ -178,7 +178,9 @@ int odevit_field_fwd(const odevit_desc* desc, const odevit_weights* w,
  *   tape (odevit_tape_bytes() bytes, 1024-aligned) or NULL: when given, the intermediates of every
  *          field evaluation (centred rows, q|k|v, [O|h], fc1 pre-activation, softmax row log-sums)
  *          are kept there for odevit_solve_bwd -- what autograd's saved tensors are in the reference
- *          (train.py:57-67), in bf16 in the bf16 mode. */
+ *          (train.py:57-67), in bf16 in the bf16 mode -- followed by the folded weights of this call: the reverse
+ *          sweep of a tape uses the WEIGHTS AS THEY WERE at the forward call (as autograd's saved tensors do) and reads
+ *          `w` only for the parameters that are not folded (biases, LayerNorm affines, res_scale). */
 int odevit_solve_fwd(const odevit_desc* desc, const odevit_weights* w, int32_t method,
                      const float* x0, const float* t_grid_host, int32_t n_grid,
                      float* states, float* final_state,

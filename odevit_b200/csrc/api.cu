@@ -276,10 +276,24 @@ StageCtx tape_ctx(const Plan& p, void* tape, long long e, size_t* total_bytes, l
   Arena a0(nullptr);
   take_ctx(p, a0, true);
   const size_t per = (a0.off + 1023) & ~size_t(1023);
-  if (total_bytes) *total_bytes = per * (size_t)n_evals;
+  if (total_bytes) {
+    Arena aw(nullptr);
+    take_weights(p, aw);                     // the folded weights of the forward, kept for the reverse sweep (tape_weights)
+    *total_bytes = per * (size_t)n_evals + ((aw.off + 1023) & ~size_t(1023));
+  }
   if (!tape) return StageCtx{};
   Arena a(reinterpret_cast<char*>(tape) + per * (size_t)e);
   return take_ctx(p, a, true);
+}
+
+// The folded / transposed weights of the forward solve, stored behind the tape's evaluation slots: the reverse sweep of
+// the same step reads them instead of folding the (unchanged) parameters a second time.
+WeightBufs tape_weights(const Plan& p, void* tape, long long n_evals) {
+  Arena a0(nullptr);
+  take_ctx(p, a0, true);
+  const size_t per = (a0.off + 1023) & ~size_t(1023);
+  Arena a(reinterpret_cast<char*>(tape) + per * (size_t)n_evals);
+  return take_weights(p, a);
 }
 
 int check_ws(const void* ws, size_t have, size_t need) {
@@ -1066,6 +1080,7 @@ int solve_fwd_impl(const odevit_desc* desc, const odevit_weights* w, int32_t met
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const size_t MD = (size_t)p.M * p.D;
   ODV_TRY(prepare_drop_keys(p, f.drop_keys, (long long)(n_grid - 1) * tb->S, s));
+  if (tape) f.w = tape_weights(p, tape, (long long)(n_grid - 1) * tb->S);   // fold once per step: the reverse sweep reuses them
   ODV_TRY(prepare_weights(p, w, f.w, s));
 
   const float* y = x0;
@@ -1221,7 +1236,12 @@ int odevit_solve_bwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
   const int S = tb->S;
   const bool need_c2 = wants_c2(gw);
   ODV_TRY(prepare_drop_keys(p, b.drop_keys, (long long)(n_grid - 1) * S, s));
-  ODV_TRY(prepare_weights(p, w, b.w, s));
+  if (tape) {   // the forward of this step left its folded weights behind the tape's slots
+    b.w = tape_weights(p, const_cast<void*>(tape), (long long)(n_grid - 1) * S);
+    b.w.user = w;
+  } else {
+    ODV_TRY(prepare_weights(p, w, b.w, s));
+  }
   ODV_CUDA(cudaMemsetAsync(b.G1, 0, b.acc_bytes, s));
 
   // cotangent of trajectory row j = g_states[j] + sum of g_rows whose index is j
@@ -1245,9 +1265,21 @@ int odevit_solve_bwd(const odevit_desc* desc, const odevit_weights* w, int32_t m
     c0.out_dd = b.dd; c0.dd_type = p.dd_type; c0.dd_scale = p.scaler;
     return vjp_combine(c0, p.M, p.D, s);
   };
-  ODV_CUDA(cudaMemsetAsync(b.gy, 0, MD * 4, s));
-  ODV_TRY(inject(n_grid - 1));
-  if (n_grid >= 2) ODV_TRY(seed_dd(t_grid_host[n_grid - 1] - t_grid_host[n_grid - 2]));
+  {
+    // G = the cotangent injected at the last row, dd = scaler * dt * b[S-1] * G: one pass (it used to be a memset, an axpy
+    // per term and a combine: 260 MB of traffic and four launches at the bench shape instead of 100 MB and one)
+    const float* terms[4];
+    const int nt_inj = injected_terms(n_grid - 1, terms, 4);
+    if (nt_inj <= 4 && MD % 4 == 0) {
+      const bool seed = n_grid >= 2;
+      const float coef = seed ? p.scaler * (t_grid_host[n_grid - 1] - t_grid_host[n_grid - 2]) * tb->b[S - 1] : 0.f;
+      ODV_TRY(seed_sweep(terms, nt_inj, b.gy, seed ? b.dd : nullptr, p.dd_type, coef, (long long)MD, s));
+    } else {
+      ODV_CUDA(cudaMemsetAsync(b.gy, 0, MD * 4, s));
+      ODV_TRY(inject(n_grid - 1));
+      if (n_grid >= 2) ODV_TRY(seed_dd(t_grid_host[n_grid - 1] - t_grid_host[n_grid - 2]));
+    }
+  }
 
   for (int j = n_grid - 2; j >= 0; --j) {
     const float dt = t_grid_host[j + 1] - t_grid_host[j];

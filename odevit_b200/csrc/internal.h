@@ -279,6 +279,9 @@ void pil_bilinear_tables(int in_size, int out_size, int32_t* bounds, int32_t* kk
 int split_bf16(const float* src, long long ld, int rows, int cols, int concat_rows, int nseg, const int* piece, void* dst,
                cudaStream_t s);
 
+// start of the reverse sweep in one pass: gy = sum of the injected cotangents, dd = cast(dd_coef * gy)
+int seed_sweep(const float* const* terms, int n_terms, float* gy, void* dd, int dd_type, float dd_coef, long long n, cudaStream_t s);
+
 // y[i] += a * x[i]
 int axpy_f32(float* y, const float* x, float a, long long n, cudaStream_t s);
 

@@ -1049,6 +1049,51 @@ int drop_inplace_f32(float* p, float* copy_to, Drop d, long long rows, int n, cu
   return 0;
 }
 
+namespace {
+struct SeedArgs {
+  const float* term[4];
+  int n_terms;
+};
+// gy = sum of the injected cotangents; dd = cast(dd_coef * gy): the start of the reverse sweep in ONE pass (float4)
+__global__ void __launch_bounds__(256) seed_sweep_kernel(SeedArgs a, float* __restrict__ gy, void* __restrict__ dd, int dd_type,
+                                                         float dd_coef, long long n4) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < 4; ++t)
+      if (t < a.n_terms) {
+        const float4 x = reinterpret_cast<const float4*>(a.term[t])[i];
+        v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+      }
+    reinterpret_cast<float4*>(gy)[i] = v;
+    if (dd) {
+      const float4 d = make_float4(dd_coef * v.x, dd_coef * v.y, dd_coef * v.z, dd_coef * v.w);
+      if (dd_type == DT_F32) {
+        reinterpret_cast<float4*>(dd)[i] = d;
+      } else {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(d.x, d.y), hi = __floats2bfloat162_rn(d.z, d.w);
+        reinterpret_cast<uint2*>(dd)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+      }
+    }
+  }
+}
+}  // namespace
+
+// gy[i] = sum_t term[t][i] (n_terms <= 4; 0 terms: zeros);  dd[i] = cast(dd_coef * gy[i]) when dd != null.  n % 4 == 0.
+int seed_sweep(const float* const* terms, int n_terms, float* gy, void* dd, int dd_type, float dd_coef, long long n, cudaStream_t s) {
+  if (n % 4 || n_terms < 0 || n_terms > 4) return set_error(ODEVIT_ERR_UNSUPPORTED, "seed_sweep: bad arguments");
+  ProfScope prof(KC_COMBINE, s);
+  SeedArgs a;
+  for (int t = 0; t < 4; ++t) a.term[t] = t < n_terms ? terms[t] : nullptr;
+  a.n_terms = n_terms;
+  const long long n4 = n / 4;
+  const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+  seed_sweep_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(a, gy, dd, dd_type, dd_coef, n4);
+  ODV_LAUNCH_CHECK();
+  return 0;
+}
+
 int axpy_f32(float* y, const float* x, float a, long long n, cudaStream_t s) {
   ProfScope prof(KC_COMBINE, s);
   const int blocks = (int)((n + 1023) / 1024 < 148 * 8 ? (n + 1023) / 1024 : 148 * 8);
