@@ -227,6 +227,161 @@ __device__ __forceinline__ float attn_softmax_row(const AttnArgs& a, uint32_t t_
   return inv;
 }
 
+// Non-exporting form of attn_softmax_row -- the hot loop of both fused forwards.  Same arithmetic in the same order
+// (bitwise equal results), but the instruction stream of a full 16-key chunk is exactly FFMA, MUFU.EX2, FADD per
+// element plus a pack per pair: the chunk that straddles N is peeled off as a tail with its column predicates against
+// compile-time column numbers, so the other chunks carry none (the generic loop spent 3 of its 7 issue slots per
+// element on them, and two warps per scheduler have no latency to hide that behind).  Loads go four chunks per
+// wait and may run past NP: they stay inside the slot's 256 columns and those registers are never used.
+// (tools/ubench/tmem_ld.cu: tensor memory delivers ~600-900 B/clk/SM to 4-8 warps and a load round trip is ~55
+// cycles -- the passes are bound by MUFU, 8 cycles per warp-wide ex2, not by the read port.)
+template <bool DROP, bool JAS>
+__device__ __forceinline__ float attn_softmax_row_fast(const AttnArgs& a, uint32_t t_row, int n_chunks, int b, int h, int row) {
+  constexpr float LOG2E = 1.4426950408889634f;
+  const int last = n_chunks - 1;            // the chunk that holds column N - 1
+  const int nv = a.N - last * 16;           // its key columns, 1..16
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  float tt[JAS ? 4 : 1][4];
+  if constexpr (JAS) {
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tt[q4][i] = -INFINITY;
+  }
+  // ---- pass 1: row max (JAS: the four largest logits) ----
+  for (int c0 = 0; c0 < last; c0 += 4) {
+    float v[4][16];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ptx::tmem_ld16(t_row + (c0 + u) * 16, v[u]);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (c0 + u < last) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if constexpr (JAS) top4_insert(tt[j & 3], v[u][j]);
+          else m4[j & 3] = fmaxf(m4[j & 3], v[u][j]);
+        }
+      }
+  }
+  if (n_chunks > 0) {
+    float v[16];
+    ptx::tmem_ld16(t_row + last * 16, v);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float x = (j < nv) ? v[j] : -INFINITY;
+      if constexpr (JAS) top4_insert(tt[j & 3], x);
+      else m4[j & 3] = fmaxf(m4[j & 3], x);
+    }
+  }
+  if constexpr (JAS) {
+#pragma unroll
+    for (int q4 = 1; q4 < 4; ++q4)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) top4_insert(tt[0], tt[q4][i]);
+    m4[0] = tt[0][0];
+  }
+  const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+  const float mxs = mx * LOG2E;
+  // ---- pass 2: un-normalised exp, row sum, bf16 P in place (P chunk c = 8 packed columns at 8 c: columns this
+  // thread has already loaded) ----
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint32_t drow = (uint32_t)(((long long)b * a.H + h) * a.N + row);   // dropout coordinate of this row
+  auto pack_store = [&](int c, float (&e)[16]) {
+    uint32_t packed[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __nv_bfloat162 hh = __floats2bfloat162_rn(e[2 * j], e[2 * j + 1]);
+      packed[j] = *reinterpret_cast<uint32_t*>(&hh);
+    }
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(t_row + c * 8),
+                 "r"(packed[0]), "r"(packed[1]), "r"(packed[2]), "r"(packed[3]), "r"(packed[4]), "r"(packed[5]),
+                 "r"(packed[6]), "r"(packed[7])
+                 : "memory");
+  };
+  for (int c0 = 0; c0 < last; c0 += 4) {
+    float v[4][16];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ptx::tmem_ld16(t_row + (c0 + u) * 16, v[u]);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (c0 + u < last) {
+        const int c = c0 + u;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float e = ex2_fast(fmaf(v[u][j], LOG2E, -mxs));
+          s4[j & 3] += e;
+          if constexpr (DROP) e *= drop_factor(a.drop, drow, c * 16 + j);
+          v[u][j] = e;
+        }
+        pack_store(c, v[u]);
+      }
+  }
+  if (n_chunks > 0) {
+    float v[16];
+    ptx::tmem_ld16(t_row + last * 16, v);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float e = ex2_fast(fmaf(v[j], LOG2E, -mxs));
+      e = (j < nv) ? e : 0.f;
+      s4[j & 3] += e;
+      if constexpr (DROP) e *= drop_factor(a.drop, drow, last * 16 + j);
+      v[j] = e;
+    }
+    pack_store(last, v);
+  }
+  const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  const float inv = 1.f / sum;
+  if (a.lse_out && row < a.N) a.lse_out[((long long)b * a.H + h) * a.N + row] = mxs + log2f(sum);
+  if constexpr (JAS) {
+    // x_(j): j-th largest probability, clamped like the reference's clamp(P, 1e-12, 1); its renormalisation by
+    // (sum of the clamped row + 1e-12) differs from 1 by < N * 1e-12 and is dropped
+    float x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = fmaxf(ex2_fast(fmaf(tt[0][i], LOG2E, -mxs)) * inv, 1e-12f);
+    const float g1 = x[0] * (1.f - x[0] + x[1]);
+    float val;
+    if (a.jas_k == 0) {
+      val = logf(g1 + 1e-12f);
+    } else {
+      const float xk = (a.jas_k == 1) ? x[0] : (a.jas_k == 2) ? x[1] : x[2];
+      const float xk1 = (a.jas_k == 1) ? x[1] : (a.jas_k == 2) ? x[2] : x[3];
+      val = logf(g1 / (xk * (1.f - xk + xk1) + 1e-12f) + 1e-12f);
+    }
+    if (!(row < a.N) || n_chunks == 0) val = -INFINITY;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) val = fmaxf(val, __shfl_xor_sync(0xffffffffu, val, o));
+    if ((threadIdx.x & 31) == 0 && val > -INFINITY) atomic_max_float(a.jas_out + (long long)b * a.H + h, val);
+  }
+  return inv;
+}
+
+// O row: tensor memory (columns t_o ..+64) -> registers, one wait for the four loads
+__device__ __forceinline__ void attn_load_o_row(uint32_t t_o, float (&v)[HD]) {
+#pragma unroll
+  for (int c = 0; c < HD / 16; ++c) ptx::tmem_ld16(t_o + c * 16, &v[c * 16]);
+  ptx::tmem_ld_wait();
+}
+// O row * inv -> bf16 -> columns [h*64, h*64+64) of the [O | h] buffer
+__device__ __forceinline__ void attn_write_o_row(const AttnArgs& a, const float (&v)[HD], int b, int h, int row, float inv) {
+  if (row < a.N) {
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.oh) + ((long long)b * a.N + row) * a.ld_oh + h * HD);
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) {
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 hh = __floats2bfloat162_rn(v[c * 8 + 2 * j] * inv, v[c * 8 + 2 * j + 1] * inv);
+        w[j] = *reinterpret_cast<uint32_t*>(&hh);
+      }
+      o[c] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
 // O row (tensor memory, columns t_o ..+64) * inv -> bf16 -> columns [h*64, h*64+64) of the [O | h] buffer
 template <bool EXPORT>
 __device__ __forceinline__ void attn_store_o_row(const AttnArgs& a, uint32_t t_o, int b, int h, int row, float inv) {
@@ -319,7 +474,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int n_chunks = (mt * BMQ + warp * 32 < a.N) ? a.NP / 16 : 0;
   const int row = mt * BMQ + warp * 32 + lane;
   float* stage = EXPORT ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 64) + warp * (32 * 33) : nullptr;
-  const float inv = attn_softmax_row<EXPORT, DROP, JAS>(a, t_row, n_chunks, b, h, row, stage);
+  float inv;
+  if constexpr (EXPORT) inv = attn_softmax_row<EXPORT, DROP, JAS>(a, t_row, n_chunks, b, h, row, stage);
+  else inv = attn_softmax_row_fast<DROP, JAS>(a, t_row, n_chunks, b, h, row);
   ptx::tmem_st_wait();
   ptx::tc_fence_before();
   __syncthreads();
@@ -354,35 +511,53 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // ------------------------------------------------------------------------------------------------
 // Persistent ping-pong variant of the forward: one CTA per SM walks the (query tile, image, head) units
 // c, c+G, c+2G, ...; two softmax warpgroups own one tensor-memory slot each (unit parity) and alternate, a
-// producer warp streams Q / K / V of the units through a ring of shared-memory stages (three when they fit:
-// loads run a full unit ahead) and issues both MMAs of every unit, S of unit u+1 BEFORE P.V of unit u, so
-// the tensor core, the TMA engine and the two warpgroups overlap.  What a CTA-per-unit launch serialises for
-// every unit (launch, TMEM allocation, barrier setup, the TMA round trip) is paid once per SM here.
-//   warp 8         TMA + MMA issue (predicated on the elected lane)
+// loader thread streams Q | K of the next unit of each slot and a ring of three V tiles, each slot has its own MMA-issuing warp (S, then P.V of the slot's units: the two
+// chains only meet in the tensor pipe), so the tensor core, the TMA engine and the two warpgroups overlap.
+// What a CTA-per-unit launch serialises for every unit (launch, TMEM allocation, barrier setup, the TMA round
+// trip) is paid once per SM here.
+//   warps 8, 11    MMA issue for slot 0 / slot 1 (predicated on the elected lane)
+//   warp 10        TMA loads of Q / K / V (lane 0)
+//   warp 9         TMA stores of the O tiles: a warpgroup parks its scaled bf16 O tile [128 x 64] in its slot's
+//                  staging tile, 128-byte swizzled, and goes on; this warp's lane 0 issues the tensor store (rows
+//                  past N are clipped by the map) and hands the tile back once it has been read.
+//                  (A thread storing its own row from registers scatters every instruction over 32 lines: that
+//                  epilogue cost a warpgroup 1.6 k cycles per unit, a fifth of its time.)
 //   warps 0-3      slot 0: units 0, 2, 4, ... of this CTA      (thread = query row, quadrant = warp & 3)
 //   warps 4-7      slot 1: units 1, 3, 5, ...
-constexpr int PP_THREADS = 288;
-constexpr int PP_MAX_STAGES = 3;
+constexpr int PP_THREADS = 384;
+constexpr int PP_V_STAGES = 3;
 
 template <bool EXPORT, bool DROP, bool JAS = false>
 __global__ void __launch_bounds__(PP_THREADS, 1)
 attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                   const __grid_constant__ AttnArgs a, int n_stages) {
+                   const __grid_constant__ CUtensorMap tmO, const __grid_constant__ AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // shared memory: Q|K of the unit in each slot (dead once S is in tensor memory: reloaded a whole softmax ahead of
+  // the slot's next unit), a ring of three V tiles (dead after P.V), one O staging tile per slot
   const int kv_bytes = a.NP * HD * 2;
-  const int stage_bytes = BMQ * HD * 2 + 2 * kv_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + n_stages * stage_bytes);
-  uint64_t* bar_qk = bars;                         // [stage] Q and K landed
-  uint64_t* bar_v = bars + PP_MAX_STAGES;          // [stage] V landed
-  uint64_t* bar_free = bars + 2 * PP_MAX_STAGES;   // [stage] P.V of the stage's unit has retired
-  uint64_t* bar_s = bars + 3 * PP_MAX_STAGES;      // [slot] S is in tensor memory
-  uint64_t* bar_p = bar_s + 2;                     // [slot] P is packed (128 arrivals)
-  uint64_t* bar_o = bar_s + 4;                     // [slot] O is in tensor memory
-  uint64_t* bar_epi = bar_s + 6;                   // [slot] the epilogue has read O (128 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 8);
+  const int qk_bytes = BMQ * HD * 2 + kv_bytes;
+  uint8_t* sm_qk = smem;                                  // [2][Q 128 x 64 | K NP x 64]
+  uint8_t* sm_v = sm_qk + 2 * qk_bytes;                   // [PP_V_STAGES][NP x 64]
+  uint8_t* sm_o = sm_v + PP_V_STAGES * kv_bytes;          // [2][128 x 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_o + 2 * BMQ * HD * 2);
+  uint64_t* bar_qk = bars;                         // [slot] Q and K landed
+  uint64_t* bar_s = bars + 2;                      // [slot] S is in tensor memory (and Q | K may be overwritten)
+  uint64_t* bar_p = bars + 4;                      // [slot] P is packed (128 arrivals)
+  uint64_t* bar_o = bars + 6;                      // [slot] O is in tensor memory
+  uint64_t* bar_epi = bars + 8;                    // [slot] the epilogue has read O (128 arrivals)
+  uint64_t* bar_ost = bars + 10;                   // [slot] the O tile is staged in shared memory (128 arrivals)
+  uint64_t* bar_ofree = bars + 12;                 // [slot] the staged O tile has been read by its tensor store
+  uint64_t* bar_v = bars + 14;                     // [v stage] V landed
+  uint64_t* bar_vfree = bar_v + PP_V_STAGES;       // [v stage] P.V of the stage's unit has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_vfree + PP_V_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef ATTN_FWD_TRACE
+  const long long ft_entry = clock64();
+  unsigned long long gt_entry;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_entry));
+#endif
   const int items = a.B * a.H;
   const int n_units = items * a.tiles_m;
   const int n_mine = (n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -390,8 +565,12 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tmQ);
     ptx::prefetch_tensormap(&tmKV);
-    for (int i = 0; i < PP_MAX_STAGES; ++i) { ptx::mbar_init(bar_qk + i, 1); ptx::mbar_init(bar_v + i, 1); ptx::mbar_init(bar_free + i, 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_s + i, 1); ptx::mbar_init(bar_p + i, 128); ptx::mbar_init(bar_o + i, 1); ptx::mbar_init(bar_epi + i, 128); }
+    ptx::prefetch_tensormap(&tmO);
+    for (int i = 0; i < PP_V_STAGES; ++i) { ptx::mbar_init(bar_v + i, 1); ptx::mbar_init(bar_vfree + i, 1); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(bar_qk + i, 1); ptx::mbar_init(bar_s + i, 1); ptx::mbar_init(bar_p + i, 128); ptx::mbar_init(bar_o + i, 1);
+      ptx::mbar_init(bar_epi + i, 128); ptx::mbar_init(bar_ost + i, 128); ptx::mbar_init(bar_ofree + i, 1);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 8) ptx::tmem_alloc(tmem_slot, 512);
@@ -408,77 +587,151 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     b = item / a.H;
   };
 
-  if (warp == 8) {
+  if (warp == 8 || warp == 11) {
+    // one issuing warp per slot: its units' S and P.V in their natural order, never waiting for the other warpgroup
+    const int sl = warp == 8 ? 0 : 1;
     const bool leader = ptx::elect_one();
     const uint32_t lead = leader ? 1u : 0u;
     const uint32_t idesc1 = ptx::idesc_bf16(BMQ, a.NP, 0, 0);
     const uint32_t idesc2 = ptx::idesc_bf16(BMQ, HD, 0, 1);
     const uint64_t DESC0 = ptx::smem_desc_sw128(0, 16, 1024);
     const uint32_t smem0 = ptx::smem_u32(smem);
-    int loaded = 0;
-    auto issue_load = [&](int i) {
-      const int st = i % n_stages;
-      if (i >= n_stages) ptx::mbar_wait(bar_free + st, (uint32_t)((i / n_stages - 1) & 1));
-      if (leader) {
-        int b, h, mt;
-        decode(i, b, h, mt);
-        uint8_t* q = smem + st * stage_bytes;
-        ptx::mbar_expect_tx(bar_qk + st, BMQ * HD * 2 + kv_bytes);
-        ptx::tma_load_3d(q, &tmQ, bar_qk + st, h * HD, mt * BMQ, b);
-        ptx::tma_load_3d(q + BMQ * HD * 2, &tmKV, bar_qk + st, a.D + h * HD, 0, b);
-        ptx::mbar_expect_tx(bar_v + st, kv_bytes);
-        ptx::tma_load_3d(q + BMQ * HD * 2 + kv_bytes, &tmKV, bar_v + st, 2 * a.D + h * HD, 0, b);
-      }
-      __syncwarp();
-    };
-    // P.V of unit v, then the refill of the oldest free stage
-    auto finish = [&](int v) {
-      const int sv = v & 1, stv = v % n_stages;
-      ptx::mbar_wait(bar_p + sv, (uint32_t)((v >> 1) & 1));
-      ptx::mbar_wait(bar_v + stv, (uint32_t)((v / n_stages) & 1));
+    const uint32_t t = tmem + sl * 256;
+#ifdef ATTN_FWD_TRACE
+    long long mt_[4] = {0, 0, 0, 0}, mt0 = 0;
+#define MT0() mt0 = clock64()
+#define MTA(i) mt_[i] += clock64() - mt0
+#else
+#define MT0() do { } while (0)
+#define MTA(i) do { } while (0)
+#endif
+    for (int u = sl; u < n_mine; u += 2) {
+      const int vs = u % PP_V_STAGES;
+      const uint32_t ph = (uint32_t)((u >> 1) & 1);
+      MT0();
+      ptx::mbar_wait(bar_qk + sl, ph);
+      MTA(0);
+      MT0();
+      if (u >= 2) ptx::mbar_wait(bar_epi + sl, ph ^ 1u);   // the slot's previous O has been read
+      MTA(1);
       ptx::tc_fence_after();
-      const uint32_t v_addr = smem0 + stv * stage_bytes + BMQ * HD * 2 + kv_bytes;
-      const uint32_t t = tmem + sv * 256;
+      const uint64_t dq = DESC0 + ((smem0 + sl * qk_bytes) >> 4), dk = dq + ((BMQ * HD * 2) >> 4);
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k) ptx::mma_ss_pred(t, dq + 2 * k, dk + 2 * k, idesc1, k > 0 ? 1u : 0u, lead);
+      ptx::commit_pred(ptx::smem_u32(bar_s + sl), lead);
+      MT0();
+      ptx::mbar_wait(bar_v + vs, (uint32_t)((u / PP_V_STAGES) & 1));
+      MTA(2);
+      MT0();
+      ptx::mbar_wait(bar_p + sl, ph);
+      MTA(3);
+      ptx::tc_fence_after();
+      const uint32_t v_addr = ptx::smem_u32(sm_v) + vs * kv_bytes;
       for (int k = 0; k < a.NP / 16; ++k)
         ptx::mma_ts_pred(t + O_COL, t + k * 8, ptx::smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc2, k > 0 ? 1u : 0u, lead);
-      ptx::commit_pred(ptx::smem_u32(bar_o + sv), lead);
-      ptx::commit_pred(ptx::smem_u32(bar_free + stv), lead);
-      if (loaded < n_mine) { issue_load(loaded); ++loaded; }
-    };
-    for (; loaded < n_stages && loaded < n_mine; ++loaded) issue_load(loaded);
-    for (int u = 0; u < n_mine; ++u) {
-      const int sl = u & 1, st = u % n_stages;
-      ptx::mbar_wait(bar_qk + st, (uint32_t)((u / n_stages) & 1));
-      if (u >= 2) ptx::mbar_wait(bar_epi + sl, (uint32_t)(((u >> 1) - 1) & 1));   // the slot's previous O has been read
-      ptx::tc_fence_after();
-      const uint64_t dq = DESC0 + ((smem0 + st * stage_bytes) >> 4), dk = dq + ((BMQ * HD * 2) >> 4);
-#pragma unroll
-      for (int k = 0; k < HD / 16; ++k) ptx::mma_ss_pred(tmem + sl * 256, dq + 2 * k, dk + 2 * k, idesc1, k > 0 ? 1u : 0u, lead);
-      ptx::commit_pred(ptx::smem_u32(bar_s + sl), lead);
-      if (u >= 1) finish(u - 1);
+      ptx::commit_pred(ptx::smem_u32(bar_o + sl), lead);
+      ptx::commit_pred(ptx::smem_u32(bar_vfree + vs), lead);
     }
-    if (n_mine > 0) finish(n_mine - 1);
+#ifdef ATTN_FWD_TRACE
+    if (blockIdx.x == 0 && lane == 0)
+      printf("FT issuer %d | wait qk %lld | wait epi %lld | wait v %lld | wait p %lld\n", sl, mt_[0], mt_[1], mt_[2], mt_[3]);
+#endif
+  } else if (warp == 10) {
+    // loads: Q | K of unit i as soon as S of the slot's previous unit is in tensor memory, V of unit i once P.V of
+    // unit i - 3 has retired.  (Their own thread: waiting for a buffer inside an MMA warp kept the next S from
+    // being issued; freeing Q | K | V together, after P.V, left a load ~1.5 us to land and S waited for it.)
+    if (lane == 0) {
+      for (int i = 0; i < n_mine; ++i) {
+        const int sl = i & 1, vs = i % PP_V_STAGES;
+        int b, h, mt;
+        decode(i, b, h, mt);
+        if (i >= 2) ptx::mbar_wait(bar_s + sl, (uint32_t)(((i >> 1) - 1) & 1));
+        uint8_t* q = sm_qk + sl * qk_bytes;
+        ptx::mbar_expect_tx(bar_qk + sl, qk_bytes);
+        ptx::tma_load_3d(q, &tmQ, bar_qk + sl, h * HD, mt * BMQ, b);
+        ptx::tma_load_3d(q + BMQ * HD * 2, &tmKV, bar_qk + sl, a.D + h * HD, 0, b);
+        if (i >= PP_V_STAGES) ptx::mbar_wait(bar_vfree + vs, (uint32_t)((i / PP_V_STAGES - 1) & 1));
+        ptx::mbar_expect_tx(bar_v + vs, kv_bytes);
+        ptx::tma_load_3d(sm_v + vs * kv_bytes, &tmKV, bar_v + vs, 2 * a.D + h * HD, 0, b);
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      for (int u = 0; u < n_mine; ++u) {
+        int b, h, mt;
+        decode(u, b, h, mt);
+        ptx::mbar_wait(bar_ost + (u & 1), (uint32_t)((u >> 1) & 1));
+        ptx::tma_store_3d(&tmO, sm_o + (u & 1) * (BMQ * HD * 2), h * HD, mt * BMQ, b);
+        ptx::bulk_commit_group();
+        ptx::bulk_wait_group_read0();
+        ptx::mbar_arrive(bar_ofree + (u & 1));
+      }
+      ptx::bulk_wait_group0();
+    }
   } else {
     const int wg = warp >> 2, quarter = warp & 3;
     const uint32_t t_row = tmem + wg * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+#ifdef ATTN_FWD_TRACE   // make trace TRACE=-DATTN_FWD_TRACE: where a softmax warp's cycles go
+    long long ft[4] = {0, 0, 0, 0}, ft0 = 0, ft_begin = clock64();
+#define FT0() ft0 = clock64()
+#define FTA(i) ft[i] += clock64() - ft0
+#else
+#define FT0() do { } while (0)
+#define FTA(i) do { } while (0)
+#endif
     for (int u = wg; u < n_mine; u += 2) {
       const uint32_t ph = (uint32_t)((u >> 1) & 1);
       int b, h, mt;
       decode(u, b, h, mt);
       const int row = mt * BMQ + quarter * 32 + lane;
       const int n_chunks = (mt * BMQ + quarter * 32 < a.N) ? a.NP / 16 : 0;
+      FT0();
       ptx::mbar_wait(bar_s + wg, ph);
+      FTA(0);
       ptx::tc_fence_after();
-      const float inv = attn_softmax_row<EXPORT, DROP, JAS>(a, t_row, n_chunks, b, h, row);
+      FT0();
+      static_assert(!EXPORT, "the ping-pong forward does not export the map");
+      const float inv = attn_softmax_row_fast<DROP, JAS>(a, t_row, n_chunks, b, h, row);
       ptx::tmem_st_wait();
+      FTA(1);
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar_p + wg);
+      FT0();
       ptx::mbar_wait(bar_o + wg, ph);
+      FTA(2);
       ptx::tc_fence_after();
-      attn_store_o_row<EXPORT>(a, t_row + O_COL, b, h, row, inv);
+      FT0();
+      // O is in registers after one round trip: the slot goes back to the MMA warp (S of this warpgroup's next unit)
+      // BEFORE the scaled row is converted and stored
+      float o[HD];
+      attn_load_o_row(t_row + O_COL, o);
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar_epi + wg);
+      {   // scaled bf16 row -> the slot's staging tile, swizzled as the tensor map expects: 16-byte chunk c of tile
+          // row r sits at chunk c ^ (r & 7)
+        const int r = quarter * 32 + lane;
+        uint8_t* dst = sm_o + wg * (BMQ * HD * 2) + r * 128;
+        if (u >= 2) ptx::mbar_wait(bar_ofree + wg, ph ^ 1u);   // the tile of this slot's previous unit has left
+#pragma unroll
+        for (int c = 0; c < HD / 8; ++c) {
+          uint32_t w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 hh = __floats2bfloat162_rn(o[c * 8 + 2 * j] * inv, o[c * 8 + 2 * j + 1] * inv);
+            w[j] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+          *reinterpret_cast<uint4*>(dst + ((c ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        ptx::fence_async_shared();
+        ptx::mbar_arrive(bar_ost + wg);
+      }
+      FTA(3);
     }
+#ifdef ATTN_FWD_TRACE
+    if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 2 || warp == 4))
+      printf("FT warp %d units %d total %lld | wait S %lld | softmax %lld | wait O %lld | store O %lld\n", warp, (n_mine - wg + 1) / 2,
+             clock64() - ft_begin, ft[0], ft[1], ft[2], ft[3]);
+#endif
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -486,6 +739,13 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem, 512);
   }
+#ifdef ATTN_FWD_TRACE
+  if ((blockIdx.x == 0 || blockIdx.x == 147) && threadIdx.x == 0) {
+    unsigned long long gt_exit;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_exit));
+    printf("FT block %d entry->exit %lld cycles, %llu ns (entry at %llu)\n", blockIdx.x, clock64() - ft_entry, gt_exit - gt_entry, gt_entry);
+  }
+#endif
 }
 
 // ================================================================================================
@@ -1100,9 +1360,10 @@ int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, float*
     fill_f32_kernel<<<(B * H + 255) / 256, 256, 0, s>>>(jas_out, -INFINITY, B * H);
     ODV_LAUNCH_CHECK();
   }
-  CUtensorMap tq, tkv;
+  CUtensorMap tq, tkv, to;
   ODV_TRY(make_tmap_3d_bf16(&tq, qkv, 3 * D, N, B, 3 * D, (uint64_t)N * 3 * D, HD, BMQ, 1));
   ODV_TRY(make_tmap_3d_bf16(&tkv, qkv, 3 * D, N, B, 3 * D, (uint64_t)N * 3 * D, HD, a.NP, 1));
+  ODV_TRY(make_tmap_3d_bf16(&to, oh, D, N, B, ld_oh, (uint64_t)N * ld_oh, HD, BMQ, 1));   // O tiles of the ping-pong kernel
   static int sms = 0;
   if (!sms) {
     int dev = 0;
@@ -1114,9 +1375,7 @@ int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, float*
   if (!(env && env[0] == '0') && n_units >= 2 * sms && !p_out) {
     // enough units for every SM to pipeline: the persistent ping-pong kernel (the exporting variant is bound
     // by its row stores and measured slower there: it stays CTA-per-unit)
-    const int stage_bytes = BMQ * HD * 2 + 2 * a.NP * HD * 2;
-    const int n_stages = (PP_MAX_STAGES * stage_bytes + 2048 <= 227 * 1024) ? PP_MAX_STAGES : 2;
-    const int smem_pp = n_stages * stage_bytes + 1024 + 256;
+    const int smem_pp = 2 * (BMQ * HD * 2 + a.NP * HD * 2) + PP_V_STAGES * a.NP * HD * 2 + 2 * BMQ * HD * 2 + 1024 + 256;
     static bool configured_pp = false;
     if (!configured_pp) {
       const int max_smem = 227 * 1024;
@@ -1126,9 +1385,9 @@ int attn_fwd_tc(const void* qkv, void* oh, long long ld_oh, float* p_out, float*
       configured_pp = true;
     }
     const int grid_pp = n_units < sms ? n_units : sms;
-    if (jas_out) attn_fwd_pp_kernel<false, false, true><<<grid_pp, PP_THREADS, smem_pp, s>>>(tq, tkv, a, n_stages);
-    else if (drop.thresh) attn_fwd_pp_kernel<false, true><<<grid_pp, PP_THREADS, smem_pp, s>>>(tq, tkv, a, n_stages);
-    else attn_fwd_pp_kernel<false, false><<<grid_pp, PP_THREADS, smem_pp, s>>>(tq, tkv, a, n_stages);
+    if (jas_out) attn_fwd_pp_kernel<false, false, true><<<grid_pp, PP_THREADS, smem_pp, s>>>(tq, tkv, to, a);
+    else if (drop.thresh) attn_fwd_pp_kernel<false, true><<<grid_pp, PP_THREADS, smem_pp, s>>>(tq, tkv, to, a);
+    else attn_fwd_pp_kernel<false, false><<<grid_pp, PP_THREADS, smem_pp, s>>>(tq, tkv, to, a);
     ODV_LAUNCH_CHECK();
     return 0;
   }
