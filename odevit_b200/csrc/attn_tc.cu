@@ -887,7 +887,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 #endif
   if (threadIdx.x == 0) {
     for (int i = 0; i < 3; ++i) { ptx::mbar_init(bar_full + i, 1); ptx::mbar_init(bar_free + i, 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_sdp + i, 1); ptx::mbar_init(bar_pds + i, BWD_COMPUTE_WARPS * 16); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_sdp + i, 1); ptx::mbar_init(bar_pds + i, BWD_COMPUTE_WARPS * 32); }
     ptx::mbar_init(bar_c, 1);
     ptx::mbar_init(bar_kv, 1);
     ptx::mbar_init(bar_staged, BWD_COMPUTE_WARPS * 32);
@@ -1027,15 +1027,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     const uint32_t id_ts = ptx::idesc_bf16(128, HD, 0, 1);   // A from TMEM, B MN-major
     const uint32_t id_dq = ptx::idesc_bf16(128, HD, 1, 1);   // A, B MN-major
     const uint64_t dds_mn = ptx::smem_desc_sw128(ptx::smem_u32(sDS), 16384, 1024);
-    // dV += P^T dO, dK += dS^T Q over the half's queries, 16 per MMA; warpgroup w = ks >> 1 keeps its packed columns
-    // at [32 w, 32 w + 16) of the tile
+    // dV += P^T dO, dK += dS^T Q over the half's queries, 16 per MMA; the packed columns of k-step ks (written by
+    // warpgroup ks & 3) sit at [16 ks, 16 ks + 8) of the tile
     auto issue_c = [&](const Iter& r, int hf) {
 #pragma unroll
       for (int k4 = 0; k4 < 4; ++k4) {
         const int ks = hf * 4 + k4;
         if (ks < r.nq) {
           const uint32_t acc = ks > 0 ? 1u : r.acc_q;
-          const uint32_t a_col = (ks >> 1) * 32 + (ks & 1) * 8;
+          const uint32_t a_col = 16 * ks;
           ptx::mma_ts_pred(tmem + T_DV, tmem + T_S0 + a_col, r.ddo_mn + 128 * ks, id_ts, acc, lead);
           ptx::mma_ts_pred(tmem + T_DK, tmem + T_DP0 + a_col, r.dq_mn + 128 * ks, id_ts, acc, lead);
         }
@@ -1155,12 +1155,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     }
   } else {
     // =========================== compute warps (thread = key row) ===========================
+    // Every warpgroup works on BOTH halves of an iteration, one after the other: in half hf it owns the 16 query
+    // columns [64 hf + 16 wg, +16).  The halves are then separated in TIME -- while the sixteen warps exponentiate
+    // half 1 the tensor core runs dV / dK of half 0 and S^T / dP^T of the next iteration's half 0 -- instead of two
+    // groups of eight warps working on both halves at once with the tensor core idle, then waiting together.
     const int wg = warp >> 2, quarter = warp & 3;
-    const int hf = wg >> 1, sh = wg & 1;   // 64-column atom of the dS^T tile and 32-column half of it: columns [32 wg, 32 wg + 32)
+    const int eh = wg >> 1, sh = wg & 1;   // read-outs: accumulator / atom of the dS^T tile and 32-column half of it
     const int trow = quarter * 32 + lane;  // row inside a 128-row tile / chunk
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t t_s = t_lane + T_S0 + hf * 64 + sh * 32, t_dp = t_lane + T_DP0 + hf * 64 + sh * 32;
-    const int col0 = hf * 64 + sh * 32;    // first query column (inside the tile) of this warpgroup
     constexpr float LOG2E = 1.4426950408889634f;
     uint32_t g = 0;  // global iteration counter (phases of bar_sdp / bar_pds / bar_c)
     uint32_t n_chunk = 0;   // key chunks finished (phase of bar_kv)
@@ -1169,36 +1171,36 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     for (int idx = 0; idx < n_mine; ++idx) {
       const int item = (int)blockIdx.x + idx * (int)gridDim.x;
       const uint32_t drow0 = (uint32_t)((long long)item * a.N);   // dropout row coordinate of query 0
-      TR(hf, 14);
+      TR(0, 14);
       ptx::mbar_wait(bar_aux, idx & 1);
-      TR(hf, 15);
+      TR(0, 15);
       for (int it = 0; it < n_iter; ++it, ++g) {
         const int kc = it / nt, qt = it - kc * nt;
         const int qw = min(128, NP - qt * 128);
-        // chunks of 16 query columns this warpgroup owns in this tile (0, 1 or 2); a warp whose 32 key rows all lie
-        // past N has nothing to do either: its S^T / dP^T rows are exact zeros (= zero bf16 pairs for the MMAs)
-        int n_c = min(2, max(0, (qw - col0) / 16));
-        if (kc * 128 + quarter * 32 >= a.N) n_c = 0;
-        TR(hf, 0);
-        ptx::mbar_wait(bar_sdp + hf, g & 1);
-        ptx::tc_fence_after();
-        TR(hf, 2);
-        // chunk by chunk (32 live accumulator registers, not 64): load, form P^T / dS^T, pack, park both in tensor memory
-        // over columns this very thread has consumed (chunk 0 of its own block); dS^T is kept for the shared tile
-        uint32_t pDS[2][8];
+        const bool rows_live = kc * 128 + quarter * 32 < a.N;   // a warp whose 32 key rows all lie past N has nothing
+                                                                // to do: its S^T / dP^T rows are exact zeros
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          if (c < n_c) {
+        for (int hf = 0; hf < 2; ++hf) {
+          const int col0 = hf * 64 + wg * 16;                   // first query column (inside the tile) of this chunk
+          const bool live = rows_live && col0 < qw;
+          const uint32_t t_s = t_lane + T_S0 + col0, t_dp = t_lane + T_DP0 + col0;
+          TR(hf, 0);
+          ptx::mbar_wait(bar_sdp + hf, g & 1);
+          ptx::tc_fence_after();
+          TR(hf, 2);
+          // load, form P^T / dS^T, pack, park both in tensor memory over columns this very thread has consumed
+          uint32_t pDS[8];
+          if (live) {
             float sv[16], dp[16];
-            ptx::tmem_ld16(t_s + c * 16, sv);
-            ptx::tmem_ld16(t_dp + c * 16, dp);
+            ptx::tmem_ld16(t_s, sv);
+            ptx::tmem_ld16(t_dp, dp);
             if constexpr (GP) {
               // + the cotangent of the exported map, read transposed: lanes = consecutive keys of query row q
               const int key = kc * 128 + trow;
               float gq[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                const int q = qt * 128 + col0 + c * 16 + j;
+                const int q = qt * 128 + col0 + j;
                 gq[j] = (key < a.N && q < a.N) ? __ldg(a.gp + ((long long)item * a.N + q) * a.N + key) : 0.f;
               }
               ptx::tmem_ld_wait();
@@ -1207,8 +1209,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             } else {
               ptx::tmem_ld_wait();
             }
-            const float4* l4p = reinterpret_cast<const float4*>(sLse + qt * 128 + col0 + c * 16);
-            const float4* d4p = reinterpret_cast<const float4*>(sDelta + qt * 128 + col0 + c * 16);
+            const float4* l4p = reinterpret_cast<const float4*>(sLse + qt * 128 + col0);
+            const float4* d4p = reinterpret_cast<const float4*>(sDelta + qt * 128 + col0);
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               const float4 l4 = l4p[j4], d4 = d4p[j4];
@@ -1219,7 +1221,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                 const float p = ex2_fast(fmaf(sv[j], LOG2E, -lsq[jj]));
                 if constexpr (DROP) {
                   // O = drop(P) V:  dV needs drop(P)^T, dS = P o (drop'(dP) - delta)
-                  const float f = drop_factor(a.drop, drow0 + qt * 128 + col0 + c * 16 + j, kc * 128 + trow);
+                  const float f = drop_factor(a.drop, drow0 + qt * 128 + col0 + j, kc * 128 + trow);
                   sv[j] = p * f;
                   dp[j] = p * (dp[j] * f - dlq[jj]);
                 } else {
@@ -1234,33 +1236,32 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
               __nv_bfloat162 hp = __floats2bfloat162_rn(sv[2 * j], sv[2 * j + 1]);
               __nv_bfloat162 hd = __floats2bfloat162_rn(dp[2 * j], dp[2 * j + 1]);
               pP[j] = *reinterpret_cast<uint32_t*>(&hp);
-              pDS[c][j] = *reinterpret_cast<uint32_t*>(&hd);
+              pDS[j] = *reinterpret_cast<uint32_t*>(&hd);
             }
-            tmem_st8(t_s + c * 8, pP);
-            tmem_st8(t_dp + c * 8, pDS[c]);
+            tmem_st8(t_s, pP);
+            tmem_st8(t_dp, pDS);
           }
-        }
-        // the dS^T tile is single-buffered: the dQ MMA of the previous iteration must have retired
-        TR(hf, 4);
-        if (g > 0) ptx::mbar_wait(bar_c, (g - 1) & 1);
-        if (store_pending) {   // the accumulator tiles staged in the dS^T tile have been read by their TMA stores
-          ptx::mbar_wait(bar_stage_free, n_grp & 1);
-          ++n_grp;
-          store_pending = false;
-        }
-        TR(hf, 6);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          if (c < n_c) {
-            store_bf16x8_sw128(sDS, trow, col0 + c * 16, pDS[c]);
-            store_bf16x8_sw128(sDS, trow, col0 + c * 16 + 8, pDS[c] + 4);
+          TR(hf, 4);
+          if (hf == 0) {
+            // the dS^T tile is single-buffered: the dQ MMA of the previous iteration must have retired
+            if (g > 0) ptx::mbar_wait(bar_c, (g - 1) & 1);
+            if (store_pending) {   // the accumulator tiles staged in the dS^T tile have been read by their TMA stores
+              ptx::mbar_wait(bar_stage_free, n_grp & 1);
+              ++n_grp;
+              store_pending = false;
+            }
           }
+          TR(hf, 6);
+          if (live) {
+            store_bf16x8_sw128(sDS, trow, col0, pDS);
+            store_bf16x8_sw128(sDS, trow, col0 + 8, pDS + 4);
+          }
+          ptx::tmem_st_wait();
+          ptx::fence_async_shared();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(bar_pds + hf);
+          TR(hf, 8);
         }
-        ptx::tmem_st_wait();
-        ptx::fence_async_shared();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(bar_pds + hf);
-        TR(hf, 8);
         if (it == n_iter - 1) ptx::mbar_arrive(bar_item);   // lse / delta of this item have been read for the last time
         if (qt == nt - 1) {
           // ---- accumulators of this key chunk, 32 rows x 32 columns per warp (thread = key row): warpgroups 0, 1 ->
@@ -1269,7 +1270,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           ptx::mbar_wait(bar_kv, n_chunk & 1);
           ++n_chunk;
           ptx::tc_fence_after();
-          TR(hf, 10);
+          TR(eh, 10);
           const bool item_end = (kc == nt - 1);
           const int key0 = kc * 128 + quarter * 32;  // first of this warp's 32 key rows
           uint32_t wkv[16];
@@ -1278,11 +1279,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_epi);
           }
-          TR(hf, 11);
+          TR(eh, 11);
           // the staging slots belong to the dS^T tile the dQ product of this iteration reads
           ptx::mbar_wait(bar_c, g & 1);
-          TR(hf, 13);
-          uint8_t* atom = sDS + hf * 16384;
+          TR(eh, 13);
+          uint8_t* atom = sDS + eh * 16384;
           if (key0 < a.N) acc_stage32(wkv, atom, trow, sh);
           ptx::fence_async_shared();
           ptx::mbar_arrive(bar_staged);      // -> the store thread (TMA warp) takes [dK | dV] out
@@ -1296,15 +1297,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             if (have) acc_load_pack32(t_lane + T_DQ + tq * 64 + (wg & 1) * 32, wkv);
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_epi);
-            TR(hf, 16);
+            TR(eh, 16);
             ptx::mbar_wait(bar_stage_free, n_grp & 1);
-            TR(hf, 17);
+            TR(eh, 17);
             ++n_grp;
             if (have) acc_stage32(wkv, atom, trow, sh);
             ptx::fence_async_shared();
             ptx::mbar_arrive(bar_staged);
           }
-          TR(hf, 12);
+          TR(eh, 12);
         }
       }
     }
