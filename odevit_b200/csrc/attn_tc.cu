@@ -1107,8 +1107,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     // =========================== lse / delta loader (64 threads) ===========================
     // The values of item idx are formed in registers while item idx-1 is being computed and dropped
     // into the (single) shared-memory buffer the moment that item is finished.
+    // (Item 0 is the exception: nothing hides these 64 threads' four dependent rounds of row loads at the start of the
+    //  kernel -- ~13 k cycles before the first exponential -- so the 512 idle compute threads form it, one round.)
     const int tl = threadIdx.x - BWD_LOADER_WARP * 32;
-    for (int idx = 0; idx < n_mine; ++idx) {
+    if (n_mine > 0) ptx::mbar_arrive(bar_aux);
+    for (int idx = 1; idx < n_mine; ++idx) {
       const int item = (int)blockIdx.x + idx * (int)gridDim.x;
       const int hh = item % a.H, bb = item / a.H;
       float lse[4], dl[4];
@@ -1141,7 +1144,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         }
       }
       TR(20, 20);
-      if (idx >= 1) ptx::mbar_wait(bar_item, (idx - 1) & 1);  // the previous item no longer reads the buffer
+      ptx::mbar_wait(bar_item, (idx - 1) & 1);  // the previous item no longer reads the buffer
       TR(20, 21);
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
@@ -1160,6 +1163,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     // half 1 the tensor core runs dV / dK of half 0 and S^T / dP^T of the next iteration's half 0 -- instead of two
     // groups of eight warps working on both halves at once with the tensor core idle, then waiting together.
     const int wg = warp >> 2, quarter = warp & 3;
+    [[maybe_unused]] const int trr = warp == 0 ? 0 : 1;   // trace role (ATTN_TRACE builds: warps 0 and 8 record)
     const int eh = wg >> 1, sh = wg & 1;   // read-outs: accumulator / atom of the dS^T tile and 32-column half of it
     const int trow = quarter * 32 + lane;  // row inside a 128-row tile / chunk
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -1168,12 +1172,48 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     uint32_t n_chunk = 0;   // key chunks finished (phase of bar_kv)
     bool store_pending = false;
     uint32_t n_grp = 0;     // store groups whose completion has been waited for (phase of bar_stage_free)
+    if (n_mine > 0) {
+      // lse / delta of the CTA's first item: two threads per query row, 32 elements of <dO, O> each
+      const int item = (int)blockIdx.x, hh = item % a.H, bb = item / a.H;
+      const int q = threadIdx.x >> 1, part = threadIdx.x & 1;
+      float acc = 0.f;
+      if (q < a.N) {
+        const uint4* pd = reinterpret_cast<const uint4*>(a.dO + ((long long)bb * a.N + q) * a.D + hh * HD) + part * 4;
+        const uint4* po = reinterpret_cast<const uint4*>(a.O + ((long long)bb * a.N + q) * a.ld_o + hh * HD) + part * 4;
+        uint4 x[4], y[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { x[i] = pd[i]; y[i] = po[i]; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t xs[4] = {x[i].x, x[i].y, x[i].z, x[i].w}, ys[4] = {y[i].x, y[i].y, y[i].z, y[i].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 xb = *reinterpret_cast<const __nv_bfloat162*>(&xs[j]);
+            const __nv_bfloat162 yb = *reinterpret_cast<const __nv_bfloat162*>(&ys[j]);
+            acc = fmaf(__low2float(xb), __low2float(yb), acc);
+            acc = fmaf(__high2float(xb), __high2float(yb), acc);
+          }
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (part == 0) {
+        float l = INFINITY, d = 0.f;
+        if (q < a.N) {
+          l = a.lse2[(long long)item * a.N + q];
+          d = acc;
+          if constexpr (GP) d += a.dext[(long long)item * a.N + q];
+        }
+        sLse[q] = l;
+        sDelta[q] = d;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(BWD_COMPUTE_WARPS * 32) : "memory");
+    }
     for (int idx = 0; idx < n_mine; ++idx) {
       const int item = (int)blockIdx.x + idx * (int)gridDim.x;
       const uint32_t drow0 = (uint32_t)((long long)item * a.N);   // dropout row coordinate of query 0
-      TR(0, 14);
+      TR(trr, 14);
       ptx::mbar_wait(bar_aux, idx & 1);
-      TR(0, 15);
+      TR(trr, 15);
       for (int it = 0; it < n_iter; ++it, ++g) {
         const int kc = it / nt, qt = it - kc * nt;
         const int qw = min(128, NP - qt * 128);
@@ -1184,10 +1224,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           const int col0 = hf * 64 + wg * 16;                   // first query column (inside the tile) of this chunk
           const bool live = rows_live && col0 < qw;
           const uint32_t t_s = t_lane + T_S0 + col0, t_dp = t_lane + T_DP0 + col0;
-          TR(hf, 0);
+          TR(trr, 0 + 32 * hf);
           ptx::mbar_wait(bar_sdp + hf, g & 1);
           ptx::tc_fence_after();
-          TR(hf, 2);
+          TR(trr, 2 + 32 * hf);
           // load, form P^T / dS^T, pack, park both in tensor memory over columns this very thread has consumed
           uint32_t pDS[8];
           if (live) {
@@ -1241,7 +1281,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             tmem_st8(t_s, pP);
             tmem_st8(t_dp, pDS);
           }
-          TR(hf, 4);
+          TR(trr, 4 + 32 * hf);
           if (hf == 0) {
             // the dS^T tile is single-buffered: the dQ MMA of the previous iteration must have retired
             if (g > 0) ptx::mbar_wait(bar_c, (g - 1) & 1);
@@ -1251,7 +1291,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
               store_pending = false;
             }
           }
-          TR(hf, 6);
+          TR(trr, 6 + 32 * hf);
           if (live) {
             store_bf16x8_sw128(sDS, trow, col0, pDS);
             store_bf16x8_sw128(sDS, trow, col0 + 8, pDS + 4);
@@ -1260,7 +1300,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           ptx::fence_async_shared();
           ptx::tc_fence_before();
           ptx::mbar_arrive(bar_pds + hf);
-          TR(hf, 8);
+          TR(trr, 8 + 32 * hf);
         }
         if (it == n_iter - 1) ptx::mbar_arrive(bar_item);   // lse / delta of this item have been read for the last time
         if (qt == nt - 1) {
@@ -1270,7 +1310,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           ptx::mbar_wait(bar_kv, n_chunk & 1);
           ++n_chunk;
           ptx::tc_fence_after();
-          TR(eh, 10);
+          TR(trr, 10);
           const bool item_end = (kc == nt - 1);
           const int key0 = kc * 128 + quarter * 32;  // first of this warp's 32 key rows
           uint32_t wkv[16];
@@ -1279,10 +1319,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_epi);
           }
-          TR(eh, 11);
+          TR(trr, 11);
           // the staging slots belong to the dS^T tile the dQ product of this iteration reads
           ptx::mbar_wait(bar_c, g & 1);
-          TR(eh, 13);
+          TR(trr, 13);
           uint8_t* atom = sDS + eh * 16384;
           if (key0 < a.N) acc_stage32(wkv, atom, trow, sh);
           ptx::fence_async_shared();
@@ -1297,15 +1337,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             if (have) acc_load_pack32(t_lane + T_DQ + tq * 64 + (wg & 1) * 32, wkv);
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_epi);
-            TR(eh, 16);
+            TR(trr, 16);
             ptx::mbar_wait(bar_stage_free, n_grp & 1);
-            TR(eh, 17);
+            TR(trr, 17);
             ++n_grp;
             if (have) acc_stage32(wkv, atom, trow, sh);
             ptx::fence_async_shared();
             ptx::mbar_arrive(bar_staged);
           }
-          TR(eh, 12);
+          TR(trr, 12);
         }
       }
     }
