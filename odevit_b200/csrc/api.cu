@@ -506,15 +506,20 @@ int attention_forward(const Plan& p, const void* qkv_v, void* oh, long long ld_o
   return 0;
 }
 
+// dq_colsum / colsum_done: the fused kernel can add the column sums of dq (the q-row bias gradient) into dq_colsum
+// on its way out; *colsum_done says whether it did
 int attention_vjp(const Plan& p, const void* qkv_v, const void* oh, long long ld_oh, const float* lse, BwdBufs& b,
-                  const float* g_p, void* dz_v, int R, Drop drop, cudaStream_t s) {
+                  const float* g_p, void* dz_v, int R, Drop drop, cudaStream_t s, float* dq_colsum, bool* colsum_done) {
+  if (colsum_done) *colsum_done = false;
   const int D = p.D;
   const bool l2 = (p.variant == ODEVIT_FIELD_PARALLEL_L2);
   const size_t e = dtype_size(p.act);
   char* dz = reinterpret_cast<char*>(dz_v);
   if (!l2 && p.precision == ODEVIT_BF16 && !g_p && lse && attn_fwd_tc_supports(p.N, D, p.H, p.act, ld_oh)) {
     // fused tcgen05 kernel (P recomputed on chip from q, k and the saved row log-sum-exp)
-    return attn_bwd_tc(qkv_v, b.dO, oh, ld_oh, lse, b.delta, dz_v, R, b.dq_scratch, p.B, p.N, p.H, D, drop, s);
+    if (colsum_done) *colsum_done = dq_colsum != nullptr;
+    return attn_bwd_tc(qkv_v, b.dO, oh, ld_oh, lse, b.delta, dz_v, R, b.dq_scratch, p.B, p.N, p.H, D, drop, s, nullptr, nullptr,
+                       dq_colsum);
   }
   if (!l2 && p.precision == ODEVIT_BF16 && g_p && lse && !drop.thresh && b.P && b.delta &&
       attn_fwd_tc_supports(p.N, D, p.H, p.act, ld_oh)) {
@@ -523,7 +528,8 @@ int attention_vjp(const Plan& p, const void* qkv_v, const void* oh, long long ld
     // the very same values) -- then the fused kernel adds g to dP on the fly
     ODV_TRY(attn_fwd_tc(qkv_v, const_cast<void*>(oh), ld_oh, b.P, nullptr, p.B, p.N, p.H, D, Drop{}, s));
     ODV_TRY(rowdot_rows(b.P, g_p, b.delta, (long long)p.B * p.H * p.N, p.N, s));
-    return attn_bwd_tc(qkv_v, b.dO, oh, ld_oh, lse, b.delta, dz_v, R, b.dq_scratch, p.B, p.N, p.H, D, drop, s, g_p, b.delta);
+    if (colsum_done) *colsum_done = dq_colsum != nullptr;
+    return attn_bwd_tc(qkv_v, b.dO, oh, ld_oh, lse, b.delta, dz_v, R, b.dq_scratch, p.B, p.N, p.H, D, drop, s, g_p, b.delta, dq_colsum);
   }
   const HeadView hv = qkv_view(p);
   const char* qkv = reinterpret_cast<const char*>(qkv_v);
@@ -796,7 +802,9 @@ int eval_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b,
   }
 
   // ---- attention VJP per (image, head) ----------------------------------------------------------
-  ODV_TRY(attention_vjp(p, c.qkv, c.oh, K2, c.lse, b, g_p, b.dz, R, make_drop(p, DS_ATTN, ev), s));
+  bool dq_colsum_done = false;   // the fused attention VJP sums the dq block on its way out
+  ODV_TRY(attention_vjp(p, c.qkv, c.oh, K2, c.lse, b, g_p, b.dz, R, make_drop(p, DS_ATTN, ev), s, fused_colsum ? b.c1 : nullptr,
+                        &dq_colsum_done));
   {  // mu = dz @ centred(W1cat), consumed by the caller's stage-combine epilogue
     GemmArgs g;
     g.M = p.M; g.N = D; g.K = R;
@@ -821,8 +829,8 @@ int eval_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b,
     g.kclass = KC_BWD_GEMM_G1;
     ODV_TRY(gemm(p, g, s));
   }
-  if (fused_colsum) ODV_TRY(colsum_accum(b.dz, p.act, R, p.M, D, b.c1, s));     // the dq block only
-  else ODV_TRY(colsum_accum(b.dz, p.act, R, p.M, R, b.c1, s));
+  if (!fused_colsum) ODV_TRY(colsum_accum(b.dz, p.act, R, p.M, R, b.c1, s));
+  else if (!dq_colsum_done) ODV_TRY(colsum_accum(b.dz, p.act, R, p.M, D, b.c1, s));     // the dq block only
   return 0;
 }
 

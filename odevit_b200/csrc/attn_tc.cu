@@ -797,6 +797,9 @@ struct AttnBwdArgs {
   // delta = <dO, O> + dext with dext[b,h,i] = sum_j P_ij gp_ij formed beforehand (rows.cu::rowdot_rows)
   const float* gp;              // [B,H,N,N] fp32 or null
   const float* dext;            // [B,H,N] fp32 or null
+  // bias gradient of the q rows of the in-projection: column sums of dq over every token, accumulated (atomics)
+  // into dq_colsum[h*64 + c] when not null -- the rows are in registers at the item's end anyway
+  float* dq_colsum;
 };
 
 constexpr int BWD_TMEM_COLS = 512;
@@ -833,6 +836,33 @@ __device__ __forceinline__ void acc_load_pack32(uint32_t t_addr, uint32_t (&w)[1
     __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
     w[j] = *reinterpret_cast<uint32_t*>(&hh);
   }
+}
+// The same read-out, plus the sums over this warp's 32 rows of each of the 32 columns: a butterfly over the lanes in
+// which every step halves the number of columns a lane carries (16 + 8 + 4 + 2 + 1 shuffles); lane j ends up with the
+// sum of column j.
+__device__ __forceinline__ float acc_load_pack32_colsum(uint32_t t_addr, uint32_t (&w)[16], int lane, bool row_live) {
+  float v[32];
+  ptx::tmem_ld32(t_addr, v);
+  ptx::tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    w[j] = *reinterpret_cast<uint32_t*>(&hh);
+  }
+  // rows past N are not zeros (their dS columns are whatever the shared tile held: the tensor store clips them)
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = row_live ? v[i] : 0.f;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float keep = up ? v[i + o] : v[i];
+      const float send = up ? v[i] : v[i + o];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
 }
 // ... -> the 16-byte slots of the dS^T tile that THIS thread writes in the main loop (row `trow`, atom `hf`, chunks
 // sh*4 .. sh*4+3 under the 128-byte swizzle).  With warpgroups (0, 1) holding the column halves of one accumulator and
@@ -1334,9 +1364,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             const int tq = wg >> 1;
             const bool have = (tq < nt) && (tq * 128 + quarter * 32 < a.N);
             ptx::tc_fence_after();
-            if (have) acc_load_pack32(t_lane + T_DQ + tq * 64 + (wg & 1) * 32, wkv);
+            float dq_cs = 0.f;
+            if (have) {
+              if (a.dq_colsum) dq_cs = acc_load_pack32_colsum(t_lane + T_DQ + tq * 64 + (wg & 1) * 32, wkv, lane, tq * 128 + trow < a.N);
+              else acc_load_pack32(t_lane + T_DQ + tq * 64 + (wg & 1) * 32, wkv);
+            }
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_epi);
+            if (have && a.dq_colsum) atomicAdd(a.dq_colsum + (item % a.H) * HD + (wg & 1) * 32 + lane, dq_cs);
             TR(trr, 16);
             ptx::mbar_wait(bar_stage_free, n_grp & 1);
             TR(trr, 17);
@@ -1467,7 +1502,7 @@ size_t attn_bwd_tc_scratch_floats(int B, int N, int H) {
 // receives dq | dk | dv.  (`delta`, `dq_scratch` are unused: delta is formed in the kernel.)
 int attn_bwd_tc(const void* qkv, const void* dO, const void* oh, long long ld_oh, const float* lse2, float* delta,
                 void* dz, int R, float* dq_scratch, int B, int N, int H, int D, Drop drop, cudaStream_t s, const float* gp,
-                const float* dext) {
+                const float* dext, float* dq_colsum) {
   (void)delta; (void)dq_scratch;
   if ((gp != nullptr) != (dext != nullptr) || (gp && drop.thresh))
     return set_error(ODEVIT_ERR_INVALID_ARG, "attn_bwd_tc: map cotangent needs its row dots and no dropout");
@@ -1481,6 +1516,7 @@ int attn_bwd_tc(const void* qkv, const void* dO, const void* oh, long long ld_oh
   a.lse2 = lse2; a.dz = dz;
   a.drop = drop;
   a.gp = gp; a.dext = dext;
+  a.dq_colsum = dq_colsum;
   a.dO = reinterpret_cast<const __nv_bfloat16*>(dO);
   a.O = reinterpret_cast<const __nv_bfloat16*>(oh);
   a.ld_o = ld_oh;

@@ -92,8 +92,11 @@ int attention_forward(const Plan& p, const void* qkv, void* oh, long long ld_oh,
                       float* lse, float* sq, Drop drop, cudaStream_t s,
                       float* jas_out = nullptr, int jas_k = 0);
 // Its VJP: dO [M,D] (act) -> dq|dk|dv into dz (leading dim R, act).  g_p: optional cotangent of P.
+// dq_colsum / colsum_done: the fused kernel can add the column sums of dq (the q-row bias gradient) into dq_colsum [D]
+// on its way out; *colsum_done says whether it did.
 int attention_vjp(const Plan& p, const void* qkv, const void* oh, long long ld_oh, const float* lse, BwdBufs& b,
-                  const float* g_p, void* dz, int R, Drop drop, cudaStream_t s);
+                  const float* g_p, void* dz, int R, Drop drop, cudaStream_t s, float* dq_colsum = nullptr,
+                  bool* colsum_done = nullptr);
 
 // On-chip-state solver for small-token shapes (solve_resident.cu): one persistent CTA per image runs
 // every step of the solve with the ODE state in shared memory.  Inference, PARALLEL field, bf16 mode.

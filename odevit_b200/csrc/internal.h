@@ -200,7 +200,7 @@ bool attn_fwd_tc_jasmin_supports(int N, int k);
 size_t attn_bwd_tc_scratch_floats(int B, int N, int H);
 int attn_bwd_tc(const void* qkv, const void* dO, const void* oh, long long ld_oh, const float* lse2, float* delta,
                 void* dz, int R, float* dq_scratch, int B, int N, int H, int D, Drop drop, cudaStream_t s, const float* gp = nullptr,
-                const float* dext = nullptr);
+                const float* dext = nullptr, float* dq_colsum = nullptr);   // dq_colsum [D] += column sums of dq
 
 // ---------------------------------------------------------------------------------------------
 // row-wise / elementwise kernels (odevit_rows.cu)
