@@ -16,13 +16,32 @@ class FlatGradAllReduce:
     """Averages `.grad` of `params` across the process group through one flat bucket.
 
     Parameters whose grad is None on this rank contribute zeros (and receive the average), so
-    ranks never disagree on the bucket layout."""
+    ranks never disagree on the bucket layout.  Replicas must start from the same weights: construction
+    broadcasts rank 0's parameters once (`sync_parameters`), so correctness does not rest on every rank
+    having seeded identically."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None,
+                 sync: bool = True):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = group
         self._flat: Optional[torch.Tensor] = None
         self._views: List[torch.Tensor] = []
+        if sync:
+            self.sync_parameters()
+
+    @torch.no_grad()
+    def sync_parameters(self) -> None:
+        """One flat broadcast of the trainable parameters from rank 0 of the group."""
+        if not self.params or not (dist.is_available() and dist.is_initialized()):
+            return
+        if dist.get_world_size(self.group) == 1:
+            return
+        flat = torch.cat([p.detach().reshape(-1).float() for p in self.params])
+        dist.broadcast(flat, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        off = 0
+        for p in self.params:
+            p.copy_(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
 
     def _ensure_bucket(self) -> None:
         if self._flat is not None:

@@ -51,6 +51,28 @@ def test_flat_bucket_allreduce_world2():
     assert torch.equal(out[0][0], out[1][0])
 
 
+def _worker_sync(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from odevit_b200.dp import FlatGradAllReduce
+    torch.manual_seed(100 + rank)                      # replicas that did NOT seed identically
+    lin = torch.nn.Linear(5, 3)
+    before = lin.weight.detach().clone()
+    FlatGradAllReduce(lin.parameters())                # construction broadcasts rank 0's weights
+    out[rank] = [before, lin.weight.detach().clone(), lin.bias.detach().clone()]
+    dist.destroy_process_group()
+
+
+def test_construction_broadcasts_rank0_parameters():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_sync, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert not torch.equal(out[0][0], out[1][0])       # they started apart
+    assert torch.equal(out[0][1], out[0][0])           # rank 0 keeps its own
+    assert torch.equal(out[1][1], out[0][1]) and torch.equal(out[1][2], out[0][2])
+
+
 def test_shard_batch_covers_everything():
     from odevit_b200.dp import shard_batch
     for n in (1, 7, 8, 64):
