@@ -626,7 +626,8 @@ int eval_forward(const Plan& p, const WeightBufs& wb, const StageCtx& c, const f
     g.epi.out = c.qkv; g.epi.out_type = p.act; g.epi.ld_out = 3 * D;
     g.epi.split = 3 * D;
     g.epi.out2 = reinterpret_cast<char*>(c.oh) + (size_t)D * dtype_size(p.act); g.epi.ld_out2 = K2;
-    g.epi.out3 = c.hpre; g.epi.ld_out3 = hid;
+    g.epi.out3 = c.hpre; g.epi.ld_out3 = hid;   // (holds GELU'(pre-activation): Epi::aux_gelu_grad)
+    g.epi.aux_gelu_grad = true;
     g.epi.aux_type = p.act;
     g.epi.drop = make_drop(p, DS_MLP_H, e);   // dropout after GELU (:196-197)
     ODV_TRY(gemm(p, g, s));
@@ -741,6 +742,7 @@ int eval_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b,
       g.epi.split = 0;
       g.epi.out2 = dz + (size_t)3 * D * e; g.epi.ld_out2 = R;
       g.epi.aux = c.hpre; g.epi.ld_aux = hid; g.epi.aux_type = p.act;
+      g.epi.aux_gelu_grad = true;
       g.epi.drop = make_drop(p, DS_MLP_H, ev);
       ODV_TRY(gemm(p, g, s));
     }
@@ -777,6 +779,7 @@ int eval_vjp(const Plan& p, const WeightBufs& wb, const StageCtx& c, BwdBufs& b,
     g.epi.split = D;
     g.epi.out2 = dz + (size_t)3 * D * e; g.epi.ld_out2 = R;
     g.epi.aux = c.hpre; g.epi.ld_aux = hid; g.epi.aux_type = p.act;
+    g.epi.aux_gelu_grad = true;
     // Bias-gradient column sums without a pass over dz (81 MB at the bench shape).  Softmax attention without map
     // dropout gives two of the four blocks for free:  sum_j dK_j = sum_i q_i (sum_j dS_ij) = 0  (rows of the softmax
     // Jacobian sum to zero) and  sum_j dV_j = sum_i (sum_j P_ij) dO_i = sum_i dO_i;  dO and d h_pre are summed in the

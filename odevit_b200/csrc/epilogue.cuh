@@ -58,7 +58,7 @@ __device__ __forceinline__ void epi_apply(const Epi& e, int m, int n, float acc,
       store_elem(e.out, (long long)m * e.ld_out + n, e.out_type, v);
     } else {
       const int c = n - e.split;
-      if (e.out3) store_elem(e.out3, (long long)m * e.ld_out3 + c, e.aux_type, v);
+      if (e.out3) store_elem(e.out3, (long long)m * e.ld_out3 + c, e.aux_type, e.aux_gelu_grad ? gelu_erf_grad(v) : v);
       float gv = gelu_erf(v);
       if constexpr ((EPI & EPI_DROP) != 0) gv *= drop_factor(e.drop, m, c);
       store_elem(e.out2, (long long)m * e.ld_out2 + c, e.aux_type, gv);
@@ -89,7 +89,7 @@ __device__ __forceinline__ void epi_apply(const Epi& e, int m, int n, float acc,
       const float hp = load_elem_rw(e.aux, (long long)m * e.ld_aux + c, e.aux_type);
       if (e.dev_scale) acc *= *e.dev_scale;
       if constexpr ((EPI & EPI_DROP) != 0) acc *= drop_factor(e.drop, m, c);
-      store_elem(e.out2, (long long)m * e.ld_out2 + c, e.aux_type, acc * gelu_erf_grad(hp));
+      store_elem(e.out2, (long long)m * e.ld_out2 + c, e.aux_type, acc * (e.aux_gelu_grad ? hp : gelu_erf_grad(hp)));
     }
   } else if constexpr ((EPI & 7) == EPI_TOKENS) {
     const int b = m / e.split, r = m - b * e.split;
@@ -160,7 +160,16 @@ __device__ __forceinline__ void epi_chunk16(const Epi& e, int m, int n, float* v
       store16(e.out, (long long)m * e.ld_out + n, e.out_type, v);
     } else {
       const int c = n - e.split;
-      if (e.out3) store16(e.out3, (long long)m * e.ld_out3 + c, e.aux_type, v);
+      if (e.out3) {
+        if (e.aux_gelu_grad) {
+          float gp[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) gp[j] = gelu_erf_grad(v[j]);
+          store16(e.out3, (long long)m * e.ld_out3 + c, e.aux_type, gp);
+        } else {
+          store16(e.out3, (long long)m * e.ld_out3 + c, e.aux_type, v);
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
       if constexpr ((EPI & EPI_DROP) != 0) {
@@ -219,7 +228,8 @@ __device__ __forceinline__ void epi_chunk16(const Epi& e, int m, int n, float* v
       load16(e.aux, (long long)m * e.ld_aux + c, e.aux_type, hp);
       const float ds = e.dev_scale ? *e.dev_scale : 1.f;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] *= ds * gelu_erf_grad(hp[j]) * ((EPI & EPI_DROP) != 0 ? drop_factor(e.drop, m, c + j) : 1.f);
+      for (int j = 0; j < 16; ++j)
+        v[j] *= ds * (e.aux_gelu_grad ? hp[j] : gelu_erf_grad(hp[j])) * ((EPI & EPI_DROP) != 0 ? drop_factor(e.drop, m, c + j) : 1.f);
       store16(e.out2, (long long)m * e.ld_out2 + c, e.aux_type, v);
     }
   } else if constexpr ((EPI & 7) == EPI_ACCUM) {
@@ -303,6 +313,15 @@ __device__ __forceinline__ float gelu_phi(float x, float x2) {
 }
 __device__ __forceinline__ float gelu_fast(float x) {
   return x * gelu_phi(x, fminf(x * x, 49.f));
+}
+// GELU and its derivative from one evaluation of Phi (the forward epilogue stores the derivative for the VJP)
+__device__ __forceinline__ void gelu_pair_fast(float x, float& g, float& dg) {
+  const float x2 = fminf(x * x, 49.f);
+  const float phi = gelu_phi(x, x2);
+  float d = fmaf(10.f * -0.000351516788525385f, x2, 6.f * 0.037005646025752466f);
+  d = fmaf(d, x2, 2.f * 0.7975078842819603f);
+  g = x * phi;
+  dg = fmaf(g - g * phi, d, phi);     // x phi (1 - phi) d + phi
 }
 __device__ __forceinline__ float gelu_grad_fast(float x) {
   const float x2 = fminf(x * x, 49.f);
@@ -470,11 +489,45 @@ __device__ __forceinline__ void epi8_finish(const Epi& e, int m0, int M, int n, 
       store_rows8<FULL>(e.out, e.out_type, (long long)m0 * e.ld_out + n, 4 * (int)e.ld_out, m0, M, w);
     } else {
       const int c = n - e.split;
-      if (e.out3) store_rows8<FULL>(e.out3, e.aux_type, (long long)m0 * e.ld_out3 + c, 4 * (int)e.ld_out3, m0, M, w);
+      const bool want_grad = e.out3 && e.aux_gelu_grad;   // (warp-uniform)
+      if (e.out3 && !want_grad) store_rows8<FULL>(e.out3, e.aux_type, (long long)m0 * e.ld_out3 + c, 4 * (int)e.ld_out3, m0, M, w);
+      if (want_grad) {
+        // GELU'(pre) goes out in two half-batches of 4 rows (16 more live registers, not 32)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float4 dg[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4& x = w[4 * h + i];
+            if constexpr ((EPI & EPI_EXACT) != 0) {
+              dg[i] = make_float4(gelu_erf_grad(x.x), gelu_erf_grad(x.y), gelu_erf_grad(x.z), gelu_erf_grad(x.w));
+              x = make_float4(gelu_erf(x.x), gelu_erf(x.y), gelu_erf(x.z), gelu_erf(x.w));
+            } else {
+              gelu_pair_fast(x.x, x.x, dg[i].x); gelu_pair_fast(x.y, x.y, dg[i].y);
+              gelu_pair_fast(x.z, x.z, dg[i].z); gelu_pair_fast(x.w, x.w, dg[i].w);
+            }
+          }
+          const long long idx0 = (long long)m0 * e.ld_out3 + c;
+          const int step = 4 * (int)e.ld_out3;
+          if (e.aux_type == DT_F32) {
+            float* p3 = reinterpret_cast<float*>(e.out3) + idx0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (row_in<FULL>(m0, 4 * h + i, M)) stg_f32x4(p3 + (4 * h + i) * step, dg[i]);
+          } else {
+            __nv_bfloat16* p3 = reinterpret_cast<__nv_bfloat16*>(e.out3) + idx0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (row_in<FULL>(m0, 4 * h + i, M)) stg_bf16x4(p3 + (4 * h + i) * step, dg[i]);
+          }
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        if constexpr ((EPI & EPI_EXACT) != 0) w[i] = make_float4(gelu_erf(w[i].x), gelu_erf(w[i].y), gelu_erf(w[i].z), gelu_erf(w[i].w));
-        else w[i] = make_float4(gelu_fast(w[i].x), gelu_fast(w[i].y), gelu_fast(w[i].z), gelu_fast(w[i].w));
+        if (!want_grad) {
+          if constexpr ((EPI & EPI_EXACT) != 0) w[i] = make_float4(gelu_erf(w[i].x), gelu_erf(w[i].y), gelu_erf(w[i].z), gelu_erf(w[i].w));
+          else w[i] = make_float4(gelu_fast(w[i].x), gelu_fast(w[i].y), gelu_fast(w[i].z), gelu_fast(w[i].w));
+        }
         if constexpr ((EPI & EPI_DROP) != 0) {
           const uint32_t r = m0 + 4 * i;
           w[i].x *= drop_factor(e.drop, r, c); w[i].y *= drop_factor(e.drop, r, c + 1);
@@ -581,7 +634,9 @@ __device__ __forceinline__ void epi8_finish(const Epi& e, int m0, int M, int n, 
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 hp = f32 ? raw_f32(pre.a[i]) : raw_bf16(pre.a[i]);
-        if constexpr ((EPI & EPI_EXACT) != 0) {
+        if (e.aux_gelu_grad) {   // the forward stored the derivative itself (warp-uniform branch)
+          w[i].x *= ds * hp.x; w[i].y *= ds * hp.y; w[i].z *= ds * hp.z; w[i].w *= ds * hp.w;
+        } else if constexpr ((EPI & EPI_EXACT) != 0) {
           w[i].x *= ds * gelu_erf_grad(hp.x); w[i].y *= ds * gelu_erf_grad(hp.y);
           w[i].z *= ds * gelu_erf_grad(hp.z); w[i].w *= ds * gelu_erf_grad(hp.w);
         } else {

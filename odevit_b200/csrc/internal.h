@@ -160,6 +160,11 @@ struct Epi {
   // the tcgen05 epilogues use GELU's erf form (set by the fp32 mode's split-bf16 GEMMs; the bf16 mode's fitted form is
   // 2.6e-5 off, inside bf16 rounding but not inside the fp32 mode's 1e-4)
   bool exact_gelu = false;
+  // EPI_FWD1 stores GELU'(pre-activation) instead of the pre-activation in out3, and EPI_BWD3 finds it in aux: the
+  // VJP's epilogue multiplies by it instead of evaluating the derivative again (~14 instructions and two MUFU
+  // operations per element less in an epilogue that was as long as its K = D main loop).  Both GEMMs of a field
+  // evaluation must agree on it.
+  bool aux_gelu_grad = false;
   // EPI_BWD3 (tcgen05 kernel): column sums of the stored values over the rows m, added atomically to colsum_a[n] for the
   // columns n < split and to colsum_b[n - split] for the rest (bias gradients without a second pass over the outputs;
   // needs N % 32 == 0 and split % 32 == 0: whole warps reduce)
