@@ -365,23 +365,6 @@ __device__ __forceinline__ void attn_load_o_row(uint32_t t_o, float (&v)[HD]) {
   for (int c = 0; c < HD / 16; ++c) ptx::tmem_ld16(t_o + c * 16, &v[c * 16]);
   ptx::tmem_ld_wait();
 }
-// O row * inv -> bf16 -> columns [h*64, h*64+64) of the [O | h] buffer
-__device__ __forceinline__ void attn_write_o_row(const AttnArgs& a, const float (&v)[HD], int b, int h, int row, float inv) {
-  if (row < a.N) {
-    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.oh) + ((long long)b * a.N + row) * a.ld_oh + h * HD);
-#pragma unroll
-    for (int c = 0; c < HD / 8; ++c) {
-      uint32_t w[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        __nv_bfloat162 hh = __floats2bfloat162_rn(v[c * 8 + 2 * j] * inv, v[c * 8 + 2 * j + 1] * inv);
-        w[j] = *reinterpret_cast<uint32_t*>(&hh);
-      }
-      o[c] = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-  }
-}
-
 // O row (tensor memory, columns t_o ..+64) * inv -> bf16 -> columns [h*64, h*64+64) of the [O | h] buffer
 template <bool EXPORT>
 __device__ __forceinline__ void attn_store_o_row(const AttnArgs& a, uint32_t t_o, int b, int h, int row, float inv) {
