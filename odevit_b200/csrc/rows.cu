@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(128) fold_w1_kernel(FoldArgs a, odevit_weights
     if (fn && msh) be += msh[i];
     const float wv = Wrow[i];
     const float f = qs * s_cn * wv * we;
-    store_elem(a.w1cat, (long long)j * D + i, a.w_type, f);
+    if (!fn) store_elem(a.w1cat, (long long)j * D + i, a.w_type, f);
     fsum += f;
     dot = fmaf(wv, be, dot);
   }
@@ -729,6 +729,18 @@ __global__ void __launch_bounds__(128) fold_w1_kernel(FoldArgs a, odevit_weights
   fsum = warp_sum(fsum);
   if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = dot; red2[threadIdx.x >> 5] = fsum; }
   __syncthreads();
+  if (fn) {
+    // The rows of W1cat are stored CENTRED over D (W1cat (I - 11^T/D)): the product with the left operand then does not
+    // change when a constant is added to a row of that operand -- (x - c 1^T)(I - 11^T/D) = x (I - 11^T/D) for ANY c --
+    // so the centring of CenterNorm lives in the weights and the operand may be the plain bf16 copy of the state that the
+    // previous GEMM's epilogue writes (api.cu: `xc_ready`); an exactly centred operand gives the same product as before.
+    const float mean = (red2[0] + red2[1] + red2[2] + red2[3]) / (float)D;
+    for (int i = threadIdx.x; i < D; i += 128) {
+      float we = nw[i];
+      if (msc) we *= (1.f + msc[i]);
+      store_elem(a.w1cat, (long long)j * D + i, a.w_type, qs * s_cn * Wrow[i] * we - mean);
+    }
+  }
   if (threadIdx.x == 0) {
     float t = red[0] + red[1] + red[2] + red[3];
     if (lb) t += lb[j - (attn ? 0 : 3 * D)];
@@ -824,6 +836,20 @@ __global__ void __launch_bounds__(128) unfold_w1_kernel(UnfoldArgs a, odevit_wei
   const float s_cn = fn ? (float)D / ((float)D - 1.f) : 1.f;
   const float qs = (j < D) ? a.q_scale : 1.f;
   const float cj = a.c1[j];
+  if (fn) {
+    // G1 was accumulated against operand rows that carry arbitrary constants (fold_w1_kernel): the gradient of the
+    // folded weight is G1 (I - 11^T/D).  Centred IN PLACE: unfold_norm_kernel, launched next, reads the same rows.
+    float rs = 0.f;
+    for (int i = threadIdx.x; i < D; i += 128) rs += a.G1[(long long)j * D + i];
+    __shared__ float red[4];
+    rs = warp_sum(rs);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = rs;
+    __syncthreads();
+    const float mean = (red[0] + red[1] + red[2] + red[3]) / (float)D;
+    float* G1w = const_cast<float*>(a.G1);
+    for (int i = threadIdx.x; i < D; i += 128) G1w[(long long)j * D + i] -= mean;
+    __syncthreads();
+  }
   if (dW) {
     for (int i = threadIdx.x; i < D; i += 128) {
       float we = fn ? nw[i] : 1.f, be = fn ? nb[i] : 0.f;
