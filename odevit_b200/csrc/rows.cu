@@ -866,7 +866,7 @@ __global__ void __launch_bounds__(128) unfold_w1_kernel(UnfoldArgs a, odevit_wei
 }
 
 // one block = 128 columns i x a slice of kUnfoldRows rows j of G1; partial sums meet through atomics
-constexpr int kUnfoldRows = 64;
+constexpr int kUnfoldRows = 16;   // (64 left 288 blocks of 64 dependent row steps each: 38 us of latency for 19 MB)
 __global__ void __launch_bounds__(128) unfold_norm_kernel(UnfoldArgs a, odevit_weights w,
                                                           odevit_weight_grads g) {
   const int D = a.D, hid = a.hid;
@@ -877,6 +877,7 @@ __global__ void __launch_bounds__(128) unfold_norm_kernel(UnfoldArgs a, odevit_w
   const float s_cn = (float)D / ((float)D - 1.f);
   const float q = a.q_scale;
   float dwa = 0.f, dba = 0.f, dwm = 0.f, dbm = 0.f;
+#pragma unroll 8
   for (int j = j0; j < j1; ++j) {
     const float g1 = a.G1[(long long)j * D + i], cj = a.c1[j];
     if (j < 3 * D) {
