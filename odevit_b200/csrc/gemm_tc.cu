@@ -85,10 +85,23 @@ struct Cfg {
 struct DevArgs {
   int M, N, K;
   int tiles_m, tiles_n, split_k, kb_per_split, num_kb;
+  // tiles are dealt in waves of num_units; in wave w unit u takes position (u + tile_skew * w) % num_units of the wave.
+  // With skew 0 a unit walks the N tiles with stride num_units % tiles_n: for in-proj + fc1 (12 N tiles, 74 units) the odd
+  // units met the two GELU tiles back to back every six tiles and the even units only one -- two long epilogues in a row
+  // stall the main loop on its accumulator buffers.  The skew makes that stride coprime with tiles_n (every unit cycles
+  // through all N tiles, the expensive ones spread out); the set of tiles in flight per wave is unchanged.
+  int tile_skew;
   int l2_prefetch;   // epilogue operand rows of the next tile -> L2 (experiment switch ODEVIT_GEMM_PREFETCH)
   int dbg;           // diagnostic builds only (ODEVIT_GEMM_DBG): 1 = skip the shared-memory transposition (wrong results)
   Epi epi;
 };
+
+// the tile of `unit` in wave w_ (see DevArgs::tile_skew); a unit without a tile in the last wave is done
+// (`it` counts the waves: the accumulator-buffer parity every role derives from it)
+#define ODV_FOR_TILES(tile, it)                                                                                     \
+  for (int tile = unit; it * num_units < total_tiles;                                                               \
+       ++it, tile = it * num_units + (unit + g.tile_skew * it) % num_units)                                         \
+    if (tile < total_tiles)
 
 // The epilogue warps' role.  (Inlined: as a real call its `g` would be a generic pointer to the kernel parameters and
 // every epilogue field a global-path load instead of a constant-bank operand -- measured 20-30 % slower.)
@@ -123,7 +136,7 @@ __device__ __forceinline__ void epilogue_role(const DevArgs& g, float* scratch, 
     const bool atomic = IS_ACCUM && g.split_k > 1;
     GT_DECL();
     int it = 0;
-    for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
+    ODV_FOR_TILES(tile, it) {
       int m_base, n_tile;
       tile_coords(tile, m_base, n_tile);
       const int acc = it & 1;
@@ -131,9 +144,10 @@ __device__ __forceinline__ void epilogue_role(const DevArgs& g, float* scratch, 
       const uint32_t taddr = tmem_base + acc * C::ACC2 + (static_cast<uint32_t>(q * 32) << 16);
       const int m0 = m_base + rsub;
       // the operand rows the NEXT tile's epilogue will load (state / GELU input / accumulator) -> L2, one tile ahead
-      if (g.l2_prefetch && tile + num_units < total_tiles) {
+      const int tile_next = (it + 1) * num_units + (unit + g.tile_skew * (it + 1)) % num_units;
+      if (g.l2_prefetch && tile_next < total_tiles) {
         int mb2, nt2;
-        tile_coords(tile + num_units, mb2, nt2);
+        tile_coords(tile_next, mb2, nt2);
         for (int k = 0; k < my_chunks; ++k) {
           if (atomic) epi_prefetch_rows<EPI, true>(g.epi, mb2 + lane, g.M, nt2 + (grp + k * EPI_GROUPS) * 32, g.N);
           else epi_prefetch_rows<EPI, false>(g.epi, mb2 + lane, g.M, nt2 + (grp + k * EPI_GROUPS) * 32, g.N);
@@ -255,7 +269,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = unit; tile < total_tiles; tile += num_units) {
+      int it = 0;
+      ODV_FOR_TILES(tile, it) {
         const int nt = tile % g.tiles_n;
         const int mt = (tile / g.tiles_n) % g.tiles_m;
         const int ks = tile / (g.tiles_n * g.tiles_m);
@@ -318,7 +333,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
+      ODV_FOR_TILES(tile, it) {
         const int ks = tile / (g.tiles_n * g.tiles_m);
         const int kb0 = ks * g.kb_per_split;
         const int kb1 = min(g.num_kb, kb0 + g.kb_per_split);
@@ -582,6 +597,7 @@ int gemm_tc(const GemmArgs& g, cudaStream_t s) {
   d.kb_per_split = (d.num_kb + d.split_k - 1) / d.split_k;
   d.split_k = (d.num_kb + d.kb_per_split - 1) / d.kb_per_split;
   d.epi = g.epi;
+  d.tile_skew = 0;
   {
     static const int pf = [] { const char* e = getenv("ODEVIT_GEMM_PREFETCH"); return e ? atoi(e) : 0; }();
     d.l2_prefetch = pf;   // off: measured neutral to slightly negative (the operand loads are not what the epilogues wait for)
@@ -600,6 +616,15 @@ int gemm_tc(const GemmArgs& g, cudaStream_t s) {
   const int total = d.tiles_m * d.tiles_n * d.split_k;
   const int max_units = sms / cg;
   const int units = total < max_units ? total : max_units;
+  if ((g.epi_mode == EPI_FWD1 || g.epi_mode == EPI_BWD3) && d.tiles_n > 2 && total > units) {
+    // epilogues whose cost depends on the N tile (GELU / GELU' on the fc1 columns only): see DevArgs::tile_skew
+    static const bool off = [] { const char* e = getenv("ODEVIT_GEMM_SKEW"); return e && e[0] == '0'; }();
+    auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+    for (int sk = 0; sk < d.tiles_n && !off; ++sk) {
+      const int stride = (units + sk) % d.tiles_n;
+      if (gcd(stride, d.tiles_n) == 1 && stride != 1 && stride != d.tiles_n - 1) { d.tile_skew = sk; break; }
+    }
+  }
   if (cg == 1) return launch_epi<1, 128>(g.epi_mode, mn, ta, tb, d, units, s);
   if (bn == 128) return launch_epi<2, 128>(g.epi_mode, mn, ta, tb, d, units, s);
   if (bn == 192) return launch_epi<2, 192>(g.epi_mode, mn, ta, tb, d, units, s);
