@@ -599,13 +599,16 @@ def jasmin_rowmax(p_maps: torch.Tensor, k: int) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------
 # patch projection (row (f1) of SURVEY section 8: the caller just before the hot path)
 # ---------------------------------------------------------------------------------------------
-def _gemm_bf16(M: int, N: int, K: int, mn_major: int, A: torch.Tensor, B: torch.Tensor, C: torch.Tensor) -> None:
-    """C[M,N] (fp32) = A . B^T on the tcgen05 GEMM (FFMA kernel for shapes it does not cover)."""
+def _gemm_bf16(M: int, N: int, K: int, mn_major: int, A: torch.Tensor, B: torch.Tensor, C: torch.Tensor,
+               accumulate: int = 0) -> None:
+    """C[M,N] (fp32) (+)= A . B^T on the tcgen05 GEMM (FFMA kernel for shapes it does not cover).  `accumulate` adds into C:
+    the library then splits a long contraction over the idle SMs (weight-gradient shapes: few output tiles, K = every
+    token of the batch) -- pass a zero-filled C."""
     L = _lib.lib()
     with torch.cuda.device(C.device):
-        st = L.odevit_gemm_bf16(M, N, K, mn_major, _ptr(A), _ptr(B), _ptr(C), 0, 1, _stream())
+        st = L.odevit_gemm_bf16(M, N, K, mn_major, _ptr(A), _ptr(B), _ptr(C), accumulate, 1, _stream())
         if st == -4:   # ODEVIT_ERR_UNSUPPORTED
-            st = L.odevit_gemm_bf16(M, N, K, mn_major, _ptr(A), _ptr(B), _ptr(C), 0, 0, _stream())
+            st = L.odevit_gemm_bf16(M, N, K, mn_major, _ptr(A), _ptr(B), _ptr(C), accumulate, 0, _stream())
     _lib.check(st, "odevit_gemm_bf16")
 
 
@@ -639,8 +642,8 @@ class _PatchProj(torch.autograd.Function):
         gy = g_out.reshape(M, D).to(torch.bfloat16).contiguous()
         g_x = g_w_ = g_b = None
         if ctx.needs_input_grad[1]:
-            g_w_ = torch.empty(D, K, dtype=torch.float32, device=gy.device)
-            _gemm_bf16(D, K, M, 1, gy, a.view(M, K), g_w_)       # dW[d,k] = sum_m gy[m,d] a[m,k]
+            g_w_ = torch.zeros(D, K, dtype=torch.float32, device=gy.device)
+            _gemm_bf16(D, K, M, 1, gy, a.view(M, K), g_w_, accumulate=1)   # dW[d,k] = sum_m gy[m,d] a[m,k], split over the SMs
             g_w_ = g_w_.view(w_shape)
         if has_bias and ctx.needs_input_grad[2]:
             g_b = g_out.reshape(M, D).sum(0)
@@ -720,8 +723,8 @@ class _TokenAssembly(torch.autograd.Function):
         if need[0] or need[1]:
             gy = gp.to(torch.bfloat16).reshape(M, D).contiguous()
             if need[1]:
-                g_w = torch.empty(D, K, dtype=torch.float32, device=g.device)
-                _gemm_bf16(D, K, M, 1, gy, a.view(M, K), g_w)
+                g_w = torch.zeros(D, K, dtype=torch.float32, device=g.device)
+                _gemm_bf16(D, K, M, 1, gy, a.view(M, K), g_w, accumulate=1)   # (9 output tiles, K = B * P: split over the SMs)
                 g_w = g_w.view(w_shape)
             if need[0]:
                 cols = torch.empty(M, K, dtype=torch.float32, device=g.device)
