@@ -91,28 +91,35 @@ __device__ __forceinline__ float attn_softmax_row(const AttnArgs& a, uint32_t t_
 #pragma unroll
       for (int i = 0; i < 4; ++i) tt[q4][i] = -INFINITY;
   }
-  for (int c0 = 0; c0 < n_chunks; c0 += 4) {
+  // (the chunk that straddles N is peeled off as a tail, as in attn_softmax_row_fast: the others carry no column tests;
+  //  loads may run past NP inside the slot's 256 columns)
+  const int last = n_chunks - 1;            // the chunk that holds column N - 1
+  const int nv = a.N - last * 16;           // its key columns, 1..16
+  for (int c0 = 0; c0 < last; c0 += 4) {
     float v[4][16];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (c0 + u < n_chunks) ptx::tmem_ld16(t_row + (c0 + u) * 16, v[u]);
+    for (int u = 0; u < 4; ++u) ptx::tmem_ld16(t_row + (c0 + u) * 16, v[u]);
     ptx::tmem_ld_wait();
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (c0 + u < n_chunks) {
-        if constexpr (JAS) {
+      if (c0 + u < last) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            top4_insert(tt[j & 3], ((c0 + u) * 16 + j < a.N) ? v[u][j] : -INFINITY);
-        } else if ((c0 + u + 1) * 16 <= a.N) {   // every column of the chunk is a key: no per-element predicate
-#pragma unroll
-          for (int j = 0; j < 16; ++j) m4[j & 3] = fmaxf(m4[j & 3], v[u][j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if ((c0 + u) * 16 + j < a.N) m4[j & 3] = fmaxf(m4[j & 3], v[u][j]);
+        for (int j = 0; j < 16; ++j) {
+          if constexpr (JAS) top4_insert(tt[j & 3], v[u][j]);
+          else m4[j & 3] = fmaxf(m4[j & 3], v[u][j]);
         }
       }
+  }
+  if (n_chunks > 0) {
+    float v[16];
+    ptx::tmem_ld16(t_row + last * 16, v);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float x = (j < nv) ? v[j] : -INFINITY;
+      if constexpr (JAS) top4_insert(tt[j & 3], x);
+      else m4[j & 3] = fmaxf(m4[j & 3], x);
+    }
   }
   if constexpr (JAS) {
 #pragma unroll
@@ -126,19 +133,27 @@ __device__ __forceinline__ float attn_softmax_row(const AttnArgs& a, uint32_t t_
   float s4[4] = {0.f, 0.f, 0.f, 0.f};
   float inv = 1.f;
   if constexpr (EXPORT) {
-    for (int c0 = 0; c0 < n_chunks; c0 += 4) {
+    for (int c0 = 0; c0 < last; c0 += 4) {
       float v[4][16];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (c0 + u < n_chunks) ptx::tmem_ld16(t_row + (c0 + u) * 16, v[u]);
+      for (int u = 0; u < 4; ++u) ptx::tmem_ld16(t_row + (c0 + u) * 16, v[u]);
       ptx::tmem_ld_wait();
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (c0 + u < n_chunks) {
+        if (c0 + u < last) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if ((c0 + u) * 16 + j < a.N) s4[j & 3] += ex2_fast(fmaf(v[u][j], LOG2E, -mxs));
+          for (int j = 0; j < 16; ++j) s4[j & 3] += ex2_fast(fmaf(v[u][j], LOG2E, -mxs));
         }
+    }
+    if (n_chunks > 0) {
+      float v[16];
+      ptx::tmem_ld16(t_row + last * 16, v);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float e = ex2_fast(fmaf(v[j], LOG2E, -mxs));
+        s4[j & 3] += (j < nv) ? e : 0.f;
+      }
     }
     inv = 1.f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
   }
@@ -163,11 +178,15 @@ __device__ __forceinline__ float attn_softmax_row(const AttnArgs& a, uint32_t t_
       const int c = c0 + u;
       if (c < n_chunks) {
         uint32_t packed[8];
-        const bool full = (c + 1) * 16 <= a.N;   // every column of the chunk is a key
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[u][j] = ex2_fast(fmaf(v[u][j], LOG2E, -mxs));
+        if (c == last) {   // (a uniform branch: only the chunk that straddles N pays for column tests)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[u][j] = (j < nv) ? v[u][j] : 0.f;
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float e = ex2_fast(fmaf(v[u][j], LOG2E, -mxs));
-          if (!full) e = (c * 16 + j < a.N) ? e : 0.f;
+          float e = v[u][j];
           if constexpr (EXPORT) {
             e *= inv;
             if constexpr (DROP) e *= drop_factor(a.drop, drow, c * 16 + j);   // the exported map is post-dropout
